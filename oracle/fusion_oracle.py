@@ -1,0 +1,188 @@
+"""CPU oracle for MERV's multi-encoder feature-fusion hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-numpy restatement of the reference algorithm.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may
+import it, and only as the checker / the timed CPU baseline.  The product path
+(``merv_b200``) never imports anything under ``oracle/`` and has no CPU fallback.
+
+Parity status: the reference ships no tests, golden vectors or KATs for this path (SURVEY.md §4,
+§8c), so the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF: ``oracle/make_golden.py``
+exec's the unmodified ``/root/reference/merv/util/nn_utils.py`` (via ``oracle/ref_loader.py``) and
+stores its outputs in ``tests/golden/*.npz``; ``tests/test_oracle.py`` checks every function below
+against those fixtures.
+
+Every function cites the reference lines it restates (paths relative to /root/reference).
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+try:  # scipy is in the image; keep a pure-python fallback so the oracle never depends on it
+    from scipy.special import erf as _erf
+except Exception:  # pragma: no cover
+    _erf = np.vectorize(math.erf, otypes=[np.float64])
+
+
+# --------------------------------------------------------------------------------------------
+# adaptive 3-D average pooling, channel-last in / channel-last out
+# --------------------------------------------------------------------------------------------
+def adaptive_windows(n_in: int, n_out: int) -> List[Tuple[int, int]]:
+    """Window i of torch's adaptive pooling is [floor(i*n_in/n_out), ceil((i+1)*n_in/n_out)).
+
+    Semantic anchor: ``F.adaptive_avg_pool3d`` as used by ``AveragePooling3DProjector``
+    (merv/util/nn_utils.py:317,328).  14 -> 8 gives the overlapping table of SURVEY.md §7.
+    """
+    return [((i * n_in) // n_out, -((-(i + 1) * n_in) // n_out)) for i in range(n_out)]
+
+
+def avg_pool3d_tokens(x: np.ndarray, out_frames: int, out_size: int) -> np.ndarray:
+    """[B, F, N, C] -> [B, T*S*S, C] with token index t*S*S + i*S + j (j fastest).
+
+    Restates merv/util/nn_utils.py:320-329: H = int(sqrt(N)); "B F (H W) C -> B C F H W";
+    AdaptiveAvgPool3d((T, S, S)); "B C F H W -> B (F H W) C".
+    """
+    B, F, N, C = x.shape
+    H = int(math.sqrt(N))
+    assert H * H == N, "reference computes H=int(sqrt(N)) and einops then requires H*W == N"
+    W = N // H
+    xv = x.reshape(B, F, H, W, C)
+    wt, wh, ww = adaptive_windows(F, out_frames), adaptive_windows(H, out_size), adaptive_windows(W, out_size)
+    acc_dtype = np.float64 if x.dtype == np.float64 else np.float32
+    out = np.empty((B, out_frames, out_size, out_size, C), dtype=acc_dtype)
+    for t, (f0, f1) in enumerate(wt):
+        for i, (h0, h1) in enumerate(wh):
+            for j, (w0, w1) in enumerate(ww):
+                win = xv[:, f0:f1, h0:h1, w0:w1, :].astype(acc_dtype)
+                out[:, t, i, j, :] = win.sum(axis=(1, 2, 3)) / float((f1 - f0) * (h1 - h0) * (w1 - w0))
+    return out.reshape(B, out_frames * out_size * out_size, C).astype(x.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# projectors
+# --------------------------------------------------------------------------------------------
+def gelu_erf(x: np.ndarray) -> np.ndarray:
+    """``nn.GELU()`` with approximate='none' (merv/util/nn_utils.py:48): x * 0.5 * (1 + erf(x / sqrt(2)))."""
+    return (x * 0.5 * (1.0 + _erf(x / math.sqrt(2.0)))).astype(x.dtype)
+
+
+def linear(x: np.ndarray, weight: np.ndarray, bias: np.ndarray) -> np.ndarray:
+    """``nn.Linear``: y = x @ W^T + b, W is [out, in] (merv/util/nn_utils.py:25,32)."""
+    return x @ weight.T + bias
+
+
+def projector_forward(x: np.ndarray, params: Dict[str, np.ndarray], mlp_type: str) -> np.ndarray:
+    """``get_mlp_projector`` variants (merv/util/nn_utils.py:22-59,86-121).
+
+    ``params`` uses the reference state-dict keys relative to ``AveragePooling3DProjector.projector``:
+    linear -> projector.{weight,bias}; gelu-mlp -> projector.{0,2}.*; fused-gelu-mlp -> projector.{0,2,4}.*.
+    """
+    if mlp_type == "linear":
+        return linear(x, params["projector.weight"], params["projector.bias"])
+    if mlp_type == "gelu-mlp":
+        h = gelu_erf(linear(x, params["projector.0.weight"], params["projector.0.bias"]))
+        return linear(h, params["projector.2.weight"], params["projector.2.bias"])
+    if mlp_type == "fused-gelu-mlp":
+        h = gelu_erf(linear(x, params["projector.0.weight"], params["projector.0.bias"]))
+        h = gelu_erf(linear(h, params["projector.2.weight"], params["projector.2.bias"]))
+        return linear(h, params["projector.4.weight"], params["projector.4.bias"])
+    if mlp_type == "none":
+        return x
+    raise ValueError(f"Projector with `{mlp_type = }` is not supported!")
+
+
+def avgpool3d_projector_forward(
+    x: np.ndarray, params: Dict[str, np.ndarray], out_frames: int, out_size: int, mlp_type: str
+) -> np.ndarray:
+    """``AveragePooling3DProjector.forward`` (merv/util/nn_utils.py:320-330): POOL first, then project."""
+    return projector_forward(avg_pool3d_tokens(x, out_frames, out_size), params, mlp_type)
+
+
+# --------------------------------------------------------------------------------------------
+# learnable-query cross-attention mixer
+# --------------------------------------------------------------------------------------------
+def _softmax_last(x: np.ndarray) -> np.ndarray:
+    z = x - x.max(axis=-1, keepdims=True)
+    e = np.exp(z)
+    return e / e.sum(axis=-1, keepdims=True)
+
+
+def fusion_weights_mha(vbar: np.ndarray, params: Dict[str, np.ndarray]) -> np.ndarray:
+    """Attention weights of the single-head ``nn.MultiheadAttention`` exactly as the reference calls it.
+
+    merv/util/nn_utils.py:464-471,499-501,512 with torch's need_weights=True path
+    (torch/nn/functional.py multi_head_attention_forward, separate q/k/v projection weights):
+    q = Q Wq^T + b_q ; k = Vbar Wk^T + b_k ; w = softmax(q k^T / sqrt(embed)).  ``vbar`` is [B, E, K].
+    """
+    Q = params["Q"]  # [1, embed]
+    embed = Q.shape[1]
+    b = params["attention.in_proj_bias"]
+    q = Q @ params["attention.q_proj_weight"].T + b[:embed]  # [1, embed]
+    k = vbar @ params["attention.k_proj_weight"].T + b[embed : 2 * embed]  # [B, E, embed]
+    scores = np.einsum("qd,bed->be", q * (1.0 / math.sqrt(embed)), k)
+    return _softmax_last(scores)
+
+
+def fusion_query_vector(params: Dict[str, np.ndarray]) -> np.ndarray:
+    """The input-independent vector u with softmax_e(u . Vbar_e) == ``fusion_weights_mha``.
+
+    u = Wk^T (Wq Q^T + b_q) / sqrt(embed); b_k only adds a per-row constant that cancels in the softmax.
+    """
+    Q = params["Q"]
+    embed = Q.shape[1]
+    q = Q @ params["attention.q_proj_weight"].T + params["attention.in_proj_bias"][:embed]
+    return (q @ params["attention.k_proj_weight"])[0] / math.sqrt(embed)
+
+
+def cross_attention_fusion_forward(
+    V: Sequence[np.ndarray], params: Dict[str, np.ndarray], token_length: int
+) -> Tuple[np.ndarray, np.ndarray]:
+    """``CrossAttentionAdapterLearnableQuery.forward`` with averagetoken=True, no positional embedding.
+
+    merv/util/nn_utils.py:487-521: assert T in {token_length, 1}; broadcast T==1 encoders; stack to
+    [B, E, T, K]; Vbar = mean over tokens; weights from the MHA; out = sum_e w[b,e] * V[b,e].
+    Returns (out [B, T, K], weights [B, E]).
+    """
+    for emb in V:
+        assert emb.shape[1] == token_length or emb.shape[1] == 1, (token_length, [e.shape for e in V])
+    Vs = [np.repeat(e, token_length, axis=1) if e.shape[1] == 1 else e for e in V]
+    stacked = np.stack(Vs, axis=1)  # [B, E, T, K]
+    vbar = stacked.mean(axis=2)
+    w = fusion_weights_mha(vbar, params)
+    out = np.einsum("be,betk->btk", w, stacked)
+    return out.astype(stacked.dtype), w.astype(stacked.dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# whole path, as MERV.forward glues it
+# --------------------------------------------------------------------------------------------
+def merv_fusion_forward(
+    features: Sequence[np.ndarray],
+    projector_params: Sequence[Dict[str, np.ndarray]],
+    fusion_params: Dict[str, np.ndarray],
+    out_frames: Sequence[int],
+    out_size: int,
+    mlp_type: str,
+    token_length: int,
+) -> Tuple[np.ndarray, np.ndarray, List[np.ndarray]]:
+    """merv/models/vidlms/merv.py:587-589 (per-encoder projector) then :607-609 (feature_fusion).
+
+    ``features[i]`` is [B, T_i, N_i, C_i] as produced by the reshape at merv.py:576-585.
+    Returns (prefix [B, T, K], weights [B, E], per-encoder projected tokens).
+    """
+    ys = [
+        avgpool3d_projector_forward(x, p, t, out_size, mlp_type)
+        for x, p, t in zip(features, projector_params, out_frames)
+    ]
+    out, w = cross_attention_fusion_forward(ys, fusion_params, token_length)
+    return out, w, ys
+
+
+def rel_err(a: np.ndarray, b: np.ndarray) -> float:
+    """Parity metric of BASELINE.md §5: max|a-b| / max|b| (element-wise relative error is ill-conditioned)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))

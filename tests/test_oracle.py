@@ -1,0 +1,96 @@
+"""CPU tests: the numpy oracle (oracle/fusion_oracle.py) against fixtures produced by the UNMODIFIED
+reference modules (oracle/make_golden.py -> tests/golden/*.npz).  The reference has no tests of its own
+(SURVEY.md §4), so these fixtures are what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import cases as C
+from oracle import fusion_oracle as O
+from tests.golden_util import regenerate
+
+FP32_TOL = 1e-5  # BASELINE.json north_star: 1e-5 relative in fp32 (metric: max|a-b| / max|b|)
+
+
+def test_window_table_14_to_8():
+    # 14 -> 8 has overlapping windows of size 2/3/3/2/2/3/3/2
+    assert O.adaptive_windows(14, 8) == [(0, 2), (1, 4), (3, 6), (5, 7), (7, 9), (8, 11), (10, 13), (12, 14)]
+    assert O.adaptive_windows(16, 8) == [(2 * i, 2 * i + 2) for i in range(8)]
+    assert O.adaptive_windows(16, 16) == [(i, i + 1) for i in range(16)]
+    assert O.adaptive_windows(5, 3) == [(0, 2), (1, 4), (3, 5)]
+
+
+def test_token_order_is_f_h_w():
+    # token index = f*S*S + h*S + w with w fastest
+    F, H, S, Cc = 2, 4, 2, 3
+    x = np.zeros((1, F, H * H, Cc), np.float32)
+    for f in range(F):
+        for h in range(H):
+            for w in range(H):
+                x[0, f, h * H + w, :] = 100 * f + 10 * (h // 2) + (w // 2)
+    y = O.avg_pool3d_tokens(x, F, S)
+    expect = [100 * f + 10 * i + j for f in range(F) for i in range(S) for j in range(S)]
+    assert np.allclose(y[0, :, 0], expect)
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_oracle_matches_reference_golden(name):
+    case = C.CASES[name]
+    g, feats, pp, fp = regenerate(case)
+    out, w, ys = O.merv_fusion_forward(feats, pp, fp, case.out_frames, case.out_size, case.mlp_type, case.token_length)
+    assert out.shape == (case.batch, case.token_length, case.llm_dim)
+    assert w.shape == (case.batch, case.num_encoders)
+    assert np.allclose(w.sum(-1), 1.0, atol=1e-5)
+    scale = float(g["out_abs_max"])
+    assert np.abs(w - g["weights"]).max() < 2e-5
+    idx = g["sample_idx"]
+    assert np.abs(out.reshape(-1)[idx] - g["out_samples"]).max() / scale < FP32_TOL
+    assert abs(float(out.astype(np.float64).sum()) - float(g["out_sum"])) < 1e-4 * max(1.0, abs(float(g["out_abs_mean"])) * out.size) 
+    for e, y in enumerate(ys):
+        ref = g["y_samples"][e]
+        assert np.abs(y.reshape(-1)[idx % y.size] - ref).max() / max(np.abs(ref).max(), 1e-6) < FP32_TOL
+    if name in C.FULL_STORE_CASES:
+        assert O.rel_err(out, g["out"]) < FP32_TOL
+        for e, x in enumerate(feats):
+            pooled = O.avg_pool3d_tokens(x, case.out_frames[e], case.out_size)
+            assert O.rel_err(pooled, g[f"pooled{e}"]) < FP32_TOL
+            assert O.rel_err(ys[e], g[f"y{e}"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["tiny_linear", "ragged_windows", "mid_linear"])
+def test_query_vector_identity(name):
+    # weights == softmax_e(u . mean_t V_e): the algebra the CUDA score kernels rely on
+    case = C.CASES[name]
+    g, feats, pp, fp = regenerate(case)
+    _, w, ys = O.merv_fusion_forward(feats, pp, fp, case.out_frames, case.out_size, case.mlp_type, case.token_length)
+    u = O.fusion_query_vector(fp)
+    s = np.stack([y.astype(np.float64).mean(1) @ u.astype(np.float64) for y in ys], axis=1)
+    e = np.exp(s - s.max(-1, keepdims=True))
+    assert np.abs(e / e.sum(-1, keepdims=True) - w).max() < 1e-5
+
+
+def test_single_encoder_is_identity():
+    case = C.CASES["single_encoder"]
+    g, feats, pp, fp = regenerate(case)
+    out, w, ys = O.merv_fusion_forward(feats, pp, fp, case.out_frames, case.out_size, case.mlp_type, case.token_length)
+    assert np.array_equal(w, np.ones_like(w))
+    assert np.array_equal(out, ys[0])
+
+
+def test_token_length_one_broadcast():
+    # nn_utils.py:502: an encoder emitting a single token is repeated to token_length
+    case = C.CASES["tiny_linear"]
+    fp = C.make_fusion_params(case)
+    rng = np.random.default_rng(0)
+    V = [rng.standard_normal((2, case.token_length, case.llm_dim)).astype(np.float32),
+         rng.standard_normal((2, 1, case.llm_dim)).astype(np.float32)]
+    out, w = O.cross_attention_fusion_forward(V, fp, case.token_length)
+    Vb = [V[0], np.repeat(V[1], case.token_length, axis=1)]
+    out2, w2 = O.cross_attention_fusion_forward(Vb, fp, case.token_length)
+    assert np.array_equal(out, out2) and np.array_equal(w, w2)
+    with pytest.raises(AssertionError):
+        O.cross_attention_fusion_forward([V[0][:, :3]], fp, case.token_length)
+
+
+def test_unsupported_projector_type():
+    with pytest.raises(ValueError):
+        O.projector_forward(np.zeros((1, 4), np.float32), {}, "relu-mlp")
