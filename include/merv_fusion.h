@@ -1,0 +1,156 @@
+/*
+ * merv_fusion.h — C ABI of libmerv_fusion.so: MERV's multi-encoder feature-fusion hot path on B200 (sm_100a).
+ *
+ * The reference (princetonvisualai/merv) is pure Python/PyTorch and has no FFI; the boundary it exposes for
+ * this path is the nn.Module surface of merv/util/nn_utils.py.  Each entry point below replaces the body of
+ * one reference method (cited as file:line, relative to the reference root) and is what a ctypes binding in
+ * that file would call.  Conventions:
+ *
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator in practice); the library allocates no device memory and keeps no reference after return;
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*), does no host
+ *     synchronisation and is CUDA-graph capturable;
+ *   - return value: 0 on success, a negative MERV_E_* code otherwise; merv_last_error() gives the message of
+ *     the calling thread's last failure.  There is NO CPU fallback: a non-sm_100 device is MERV_E_ARCH;
+ *   - tensors are row-major with the channel/feature dimension contiguous; `dtype` selects the element type of
+ *     activations AND weights (MERV_BF16: bf16 storage, fp32 accumulation, tcgen05 tensor cores for the
+ *     projector GEMMs; MERV_F32: fp32 storage and SIMT fp32 arithmetic, the 1e-5 parity path).
+ */
+#ifndef MERV_FUSION_H_
+#define MERV_FUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MERV_ABI_VERSION 1
+
+enum { MERV_F32 = 0, MERV_BF16 = 1 };
+enum { MERV_ACT_NONE = 0, MERV_ACT_GELU_ERF = 1 };
+enum {
+  MERV_OK = 0,
+  MERV_E_SHAPE = -1,   /* a dimension is non-positive / inconsistent / unsupported */
+  MERV_E_ALIGN = -2,   /* a pointer or leading dimension violates the 16-byte alignment the kernels need */
+  MERV_E_DTYPE = -3,   /* unknown dtype / activation code, or combination not implemented */
+  MERV_E_ARCH = -4,    /* current device is not compute capability 10.x */
+  MERV_E_CUDA = -5,    /* a CUDA runtime / driver call failed (message has the CUDA error string) */
+  MERV_E_ARG = -6      /* null pointer where one is required, too many encoders, ... */
+};
+
+#define MERV_MAX_ENCODERS 8
+#define MERV_MAX_SEGMENTS 4
+#define MERV_ROWDOT_BLOCK 128 /* column-block width of the row-dot partials emitted by the GEMM epilogue */
+
+int merv_abi_version(void);
+const char* merv_last_error(void);
+/* 0 if the CURRENT device can run the library (sm_100), MERV_E_ARCH otherwise. */
+int merv_device_check(void);
+int merv_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Adaptive spatio-temporal average pooling, channel-last in and out.
+ * Replaces AveragePooling3DProjector.forward's rearrange -> AdaptiveAvgPool3d -> rearrange
+ * (merv/util/nn_utils.py:320-329) for up to MERV_MAX_ENCODERS encoders in ONE launch.
+ *
+ *   x : [B, F, H*W, C]  (element strides x_batch_stride / x_frame_stride / x_token_stride, channel stride 1)
+ *   y : [B, T*S*S, C]   token index t*S*S + i*S + j (j fastest); row stride y_row_stride elements
+ *   window k of an axis n_in -> n_out is [floor(k*n_in/n_out), ceil((k+1)*n_in/n_out))
+ *   colsum (optional, fp32): [B, colsum_parts, C] partial sums over tokens of the POOLED features, written
+ *     (not accumulated) deterministically; colsum_parts must equal merv_pool3d_colsum_parts(T, S, B).
+ * Accumulation is fp32 for both dtypes (as ATen's kernel does).  C % 8 == 0 (bf16) or C % 4 == 0 (fp32).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* x;
+  void* y;
+  float* colsum; /* may be NULL */
+  int32_t F, H, W, C, T, S;
+  int64_t x_batch_stride, x_frame_stride, x_token_stride;
+  int64_t y_batch_stride, y_row_stride;
+} merv_pool_desc;
+
+int merv_pool3d_colsum_parts(int T, int S, int B);
+int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Projector layer: Y = act(A W^T + bias).  Replaces nn.Linear (+ nn.GELU) inside LinearProjector.forward /
+ * MLPProjector.forward / FusedMLPProjector.forward (merv/util/nn_utils.py:31-32,46-55,97-108).
+ *
+ *   A [M, K] (lda), W [N, K] (ldw, PyTorch nn.Linear layout), bias [N] (dtype of W; may be NULL), Y [M, N] (ldy)
+ *   act: MERV_ACT_NONE | MERV_ACT_GELU_ERF (exact erf GELU, nn.GELU() default)
+ *   rowdot_vec / rowdot_out (optional, bf16 path only): rowdot_out[m, j] = sum over columns n of block j
+ *     (MERV_ROWDOT_BLOCK wide) of rowdot_vec[n] * Y[m, n] (Y as rounded to the output dtype); shape
+ *     [M, ceil(N / MERV_ROWDOT_BLOCK)] fp32.  Feeds the encoder scores without re-reading Y.
+ * MERV_BF16 runs on tcgen05 (TMA-fed, TMEM accumulators); needs K % 8 == 0, N % 8 == 0, 16-byte aligned bases.
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_linear_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* Y,
+                         int64_t ldy, int M, int N, int K, int act, int dtype, const float* rowdot_vec,
+                         float* rowdot_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * The learnable-query "cross attention" collapses to a dot product with an input-independent vector
+ * (SURVEY.md §3.3): weights[b,:] = softmax_e(u . mean_t V[b,e,t,:]),
+ *   u = Wk^T (Wq Q^T + b_q) / sqrt(embed).
+ * Replaces the q/k projections inside nn.MultiheadAttention as called at merv/util/nn_utils.py:499-512.
+ *   Q [1, embed], Wq [embed, embed], Wk [embed, llm_dim], in_proj_bias [3*embed] (dtype); u [llm_dim] fp32;
+ *   workspace: embed floats.
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_fusion_query_vec(const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias, float* u,
+                          float* workspace, int embed, int llm_dim, int dtype, void* stream);
+
+/* For an affine last projector layer y = W x + b:  u . y = (W^T u) . x + u . b.
+ *   W [N, K] (ldw), bias [N] or NULL, u [N] fp32  ->  v [K] fp32, c [1] fp32. */
+int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, int N,
+                          int K, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Scores -> softmax over encoders -> mixing weights.  Three sources for the scores:
+ *   merv_scores_from_tokens : s[b,e] = mean_t(u . V_e[b,t,:]) read from the projected tokens themselves
+ *                             (general path; V_e [B, T_e, K] with T_e in {T, 1}, nn_utils.py:494-509)
+ *   merv_scores_from_rowdot : the same from the GEMM epilogue's row-dot partials (no re-read of V):
+ *                             s[b,e] = (1/T) sum_{t,j} rowdot_e[b*T+t, j] + c_e
+ *   merv_scores_from_colsum : affine projectors, from the pool kernel's column sums:
+ *                             s[b,e] = v_e . mean_t P_e[b,t,:] + c_e
+ * each writes raw scores [B, E] fp32 (deterministic reduction order).
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const float* u, float* scores,
+                            float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
+                            void* stream);
+size_t merv_scores_from_tokens_workspace(int B, int E, int T, int K);
+int merv_scores_from_rowdot(const float* const* rowdot, const float* const* c /* per-encoder additive constant, may be NULL */,
+                            float* scores, int B, int E, int T, int nblk, void* stream);
+int merv_scores_from_colsum(const float* const* colsum, const float* const* v, const float* const* c,
+                            const int32_t* C, const int32_t* parts, float* scores, int B, int E, int T,
+                            void* stream);
+
+/* weights[b,:] = softmax(scores[b,:]) (fp32);  optionally bias_mix[b,n] = sum_e weights[b,e] * bias_e[n]
+ * (the per-video bias of the fused affine path; bias_e in `dtype`, may contain NULL entries). */
+int merv_softmax_weights(const float* scores, float* weights, const void* const* bias, float* bias_mix, int B,
+                         int E, int N, int dtype, void* stream);
+
+/* out[b,t,:] = sum_e weights[b,e] * V_e[b,t,:]   — replaces torch.stack + torch.bmm at nn_utils.py:503,521.
+ * Reads every V_e element once, writes every fused token once.  T_e in {T, 1} (broadcast, nn_utils.py:502).
+ * If `scores` is non-NULL the softmax is done in-kernel (warp shuffles over the E lanes) and `weights` is an
+ * output; otherwise `weights` is an input. */
+int merv_softmax_mix(const void* const* V, const int32_t* tokens, const float* scores, float* weights, void* out,
+                     int B, int E, int T, int K, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused affine path (the shipped "3davg+linear" + "cross_attention_avg_lq" configuration):
+ *   out[m,:] = sum_s scale[video(m), s] * (A_s[m,:] W_s^T) + bias_mix[video(m), :]
+ * One persistent tcgen05 kernel; per-encoder projected tokens are never written to HBM; each fused token is
+ * written exactly once.  A_s [M, K_s] (lda[s]) are the pooled features, W_s [N, K_s] (ldw[s]);
+ * scale [M / rows_per_video, nseg] fp32 (the mixing weights), bias_mix [M / rows_per_video, N] fp32.
+ * Replaces LinearProjector.forward x E + CrossAttentionAdapterLearnableQuery.forward's stack/bmm
+ * (nn_utils.py:31-32,503,521).  bf16 only.
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                          const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                          int64_t ldo, int M, int N, int rows_per_video, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MERV_FUSION_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libmerv_fusion.so (the C ABI declared in include/merv_fusion.h).
+
+The library is the product: if it is missing this module raises ImportError-grade errors loudly —
+there is no Python/torch/CPU fallback for any of the entry points.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
+
+MERV_F32, MERV_BF16 = 0, 1
+ACT_NONE, ACT_GELU_ERF = 0, 1
+MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 128
+ABI_VERSION = 1
+
+ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}
+
+
+class MervError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class PoolDesc(C.Structure):
+    """merv_pool_desc"""
+
+    _fields_ = [
+        ("x", c_void_p), ("y", c_void_p), ("colsum", c_void_p),
+        ("F", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("T", c_int32), ("S", c_int32),
+        ("x_batch_stride", c_int64), ("x_frame_stride", c_int64), ("x_token_stride", c_int64),
+        ("y_batch_stride", c_int64), ("y_row_stride", c_int64),
+    ]
+
+
+_PP = POINTER(c_void_p)
+_SIGNATURES = {
+    # name: (restype, argtypes) — keep in lock-step with include/merv_fusion.h (tests/test_abi.py checks the export list)
+    "merv_abi_version": (c_int, []),
+    "merv_last_error": (c_char_p, []),
+    "merv_device_check": (c_int, []),
+    "merv_num_sms": (c_int, []),
+    "merv_pool3d_colsum_parts": (c_int, [c_int, c_int, c_int]),
+    "merv_pool3d": (c_int, [POINTER(PoolDesc), c_int, c_int, c_int, c_void_p]),
+    "merv_linear_bias_act": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                     c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "merv_fusion_query_vec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_affine_score_vec": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_scores_from_tokens": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
+                                        c_int, c_void_p]),
+    "merv_scores_from_tokens_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "merv_scores_from_rowdot": (c_int, [_PP, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "merv_scores_from_colsum": (c_int, [_PP, _PP, _PP, POINTER(c_int32), POINTER(c_int32), c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_softmax_weights": (c_int, [c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "merv_softmax_mix": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "merv_fused_linear_mix": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
+                                      c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libmerv_fusion.so; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m merv_b200.build` (needs nvcc). "
+            "merv_b200 has no CPU or pure-PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    got = lib.merv_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {got}, the Python binding expects {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise MervError(rc, (load().merv_last_error() or b"").decode("utf-8", "replace"))
+
+
+def ptr_array(ptrs) -> "C.Array":
+    return (c_void_p * len(ptrs))(*[c_void_p(p) if p else c_void_p(None) for p in ptrs])
+
+
+def i32_array(vals) -> "C.Array":
+    return (c_int32 * len(vals))(*vals)
+
+
+def i64_array(vals) -> "C.Array":
+    return (c_int64 * len(vals))(*vals)

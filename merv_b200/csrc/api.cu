@@ -1,0 +1,110 @@
+// extern "C" surface shared by all kernels: error state, device checks, GEMM entry points.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace merv {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int g_dev_ok[64];    // 0 unknown, 1 ok, -1 wrong arch
+static int g_dev_sms[64];
+
+int require_sm100() {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(MERV_E_CUDA, "cudaGetDevice failed: %s (no CUDA device? this library has no CPU path)", cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return fail(MERV_E_CUDA, "device index %d out of range", dev);
+  if (g_dev_ok[dev] == 0) {
+    int major = 0, sms = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(MERV_E_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
+    g_dev_sms[dev] = sms;
+    g_dev_ok[dev] = (major == 10) ? 1 : -1;
+  }
+  if (g_dev_ok[dev] < 0) return fail(MERV_E_ARCH, "device %d is not compute capability 10.x; libmerv_fusion is built for sm_100a only", dev);
+  return MERV_OK;
+}
+
+int sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (g_dev_sms[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    g_dev_sms[dev] = sms;
+  }
+  return g_dev_sms[dev];
+}
+
+}  // namespace merv
+
+using namespace merv;
+
+extern "C" int merv_abi_version(void) { return MERV_ABI_VERSION; }
+extern "C" const char* merv_last_error(void) { return g_error; }
+extern "C" int merv_device_check(void) { return require_sm100(); }
+extern "C" int merv_num_sms(void) { return sm_count(); }
+
+// impl: 0 = default for the dtype (bf16 -> tcgen05, fp32 -> SIMT); MERV_GEMM_IMPL=simt forces the SIMT kernel for
+// bf16 too (used by the tests to cross-check the tensor-core kernel on the GPU; never a CPU path).
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MERV_GEMM_IMPL");
+    v = (e != nullptr && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* Y,
+                                    int64_t ldy, int M, int N, int K, int act, int dtype, const float* rowdot_vec,
+                                    float* rowdot_out, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_linear_bias_act: unknown dtype %d", dtype);
+  MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_DTYPE, "merv_linear_bias_act: unknown activation %d", act);
+  MERV_REQUIRE(A && W && Y, MERV_E_ARG, "merv_linear_bias_act: NULL operand");
+  MERV_REQUIRE(M >= 0 && N > 0 && K > 0, MERV_E_SHAPE, "merv_linear_bias_act: M=%d N=%d K=%d", M, N, K);
+  MERV_REQUIRE(lda >= K && ldw >= K && ldy >= N, MERV_E_SHAPE, "merv_linear_bias_act: leading dimensions lda=%lld ldw=%lld ldy=%lld too small",
+               (long long)lda, (long long)ldw, (long long)ldy);
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16 && !force_simt()) {
+    GemmSegment seg = {A, lda, W, ldw, K};
+    return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, rowdot_vec, rowdot_out, Y, ldy, M, N, s);
+  }
+  MERV_REQUIRE(rowdot_vec == nullptr && rowdot_out == nullptr, MERV_E_DTYPE,
+               "merv_linear_bias_act: the row-dot epilogue exists only on the bf16 tensor-core path");
+  return launch_gemm_simt(A, lda, W, ldw, bias, Y, ldy, M, N, K, act, dtype, s);
+}
+
+extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                     const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                     int64_t ldo, int M, int N, int rows_per_video, void* stream) {
+  MERV_REQUIRE(A && lda && W && ldw && K && scale && out, MERV_E_ARG, "merv_fused_linear_mix: NULL pointer");
+  MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_linear_mix: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
+  MERV_REQUIRE(M >= 0 && N > 0 && rows_per_video > 0, MERV_E_SHAPE, "merv_fused_linear_mix: M=%d N=%d rows_per_video=%d", M, N, rows_per_video);
+  MERV_REQUIRE(M % rows_per_video == 0, MERV_E_SHAPE, "merv_fused_linear_mix: M=%d is not a multiple of rows_per_video=%d", M, rows_per_video);
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  GemmSegment seg[MERV_MAX_SEGMENTS];
+  for (int s = 0; s < nseg; ++s) seg[s] = GemmSegment{A[s], lda[s], W[s], ldw[s], K[s]};
+  return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, M, N,
+                             static_cast<cudaStream_t>(stream));
+}

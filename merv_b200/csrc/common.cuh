@@ -1,0 +1,116 @@
+// Shared helpers for libmerv_fusion.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "merv_fusion.h"
+
+namespace merv {
+
+// ---- host-side error plumbing -----------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define MERV_CUDA_OK(expr)                                                                            \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return ::merv::fail(MERV_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MERV_REQUIRE(cond, code, ...) \
+  do {                                \
+    if (!(cond)) return ::merv::fail(code, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int require_sm100();   // MERV_OK or MERV_E_ARCH for the current device (cached per device)
+int sm_count();        // SM count of the current device
+
+// one (A_s, W_s, K_s) product of the tcgen05 GEMM (see gemm_tcgen05.cu)
+struct GemmSegment {
+  const void* A;
+  long long lda;
+  const void* W;
+  long long ldw;
+  int K;
+};
+int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
+                        const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, int M,
+                        int N, cudaStream_t stream);
+int launch_gemm_simt(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* Y, long long ldy,
+                     int M, int N, int K, int act, int dtype, cudaStream_t s);
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+template <typename T> struct VecTraits;
+template <> struct VecTraits<__nv_bfloat16> { static constexpr int kVec = 8; };  // 16 bytes
+template <> struct VecTraits<float> { static constexpr int kVec = 4; };          // 16 bytes
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+// cached variant (lets L1 absorb the window overlap re-reads of the pool kernel)
+__device__ __forceinline__ uint4 ldg_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_na_v4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// 16-byte vector <-> fp32 lanes
+template <typename T> struct Vec16;
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
+    f[0] = bf16_lo(r.x); f[1] = bf16_hi(r.x); f[2] = bf16_lo(r.y); f[3] = bf16_hi(r.y);
+    f[4] = bf16_lo(r.z); f[5] = bf16_hi(r.z); f[6] = bf16_lo(r.w); f[7] = bf16_hi(r.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+};
+template <> struct Vec16<float> {
+  static constexpr int kN = 4;
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y); f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+  }
+  __device__ static __forceinline__ uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+};
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// nn.GELU() default (approximate='none'): 0.5 x (1 + erf(x / sqrt 2))   [merv/util/nn_utils.py:48]
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace merv

@@ -1,0 +1,402 @@
+// bf16 projector GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands by TMA).
+//
+// One persistent, warp-specialised kernel serves two entry points:
+//
+//   merv_linear_bias_act   Y = act(A W^T + bias)                  (nn.Linear [+ nn.GELU], merv/util/nn_utils.py:31-32,46-55)
+//   merv_fused_linear_mix  out = sum_s w[video,s] * (A_s W_s^T) + bias_mix[video]
+//                          (E LinearProjectors + the stack/bmm of CrossAttentionAdapterLearnableQuery.forward,
+//                           nn_utils.py:31-32,503,521, without ever writing the per-encoder projections to HBM)
+//
+// Tile 128 x 256 x 64 per CTA (cta_group::1, UMMA 128x256x16), 4-stage TMA->smem ring (128B swizzle, K-major
+// A and W), two 256-column TMEM accumulators.  A "segment" is one (A_s, W_s, K_s) product; the MMA warp
+// alternates accumulators per segment, the 8 epilogue warps drain each finished accumulator into fp32
+// registers scaled by the segment's mixing weight while the next segment (or next tile) is being multiplied,
+// and after the last segment apply bias / exact-erf GELU / optional row-dot and store bf16 — each output
+// element is written exactly once.
+//
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      tcgen05.mma issuer (one elected lane)
+//   warp 2      TMEM allocator
+//   warp 3      idle
+//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 and columns 128*((w-4)/4)..+127 of the tile
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace merv {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int B_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int TMEM_COLS = 512;
+
+struct GemmParams {
+  int M, N;
+  int nseg;
+  int kblocks[MERV_MAX_SEGMENTS];
+  const float* seg_scale;  // [videos, nseg] or NULL (=1)
+  const float* bias_rows;  // [videos, N] fp32 or NULL
+  int rows_per_video;
+  int num_videos;
+  const __nv_bfloat16* bias;  // [N] or NULL
+  int act;
+  const float* rowdot_vec;  // [N] or NULL
+  float* rowdot_out;        // [M, rowdot_nblk]
+  int rowdot_nblk;
+  __nv_bfloat16* Y;
+  long long ldy;
+  int m_blocks, n_blocks;
+};
+
+struct TensorMaps {
+  CUtensorMap a[MERV_MAX_SEGMENTS];
+  CUtensorMap b[MERV_MAX_SEGMENTS];
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin with a watchdog: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
+// hung GPU.  The timer is only read on the slow path.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (globaltimer_ns() - t0 > 4000000000ull) {
+      printf("merv gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// smem matrix descriptor: K-major, 128-byte swizzle, 8-row atoms of 1024 B (SBO), Blackwell descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                      // version [46,48)
+  d |= static_cast<uint64_t>(2) << 61;                      // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the kernel -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  const uint32_t full_bar = smem_u32(bars);                  // [STAGES]
+  const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
+  const uint32_t tfull_bar = empty_bar + 8 * STAGES;         // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;                // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_blocks * p.n_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      prefetch_tmap(&maps.a[s]);
+      prefetch_tmap(&maps.b[s]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int nkb = p.kblocks[s];
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            mbar_wait(empty_bar + 8 * stage, ph ^ 1u);
+            mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+            const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
+            tma_load_2d(&maps.a[s], full_bar + 8 * stage, sa, kb * BK, m_blk * BM);
+            tma_load_2d(&maps.b[s], full_bar + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN);
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+          const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          mbar_wait(tempty_bar + 8 * buf, aph ^ 1u);  // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          const int nkb = p.kblocks[s];
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
+            mbar_wait(full_bar + 8 * stage, ph);
+            tc_fence_after();
+            const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
+            const uint64_t a_desc = umma_desc_sw128(sa), b_desc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the address field
+              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(empty_bar + 8 * stage);  // frees the smem stage once these MMAs have read it
+          }
+          umma_commit(tfull_bar + 8 * buf);  // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===== epilogue =====
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int h = (warp - 4) >> 2;   // column half of the tile
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+      const int row = m_blk * BM + q * 32 + lane;
+      int video = row / p.rows_per_video;
+      if (video >= p.num_videos) video = p.num_videos - 1;
+      float sum[128];
+#pragma unroll
+      for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+      for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        const float scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
+        mbar_wait(tfull_bar + 8 * buf, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fmaf(scale, __uint_as_float(v[i]), sum[c * 32 + i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);  // accumulator may be overwritten
+      }
+      // ---- finalize: bias, activation, optional row-dot, bf16 store (each element written once) ----
+      const int col0 = n_blk * BN + h * 128;
+      const bool row_ok = row < p.M;
+      float rowdot = 0.f;
+      __nv_bfloat16* yrow = p.Y + (long long)row * p.ldy;
+#pragma unroll
+      for (int c8 = 0; c8 < 16; ++c8) {
+        const int n = col0 + c8 * 8;
+        if (n < p.N) {  // N % 8 == 0 is enforced on the host
+          float b[8];
+          if (p.bias != nullptr) {
+            Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
+          } else if (p.bias_rows != nullptr) {
+            const float4* br = reinterpret_cast<const float4*>(p.bias_rows + (long long)video * p.N + n);
+            const float4 b0 = __ldg(br), b1 = __ldg(br + 1);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = 0.f;
+          }
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] = sum[c8 * 8 + i] + b[i];
+            if (p.act == MERV_ACT_GELU_ERF) o[i] = gelu_erf(o[i]);
+          }
+          const uint4 packed = Vec16<__nv_bfloat16>::pack(o);
+          if (p.rowdot_vec != nullptr) {
+            float r[8];
+            Vec16<__nv_bfloat16>::unpack(packed, r);  // dot with the values as stored
+            const float4* rv = reinterpret_cast<const float4*>(p.rowdot_vec + n);
+            const float4 r0 = __ldg(rv), r1 = __ldg(rv + 1);
+            rowdot += r[0] * r0.x + r[1] * r0.y + r[2] * r0.z + r[3] * r0.w + r[4] * r1.x + r[5] * r1.y + r[6] * r1.z + r[7] * r1.w;
+          }
+          if (row_ok) *reinterpret_cast<uint4*>(yrow + n) = packed;
+        }
+      }
+      if (p.rowdot_vec != nullptr && row_ok && col0 < p.N) p.rowdot_out[(long long)row * p.rowdot_nblk + (col0 / MERV_ROWDOT_BLOCK)] = rowdot;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, 64] with 128-byte swizzle
+static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", int(r), rows, cols, ld);
+  return MERV_OK;
+}
+
+
+int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
+                        const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, int M,
+                        int N, cudaStream_t stream) {
+  MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
+  MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
+  MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
+  MERV_REQUIRE(aligned16(Y) && (bias == nullptr || aligned16(bias)) && (bias_rows == nullptr || aligned16(bias_rows)) &&
+                   (rowdot_vec == nullptr || aligned16(rowdot_vec)),
+               MERV_E_ALIGN, "gemm: Y / bias / rowdot_vec must be 16-byte aligned");
+  MERV_REQUIRE(rows_per_video > 0, MERV_E_SHAPE, "gemm: rows_per_video=%d", rows_per_video);
+  MERV_REQUIRE((rowdot_vec == nullptr) == (rowdot_out == nullptr), MERV_E_ARG, "gemm: rowdot_vec and rowdot_out go together");
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  // (per-device attribute; cheap enough to set on every call, but once per process per device is enough)
+  attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  (void)attr_once;
+  MERV_REQUIRE(attr_err == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", SMEM_BYTES,
+               cudaGetErrorString(attr_err));
+
+  TensorMaps maps;
+  GemmParams p = {};
+  p.M = M; p.N = N; p.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    const GemmSegment& g = seg[s];
+    MERV_REQUIRE(g.A && g.W, MERV_E_ARG, "gemm: segment %d has a NULL operand", s);
+    MERV_REQUIRE(g.K > 0 && g.K % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.lda >= g.K && g.ldw >= g.K, MERV_E_ALIGN,
+                 "gemm: segment %d: K=%d lda=%lld ldw=%lld must be multiples of 8 with ld >= K", s, g.K, g.lda, g.ldw);
+    MERV_REQUIRE(aligned16(g.A) && aligned16(g.W), MERV_E_ALIGN, "gemm: segment %d: operands must be 16-byte aligned", s);
+    if (int rc = make_tmap(&maps.a[s], g.A, M, g.K, g.lda, BM)) return rc;
+    if (int rc = make_tmap(&maps.b[s], g.W, N, g.K, g.ldw, BN)) return rc;
+    p.kblocks[s] = (g.K + BK - 1) / BK;  // the K tail is zero-filled by TMA
+  }
+  for (int s = nseg; s < MERV_MAX_SEGMENTS; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
+  p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;
+  p.num_videos = (M + rows_per_video - 1) / rows_per_video;
+  p.bias = static_cast<const __nv_bfloat16*>(bias); p.act = act;
+  p.rowdot_vec = rowdot_vec; p.rowdot_out = rowdot_out; p.rowdot_nblk = (N + MERV_ROWDOT_BLOCK - 1) / MERV_ROWDOT_BLOCK;
+  p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy;
+  p.m_blocks = (M + BM - 1) / BM; p.n_blocks = (N + BN - 1) / BN;
+  const long long total = (long long)p.m_blocks * p.n_blocks;
+  const int sms = sm_count();
+  const int grid = int(total < sms ? total : sms);
+  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(maps, p);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+}  // namespace merv

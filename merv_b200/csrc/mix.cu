@@ -1,0 +1,458 @@
+// Encoder scores, softmax over encoders and the weighted mix of CrossAttentionAdapterLearnableQuery.forward
+// (reference merv/util/nn_utils.py:487-521), restated through the identity of SURVEY.md §3.3:
+//     weights[b,:] = softmax_e(u . mean_t V[b,e,t,:]),   u = Wk^T (Wq Q^T + b_q) / sqrt(embed)
+// (b_k adds a per-row constant that cancels in the softmax; Wv, b_v and out_proj never reach an output).
+// All reductions use a fixed order (no float atomics) so results are bit-reproducible per video, independent
+// of batch size and of how the batch is sharded across GPUs.
+#include "common.cuh"
+
+namespace merv {
+
+// block-wide sum with a fixed reduction tree; result valid in every thread
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* smem /* >= 32 floats */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  float r = (lane < kThreads / 32) ? smem[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// ---- u = Wk^T (Wq Q^T + b_q) / sqrt(embed) --------------------------------------------------------------
+// q[d] = sum_j Wq[d,j] Q[j] + b_q[d] : one warp per row, coalesced along j
+template <typename T>
+__global__ void __launch_bounds__(256) qproj_kernel(const T* __restrict__ Wq, const T* __restrict__ Q,
+                                                    const T* __restrict__ bias, float* __restrict__ q, int embed) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= embed) return;
+  const int lane = threadIdx.x & 31;
+  const T* w = Wq + (long long)row * embed;
+  float acc = 0.f;
+  for (int j = lane; j < embed; j += 32) acc += to_float(w[j]) * to_float(Q[j]);
+  acc = warp_sum(acc);
+  if (lane == 0) q[row] = acc + (bias ? to_float(bias[row]) : 0.f);
+}
+
+// out[k] = scale * sum_d W[d,k] * x[d]  (W row-major [D, K], leading dimension ldw): 32 columns x 8 row-lanes
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_t_kernel(const T* __restrict__ W, long long ldw, const float* __restrict__ x,
+                                                     float* __restrict__ out, int D, int K, float scale) {
+  __shared__ float part[8][33];
+  const int kx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
+  float acc = 0.f;
+  if (k < K)
+    for (int d = dy; d < D; d += 8) acc += to_float(W[(long long)d * ldw + k]) * x[d];
+  part[dy][kx] = acc;
+  __syncthreads();
+  if (dy == 0 && k < K) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][kx];
+    out[k] = s * scale;
+  }
+}
+
+// c = sum_n u[n] * bias[n]
+template <typename T>
+__global__ void __launch_bounds__(256) dot_kernel(const T* __restrict__ bias, const float* __restrict__ u, float* __restrict__ c, int N) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  if (bias != nullptr)
+    for (int n = threadIdx.x; n < N; n += 256) acc += u[n] * to_float(bias[n]);
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) *c = acc;
+}
+
+// ---- scores from the projected tokens themselves ----------------------------------------------------------
+struct TokenScoreParams {
+  const void* V[MERV_MAX_ENCODERS];
+  int tokens[MERV_MAX_ENCODERS];
+};
+
+// partial[(b*E+e)*chunks + chunk] = sum_{t in chunk} sum_k u[k] * V_e[b,t,k]
+template <typename T>
+__global__ void __launch_bounds__(256) token_score_kernel(const __grid_constant__ TokenScoreParams p, const float* __restrict__ u,
+                                                          float* __restrict__ partial, int E, int K, int chunks) {
+  constexpr int VEC = Vec16<T>::kN;
+  __shared__ float red[32];
+  const int chunk = blockIdx.x, e = blockIdx.y, b = blockIdx.z;
+  const int Te = p.tokens[e];
+  const int per = (Te + chunks - 1) / chunks;
+  const int t0 = chunk * per, t1 = min(Te, t0 + per);
+  const T* base = static_cast<const T*>(p.V[e]) + (long long)b * Te * K;
+  const int nvec = K / VEC;
+  float acc = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const T* row = base + (long long)t * K;
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+      float x[VEC];
+      Vec16<T>::unpack(ldg_nc_v4(row + v * VEC), x);
+      const float4* uu = reinterpret_cast<const float4*>(u + v * VEC);
+#pragma unroll
+      for (int c = 0; c < VEC; c += 4) {
+        const float4 w = uu[c / 4];
+        acc += x[c] * w.x + x[c + 1] * w.y + x[c + 2] * w.z + x[c + 3] * w.w;
+      }
+    }
+  }
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) partial[((long long)b * E + e) * chunks + chunk] = acc;
+}
+
+// scores[b,e] = (sum of n contiguous partials) / T_e  — one warp per (b,e), fixed order
+struct ScaleParams {
+  float inv[MERV_MAX_ENCODERS];
+};
+__global__ void __launch_bounds__(32) reduce_scale_kernel(const float* __restrict__ partial, float* __restrict__ scores,
+                                                          const __grid_constant__ ScaleParams sp, int n, int E) {
+  const long long id = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) acc += partial[id * n + i];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) scores[id] = acc * sp.inv[id % E];
+}
+
+// ---- scores from the GEMM epilogue's row-dot partials ----------------------------------------------------
+struct PtrParams {
+  const float* p[MERV_MAX_ENCODERS];
+  const float* v[MERV_MAX_ENCODERS];
+  const float* c[MERV_MAX_ENCODERS];
+  int C[MERV_MAX_ENCODERS];
+  int parts[MERV_MAX_ENCODERS];
+};
+
+// rowdot_e [B*T, nblk]: scores[b,e] = (1/T) * sum over the T*nblk floats of video b
+__global__ void __launch_bounds__(256) rowdot_score_kernel(const __grid_constant__ PtrParams p, float* __restrict__ scores, int E,
+                                                           int T, int nblk) {
+  __shared__ float red[32];
+  const int e = blockIdx.x, b = blockIdx.y;
+  const long long n = (long long)T * nblk;
+  const float* src = p.p[e] + (long long)b * n;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) acc += src[i];
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) scores[(long long)b * E + e] = acc / float(T) + (p.c[e] ? *p.c[e] : 0.f);
+}
+
+// colsum_e [B, parts_e, C_e]: scores[b,e] = (1/T) * sum_c v_e[c] * (sum_parts colsum[b,part,c]) + c_e
+__global__ void __launch_bounds__(256) colsum_score_kernel(const __grid_constant__ PtrParams p, float* __restrict__ scores, int E,
+                                                           int T) {
+  __shared__ float red[32];
+  const int e = blockIdx.x, b = blockIdx.y;
+  const int C = p.C[e], parts = p.parts[e];
+  const float* src = p.p[e] + (long long)b * parts * C;
+  const float* v = p.v[e];
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (int k = 0; k < parts; ++k) s += src[(long long)k * C + c];
+    acc += s * v[c];
+  }
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) scores[(long long)b * E + e] = acc / float(T) + (p.c[e] ? *p.c[e] : 0.f);
+}
+
+// ---- softmax over the E encoders with warp shuffles -------------------------------------------------------
+// lane e (< E) passes its score; every lane gets weight of lane e back in the same lane
+__device__ __forceinline__ float warp_softmax_over_encoders(float score, int lane, int E) {
+  const float s = lane < E ? score : -INFINITY;
+  const float m = warp_max(s);
+  const float ex = lane < E ? expf(s - m) : 0.f;
+  const float den = warp_sum(ex);
+  return ex / den;
+}
+
+struct BiasParams {
+  const void* bias[MERV_MAX_ENCODERS];
+};
+
+// weights[b,:] = softmax(scores[b,:]);  bias_mix[b,n] = sum_e weights[b,e] * bias_e[n]
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_weights_kernel(const float* __restrict__ scores, float* __restrict__ weights,
+                                                              const __grid_constant__ BiasParams bp, float* __restrict__ bias_mix,
+                                                              int E, int N) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const float w = warp_softmax_over_encoders(lane < E ? scores[(long long)b * E + lane] : 0.f, lane, E);
+  if (blockIdx.x == 0 && threadIdx.x < E) weights[(long long)b * E + threadIdx.x] = w;
+  if (bias_mix == nullptr) return;
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  float acc = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const float we = __shfl_sync(0xffffffffu, w, e);
+    const T* be = static_cast<const T*>(bp.bias[e]);
+    if (be != nullptr && n < N) acc += we * to_float(be[n]);
+  }
+  if (n < N) bias_mix[(long long)b * N + n] = acc;
+}
+
+// ---- out[b,t,:] = sum_e w[b,e] * V_e[b,t,:]  (HBM-bound: E reads + 1 write per element, each exactly once) --
+struct MixParams {
+  const void* V[MERV_MAX_ENCODERS];
+  int tokens[MERV_MAX_ENCODERS];  // T or 1 (broadcast, nn_utils.py:502)
+};
+
+template <typename T, int E>
+__global__ void __launch_bounds__(256) softmax_mix_kernel(const __grid_constant__ MixParams p, const float* __restrict__ scores,
+                                                          float* __restrict__ weights, T* __restrict__ out, int Ttok, int K) {
+  constexpr int VEC = Vec16<T>::kN;
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  float wl;
+  if (scores != nullptr) {
+    wl = warp_softmax_over_encoders(lane < E ? scores[(long long)b * E + lane] : 0.f, lane, E);
+    if (blockIdx.x == 0 && threadIdx.x < E) weights[(long long)b * E + threadIdx.x] = wl;
+  } else {
+    wl = lane < E ? weights[(long long)b * E + lane] : 0.f;
+  }
+  float w[E];
+  const T* src[E];
+  long long tstride[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    w[e] = __shfl_sync(0xffffffffu, wl, e);
+    const int Te = p.tokens[e];
+    src[e] = static_cast<const T*>(p.V[e]) + (long long)b * Te * K;
+    tstride[e] = Te == 1 ? 0 : K;
+  }
+  const int kvec = K / VEC;
+  const long long nvec = (long long)Ttok * kvec;
+  T* ob = out + (long long)b * Ttok * K;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool has2 = i2 < nvec;
+    const long long t1 = i / kvec, t2 = has2 ? i2 / kvec : 0;
+    const int c1 = int(i - t1 * kvec) * VEC, c2 = has2 ? int(i2 - t2 * kvec) * VEC : 0;
+    uint4 r1[E], r2[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) r1[e] = ldg_nc_v4(src[e] + t1 * tstride[e] + c1);
+    if (has2) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) r2[e] = ldg_nc_v4(src[e] + t2 * tstride[e] + c2);
+    }
+    float acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      float x[VEC];
+      Vec16<T>::unpack(r1[e], x);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[e], x[c], acc[c]);
+    }
+    stg_na_v4(ob + t1 * K + c1, Vec16<T>::pack(acc));
+    if (has2) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        float x[VEC];
+        Vec16<T>::unpack(r2[e], x);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[e], x[c], acc[c]);
+      }
+      stg_na_v4(ob + t2 * K + c2, Vec16<T>::pack(acc));
+    }
+  }
+}
+
+template <typename T>
+static int launch_mix(const MixParams& p, const float* scores, float* weights, void* out, int B, int E, int Ttok, int K,
+                      cudaStream_t s) {
+  constexpr int VEC = Vec16<T>::kN;
+  const long long nvec = (long long)Ttok * (K / VEC);
+  // ~8 waves of 256-thread CTAs in total across the batch, at least 1 and at most what the video needs
+  long long per_video = (nvec + 511) / 512;
+  long long want = (long long)sm_count() * 8 * 8 / (B > 0 ? B : 1);
+  if (want < 1) want = 1;
+  const int gx = int(per_video < want ? per_video : want);
+  dim3 grid(gx, B);
+  T* o = static_cast<T*>(out);
+  switch (E) {
+#define MERV_MIX_CASE(n) \
+  case n: softmax_mix_kernel<T, n><<<grid, 256, 0, s>>>(p, scores, weights, o, Ttok, K); break;
+    MERV_MIX_CASE(1) MERV_MIX_CASE(2) MERV_MIX_CASE(3) MERV_MIX_CASE(4) MERV_MIX_CASE(5) MERV_MIX_CASE(6) MERV_MIX_CASE(7) MERV_MIX_CASE(8)
+#undef MERV_MIX_CASE
+    default: return fail(MERV_E_ARG, "merv_softmax_mix: E=%d not in [1,%d]", E, MERV_MAX_ENCODERS);
+  }
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+}  // namespace merv
+
+using namespace merv;
+
+#define MERV_DTYPE_OK(fn) MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, fn ": unknown dtype %d", dtype)
+
+extern "C" int merv_fusion_query_vec(const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias, float* u,
+                                     float* workspace, int embed, int llm_dim, int dtype, void* stream) {
+  MERV_DTYPE_OK("merv_fusion_query_vec");
+  MERV_REQUIRE(Q && Wq && Wk && u && workspace, MERV_E_ARG, "merv_fusion_query_vec: NULL pointer");
+  MERV_REQUIRE(embed > 0 && llm_dim > 0, MERV_E_SHAPE, "merv_fusion_query_vec: embed=%d llm_dim=%d", embed, llm_dim);
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float scale = 1.0f / sqrtf(float(embed));
+  if (dtype == MERV_BF16) {
+    using T = __nv_bfloat16;
+    qproj_kernel<T><<<(embed + 7) / 8, 256, 0, s>>>((const T*)Wq, (const T*)Q, (const T*)in_proj_bias, workspace, embed);
+    gemv_t_kernel<T><<<(llm_dim + 31) / 32, 256, 0, s>>>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale);
+  } else {
+    using T = float;
+    qproj_kernel<T><<<(embed + 7) / 8, 256, 0, s>>>((const T*)Wq, (const T*)Q, (const T*)in_proj_bias, workspace, embed);
+    gemv_t_kernel<T><<<(llm_dim + 31) / 32, 256, 0, s>>>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale);
+  }
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, int N,
+                                     int K, int dtype, void* stream) {
+  MERV_DTYPE_OK("merv_affine_score_vec");
+  MERV_REQUIRE(W && u && v && c, MERV_E_ARG, "merv_affine_score_vec: NULL pointer");
+  MERV_REQUIRE(N > 0 && K > 0 && ldw >= K, MERV_E_SHAPE, "merv_affine_score_vec: N=%d K=%d ldw=%lld", N, K, (long long)ldw);
+  if (int rc = require_sm100()) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16) {
+    using T = __nv_bfloat16;
+    gemv_t_kernel<T><<<(K + 31) / 32, 256, 0, s>>>((const T*)W, ldw, u, v, N, K, 1.0f);
+    dot_kernel<T><<<1, 256, 0, s>>>((const T*)bias, u, c, N);
+  } else {
+    using T = float;
+    gemv_t_kernel<T><<<(K + 31) / 32, 256, 0, s>>>((const T*)W, ldw, u, v, N, K, 1.0f);
+    dot_kernel<T><<<1, 256, 0, s>>>((const T*)bias, u, c, N);
+  }
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+static int token_score_chunks(int T) { return T < 32 ? T : 32; }
+
+extern "C" size_t merv_scores_from_tokens_workspace(int B, int E, int T, int K) {
+  (void)K;
+  if (B <= 0 || E <= 0 || T <= 0) return 0;
+  return (size_t)B * E * token_score_chunks(T);
+}
+
+extern "C" int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const float* u, float* scores,
+                                       float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
+                                       void* stream) {
+  MERV_DTYPE_OK("merv_scores_from_tokens");
+  MERV_REQUIRE(V && tokens && u && scores && workspace, MERV_E_ARG, "merv_scores_from_tokens: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_tokens: E=%d", E);
+  MERV_REQUIRE(B >= 0 && T > 0 && K > 0, MERV_E_SHAPE, "merv_scores_from_tokens: B=%d T=%d K=%d", B, T, K);
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(K % vec == 0, MERV_E_SHAPE, "merv_scores_from_tokens: K=%d must be a multiple of %d", K, vec);
+  MERV_REQUIRE(workspace_floats >= merv_scores_from_tokens_workspace(B, E, T, K), MERV_E_ARG,
+               "merv_scores_from_tokens: workspace too small");
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  TokenScoreParams p;
+  ScaleParams sp;
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(V[e] && aligned16(V[e]), MERV_E_ALIGN, "merv_scores_from_tokens: V[%d] NULL or not 16-byte aligned", e);
+    // reference assert (nn_utils.py:494-495): every encoder has token_length tokens, or exactly 1
+    MERV_REQUIRE(tokens[e] == T || tokens[e] == 1, MERV_E_SHAPE, "merv_scores_from_tokens: encoder %d has %d tokens, expected %d or 1",
+                 e, tokens[e], T);
+    p.V[e] = V[e];
+    p.tokens[e] = tokens[e];
+    sp.inv[e] = 1.0f / float(tokens[e]);
+  }
+  const int chunks = token_score_chunks(T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(chunks, E, B);
+  if (dtype == MERV_BF16)
+    token_score_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks);
+  else
+    token_score_kernel<float><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks);
+  reduce_scale_kernel<<<B * E, 32, 0, s>>>(workspace, scores, sp, chunks, E);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_scores_from_rowdot(const float* const* rowdot, const float* const* c, float* scores, int B, int E, int T,
+                                       int nblk, void* stream) {
+  MERV_REQUIRE(rowdot && scores, MERV_E_ARG, "merv_scores_from_rowdot: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_rowdot: E=%d", E);
+  MERV_REQUIRE(B >= 0 && T > 0 && nblk > 0, MERV_E_SHAPE, "merv_scores_from_rowdot: B=%d T=%d nblk=%d", B, T, nblk);
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  PtrParams p = {};
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(rowdot[e], MERV_E_ARG, "merv_scores_from_rowdot: rowdot[%d] is NULL", e);
+    p.p[e] = rowdot[e];
+    p.c[e] = c ? c[e] : nullptr;
+  }
+  rowdot_score_kernel<<<dim3(E, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, scores, E, T, nblk);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_scores_from_colsum(const float* const* colsum, const float* const* v, const float* const* c,
+                                       const int32_t* C, const int32_t* parts, float* scores, int B, int E, int T,
+                                       void* stream) {
+  MERV_REQUIRE(colsum && v && c && C && parts && scores, MERV_E_ARG, "merv_scores_from_colsum: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_colsum: E=%d", E);
+  MERV_REQUIRE(B >= 0 && T > 0, MERV_E_SHAPE, "merv_scores_from_colsum: B=%d T=%d", B, T);
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  PtrParams p = {};
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(colsum[e] && v[e], MERV_E_ARG, "merv_scores_from_colsum: encoder %d has a NULL pointer", e);
+    MERV_REQUIRE(C[e] > 0 && parts[e] > 0, MERV_E_SHAPE, "merv_scores_from_colsum: encoder %d: C=%d parts=%d", e, C[e], parts[e]);
+    p.p[e] = colsum[e]; p.v[e] = v[e]; p.c[e] = c[e]; p.C[e] = C[e]; p.parts[e] = parts[e];
+  }
+  colsum_score_kernel<<<dim3(E, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, scores, E, T);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_softmax_weights(const float* scores, float* weights, const void* const* bias, float* bias_mix, int B,
+                                    int E, int N, int dtype, void* stream) {
+  MERV_DTYPE_OK("merv_softmax_weights");
+  MERV_REQUIRE(scores && weights, MERV_E_ARG, "merv_softmax_weights: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_softmax_weights: E=%d", E);
+  MERV_REQUIRE(B >= 0 && (bias_mix == nullptr || N > 0), MERV_E_SHAPE, "merv_softmax_weights: B=%d N=%d", B, N);
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  BiasParams bp = {};
+  if (bias_mix != nullptr) {
+    MERV_REQUIRE(bias != nullptr, MERV_E_ARG, "merv_softmax_weights: bias_mix requested but bias is NULL");
+    for (int e = 0; e < E; ++e) bp.bias[e] = bias[e];
+  }
+  const int gx = bias_mix ? (N + 255) / 256 : 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16)
+    softmax_weights_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, s>>>(scores, weights, bp, bias_mix, E, N);
+  else
+    softmax_weights_kernel<float><<<dim3(gx, B), 256, 0, s>>>(scores, weights, bp, bias_mix, E, N);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_softmax_mix(const void* const* V, const int32_t* tokens, const float* scores, float* weights, void* out,
+                                int B, int E, int T, int K, int dtype, void* stream) {
+  MERV_DTYPE_OK("merv_softmax_mix");
+  MERV_REQUIRE(V && tokens && weights && out, MERV_E_ARG, "merv_softmax_mix: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_softmax_mix: E=%d not in [1,%d]", E, MERV_MAX_ENCODERS);
+  MERV_REQUIRE(B >= 0 && T > 0 && K > 0, MERV_E_SHAPE, "merv_softmax_mix: B=%d T=%d K=%d", B, T, K);
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(K % vec == 0, MERV_E_SHAPE, "merv_softmax_mix: K=%d must be a multiple of %d", K, vec);
+  MERV_REQUIRE(aligned16(out), MERV_E_ALIGN, "merv_softmax_mix: out not 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  MixParams p;
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(V[e] && aligned16(V[e]), MERV_E_ALIGN, "merv_softmax_mix: V[%d] NULL or not 16-byte aligned", e);
+    MERV_REQUIRE(tokens[e] == T || tokens[e] == 1, MERV_E_SHAPE, "merv_softmax_mix: encoder %d has %d tokens, expected %d or 1", e,
+                 tokens[e], T);
+    p.V[e] = V[e];
+    p.tokens[e] = tokens[e];
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16) return launch_mix<__nv_bfloat16>(p, scores, weights, out, B, E, T, K, s);
+  return launch_mix<float>(p, scores, weights, out, B, E, T, K, s);
+}

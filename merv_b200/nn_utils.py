@@ -1,0 +1,504 @@
+"""B200-native drop-ins for the hot-path modules of the reference's ``merv/util/nn_utils.py``.
+
+Same class names, constructor signatures, parameter names/shapes (hence state-dict keys), properties and
+error behaviour as the reference (paths below are relative to the reference root):
+
+    LinearProjector                      merv/util/nn_utils.py:22-32
+    MLPProjector                         merv/util/nn_utils.py:35-59
+    FusedMLPProjector                    merv/util/nn_utils.py:86-108
+    get_mlp_projector                    merv/util/nn_utils.py:111-121
+    TokenResampler                       merv/util/nn_utils.py:124-133
+    AveragePooling3DProjector            merv/util/nn_utils.py:306-338
+    CrossAttentionAdapterLearnableQuery  merv/util/nn_utils.py:455-521
+
+``forward`` runs hand-written sm_100a kernels through the C ABI (``merv_b200.ops``); nothing here calls a
+torch compute op on the data path, and CPU tensors raise.  ``nn.Linear`` / ``nn.MultiheadAttention`` are used
+purely as parameter containers so initialisation (RNG consumption order under ``torch.manual_seed``,
+merv.py:87), ``state_dict`` keys and FSDP wrapping behave exactly like the reference.
+
+Two execution modes:
+
+* module-by-module (default): each projector returns its ``[B, T*S*S, llm_dim]`` tokens, the adapter scores,
+  soft-maxes and mixes them — a drop-in for any caller of the individual modules;
+* linked (``link_fused`` / ``MervFusion`` / ``patch_merv``): projectors return a ``DeferredProjection`` and the
+  adapter runs the whole path as pool -> [hidden layers] -> scores -> ONE tcgen05 GEMM whose epilogue applies the
+  mixing weights, so the per-encoder projections never touch HBM.  Valid whenever the LAST projector layer is
+  affine (true for every projector type of the reference), inference only.
+"""
+
+from __future__ import annotations
+
+import math
+import weakref
+from abc import ABC, abstractmethod
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch.nn.init import xavier_uniform_
+from torch.nn.parameter import Parameter
+
+from . import ops
+from ._lib import ACT_GELU_ERF, ACT_NONE
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------
+def _compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """bf16 under torch.autocast('cuda', bfloat16) (merv.py:816, base_strategy.py:210-214), else the input dtype."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        if dt != torch.bfloat16:
+            raise TypeError(f"merv_b200 supports bf16 autocast only, got {dt}")
+        return dt
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError(f"merv_b200 supports float32 and bfloat16, got {x.dtype}")
+    return x.dtype
+
+
+def _no_autograd(module: nn.Module, *tensors) -> None:
+    if torch.is_grad_enabled() and (
+        any(p.requires_grad for p in module.parameters()) or any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+    ):
+        raise NotImplementedError(
+            f"{type(module).__name__}: the backward of the sm_100a fusion kernels is not implemented yet (SURVEY.md §8 f-1); "
+            "run under torch.no_grad()/inference_mode() or freeze the module (requires_grad_(False))."
+        )
+
+
+class _CastCache:
+    """Weights cast to the compute dtype, keyed on (storage, version) so in-place optimiser updates invalidate them."""
+
+    def __init__(self) -> None:
+        self._store = {}
+
+    def get(self, p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
+        if p is None:
+            return None
+        if p.dtype == dtype:
+            return p.detach()
+        key = (id(p), dtype)
+        tag = (p.data_ptr(), p._version, tuple(p.shape))
+        hit = self._store.get(key)
+        if hit is None or hit[0] != tag:
+            hit = (tag, p.detach().to(dtype))
+            self._store[key] = hit
+        return hit[1]
+
+
+def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
+    """[(linear, activation applied AFTER it)] for every reference projector type."""
+    if isinstance(projector, LinearProjector):
+        return [(projector.projector, ACT_NONE)]
+    if isinstance(projector, (MLPProjector, FusedMLPProjector)):
+        mods = list(projector.projector)
+        layers = []
+        for i, m in enumerate(mods):
+            if isinstance(m, nn.Linear):
+                act = ACT_GELU_ERF if i + 1 < len(mods) and isinstance(mods[i + 1], nn.GELU) else ACT_NONE
+                layers.append((m, act))
+        return layers
+    if isinstance(projector, nn.Identity):
+        return []
+    raise TypeError(f"unsupported projector module {type(projector).__name__}")
+
+
+def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None):
+    rd = None
+    for i, (lin, act) in enumerate(layers):
+        rv = last_rowdot_vec if i == len(layers) - 1 else None
+        x, rd = ops.linear_bias_act(x, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), act, rv)
+    return x, rd
+
+
+# === Definitions for Various Projection Modules, with Signature :: [..., in_dim] --> [..., out_dim] ===
+class _ProjectorBase(nn.Module):
+    def _check_ln(self) -> None:
+        if not isinstance(self.layernorm, nn.Identity):
+            raise NotImplementedError(
+                "pre_proj_layernorm=True is outside the accelerated hot path (off in every shipped config, merv.py:67)"
+            )
+
+    def forward(self, img_patches: torch.Tensor) -> torch.Tensor:
+        self._check_ln()
+        _no_autograd(self, img_patches)
+        dtype = _compute_dtype(img_patches)
+        if not hasattr(self, "_cast_cache"):
+            self._cast_cache = _CastCache()
+        x = img_patches if img_patches.dtype == dtype else img_patches.to(dtype)
+        y, _ = _run_layers(x, _projector_layers(self), self._cast_cache, dtype)
+        return y
+
+
+class LinearProjector(_ProjectorBase):
+    def __init__(self, vision_dim: int, llm_dim: int, pre_proj_layernorm: bool = False) -> None:
+        super().__init__()
+        self.projector = nn.Linear(vision_dim, llm_dim, bias=True)
+        if pre_proj_layernorm:
+            self.layernorm = nn.LayerNorm(vision_dim)
+        else:
+            self.layernorm = nn.Identity()
+
+
+class MLPProjector(_ProjectorBase):
+    def __init__(
+        self, vision_dim: int, llm_dim: int, mlp_type: str = "gelu-mlp", pre_proj_layernorm: bool = False
+    ) -> None:
+        super().__init__()
+        if pre_proj_layernorm:
+            self.layernorm = nn.LayerNorm(vision_dim)
+        else:
+            self.layernorm = nn.Identity()
+        if mlp_type == "gelu-mlp":
+            self.projector = nn.Sequential(
+                nn.Linear(vision_dim, llm_dim, bias=True),
+                nn.GELU(),
+                nn.Linear(llm_dim, llm_dim, bias=True),
+            )
+        else:
+            raise ValueError(f"Projector with `{mlp_type = }` is not supported!")
+
+    @property
+    def output_token_length(self) -> int:
+        return 1
+
+
+class FusedMLPProjector(_ProjectorBase):
+    def __init__(
+        self, fused_vision_dim: int, llm_dim: int, mlp_type: str = "fused-gelu-mlp", pre_proj_layernorm: bool = False
+    ) -> None:
+        super().__init__()
+        if pre_proj_layernorm:
+            self.layernorm = nn.LayerNorm(fused_vision_dim)
+        else:
+            self.layernorm = nn.Identity()
+        self.initial_projection_dim = fused_vision_dim * 4
+        if mlp_type == "fused-gelu-mlp":
+            self.projector = nn.Sequential(
+                nn.Linear(fused_vision_dim, self.initial_projection_dim, bias=True),
+                nn.GELU(),
+                nn.Linear(self.initial_projection_dim, llm_dim, bias=True),
+                nn.GELU(),
+                nn.Linear(llm_dim, llm_dim, bias=True),
+            )
+        else:
+            raise ValueError(f"Fused Projector with `{mlp_type = }` is not supported!")
+
+
+def get_mlp_projector(fused_vision_dim: int, llm_dim: int, mlp_type: str = "gelu-mlp") -> nn.Module:
+    if mlp_type == "linear":
+        return LinearProjector(fused_vision_dim, llm_dim)
+    elif mlp_type == "gelu-mlp":
+        return MLPProjector(fused_vision_dim, llm_dim, mlp_type)
+    elif mlp_type == "fused-gelu-mlp":
+        return FusedMLPProjector(fused_vision_dim, llm_dim, mlp_type)
+    elif mlp_type == "none":
+        return nn.Identity()
+    else:
+        raise ValueError(f"Projector with `{mlp_type = }` is not supported!")
+
+
+class TokenResampler(nn.Module, ABC):
+    """Resamples token length as well. Abstract class for interfacing resulting token length."""
+
+    @property
+    @abstractmethod
+    def output_token_length(self) -> int: ...
+
+    @property
+    @abstractmethod
+    def output_frame_length(self) -> int: ...
+
+
+class DeferredProjection:
+    """What a *linked* ``AveragePooling3DProjector`` returns: the un-projected features plus the module that owns
+    the weights.  ``MERV.forward`` only threads the projector outputs into ``feature_fusion`` (merv.py:587-589,608),
+    which consumes these and runs the fused pipeline.  ``materialize()`` gives the ordinary tensor."""
+
+    def __init__(self, projector: "AveragePooling3DProjector", features: torch.Tensor) -> None:
+        self.projector, self.features = projector, features
+
+    @property
+    def shape(self) -> torch.Size:
+        p = self.projector
+        return torch.Size((self.features.shape[0], p.output_frames * p.output_size * p.output_size, p.llm_dim))
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return _compute_dtype(self.features)
+
+    @property
+    def device(self) -> torch.device:
+        return self.features.device
+
+    def materialize(self) -> torch.Tensor:
+        return self.projector._forward_unfused(self.features)
+
+
+class AveragePooling3DProjector(TokenResampler):
+    """3D-average pooling projector (pool FIRST, then project: nn_utils.py:328-330)."""
+
+    def __init__(
+        self, fused_vision_dim: int, llm_dim: int, output_frames: int, output_size: int, mlp_type: str = "gelu-mlp"
+    ) -> None:
+        super().__init__()
+        self.output_frames = output_frames
+        self.output_size = output_size
+        self.llm_dim = llm_dim
+        self.fused_vision_dim = fused_vision_dim
+        # kept for state-dict/module-tree parity with the reference (it has no parameters)
+        self.avg_pooling = nn.AdaptiveAvgPool3d((output_frames, output_size, output_size))
+        self.projector = get_mlp_projector(fused_vision_dim, llm_dim, mlp_type)
+        self._cast_cache = _CastCache()
+        self._linked_fusion = None  # weakref to the adapter when linked
+
+    @classmethod
+    def from_reference(cls, ref_module: nn.Module) -> "AveragePooling3DProjector":
+        """Adopt a reference ``AveragePooling3DProjector``: same ``projector`` submodule objects (parameters shared)."""
+        inner = ref_module.projector
+        lins = [m for m in inner.modules() if isinstance(m, nn.Linear)]
+        if not lins:
+            raise ValueError("reference projector has no Linear layer (mlp_type 'none' has nothing to accelerate)")
+        n = len(lins)
+        mlp_type = {1: "linear", 2: "gelu-mlp", 3: "fused-gelu-mlp"}[n]
+        new = cls(lins[0].in_features, lins[-1].out_features, ref_module.output_frames, ref_module.output_size, mlp_type)
+        if n == 1:
+            new.projector.projector = inner.projector
+        else:
+            new.projector.projector = inner.projector
+        return new
+
+    def layers(self) -> List[Tuple[nn.Linear, int]]:
+        return _projector_layers(self.projector)
+
+    def _forward_unfused(self, fused_img_patches: torch.Tensor, rowdot_vec: Optional[torch.Tensor] = None):
+        dtype = _compute_dtype(fused_img_patches)
+        x = fused_img_patches if fused_img_patches.dtype == dtype else fused_img_patches.to(dtype)
+        (pooled,), _ = ops.pool3d([x], [self.output_frames], self.output_size)
+        y, rd = _run_layers(pooled, self.layers(), self._cast_cache, dtype, rowdot_vec)
+        return (y, rd) if rowdot_vec is not None else y
+
+    def forward(self, fused_img_patches: torch.Tensor) -> Union[torch.Tensor, DeferredProjection]:
+        assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
+        _no_autograd(self, fused_img_patches)
+        if not fused_img_patches.is_cuda:
+            raise RuntimeError("merv_b200 runs only on CUDA (sm_100a) tensors; there is deliberately no CPU fallback.")
+        fusion = self._linked_fusion() if self._linked_fusion is not None else None
+        if fusion is not None and not torch.is_grad_enabled():
+            return DeferredProjection(self, fused_img_patches)
+        return self._forward_unfused(fused_img_patches)
+
+    @property
+    def output_token_length(self) -> int:
+        return self.output_size * self.output_size
+
+    @property
+    def output_frame_length(self) -> int:
+        return self.output_frames
+
+
+# Adapters here
+class CrossAttentionAdapterLearnableQuery(nn.Module):
+    def __init__(
+        self, embed_dim=3072, llm_dim=4098, token_length=8, averagetoken=False, num_encoder=4, positional_embedding=False
+    ) -> None:
+        super().__init__()
+        self.llm_dim = llm_dim
+        self.token_length = token_length
+        self.averagetoken = averagetoken
+        # parameter container only: forward never calls it (v_proj_weight / out_proj are dead in the reference too)
+        self.attention = nn.MultiheadAttention(
+            embed_dim=embed_dim,
+            num_heads=1,
+            dropout=0.0,
+            batch_first=True,
+            kdim=llm_dim if averagetoken else token_length * llm_dim,
+            vdim=llm_dim if averagetoken else token_length * llm_dim,
+        )
+        self.Q = Parameter(torch.empty((1, embed_dim)))
+        self.num_encoder = num_encoder
+        self.positional_embedding = positional_embedding
+        if positional_embedding:
+            self.pe = Parameter(torch.empty((self.num_encoder, llm_dim)))
+        self._reset_parameters()
+        self._cast_cache = _CastCache()
+        self._u_cache = {}
+        self._vc_cache = {}
+
+    def _reset_parameters(self):
+        xavier_uniform_(self.Q)
+        if self.positional_embedding:
+            xavier_uniform_(self.pe)
+
+    @classmethod
+    def from_reference(cls, ref_module: nn.Module) -> "CrossAttentionAdapterLearnableQuery":
+        att = ref_module.attention
+        new = cls(att.embed_dim, ref_module.llm_dim, ref_module.token_length, ref_module.averagetoken,
+                  ref_module.num_encoder, ref_module.positional_embedding)
+        new.attention, new.Q = att, ref_module.Q
+        if ref_module.positional_embedding:
+            new.pe = ref_module.pe
+        return new
+
+    # ---- cached, input-independent vectors ----------------------------------------------------------------
+    def query_vector(self, dtype: torch.dtype) -> torch.Tensor:
+        """u (fp32 [llm_dim]) with weights == softmax_e(u . mean_t V_e); recomputed when a parameter changes."""
+        att = self.attention
+        params = (self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias)
+        tag = tuple((p.data_ptr(), p._version) for p in params if p is not None) + (dtype, self.Q.device)
+        hit = self._u_cache.get("u")
+        if hit is None or hit[0] != tag:
+            c = self._cast_cache
+            u = ops.fusion_query_vec(c.get(self.Q, dtype), c.get(att.q_proj_weight, dtype), c.get(att.k_proj_weight, dtype),
+                                     c.get(att.in_proj_bias, dtype))
+            hit = (tag, u)
+            self._u_cache["u"] = hit
+            self._vc_cache.clear()
+        return hit[1]
+
+    def _affine_vec(self, lin: nn.Linear, cache: _CastCache, dtype: torch.dtype):
+        """(v, c) for the last (affine) projector layer: u . (W x + b) = v . x + c."""
+        u = self.query_vector(dtype)
+        tag = (lin.weight.data_ptr(), lin.weight._version, None if lin.bias is None else lin.bias._version, dtype, id(u))
+        hit = self._vc_cache.get(id(lin))
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.affine_score_vec(cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), u))
+            self._vc_cache[id(lin)] = hit
+        return hit[1]
+
+    # ---- forward --------------------------------------------------------------------------------------------
+    def forward(self, V):
+        # V is a list of tensors with size (B, T, K). T should all be same, or 1.  (nn_utils.py:491-495)
+        for emb in V:
+            assert emb.shape[1] == self.token_length or emb.shape[1] == 1, (self.token_length, [e.shape for e in V])
+        if not self.averagetoken:
+            raise NotImplementedError(
+                "averagetoken=False (scores from the flattened T*K tokens) is not used by any shipped config "
+                "(merv.py:214-216 passes averagetoken=True) and is outside the accelerated hot path"
+            )
+        if self.positional_embedding:
+            raise NotImplementedError("positional_embedding=True is outside the accelerated hot path (default False)")
+        assert 1 <= len(V) <= 8, f"1..8 encoders supported, got {len(V)}"
+        _no_autograd(self, *[v for v in V if isinstance(v, torch.Tensor)])
+
+        if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
+            return self._forward_fused(V)
+        V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
+        return self._forward_tokens(V)
+
+    def _forward_tokens(self, V: Sequence[torch.Tensor], rowdots=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        dtype = _compute_dtype(V[0])
+        V = [v if v.dtype == dtype else v.to(dtype) for v in V]
+        u = self.query_vector(dtype)
+        if rowdots is not None:
+            scores = ops.scores_from_rowdot(rowdots, None, V[0].shape[0], self.token_length)
+        else:
+            scores = ops.scores_from_tokens(V, u, self.token_length)
+        out, weights = ops.softmax_mix(V, self.token_length, scores=scores)
+        return out, weights.to(dtype)
+
+    def _can_fuse(self, V: Sequence[DeferredProjection]) -> bool:
+        if len(V) > 4 or any(v.dtype != torch.bfloat16 for v in V):
+            return False
+        if any(v.shape[1] != self.token_length for v in V):
+            return False
+        return all(len(v.projector.layers()) >= 1 for v in V)
+
+    def _forward_fused(self, V: Sequence[DeferredProjection]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """pool (one launch) -> hidden layers -> scores -> one tcgen05 GEMM with the mix in its epilogue."""
+        dtype = torch.bfloat16
+        projs = [v.projector for v in V]
+        xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
+        B, T = xs[0].shape[0], self.token_length
+        all_linear = all(len(p.layers()) == 1 for p in projs)
+        pooled, colsums = ops.pool3d(xs, [p.output_frames for p in projs], projs[0].output_size, want_colsum=all_linear)
+        lasts = [p.layers()[-1][0] for p in projs]
+        vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
+        if all_linear:
+            acts = pooled
+            scores = ops.scores_from_colsum(colsums, [vc[0] for vc in vcs], [vc[1] for vc in vcs], T)
+        else:
+            acts, rowdots = [], []
+            for p, x, (v, _) in zip(projs, pooled, vcs):
+                h, rd = _run_layers(x, p.layers()[:-1], p._cast_cache, dtype, last_rowdot_vec=v)
+                acts.append(h)
+                rowdots.append(rd)
+            scores = ops.scores_from_rowdot(rowdots, [vc[1] for vc in vcs], B, T)
+        biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
+        weights, bias_mix = ops.softmax_weights(scores, biases, self.llm_dim)
+        out = ops.fused_linear_mix(acts, [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)], weights, bias_mix, T)
+        return out.view(B, T, self.llm_dim), weights.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# linking: the fused pipeline behind the unchanged MERV.forward glue
+# ------------------------------------------------------------------------------------------------------------
+def link_fused(projectors: Sequence[AveragePooling3DProjector], feature_fusion: CrossAttentionAdapterLearnableQuery) -> None:
+    """Make ``projector(x)`` return a DeferredProjection that ``feature_fusion`` turns into the fused pipeline."""
+    for p in projectors:
+        p._linked_fusion = weakref.ref(feature_fusion)
+
+
+def unlink(projectors: Sequence[AveragePooling3DProjector]) -> None:
+    for p in projectors:
+        p._linked_fusion = None
+
+
+class MervFusion(nn.Module):
+    """projectors + feature_fusion as one module: ``forward(patch_features) -> (prefix [B,T,K], weights [B,E])``.
+
+    Restates the glue of merv/models/vidlms/merv.py:587-589,607-609 with the sub-module names MERV uses
+    (``projectors``, ``feature_fusion``) so ``state_dict()`` keys match a MERV checkpoint's.
+    """
+
+    def __init__(self, projectors: Sequence[AveragePooling3DProjector], feature_fusion: CrossAttentionAdapterLearnableQuery,
+                 fused: bool = True) -> None:
+        super().__init__()
+        self.projectors = nn.ModuleList(projectors)
+        self.feature_fusion = feature_fusion
+        if fused:
+            link_fused(self.projectors, self.feature_fusion)
+
+    @classmethod
+    def build(cls, vision_dims: Sequence[int], llm_dim: int, output_frames: Sequence[int], projector_token_length: int = 64,
+              mlp_type: str = "linear", text_embedding_dim: int = 3072, seed: Optional[int] = None, fused: bool = True) -> "MervFusion":
+        """Construct as MERV.__init__ does (merv.py:87,110-163,214-216), including the projector-consistency seed."""
+        if seed is not None:
+            torch.manual_seed(seed)
+        size = int(projector_token_length**0.5)
+        assert projector_token_length == size**2, "projector_token_length should be square number"
+        projs = [AveragePooling3DProjector(c, llm_dim, output_frames=t, output_size=size, mlp_type=mlp_type)
+                 for c, t in zip(vision_dims, output_frames)]
+        lengths = {p.output_token_length * p.output_frame_length for p in projs}
+        assert len(lengths) == 1, f"Output token length is not consistent across all projectors! {sorted(lengths)}"
+        fusion = CrossAttentionAdapterLearnableQuery(embed_dim=text_embedding_dim, llm_dim=llm_dim, token_length=lengths.pop(),
+                                                     averagetoken=True, num_encoder=len(projs))
+        return cls(projs, fusion, fused=fused)
+
+    def forward(self, patch_features: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
+        return self.feature_fusion(projected)
+
+
+def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
+    """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
+
+    ``vidlm.projectors[i]`` (reference AveragePooling3DProjector) and ``vidlm.feature_fusion`` (reference
+    CrossAttentionAdapterLearnableQuery) keep their names, so checkpoints, ``all_module_keys`` (merv.py:235) and the
+    FSDP wrap policy (merv.py:473-497, extended via isinstance on these classes) keep working.
+    """
+    new_projs = []
+    for p in vidlm.projectors:
+        if type(p).__name__ != "AveragePooling3DProjector":
+            raise TypeError(f"patch_merv supports 3davg arch_specifiers only, found projector {type(p).__name__}")
+        new_projs.append(p if isinstance(p, AveragePooling3DProjector) else AveragePooling3DProjector.from_reference(p))
+    ff = vidlm.feature_fusion
+    if type(ff).__name__ != "CrossAttentionAdapterLearnableQuery":
+        raise TypeError(f"patch_merv supports feature_fusion='cross_attention_avg_lq' only, found {type(ff).__name__}")
+    new_ff = ff if isinstance(ff, CrossAttentionAdapterLearnableQuery) else CrossAttentionAdapterLearnableQuery.from_reference(ff)
+    vidlm.projectors = nn.ModuleList(new_projs)
+    vidlm.feature_fusion = new_ff
+    if fused:
+        link_fused(new_projs, new_ff)
+    return vidlm

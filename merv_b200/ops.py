@@ -1,0 +1,315 @@
+"""Functional layer: torch tensors in, torch tensors out, every op one call into libmerv_fusion.so.
+
+PyTorch is plumbing here (device memory from its caching allocator, the current CUDA stream); all arithmetic
+happens in the hand-written sm_100a kernels.  CPU tensors are rejected: there is no fallback.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, MERV_BF16, MERV_F32, ROWDOT_BLOCK, PoolDesc, check, i32_array, i64_array, ptr_array
+
+_DTYPES = {torch.float32: MERV_F32, torch.bfloat16: MERV_BF16}
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise TypeError(f"merv_b200 supports float32 and bfloat16 tensors, got {dtype}") from None
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "merv_b200 runs only on CUDA (sm_100a) tensors; got a tensor on "
+                f"{t.device}. There is deliberately no CPU fallback."
+            )
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ---- launch accounting ----------------------------------------------------------------------------------------
+# kernels launched by one call of each entry point (used for bench.py's `gpu_launches` and per-kernel timing)
+KERNELS_PER_CALL = {
+    "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
+    "merv_scores_from_tokens": 2, "merv_scores_from_rowdot": 1, "merv_scores_from_colsum": 1, "merv_softmax_weights": 1,
+    "merv_softmax_mix": 1, "merv_fused_linear_mix": 1,
+}
+
+
+class KernelTimer:
+    """Optional per-entry-point accounting: counts kernel launches and, if `timing`, brackets every library call
+    with CUDA events on the launching stream (bench.py uses it for the roofline of the dominant kernel)."""
+
+    def __init__(self, timing: bool = False) -> None:
+        self.timing = timing
+        self.launches = 0
+        self.calls = {}
+        self._events = []
+
+    def __enter__(self):
+        global _timer
+        self._prev, _timer = _timer, self
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = self._prev
+        return False
+
+    def durations_ms(self):
+        """{entry point: [ms per call]} — synchronises."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self._events:
+            out.setdefault(name, []).append(e0.elapsed_time(e1))
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def _call(name, fn, *args) -> None:
+    t = _timer
+    if t is None:
+        check(fn(*args))
+        return
+    t.launches += KERNELS_PER_CALL[name]
+    t.calls[name] = t.calls.get(name, 0) + 1
+    if t.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args))
+        e1.record()
+        t._events.append((name, e0, e1))
+    else:
+        check(fn(*args))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def pool3d(
+    xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int, want_colsum: bool = False
+) -> Tuple[List[torch.Tensor], Optional[List[torch.Tensor]]]:
+    """Adaptive 3-D average pooling of every encoder's [B, F, N, C] features in ONE launch -> [B, T*S*S, C].
+
+    Reference: AveragePooling3DProjector.forward, merv/util/nn_utils.py:320-329.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(*xs)
+    B = xs[0].shape[0]
+    code = dtype_code(xs[0].dtype)
+    descs = (PoolDesc * len(xs))()
+    ys, colsums, keep = [], [], []
+    with torch.cuda.device(dev):
+        for i, (x, T) in enumerate(zip(xs, out_frames)):
+            assert x.dim() == 4, f"expected [B, F, N, C] features, got {tuple(x.shape)}"
+            assert x.shape[0] == B and x.dtype == xs[0].dtype
+            if x.stride(3) != 1 or any(s % 8 for s in x.stride()[:3]):
+                x = x.contiguous()
+            keep.append(x)
+            _, F, N, Cc = x.shape
+            H = int(math.sqrt(N))  # nn_utils.py:322
+            assert H * H == N, f"patch count {N} is not a perfect square (einops would reject it at nn_utils.py:323-327)"
+            y = torch.empty((B, T * out_size * out_size, Cc), dtype=x.dtype, device=dev)
+            parts = lib.merv_pool3d_colsum_parts(T, out_size, B) if want_colsum else 0
+            cs = torch.empty((B, parts, Cc), dtype=torch.float32, device=dev) if want_colsum else None
+            d = descs[i]
+            d.x, d.y, d.colsum = x.data_ptr(), y.data_ptr(), _p(cs)
+            d.F, d.H, d.W, d.C, d.T, d.S = F, H, H, Cc, T, out_size
+            d.x_batch_stride, d.x_frame_stride, d.x_token_stride = x.stride(0), x.stride(1), x.stride(2)
+            d.y_batch_stride, d.y_row_stride = y.stride(0), y.stride(1)
+            ys.append(y)
+            colsums.append(cs)
+        _call('merv_pool3d', lib.merv_pool3d, descs, len(xs), B, code, _stream())
+    return ys, (colsums if want_colsum else None)
+
+
+def linear_bias_act(
+    a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = ACT_NONE,
+    rowdot_vec: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """y = act(a @ w.T + bias) for a [..., K], w [N, K]; optional row-dot partials [M, ceil(N/128)] (bf16 path).
+
+    Reference: nn.Linear (+ nn.GELU) in merv/util/nn_utils.py:31-32,46-55,97-108.
+    """
+    lib = _lib.load()
+    dev = _require_cuda(a, w, bias, rowdot_vec)
+    code = dtype_code(a.dtype)
+    assert w.dtype == a.dtype and (bias is None or bias.dtype == a.dtype), "weights must be in the activation dtype"
+    K = a.shape[-1]
+    N = w.shape[0]
+    assert w.shape[1] == K, f"weight {tuple(w.shape)} does not match input features {K}"
+    a2 = a.reshape(-1, K)
+    if a2.stride(1) != 1:
+        a2 = a2.contiguous()
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    M = a2.shape[0]
+    with torch.cuda.device(dev):
+        y = torch.empty((M, N), dtype=a.dtype, device=dev)
+        rd = None
+        if rowdot_vec is not None:
+            assert rowdot_vec.dtype == torch.float32 and rowdot_vec.numel() == N
+            rd = torch.empty((M, (N + ROWDOT_BLOCK - 1) // ROWDOT_BLOCK), dtype=torch.float32, device=dev)
+        _call('merv_linear_bias_act', lib.merv_linear_bias_act, a2.data_ptr(), a2.stride(0), w.data_ptr(), w.stride(0), _p(bias), y.data_ptr(), y.stride(0),
+                                       M, N, K, act, code, _p(rowdot_vec), _p(rd), _stream())
+    return y.reshape(*a.shape[:-1], N), rd
+
+
+def fusion_query_vec(Q: torch.Tensor, Wq: torch.Tensor, Wk: torch.Tensor, in_proj_bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """u = Wk^T (Wq Q^T + b_q) / sqrt(embed), fp32 [llm_dim] (nn_utils.py:499-512)."""
+    lib = _lib.load()
+    dev = _require_cuda(Q, Wq, Wk, in_proj_bias)
+    code = dtype_code(Q.dtype)
+    embed, llm_dim = Wk.shape
+    assert Wq.shape == (embed, embed) and Q.numel() == embed
+    Q, Wq, Wk = Q.contiguous(), Wq.contiguous(), Wk.contiguous()
+    with torch.cuda.device(dev):
+        u = torch.empty(llm_dim, dtype=torch.float32, device=dev)
+        ws = torch.empty(embed, dtype=torch.float32, device=dev)
+        _call('merv_fusion_query_vec', lib.merv_fusion_query_vec, Q.data_ptr(), Wq.data_ptr(), Wk.data_ptr(), _p(in_proj_bias), u.data_ptr(), ws.data_ptr(),
+                                        embed, llm_dim, code, _stream())
+    return u
+
+
+def affine_score_vec(W: torch.Tensor, bias: Optional[torch.Tensor], u: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(v, c) with u . (W x + b) == v . x + c: v = W^T u [K] fp32, c = u . b [1] fp32."""
+    lib = _lib.load()
+    dev = _require_cuda(W, bias, u)
+    N, K = W.shape
+    if W.stride(1) != 1:
+        W = W.contiguous()
+    with torch.cuda.device(dev):
+        v = torch.empty(K, dtype=torch.float32, device=dev)
+        c = torch.empty(1, dtype=torch.float32, device=dev)
+        _call('merv_affine_score_vec', lib.merv_affine_score_vec, W.data_ptr(), W.stride(0), _p(bias), u.data_ptr(), v.data_ptr(), c.data_ptr(), N, K,
+                                        dtype_code(W.dtype), _stream())
+    return v, c
+
+
+def scores_from_tokens(Vs: Sequence[torch.Tensor], u: torch.Tensor, token_length: int) -> torch.Tensor:
+    """scores[b, e] = mean_t(u . V_e[b, t, :]) read from the tokens (general path)."""
+    lib = _lib.load()
+    dev = _require_cuda(*Vs, u)
+    B, _, K = Vs[0].shape
+    E = len(Vs)
+    Vs = [v.contiguous() for v in Vs]
+    with torch.cuda.device(dev):
+        scores = torch.empty((B, E), dtype=torch.float32, device=dev)
+        n = lib.merv_scores_from_tokens_workspace(B, E, token_length, K)
+        ws = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        _call('merv_scores_from_tokens', lib.merv_scores_from_tokens, ptr_array([v.data_ptr() for v in Vs]), i32_array([v.shape[1] for v in Vs]), u.data_ptr(),
+                                          scores.data_ptr(), ws.data_ptr(), n, B, E, token_length, K, dtype_code(Vs[0].dtype), _stream())
+    return scores
+
+
+def scores_from_rowdot(rowdots: Sequence[torch.Tensor], consts: Optional[Sequence[Optional[torch.Tensor]]], B: int, T: int) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _require_cuda(*rowdots)
+    E, nblk = len(rowdots), rowdots[0].shape[1]
+    with torch.cuda.device(dev):
+        scores = torch.empty((B, E), dtype=torch.float32, device=dev)
+        cptr = ptr_array([_p(c) for c in consts]) if consts is not None else None
+        _call('merv_scores_from_rowdot', lib.merv_scores_from_rowdot, ptr_array([r.data_ptr() for r in rowdots]), cptr, scores.data_ptr(), B, E, T, nblk, _stream())
+    return scores
+
+
+def scores_from_colsum(colsums: Sequence[torch.Tensor], vs: Sequence[torch.Tensor], cs: Sequence[Optional[torch.Tensor]], T: int) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _require_cuda(*colsums, *vs)
+    B, E = colsums[0].shape[0], len(colsums)
+    with torch.cuda.device(dev):
+        scores = torch.empty((B, E), dtype=torch.float32, device=dev)
+        _call('merv_scores_from_colsum', lib.merv_scores_from_colsum, ptr_array([c.data_ptr() for c in colsums]), ptr_array([v.data_ptr() for v in vs]),
+                                          ptr_array([_p(c) for c in cs]), i32_array([c.shape[2] for c in colsums]),
+                                          i32_array([c.shape[1] for c in colsums]), scores.data_ptr(), B, E, T, _stream())
+    return scores
+
+
+def softmax_weights(
+    scores: torch.Tensor, biases: Optional[Sequence[Optional[torch.Tensor]]] = None, N: int = 0
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """weights = softmax(scores, -1) (fp32) and, if `biases` is given, bias_mix[b] = sum_e weights[b,e] * bias_e (fp32 [B, N])."""
+    lib = _lib.load()
+    dev = _require_cuda(scores)
+    B, E = scores.shape
+    with torch.cuda.device(dev):
+        weights = torch.empty((B, E), dtype=torch.float32, device=dev)
+        bias_mix, bptr, code = None, None, MERV_F32
+        if biases is not None:
+            bias_mix = torch.empty((B, N), dtype=torch.float32, device=dev)
+            bptr = ptr_array([_p(b) for b in biases])
+            present = [b for b in biases if b is not None]
+            code = dtype_code(present[0].dtype) if present else MERV_F32
+        _call('merv_softmax_weights', lib.merv_softmax_weights, scores.data_ptr(), weights.data_ptr(), bptr, _p(bias_mix), B, E, N, code, _stream())
+    return weights, bias_mix
+
+
+def softmax_mix(
+    Vs: Sequence[torch.Tensor], token_length: int, scores: Optional[torch.Tensor] = None, weights: Optional[torch.Tensor] = None
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """out[b,t,:] = sum_e w[b,e] V_e[b,t,:] with w = softmax(scores) computed in-kernel (or given `weights`).
+
+    Reference: torch.stack + torch.bmm at merv/util/nn_utils.py:503,521.  Returns (out [B,T,K], weights fp32 [B,E]).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(*Vs, scores, weights)
+    assert (scores is None) != (weights is None)
+    B, _, K = Vs[0].shape
+    E = len(Vs)
+    Vs = [v.contiguous() for v in Vs]
+    with torch.cuda.device(dev):
+        out = torch.empty((B, token_length, K), dtype=Vs[0].dtype, device=dev)
+        if weights is None:
+            weights = torch.empty((B, E), dtype=torch.float32, device=dev)
+        _call('merv_softmax_mix', lib.merv_softmax_mix, ptr_array([v.data_ptr() for v in Vs]), i32_array([v.shape[1] for v in Vs]), _p(scores),
+                                   weights.data_ptr(), out.data_ptr(), B, E, token_length, K, dtype_code(Vs[0].dtype), _stream())
+    return out, weights
+
+
+def fused_linear_mix(
+    As: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor], scale: torch.Tensor, bias_mix: Optional[torch.Tensor],
+    rows_per_video: int, out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """out[m] = sum_s scale[m // rows_per_video, s] * (A_s[m] @ W_s.T) + bias_mix[m // rows_per_video]  (bf16, tcgen05).
+
+    `out` may be a preallocated [M, N] view with row stride >= N (e.g. a slice of the multimodal embedding buffer).
+    """
+    lib = _lib.load()
+    dev = _require_cuda(*As, *Ws, scale, bias_mix)
+    assert all(a.dtype == torch.bfloat16 for a in As) and all(w.dtype == torch.bfloat16 for w in Ws), "fused path is bf16 only"
+    As = [a.reshape(-1, a.shape[-1]) for a in As]
+    As = [a if a.stride(1) == 1 else a.contiguous() for a in As]
+    Ws = [w if w.stride(1) == 1 else w.contiguous() for w in Ws]
+    M, N = As[0].shape[0], Ws[0].shape[0]
+    assert scale.dtype == torch.float32 and scale.is_contiguous() and scale.shape == (M // rows_per_video, len(As))
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        assert out.shape == (M, N) and out.stride(1) == 1
+        _call('merv_fused_linear_mix', lib.merv_fused_linear_mix, ptr_array([a.data_ptr() for a in As]), i64_array([a.stride(0) for a in As]),
+                                        ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]),
+                                        i32_array([a.shape[1] for a in As]), len(As), scale.data_ptr(), _p(bias_mix), out.data_ptr(),
+                                        out.stride(0), M, N, rows_per_video, _stream())
+    return out

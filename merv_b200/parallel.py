@@ -1,0 +1,70 @@
+"""Data-parallel sharding of the fusion path: one process per GPU, videos are independent units.
+
+The reference has no parallelism on this path beyond data parallel: every video's
+fusion depends only on its own features and the replicated weights.  So the batch is split into contiguous
+blocks, rank r owning videos [r*ceil(B/G), ...), there is NO collective on the compute path, and the only
+optional exchange is one all-gather of the fused prefixes when a consumer wants them on every rank
+(NCCL over NVLink on GPUs; the same code runs on gloo for the CPU tests).
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block of videos owned by `rank`: rank-major order == batch order after the gather."""
+    per = (batch + world - 1) // world
+    lo = min(batch, rank * per)
+    return lo, min(batch, lo + per)
+
+
+def shard_features(features: Sequence[torch.Tensor], rank: int, world: int) -> List[torch.Tensor]:
+    lo, hi = shard_bounds(features[0].shape[0], rank, world)
+    return [f[lo:hi] for f in features]
+
+
+def all_gather_prefix(local: torch.Tensor, batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Gather per-rank prefixes [b_r, T, K] into [batch, T, K] on every rank (rank-major == batch order).
+
+    Ranks may own unequal (even empty) blocks when `batch` is not a multiple of the world size: blocks are
+    padded to ceil(batch/world) videos for the collective and the padding is dropped afterwards.
+    """
+    world = dist.get_world_size(group)
+    per = (batch + world - 1) // world
+    T, K = local.shape[1], local.shape[2]
+    if local.shape[0] != per:
+        padded = local.new_zeros((per, T, K))
+        padded[: local.shape[0]] = local
+    else:
+        padded = local.contiguous()
+    out = local.new_empty((world * per, T, K))
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(out, padded, group=group)
+    else:
+        dist.all_gather(list(out.view(world, per, T, K).unbind(0)), padded, group=group)
+    return out[:batch]
+
+
+def fusion_forward_sharded(module, features: Sequence[torch.Tensor], gather: bool = False,
+                           group: Optional[dist.ProcessGroup] = None):
+    """Run `module` (a MervFusion) on this rank's block of the GLOBAL batch held in `features`.
+
+    Returns (prefix, weights) for the local block, or for the whole batch on every rank when gather=True.
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    batch = features[0].shape[0]
+    local = shard_features(features, rank, world)
+    if local[0].shape[0] > 0:
+        prefix, weights = module(local)
+    else:  # more ranks than videos
+        T, K = module.feature_fusion.token_length, module.feature_fusion.llm_dim
+        prefix = features[0].new_zeros((0, T, K))
+        weights = features[0].new_zeros((0, len(features)))
+    if not gather:
+        return prefix, weights
+    w3 = all_gather_prefix(weights.unsqueeze(-1), batch, group).squeeze(-1)
+    return all_gather_prefix(prefix, batch, group), w3

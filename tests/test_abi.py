@@ -1,0 +1,136 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU and exports exactly what
+include/merv_fusion.h declares; the Python mirror keeps the reference's names, signatures, state-dict keys,
+initialisation and error behaviour."""
+import ctypes
+import inspect
+import json
+import os
+import re
+
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(REPO, "include", "merv_fusion.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(merv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from merv_b200 import _lib
+
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _header_functions()
+    assert declared, "no declarations parsed from include/merv_fusion.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in merv_fusion.h but not exported by libmerv_fusion.so"
+    assert sorted(_lib.EXPORTS) == declared, "Python binding and header disagree on the entry points"
+    assert lib.merv_abi_version() == _lib.ABI_VERSION
+
+
+def test_host_only_entry_points_work_without_gpu():
+    from merv_b200 import _lib
+
+    lib = _lib.load()
+    assert lib.merv_pool3d_colsum_parts(16, 8, 64) == 16 * 4
+    assert lib.merv_pool3d_colsum_parts(16, 8, 1) == 16 * 8
+    assert lib.merv_pool3d_colsum_parts(16, 8, 4096) == 16
+    assert lib.merv_scores_from_tokens_workspace(2, 4, 1024, 4096) == 2 * 4 * 32
+
+
+def test_argument_errors_are_reported_not_crashed():
+    from merv_b200 import _lib
+
+    lib = _lib.load()
+    rc = lib.merv_pool3d(None, 1, 1, _lib.MERV_BF16, None)
+    assert rc == -6 and b"NULL" in lib.merv_last_error()
+    rc = lib.merv_linear_bias_act(None, 0, None, 0, None, None, 0, 1, 1, 1, 0, 7, None, None, None)
+    assert rc == -3 and b"dtype" in lib.merv_last_error()
+    with pytest.raises(_lib.MervError):
+        _lib.check(rc)
+
+
+def test_no_cpu_fallback():
+    import merv_b200 as M
+
+    m = M.MervFusion.build([64, 48], 128, [4, 4], 16, "linear", text_embedding_dim=96).eval().requires_grad_(False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m([torch.zeros(1, 4, 16, 64), torch.zeros(1, 4, 49, 48)])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.feature_fusion([torch.zeros(1, 64, 128), torch.zeros(1, 64, 128)])
+
+
+def test_state_dict_keys_and_seeded_init_match_reference():
+    # digests recorded from the UNMODIFIED reference built under torch.manual_seed(1024) (merv.py:87)
+    import merv_b200 as M
+
+    want = json.load(open(os.path.join(REPO, "tests", "golden", "ref_init_seed1024.json")))
+    m = M.MervFusion.build([1024, 1024, 768, 768], 4096, [16] * 4, 64, "linear", seed=1024)
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(want)
+    for k, (shape, s, a) in want.items():
+        assert list(sd[k].shape) == shape
+        assert sd[k].double().sum().item() == pytest.approx(s, rel=0, abs=1e-9)
+        assert sd[k].double().abs().sum().item() == pytest.approx(a, rel=1e-12)
+
+
+@pytest.mark.parametrize("mlp_type,keys", [
+    ("linear", ["projector.projector.weight", "projector.projector.bias"]),
+    ("gelu-mlp", [f"projector.projector.{i}.{p}" for i in (0, 2) for p in ("weight", "bias")]),
+    ("fused-gelu-mlp", [f"projector.projector.{i}.{p}" for i in (0, 2, 4) for p in ("weight", "bias")]),
+])
+def test_projector_state_dict_keys(mlp_type, keys):
+    import merv_b200 as M
+
+    p = M.AveragePooling3DProjector(32, 64, output_frames=4, output_size=2, mlp_type=mlp_type)
+    assert sorted(p.state_dict()) == sorted(keys)
+    assert p.output_token_length == 4 and p.output_frame_length == 4
+
+
+def test_signatures_and_errors_mirror_reference():
+    import merv_b200 as M
+
+    sig = inspect.signature(M.AveragePooling3DProjector.__init__)
+    assert list(sig.parameters)[1:] == ["fused_vision_dim", "llm_dim", "output_frames", "output_size", "mlp_type"]
+    assert sig.parameters["mlp_type"].default == "gelu-mlp"
+    sig = inspect.signature(M.CrossAttentionAdapterLearnableQuery.__init__)
+    assert [(k, v.default) for k, v in list(sig.parameters.items())[1:]] == [
+        ("embed_dim", 3072), ("llm_dim", 4098), ("token_length", 8), ("averagetoken", False), ("num_encoder", 4),
+        ("positional_embedding", False)]
+    with pytest.raises(ValueError, match="is not supported"):
+        M.get_mlp_projector(8, 8, "relu-mlp")
+    with pytest.raises(ValueError, match="is not supported"):
+        M.MLPProjector(8, 8, "linear")
+    assert isinstance(M.get_mlp_projector(8, 8, "none"), torch.nn.Identity)
+    assert M.MLPProjector(8, 8).output_token_length == 1
+    ff = M.CrossAttentionAdapterLearnableQuery(16, 8, 4, averagetoken=True)
+    with pytest.raises(AssertionError):  # nn_utils.py:494-495
+        ff([torch.zeros(1, 3, 8)])
+
+
+def test_adopts_reference_modules_in_place():
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference only exists in the build container")
+    import merv_b200 as M
+
+    ref = load_reference_nn_utils()
+
+    class FakeMerv(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.projectors = torch.nn.ModuleList(
+                [ref.AveragePooling3DProjector(c, 64, output_frames=4, output_size=2, mlp_type="gelu-mlp") for c in (32, 24)])
+            self.feature_fusion = ref.CrossAttentionAdapterLearnableQuery(48, 64, 16, averagetoken=True)
+
+    v = FakeMerv()
+    before = {k: t.data_ptr() for k, t in v.state_dict().items()}
+    M.patch_merv(v)
+    after = {k: t.data_ptr() for k, t in v.state_dict().items()}
+    assert before == after, "patch_merv must keep state-dict keys and share (not copy) the parameters"
+    assert isinstance(v.projectors[0], M.AveragePooling3DProjector)
+    assert isinstance(v.feature_fusion, M.CrossAttentionAdapterLearnableQuery)

@@ -1,0 +1,342 @@
+"""GPU parity tests (B200): every kernel and both module paths, called through the C ABI, against the numpy
+oracle on the same seeded inputs and against the golden fixtures recorded from the unmodified reference.
+
+Tolerances (BASELINE.json north_star; metric max|a-b| / max|b|):
+    fp32 : 1e-5      bf16 : 2e-2
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases as C
+from oracle import fusion_oracle as O
+from tests.golden_util import regenerate
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+DEV = "cuda:0"
+
+
+def _t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV).to(dtype)
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _bf16_round(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+def build_module(case, pp, fp, dtype, fused):
+    import merv_b200 as M
+
+    m = M.MervFusion.build(case.dims, case.llm_dim, case.out_frames, case.out_size**2, case.mlp_type,
+                           text_embedding_dim=case.embed_dim, fused=fused)
+    for proj, p in zip(m.projectors, pp):
+        proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    m.feature_fusion.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()})
+    return m.to(device=DEV, dtype=dtype).eval().requires_grad_(False)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny_linear", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pool3d_matches_oracle(name, dtype):
+    from merv_b200 import ops
+
+    case = C.CASES[name]
+    g, feats, _, _ = regenerate(case)
+    vec = 8 if dtype == torch.bfloat16 else 4
+    if any(c % vec for c in case.dims):
+        pytest.skip("channel count not a multiple of the 16-byte vector for this dtype")
+    xs = [_t(f, dtype) for f in feats]
+    ys, colsums = ops.pool3d(xs, case.out_frames, case.out_size, want_colsum=True)
+    torch.cuda.synchronize()
+    for e, (x, y, cs) in enumerate(zip(xs, ys, colsums)):
+        want = O.avg_pool3d_tokens(_np(x), case.out_frames[e], case.out_size)  # oracle on the dtype-rounded input
+        assert y.shape == want.shape and y.dtype == dtype
+        tol = 1e-6 if dtype == torch.float32 else 4e-3  # bf16: one rounding of the fp32 mean
+        assert O.rel_err(_np(y), want) < tol
+        if name in C.FULL_STORE_CASES and dtype == torch.float32:
+            assert O.rel_err(_np(y), g[f"pooled{e}"]) < FP32_TOL
+        # deterministic partial column sums of the pooled tokens as stored
+        got = _np(cs).sum(1)
+        assert np.abs(got - _np(y).astype(np.float64).sum(1)).max() < 1e-3 * max(1.0, np.abs(got).max())
+
+
+def test_pool3d_strided_input_drops_cls_token():
+    # backbones hand over slices that drop a CLS token (languagebind/__init__.py:94): token stride stays C,
+    # frame stride is (N+1)*C — the kernel must honour strides instead of forcing a copy
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(3)
+    full = _t(rng.standard_normal((2, 4, 17, 64), dtype=np.float32), torch.bfloat16)
+    x = full[:, :, 1:, :]
+    assert not x.is_contiguous()
+    (y,), _ = ops.pool3d([x], [4], 2)
+    want = O.avg_pool3d_tokens(_np(x), 4, 2)
+    assert O.rel_err(_np(y), want) < 4e-3
+
+
+GEMM_SHAPES = [
+    (256, 512, 256), (128, 256, 64), (100, 136, 72), (1000, 264, 200), (2048, 4096, 1024), (384, 768, 4096),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("act", [0, 1])
+def test_tcgen05_linear_matches_oracle(M, N, K, act):
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(M + N + K)
+    a = _bf16_round(rng.standard_normal((M, K), dtype=np.float32))
+    w = _bf16_round(rng.uniform(-1, 1, (N, K)).astype(np.float32) / np.sqrt(K))
+    b = _bf16_round(rng.uniform(-0.5, 0.5, N).astype(np.float32))
+    rv = rng.standard_normal(N).astype(np.float32)
+    y, rd = ops.linear_bias_act(_t(a, torch.bfloat16), _t(w, torch.bfloat16), _t(b, torch.bfloat16), act, rowdot_vec=_t(rv))
+    torch.cuda.synchronize()
+    want = a.astype(np.float64) @ w.astype(np.float64).T + b
+    if act:
+        want = O.gelu_erf(want)
+    assert y.shape == (M, N)
+    assert O.rel_err(_np(y), want) < 6e-3  # fp32 accumulate, one bf16 rounding of the output
+    # row-dot partials: dot of the STORED row with rv, per 128-column block
+    nblk = (N + 127) // 128
+    yy = _np(y).astype(np.float64)
+    want_rd = np.stack([(yy[:, j * 128:(j + 1) * 128] * rv[j * 128:(j + 1) * 128]).sum(1) for j in range(nblk)], 1)
+    assert rd.shape == (M, nblk)
+    assert np.abs(_np(rd) - want_rd).max() < 1e-3 * max(1.0, np.abs(want_rd).max())
+
+
+def test_simt_fp32_linear_matches_oracle():
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(5)
+    for M, N, K in [(130, 70, 50), (256, 512, 768)]:
+        a = rng.standard_normal((M, K), dtype=np.float32)
+        w = rng.uniform(-1, 1, (N, K)).astype(np.float32) / np.sqrt(K)
+        b = rng.uniform(-0.5, 0.5, N).astype(np.float32)
+        for act in (0, 1):
+            y, _ = ops.linear_bias_act(_t(a), _t(w), _t(b), act)
+            want = a.astype(np.float64) @ w.astype(np.float64).T + b
+            if act:
+                want = O.gelu_erf(want)
+            assert O.rel_err(_np(y), want) < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_query_vector_matches_oracle(dtype):
+    from merv_b200 import ops
+
+    case = C.CASES["mid_linear"]
+    fp = C.make_fusion_params(case)
+    if dtype == torch.bfloat16:
+        fp = {k: _bf16_round(v) for k, v in fp.items()}
+    u = ops.fusion_query_vec(_t(fp["Q"], dtype), _t(fp["attention.q_proj_weight"], dtype), _t(fp["attention.k_proj_weight"], dtype),
+                             _t(fp["attention.in_proj_bias"], dtype))
+    want = O.fusion_query_vector({k: v.astype(np.float64) for k, v in fp.items()})
+    assert O.rel_err(_np(u), want) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_mix_kernels_match_oracle_incl_broadcast(dtype):
+    # general adapter path on arbitrary tensors, including a T==1 encoder (nn_utils.py:502)
+    import merv_b200 as M
+
+    case = C.CASES["mid_linear"]
+    fp = C.make_fusion_params(case)
+    rng = np.random.default_rng(11)
+    T, K, B = case.token_length, case.llm_dim, 3
+    V = [rng.standard_normal((B, T, K), dtype=np.float32) + 0.3, rng.standard_normal((B, 1, K), dtype=np.float32),
+         rng.standard_normal((B, T, K), dtype=np.float32) - 0.2]
+    ff = M.CrossAttentionAdapterLearnableQuery(case.embed_dim, K, T, averagetoken=True, num_encoder=3)
+    ff.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()})
+    ff = ff.to(device=DEV, dtype=dtype).eval().requires_grad_(False)
+    out, w = ff([_t(v, dtype) for v in V])
+    Vr = [_np(_t(v, dtype)) for v in V]
+    fpr = {k: _np(_t(v, dtype)) for k, v in fp.items()}
+    want_out, want_w = O.cross_attention_fusion_forward([v.astype(np.float64) for v in Vr], {k: v.astype(np.float64) for k, v in fpr.items()}, T)
+    tol = FP32_TOL if dtype == torch.float32 else 6e-3
+    assert out.shape == (B, T, K) and w.shape == (B, 3) and out.dtype == dtype
+    assert np.abs(_np(w) - want_w).max() < (2e-5 if dtype == torch.float32 else 4e-3)
+    assert O.rel_err(_np(out), want_out) < tol
+
+
+# ---------------------------------------------------------------------------------------------------------
+# module paths vs the reference goldens
+# ---------------------------------------------------------------------------------------------------------
+SMALL = ["tiny_linear", "tiny_gelu", "tiny_fused_gelu", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear", "mid_gelu"]
+
+
+def _check_against_golden(case, g, out, w, tol, wtol):
+    out_np, w_np = _np(out), _np(w)
+    assert out.shape == (case.batch, case.token_length, case.llm_dim)
+    assert w.shape == (case.batch, case.num_encoders)
+    assert np.allclose(w_np.sum(-1), 1.0, atol=1e-2 if wtol > 1e-4 else 1e-5)
+    scale = float(g["out_abs_max"])
+    idx = g["sample_idx"]
+    assert np.abs(out_np.reshape(-1)[idx] - g["out_samples"]).max() / scale < tol
+    assert np.abs(w_np - g["weights"]).max() < wtol
+    if case.name in C.FULL_STORE_CASES:
+        assert O.rel_err(out_np, g["out"]) < tol
+
+
+@pytest.mark.parametrize("name", SMALL + ["merv_full_b1"])
+def test_modules_fp32_match_reference(name):
+    case = C.CASES[name]
+    if any(c % 4 for c in case.dims):
+        pytest.skip("fp32 path needs C % 4 == 0")
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.float32, fused=False)
+    with torch.inference_mode():
+        out, w = m([_t(f) for f in feats])
+    assert out.dtype == torch.float32
+    _check_against_golden(case, g, out, w, FP32_TOL, 2e-5)
+
+
+@pytest.mark.parametrize("name", SMALL + ["merv_full_b1", "merv_full_b1_gelu"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_modules_bf16_match_reference(name, fused):
+    case = C.CASES[name]
+    if any(c % 8 for c in case.dims):
+        pytest.skip("bf16 path needs C % 8 == 0")
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=fused)
+    with torch.inference_mode():
+        out, w = m([_t(f, torch.bfloat16) for f in feats])
+    assert out.dtype == torch.bfloat16 and out.is_contiguous()
+    _check_against_golden(case, g, out, w, BF16_TOL, 2e-2)
+    # also against the reference's own bf16 run (what a user switching frameworks would compare with)
+    idx = g["sample_idx"]
+    assert np.abs(_np(out).reshape(-1)[idx] - g["out_samples_bf16"]).max() / float(g["out_abs_max"]) < BF16_TOL
+
+
+@pytest.mark.parametrize("name", ["mid_linear", "mid_gelu"])
+def test_autocast_fp32_master_weights(name):
+    # training-style call: fp32 parameters under torch.autocast(bf16) (base_strategy.py:210-214)
+    case = C.CASES[name]
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.float32, fused=True)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out, w = m([_t(f, torch.bfloat16) for f in feats])
+    assert out.dtype == torch.bfloat16
+    _check_against_golden(case, g, out, w, BF16_TOL, 2e-2)
+
+
+def test_fused_equals_unfused_and_oracle_on_rounded_inputs():
+    # isolate kernel error from bf16 input rounding: oracle run in fp64 on the bf16-rounded inputs/weights
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    feats_r = [_bf16_round(f) for f in feats]
+    pp_r = [{k: _bf16_round(v) for k, v in p.items()} for p in pp]
+    fp_r = {k: _bf16_round(v) for k, v in fp.items()}
+    want, want_w, _ = O.merv_fusion_forward([f.astype(np.float64) for f in feats_r], [{k: v.astype(np.float64) for k, v in p.items()} for p in pp_r],
+                                            {k: v.astype(np.float64) for k, v in fp_r.items()}, case.out_frames, case.out_size,
+                                            case.mlp_type, case.token_length)
+    outs = {}
+    for fused in (False, True):
+        m = build_module(case, pp, fp, torch.bfloat16, fused=fused)
+        with torch.inference_mode():
+            out, w = m([_t(f, torch.bfloat16) for f in feats])
+        outs[fused] = _np(out)
+        assert O.rel_err(_np(out), want) < 8e-3
+        assert np.abs(_np(w) - want_w).max() < 5e-3
+    assert O.rel_err(outs[True], outs[False]) < 8e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties at the benchmark shape (merv-full, bf16)
+# ---------------------------------------------------------------------------------------------------------
+def _full_module(fused=True, mlp_type="linear"):
+    import merv_b200 as M
+
+    m = M.MervFusion.build([1024, 1024, 768, 768], 4096, [16] * 4, 64, mlp_type, seed=1024, fused=fused)
+    with torch.no_grad():
+        m.feature_fusion.Q.mul_(64.0)  # non-degenerate softmax
+    return m.to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+
+
+def _full_features(B, seed=7):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    shapes = [(B, 16, 256, 1024), (B, 16, 256, 1024), (B, 16, 196, 768), (B, 16, 196, 768)]
+    mus = [0.0, 0.5, -0.5, 0.25]
+    return [(torch.randn(s, generator=g, device=DEV) + mu).to(torch.bfloat16) for s, mu in zip(shapes, mus)]
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_full_size_batch_properties(fused):
+    B = 16
+    m = _full_module(fused)
+    feats = _full_features(B)
+    with torch.inference_mode():
+        out, w = m(feats)
+        out2, w2 = m(feats)
+        torch.cuda.synchronize()
+        assert out.shape == (B, 1024, 4096) and w.shape == (B, 4)
+        assert torch.isfinite(out.float()).all()
+        assert torch.allclose(w.float().sum(-1), torch.ones(B, device=DEV), atol=1e-2)
+        assert (w.float().max(-1).values - w.float().min(-1).values).mean() > 0.02, "softmax is degenerate: test would not see a broken score path"
+        # determinism: fixed-order reductions, no atomics
+        assert torch.equal(out, out2) and torch.equal(w, w2)
+        # videos are independent: a video computed alone (as another rank would) is bit-identical
+        for b in (0, B - 1):
+            ob, wb = m([f[b:b + 1] for f in feats])
+            assert torch.equal(ob[0], out[b]) and torch.equal(wb[0], w[b])
+        # a contiguous shard equals the same rows of the full batch (what batch-sharding across GPUs relies on)
+        oh, wh = m([f[B // 2:] for f in feats])
+        assert torch.equal(oh, out[B // 2:]) and torch.equal(wh, w[B // 2:])
+
+
+def test_full_size_fused_matches_unfused():
+    B = 4
+    feats = _full_features(B, seed=9)
+    with torch.inference_mode():
+        of, wf = _full_module(True)(feats)
+        ou, wu = _full_module(False)(feats)
+    scale = ou.float().abs().max().item()
+    assert (of.float() - ou.float()).abs().max().item() / scale < 1.2e-2
+    assert (wf.float() - wu.float()).abs().max().item() < 1e-2
+
+
+def test_single_encoder_siglip_config():
+    # BASELINE.json config 4: one encoder (SigLIP), E=1 -> weights == 1 and prefix == projected tokens
+    import merv_b200 as M
+
+    m = M.MervFusion.build([768], 4096, [16], 64, "linear", seed=768, fused=True).to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+    mu = M.MervFusion(list(m.projectors), m.feature_fusion, fused=False)
+    x = _full_features(2)[3]
+    with torch.inference_mode():
+        out, w = m([x])
+        M.unlink(m.projectors)
+        y = m.projectors[0](x)
+    assert torch.equal(w.float(), torch.ones_like(w.float()))
+    assert (out.float() - y.float()).abs().max().item() / y.float().abs().max().item() < 8e-3
+    del mu
+
+
+# ---------------------------------------------------------------------------------------------------------
+# error behaviour mirrors the reference
+# ---------------------------------------------------------------------------------------------------------
+def test_error_behaviour():
+    import merv_b200 as M
+    from merv_b200 import _lib, ops
+
+    ff = M.CrossAttentionAdapterLearnableQuery(96, 128, 64, averagetoken=True).to(DEV).eval().requires_grad_(False)
+    with pytest.raises(AssertionError):  # nn_utils.py:494-495
+        ff([torch.zeros(1, 63, 128, device=DEV)])
+    with pytest.raises(TypeError):
+        ops.linear_bias_act(torch.zeros(4, 8, device=DEV, dtype=torch.float16), torch.zeros(8, 8, device=DEV, dtype=torch.float16), None)
+    with pytest.raises(_lib.MervError, match="MERV_E_ALIGN|MERV_E_SHAPE"):
+        ops.linear_bias_act(torch.zeros(4, 12, device=DEV, dtype=torch.bfloat16), torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16), None)
+    p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(DEV)
+    with pytest.raises(NotImplementedError, match="backward"):
+        p(torch.zeros(1, 4, 16, 64, device=DEV))
+    p.requires_grad_(False)
+    with pytest.raises(AssertionError):  # 15 patches: not a square grid
+        p(torch.zeros(1, 4, 15, 64, device=DEV))

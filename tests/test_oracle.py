@@ -94,3 +94,20 @@ def test_token_length_one_broadcast():
 def test_unsupported_projector_type():
     with pytest.raises(ValueError):
         O.projector_forward(np.zeros((1, 4), np.float32), {}, "relu-mlp")
+
+
+@pytest.mark.parametrize("name", ["tiny_linear", "tiny_gelu", "tiny_fused_gelu", "ragged_windows", "mid_linear"])
+def test_torch_port_cpu_baseline_matches_golden(name):
+    # the timed CPU baseline (bench.py cpu_baseline / --impl reference) must compute the same thing
+    import torch
+
+    from oracle import torch_port
+
+    case = C.CASES[name]
+    g, feats, pp, fp = regenerate(case)
+    tt = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}  # noqa: E731
+    out, w = torch_port.fusion_forward([torch.from_numpy(f) for f in feats], [tt(p) for p in pp], tt(fp), case.out_frames,
+                                       case.out_size, case.mlp_type, case.token_length)
+    idx = g["sample_idx"]
+    assert np.abs(out.numpy().reshape(-1)[idx] - g["out_samples"]).max() / float(g["out_abs_max"]) < FP32_TOL
+    assert np.abs(w.numpy() - g["weights"]).max() < 2e-5
