@@ -67,6 +67,15 @@ def _no_autograd(module: nn.Module, *tensors) -> None:
         )
 
 
+def _version(p: torch.Tensor) -> int:
+    """In-place-update counter of a parameter; inference tensors do not track one (and cannot be updated in place
+    outside inference mode), so they count as version 0."""
+    try:
+        return p._version
+    except RuntimeError:
+        return 0
+
+
 class _CastCache:
     """Weights cast to the compute dtype, keyed on (storage, version) so in-place optimiser updates invalidate them."""
 
@@ -79,7 +88,7 @@ class _CastCache:
         if p.dtype == dtype:
             return p.detach()
         key = (id(p), dtype)
-        tag = (p.data_ptr(), p._version, tuple(p.shape))
+        tag = (p.data_ptr(), _version(p), tuple(p.shape))
         hit = self._store.get(key)
         if hit is None or hit[0] != tag:
             hit = (tag, p.detach().to(dtype))
@@ -346,7 +355,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         """u (fp32 [llm_dim]) with weights == softmax_e(u . mean_t V_e); recomputed when a parameter changes."""
         att = self.attention
         params = (self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias)
-        tag = tuple((p.data_ptr(), p._version) for p in params if p is not None) + (dtype, self.Q.device)
+        tag = tuple((p.data_ptr(), _version(p)) for p in params if p is not None) + (dtype, self.Q.device)
         hit = self._u_cache.get("u")
         if hit is None or hit[0] != tag:
             c = self._cast_cache
@@ -360,7 +369,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
     def _affine_vec(self, lin: nn.Linear, cache: _CastCache, dtype: torch.dtype):
         """(v, c) for the last (affine) projector layer: u . (W x + b) = v . x + c."""
         u = self.query_vector(dtype)
-        tag = (lin.weight.data_ptr(), lin.weight._version, None if lin.bias is None else lin.bias._version, dtype, id(u))
+        tag = (lin.weight.data_ptr(), _version(lin.weight), None if lin.bias is None else _version(lin.bias), dtype, id(u))
         hit = self._vc_cache.get(id(lin))
         if hit is None or hit[0] != tag:
             hit = (tag, ops.affine_score_vec(cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), u))
