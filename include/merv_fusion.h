@@ -58,20 +58,26 @@ int merv_num_sms(void);
  *   x : [B, F, H*W, C]  (element strides x_batch_stride / x_frame_stride / x_token_stride, channel stride 1)
  *   y : [B, T*S*S, C]   token index t*S*S + i*S + j (j fastest); row stride y_row_stride elements
  *   window k of an axis n_in -> n_out is [floor(k*n_in/n_out), ceil((k+1)*n_in/n_out))
- *   colsum (optional, fp32): [B, colsum_parts, C] partial sums over tokens of the POOLED features, written
- *     (not accumulated) deterministically; colsum_parts must equal merv_pool3d_colsum_parts(T, S, B).
+ *   score_vec / score_partial (optional, fp32): score_partial[b, i] = partial sums (one per internal work
+ *     item i of video b, deterministic order) of sum_{tokens, channels} score_vec[c] * Y[b, token, c] with Y as
+ *     rounded to the storage dtype; the number of partials per video is shape-dependent only and is given by
+ *     merv_pool3d_score_parts().  Feeds the encoder scores of the affine fast path (see merv_affine_score_vec).
  * Accumulation is fp32 for both dtypes (as ATen's kernel does).  C % 8 == 0 (bf16) or C % 4 == 0 (fp32).
+ * The main kernel streams the input through shared memory with 5-D TMA; unusual shapes (more than 2048 patch
+ * tokens per frame) take a plain vectorised-load kernel.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* x;
   void* y;
-  float* colsum; /* may be NULL */
+  const float* score_vec; /* [C] or NULL */
+  float* score_partial;   /* [B, parts] or NULL (both or neither) */
   int32_t F, H, W, C, T, S;
   int64_t x_batch_stride, x_frame_stride, x_token_stride;
   int64_t y_batch_stride, y_row_stride;
 } merv_pool_desc;
 
-int merv_pool3d_colsum_parts(int T, int S, int B);
+/* parts[e] = number of score partials per video the pool kernel emits for encoder e (independent of B). */
+int merv_pool3d_score_parts(const merv_pool_desc* enc, int num_encoders, int dtype, int32_t* parts);
 int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
@@ -106,24 +112,21 @@ int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const fl
                           int K, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Scores -> softmax over encoders -> mixing weights.  Three sources for the scores:
- *   merv_scores_from_tokens : s[b,e] = mean_t(u . V_e[b,t,:]) read from the projected tokens themselves
- *                             (general path; V_e [B, T_e, K] with T_e in {T, 1}, nn_utils.py:494-509)
- *   merv_scores_from_rowdot : the same from the GEMM epilogue's row-dot partials (no re-read of V):
- *                             s[b,e] = (1/T) sum_{t,j} rowdot_e[b*T+t, j] + c_e
- *   merv_scores_from_colsum : affine projectors, from the pool kernel's column sums:
- *                             s[b,e] = v_e . mean_t P_e[b,t,:] + c_e
- * each writes raw scores [B, E] fp32 (deterministic reduction order).
+ * Scores -> softmax over encoders -> mixing weights.  Two sources for the raw scores [B, E] (fp32):
+ *   merv_scores_from_tokens   : s[b,e] = mean_t(u . V_e[b,t,:]) read from the projected tokens themselves
+ *                               (general path; V_e [B, T_e, K] with T_e in {T, 1}, nn_utils.py:494-509)
+ *   merv_scores_from_partials : s[b,e] = (1/T) * sum_{i < count[e]} partial_e[b, i] + c_e, from partial dot
+ *                               products emitted by the pool kernel (score_partial) or by the GEMM epilogue
+ *                               (rowdot_out, count = T * ceil(N / MERV_ROWDOT_BLOCK)) — no re-read of V.
+ * Both use a fixed reduction order (no atomics): results are bit-reproducible per video.
  * ------------------------------------------------------------------------------------------------------- */
 int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const float* u, float* scores,
                             float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
                             void* stream);
 size_t merv_scores_from_tokens_workspace(int B, int E, int T, int K);
-int merv_scores_from_rowdot(const float* const* rowdot, const float* const* c /* per-encoder additive constant, may be NULL */,
-                            float* scores, int B, int E, int T, int nblk, void* stream);
-int merv_scores_from_colsum(const float* const* colsum, const float* const* v, const float* const* c,
-                            const int32_t* C, const int32_t* parts, float* scores, int B, int E, int T,
-                            void* stream);
+int merv_scores_from_partials(const float* const* partial, const int32_t* count,
+                              const float* const* c /* per-encoder additive constants, entries or array may be NULL */,
+                              float* scores, int B, int E, int T, void* stream);
 
 /* weights[b,:] = softmax(scores[b,:]) (fp32);  optionally bias_mix[b,n] = sum_e weights[b,e] * bias_e[n]
  * (the per-video bias of the fused affine path; bias_e in `dtype`, may contain NULL entries). */

@@ -31,7 +31,7 @@ class PoolDesc(C.Structure):
     """merv_pool_desc"""
 
     _fields_ = [
-        ("x", c_void_p), ("y", c_void_p), ("colsum", c_void_p),
+        ("x", c_void_p), ("y", c_void_p), ("score_vec", c_void_p), ("score_partial", c_void_p),
         ("F", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("T", c_int32), ("S", c_int32),
         ("x_batch_stride", c_int64), ("x_frame_stride", c_int64), ("x_token_stride", c_int64),
         ("y_batch_stride", c_int64), ("y_row_stride", c_int64),
@@ -45,7 +45,7 @@ _SIGNATURES = {
     "merv_last_error": (c_char_p, []),
     "merv_device_check": (c_int, []),
     "merv_num_sms": (c_int, []),
-    "merv_pool3d_colsum_parts": (c_int, [c_int, c_int, c_int]),
+    "merv_pool3d_score_parts": (c_int, [POINTER(PoolDesc), c_int, c_int, POINTER(c_int32)]),
     "merv_pool3d": (c_int, [POINTER(PoolDesc), c_int, c_int, c_int, c_void_p]),
     "merv_linear_bias_act": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -54,8 +54,7 @@ _SIGNATURES = {
     "merv_scores_from_tokens": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                                         c_int, c_void_p]),
     "merv_scores_from_tokens_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "merv_scores_from_rowdot": (c_int, [_PP, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "merv_scores_from_colsum": (c_int, [_PP, _PP, _PP, POINTER(c_int32), POINTER(c_int32), c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_scores_from_partials": (c_int, [_PP, POINTER(c_int32), _PP, c_void_p, c_int, c_int, c_int, c_void_p]),
     "merv_softmax_weights": (c_int, [c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_softmax_mix": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_fused_linear_mix": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
@@ -73,7 +72,7 @@ def load() -> C.CDLL:
         return _lib
     if not os.path.isfile(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m merv_b200.build` (needs nvcc). "
+            f"{LIB_PATH} is missing: build it with `python merv_b200/build.py` (needs nvcc). "
             "merv_b200 has no CPU or pure-PyTorch fallback."
         )
     lib = C.CDLL(LIB_PATH)

@@ -1,6 +1,6 @@
 """Build libmerv_fusion.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m merv_b200.build [--force]
+    python merv_b200/build.py [--force] [-v]      (run as a script: importing the package needs the library)
 
 The shared library is a plain C-ABI object (include/merv_fusion.h); it is git-ignored but travels with the
 repo snapshot to the GPU box.  No torch headers are involved.

@@ -116,42 +116,21 @@ __global__ void __launch_bounds__(32) reduce_scale_kernel(const float* __restric
   if (threadIdx.x == 0) scores[id] = acc * sp.inv[id % E];
 }
 
-// ---- scores from the GEMM epilogue's row-dot partials ----------------------------------------------------
-struct PtrParams {
+// ---- scores from partial dot products (pool kernel's score_partial / GEMM epilogue's rowdot_out) ----------
+struct PartialParams {
   const float* p[MERV_MAX_ENCODERS];
-  const float* v[MERV_MAX_ENCODERS];
   const float* c[MERV_MAX_ENCODERS];
-  int C[MERV_MAX_ENCODERS];
-  int parts[MERV_MAX_ENCODERS];
+  int count[MERV_MAX_ENCODERS];
 };
 
-// rowdot_e [B*T, nblk]: scores[b,e] = (1/T) * sum over the T*nblk floats of video b
-__global__ void __launch_bounds__(256) rowdot_score_kernel(const __grid_constant__ PtrParams p, float* __restrict__ scores, int E,
-                                                           int T, int nblk) {
+// scores[b,e] = (1/T) * sum_{i<count[e]} partial_e[b*count[e] + i] + c_e   (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) partial_score_kernel(const __grid_constant__ PartialParams p, float* __restrict__ scores, int E, int T) {
   __shared__ float red[32];
   const int e = blockIdx.x, b = blockIdx.y;
-  const long long n = (long long)T * nblk;
+  const int n = p.count[e];
   const float* src = p.p[e] + (long long)b * n;
   float acc = 0.f;
-  for (long long i = threadIdx.x; i < n; i += 256) acc += src[i];
-  acc = block_sum<256>(acc, red);
-  if (threadIdx.x == 0) scores[(long long)b * E + e] = acc / float(T) + (p.c[e] ? *p.c[e] : 0.f);
-}
-
-// colsum_e [B, parts_e, C_e]: scores[b,e] = (1/T) * sum_c v_e[c] * (sum_parts colsum[b,part,c]) + c_e
-__global__ void __launch_bounds__(256) colsum_score_kernel(const __grid_constant__ PtrParams p, float* __restrict__ scores, int E,
-                                                           int T) {
-  __shared__ float red[32];
-  const int e = blockIdx.x, b = blockIdx.y;
-  const int C = p.C[e], parts = p.parts[e];
-  const float* src = p.p[e] + (long long)b * parts * C;
-  const float* v = p.v[e];
-  float acc = 0.f;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f;
-    for (int k = 0; k < parts; ++k) s += src[(long long)k * C + c];
-    acc += s * v[c];
-  }
+  for (int i = threadIdx.x; i < n; i += 256) acc += src[i];
   acc = block_sum<256>(acc, red);
   if (threadIdx.x == 0) scores[(long long)b * E + e] = acc / float(T) + (p.c[e] ? *p.c[e] : 0.f);
 }
@@ -373,39 +352,21 @@ extern "C" int merv_scores_from_tokens(const void* const* V, const int32_t* toke
   return MERV_OK;
 }
 
-extern "C" int merv_scores_from_rowdot(const float* const* rowdot, const float* const* c, float* scores, int B, int E, int T,
-                                       int nblk, void* stream) {
-  MERV_REQUIRE(rowdot && scores, MERV_E_ARG, "merv_scores_from_rowdot: NULL pointer");
-  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_rowdot: E=%d", E);
-  MERV_REQUIRE(B >= 0 && T > 0 && nblk > 0, MERV_E_SHAPE, "merv_scores_from_rowdot: B=%d T=%d nblk=%d", B, T, nblk);
+extern "C" int merv_scores_from_partials(const float* const* partial, const int32_t* count, const float* const* c, float* scores,
+                                         int B, int E, int T, void* stream) {
+  MERV_REQUIRE(partial && count && scores, MERV_E_ARG, "merv_scores_from_partials: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_partials: E=%d", E);
+  MERV_REQUIRE(B >= 0 && T > 0, MERV_E_SHAPE, "merv_scores_from_partials: B=%d T=%d", B, T);
   if (int rc = require_sm100()) return rc;
   if (B == 0) return MERV_OK;
-  PtrParams p = {};
+  PartialParams p = {};
   for (int e = 0; e < E; ++e) {
-    MERV_REQUIRE(rowdot[e], MERV_E_ARG, "merv_scores_from_rowdot: rowdot[%d] is NULL", e);
-    p.p[e] = rowdot[e];
+    MERV_REQUIRE(partial[e] && count[e] > 0, MERV_E_ARG, "merv_scores_from_partials: encoder %d: NULL partials or count=%d", e, count[e]);
+    p.p[e] = partial[e];
     p.c[e] = c ? c[e] : nullptr;
+    p.count[e] = count[e];
   }
-  rowdot_score_kernel<<<dim3(E, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, scores, E, T, nblk);
-  MERV_CUDA_OK(cudaGetLastError());
-  return MERV_OK;
-}
-
-extern "C" int merv_scores_from_colsum(const float* const* colsum, const float* const* v, const float* const* c,
-                                       const int32_t* C, const int32_t* parts, float* scores, int B, int E, int T,
-                                       void* stream) {
-  MERV_REQUIRE(colsum && v && c && C && parts && scores, MERV_E_ARG, "merv_scores_from_colsum: NULL pointer");
-  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_colsum: E=%d", E);
-  MERV_REQUIRE(B >= 0 && T > 0, MERV_E_SHAPE, "merv_scores_from_colsum: B=%d T=%d", B, T);
-  if (int rc = require_sm100()) return rc;
-  if (B == 0) return MERV_OK;
-  PtrParams p = {};
-  for (int e = 0; e < E; ++e) {
-    MERV_REQUIRE(colsum[e] && v[e], MERV_E_ARG, "merv_scores_from_colsum: encoder %d has a NULL pointer", e);
-    MERV_REQUIRE(C[e] > 0 && parts[e] > 0, MERV_E_SHAPE, "merv_scores_from_colsum: encoder %d: C=%d parts=%d", e, C[e], parts[e]);
-    p.p[e] = colsum[e]; p.v[e] = v[e]; p.c[e] = c[e]; p.C[e] = C[e]; p.parts[e] = parts[e];
-  }
-  colsum_score_kernel<<<dim3(E, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, scores, E, T);
+  partial_score_kernel<<<dim3(E, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, scores, E, T);
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }

@@ -401,7 +401,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         V = [v if v.dtype == dtype else v.to(dtype) for v in V]
         u = self.query_vector(dtype)
         if rowdots is not None:
-            scores = ops.scores_from_rowdot(rowdots, None, V[0].shape[0], self.token_length)
+            scores = ops.scores_from_partials(rowdots, None, V[0].shape[0], self.token_length)
         else:
             scores = ops.scores_from_tokens(V, u, self.token_length)
         out, weights = ops.softmax_mix(V, self.token_length, scores=scores)
@@ -421,19 +421,20 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
         B, T = xs[0].shape[0], self.token_length
         all_linear = all(len(p.layers()) == 1 for p in projs)
-        pooled, colsums = ops.pool3d(xs, [p.output_frames for p in projs], projs[0].output_size, want_colsum=all_linear)
         lasts = [p.layers()[-1][0] for p in projs]
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
+        frames, size = [p.output_frames for p in projs], projs[0].output_size
         if all_linear:
-            acts = pooled
-            scores = ops.scores_from_colsum(colsums, [vc[0] for vc in vcs], [vc[1] for vc in vcs], T)
+            # scores straight from the pool kernel: u . y = v . pooled + c for the affine projector
+            acts, partials = ops.pool3d(xs, frames, size, score_vecs=[vc[0] for vc in vcs])
         else:
-            acts, rowdots = [], []
+            pooled, _ = ops.pool3d(xs, frames, size)
+            acts, partials = [], []
             for p, x, (v, _) in zip(projs, pooled, vcs):
                 h, rd = _run_layers(x, p.layers()[:-1], p._cast_cache, dtype, last_rowdot_vec=v)
                 acts.append(h)
-                rowdots.append(rd)
-            scores = ops.scores_from_rowdot(rowdots, [vc[1] for vc in vcs], B, T)
+                partials.append(rd)
+        scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
         biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
         weights, bias_mix = ops.softmax_weights(scores, biases, self.llm_dim)
         out = ops.fused_linear_mix(acts, [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)], weights, bias_mix, T)

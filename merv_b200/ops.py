@@ -53,7 +53,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 # kernels launched by one call of each entry point (used for bench.py's `gpu_launches` and per-kernel timing)
 KERNELS_PER_CALL = {
     "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
-    "merv_scores_from_tokens": 2, "merv_scores_from_rowdot": 1, "merv_scores_from_colsum": 1, "merv_softmax_weights": 1,
+    "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1,
 }
 
@@ -109,18 +109,21 @@ def _call(name, fn, *args) -> None:
 
 # ------------------------------------------------------------------------------------------------------------
 def pool3d(
-    xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int, want_colsum: bool = False
+    xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int,
+    score_vecs: Optional[Sequence[torch.Tensor]] = None,
 ) -> Tuple[List[torch.Tensor], Optional[List[torch.Tensor]]]:
     """Adaptive 3-D average pooling of every encoder's [B, F, N, C] features in ONE launch -> [B, T*S*S, C].
 
-    Reference: AveragePooling3DProjector.forward, merv/util/nn_utils.py:320-329.
+    Reference: AveragePooling3DProjector.forward, merv/util/nn_utils.py:320-329.  With `score_vecs` (fp32 [C_e] each)
+    also returns per-encoder partial dot products [B, parts_e] of the pooled tokens with that vector.
     """
     lib = _lib.load()
-    dev = _require_cuda(*xs)
+    dev = _require_cuda(*xs, *(score_vecs or []))
     B = xs[0].shape[0]
     code = dtype_code(xs[0].dtype)
-    descs = (PoolDesc * len(xs))()
-    ys, colsums, keep = [], [], []
+    n = len(xs)
+    descs = (PoolDesc * n)()
+    ys, keep = [], []
     with torch.cuda.device(dev):
         for i, (x, T) in enumerate(zip(xs, out_frames)):
             assert x.dim() == 4, f"expected [B, F, N, C] features, got {tuple(x.shape)}"
@@ -132,17 +135,24 @@ def pool3d(
             H = int(math.sqrt(N))  # nn_utils.py:322
             assert H * H == N, f"patch count {N} is not a perfect square (einops would reject it at nn_utils.py:323-327)"
             y = torch.empty((B, T * out_size * out_size, Cc), dtype=x.dtype, device=dev)
-            parts = lib.merv_pool3d_colsum_parts(T, out_size, B) if want_colsum else 0
-            cs = torch.empty((B, parts, Cc), dtype=torch.float32, device=dev) if want_colsum else None
             d = descs[i]
-            d.x, d.y, d.colsum = x.data_ptr(), y.data_ptr(), _p(cs)
+            d.x, d.y, d.score_vec, d.score_partial = x.data_ptr(), y.data_ptr(), None, None
             d.F, d.H, d.W, d.C, d.T, d.S = F, H, H, Cc, T, out_size
             d.x_batch_stride, d.x_frame_stride, d.x_token_stride = x.stride(0), x.stride(1), x.stride(2)
             d.y_batch_stride, d.y_row_stride = y.stride(0), y.stride(1)
             ys.append(y)
-            colsums.append(cs)
-        _call('merv_pool3d', lib.merv_pool3d, descs, len(xs), B, code, _stream())
-    return ys, (colsums if want_colsum else None)
+        partials = None
+        if score_vecs is not None:
+            parts = i32_array([0] * n)
+            check(lib.merv_pool3d_score_parts(descs, n, code, parts))
+            partials = []
+            for i, sv in enumerate(score_vecs):
+                assert sv.dtype == torch.float32 and sv.numel() == xs[i].shape[3] and sv.is_contiguous()
+                pt = torch.empty((B, parts[i]), dtype=torch.float32, device=dev)
+                descs[i].score_vec, descs[i].score_partial = sv.data_ptr(), pt.data_ptr()
+                partials.append(pt)
+        _call('merv_pool3d', lib.merv_pool3d, descs, n, B, code, _stream())
+    return ys, partials
 
 
 def linear_bias_act(
@@ -224,26 +234,17 @@ def scores_from_tokens(Vs: Sequence[torch.Tensor], u: torch.Tensor, token_length
     return scores
 
 
-def scores_from_rowdot(rowdots: Sequence[torch.Tensor], consts: Optional[Sequence[Optional[torch.Tensor]]], B: int, T: int) -> torch.Tensor:
+def scores_from_partials(partials: Sequence[torch.Tensor], consts: Optional[Sequence[Optional[torch.Tensor]]], B: int, T: int) -> torch.Tensor:
+    """scores[b,e] = (1/T) * sum(partials_e[b]) + c_e from the pool kernel's / GEMM epilogue's partial dot products."""
     lib = _lib.load()
-    dev = _require_cuda(*rowdots)
-    E, nblk = len(rowdots), rowdots[0].shape[1]
+    dev = _require_cuda(*partials)
+    E = len(partials)
+    counts = [p.numel() // B for p in partials]
     with torch.cuda.device(dev):
         scores = torch.empty((B, E), dtype=torch.float32, device=dev)
         cptr = ptr_array([_p(c) for c in consts]) if consts is not None else None
-        _call('merv_scores_from_rowdot', lib.merv_scores_from_rowdot, ptr_array([r.data_ptr() for r in rowdots]), cptr, scores.data_ptr(), B, E, T, nblk, _stream())
-    return scores
-
-
-def scores_from_colsum(colsums: Sequence[torch.Tensor], vs: Sequence[torch.Tensor], cs: Sequence[Optional[torch.Tensor]], T: int) -> torch.Tensor:
-    lib = _lib.load()
-    dev = _require_cuda(*colsums, *vs)
-    B, E = colsums[0].shape[0], len(colsums)
-    with torch.cuda.device(dev):
-        scores = torch.empty((B, E), dtype=torch.float32, device=dev)
-        _call('merv_scores_from_colsum', lib.merv_scores_from_colsum, ptr_array([c.data_ptr() for c in colsums]), ptr_array([v.data_ptr() for v in vs]),
-                                          ptr_array([_p(c) for c in cs]), i32_array([c.shape[2] for c in colsums]),
-                                          i32_array([c.shape[1] for c in colsums]), scores.data_ptr(), B, E, T, _stream())
+        _call('merv_scores_from_partials', lib.merv_scores_from_partials, ptr_array([p.data_ptr() for p in partials]), i32_array(counts),
+              cptr, scores.data_ptr(), B, E, T, _stream())
     return scores
 
 

@@ -80,17 +80,23 @@ try:
     xs = [torch.randn(s, generator=g, device=dev).to(torch.bfloat16) for s in shapes]
     in_bytes = sum(x.numel() * 2 for x in xs)
     out_bytes = sum(B * 1024 * s[3] * 2 for s in shapes)
-    t = timeit(lambda: ops.pool3d(xs, [16] * 4, 8, want_colsum=True))
+    svs = [torch.randn(s[3], device=dev) for s in shapes]
+    t = timeit(lambda: ops.pool3d(xs, [16] * 4, 8, score_vecs=svs))
     report["pool_ms"] = t
     report["pool_GBps"] = (in_bytes + out_bytes) / t / 1e6
-    t2 = timeit(lambda: ops.pool3d(xs, [16] * 4, 8, want_colsum=False))
-    report["pool_nocolsum_ms"] = t2
-    print(f"pool3d B=64: {t:.3f} ms = {report['pool_GBps']:.0f} GB/s (no colsum {t2:.3f} ms)", flush=True)
+    t2 = timeit(lambda: ops.pool3d(xs, [16] * 4, 8))
+    report["pool_noscore_ms"] = t2
+    print(f"pool3d B=64: {t:.3f} ms = {report['pool_GBps']:.0f} GB/s (without score partials {t2:.3f} ms)", flush=True)
     for i in (0, 2):
         ti = timeit(lambda: ops.pool3d([xs[i]], [16], 8))
         b = xs[i].numel() * 2 + B * 1024 * shapes[i][3] * 2
         print(f"  pool3d encoder {i} alone: {ti:.3f} ms = {b / ti / 1e6:.0f} GB/s", flush=True)
         report[f"pool_enc{i}_GBps"] = b / ti / 1e6
+    os.environ["MERV_POOL_IMPL"] = "direct"
+    td = timeit(lambda: ops.pool3d(xs, [16] * 4, 8, score_vecs=svs))
+    del os.environ["MERV_POOL_IMPL"]
+    report["pool_direct_ms"] = td
+    print(f"  direct (non-TMA) kernel: {td:.3f} ms = {(in_bytes + out_bytes) / td / 1e6:.0f} GB/s", flush=True)
     del xs
     Ys = [torch.randn(B, 1024, 4096, generator=g, device=dev).to(torch.bfloat16) for _ in range(4)]
     sc = torch.randn(B, 4, device=dev)

@@ -35,9 +35,12 @@ def test_host_only_entry_points_work_without_gpu():
     from merv_b200 import _lib
 
     lib = _lib.load()
-    # independent of the batch size, so per-video results do not depend on how the batch is sharded
-    assert lib.merv_pool3d_colsum_parts(16, 8, 64) == lib.merv_pool3d_colsum_parts(16, 8, 1) == 16 * 4
-    assert lib.merv_pool3d_colsum_parts(3, 3, 2) == 9
+    descs = (_lib.PoolDesc * 2)()
+    for d, (H, Cc) in zip(descs, ((16, 1024), (14, 768))):
+        d.F, d.H, d.W, d.C, d.T, d.S = 16, H, H, Cc, 16, 8
+    parts = _lib.i32_array([0, 0])
+    assert lib.merv_pool3d_score_parts(descs, 2, _lib.MERV_BF16, parts) == 0
+    assert list(parts) == [16 * 16 * 4, 16 * 12 * 4]  # T x (C / 64-channel slabs) x 4 warps per slab: shape-dependent only, never batch-dependent
     assert lib.merv_scores_from_tokens_workspace(2, 4, 1024, 4096) == 2 * 4 * 32
 
 

@@ -47,27 +47,37 @@ def build_module(case, pp, fp, dtype, fused):
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["tiny_linear", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_pool3d_matches_oracle(name, dtype):
+@pytest.mark.parametrize("impl", ["tma", "direct"])
+def test_pool3d_matches_oracle(name, dtype, impl, monkeypatch):
     from merv_b200 import ops
 
+    if impl == "direct":
+        monkeypatch.setenv("MERV_POOL_IMPL", "direct")  # the plain-load fallback kernel
     case = C.CASES[name]
     g, feats, _, _ = regenerate(case)
     vec = 8 if dtype == torch.bfloat16 else 4
     if any(c % vec for c in case.dims):
         pytest.skip("channel count not a multiple of the 16-byte vector for this dtype")
     xs = [_t(f, dtype) for f in feats]
-    ys, colsums = ops.pool3d(xs, case.out_frames, case.out_size, want_colsum=True)
+    rng = np.random.default_rng(1)
+    svs = [rng.standard_normal(c).astype(np.float32) for c in case.dims]
+    ys, partials = ops.pool3d(xs, case.out_frames, case.out_size, score_vecs=[_t(v) for v in svs])
+    ys2, none = ops.pool3d(xs, case.out_frames, case.out_size)
     torch.cuda.synchronize()
-    for e, (x, y, cs) in enumerate(zip(xs, ys, colsums)):
+    assert none is None
+    for e, (x, y, pt) in enumerate(zip(xs, ys, partials)):
         want = O.avg_pool3d_tokens(_np(x), case.out_frames[e], case.out_size)  # oracle on the dtype-rounded input
         assert y.shape == want.shape and y.dtype == dtype
         tol = 1e-6 if dtype == torch.float32 else 4e-3  # bf16: one rounding of the fp32 mean
         assert O.rel_err(_np(y), want) < tol
+        assert torch.equal(y, ys2[e])
         if name in C.FULL_STORE_CASES and dtype == torch.float32:
             assert O.rel_err(_np(y), g[f"pooled{e}"]) < FP32_TOL
-        # deterministic partial column sums of the pooled tokens as stored
-        got = _np(cs).sum(1)
-        assert np.abs(got - _np(y).astype(np.float64).sum(1)).max() < 1e-3 * max(1.0, np.abs(got).max())
+        # deterministic partial dot products of the pooled tokens (as stored) with the score vector
+        want_dot = (_np(y).astype(np.float64).sum(1) * svs[e]).sum(-1)
+        got = _np(pt).astype(np.float64).sum(1)
+        assert pt.shape[0] == case.batch
+        assert np.abs(got - want_dot).max() < 2e-4 * max(1.0, np.abs(want_dot).max())
 
 
 def test_pool3d_strided_input_drops_cls_token():
