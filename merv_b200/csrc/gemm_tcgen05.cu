@@ -11,8 +11,8 @@
 // A and W), two 256-column TMEM accumulators.  A "segment" is one (A_s, W_s, K_s) product; the MMA warp
 // alternates accumulators per segment, the 8 epilogue warps drain each finished accumulator into fp32
 // registers scaled by the segment's mixing weight while the next segment (or next tile) is being multiplied,
-// and after the last segment apply bias / exact-erf GELU / optional row-dot and store bf16 — each output
-// element is written exactly once.
+// and after the last segment apply bias / erf-GELU / optional row-dot, stage the bf16 rows in shared memory and
+// write them with TMA stores — each output element is written exactly once.
 //
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      tcgen05.mma issuer (one elected lane)
@@ -34,7 +34,9 @@ constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int OUT_BOX_COLS = 64;                       // one staged output box: 128 rows x 64 bf16 (128-byte rows, 128B swizzle)
+constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;   // 16 KB per column half
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * OUT_BOX_BYTES + 256 /*barriers*/;
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
@@ -58,6 +60,7 @@ struct GemmParams {
 struct TensorMaps {
   CUtensorMap a[MERV_MAX_SEGMENTS];
   CUtensorMap b[MERV_MAX_SEGMENTS];
+  CUtensorMap out;  // Y as [M, N] boxes of 128 x 64 for the epilogue's TMA stores
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -102,6 +105,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -155,7 +168,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  const uint32_t stage_out_addr = tiles_addr + STAGES * STAGE_BYTES;  // 2 x 16 KB, 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + 2 * OUT_BOX_BYTES);
   const uint32_t full_bar = smem_u32(bars);                  // [STAGES]
   const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
   const uint32_t tfull_bar = empty_bar + 8 * STAGES;         // [2]
@@ -170,6 +184,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       prefetch_tmap(&maps.a[s]);
       prefetch_tmap(&maps.b[s]);
     }
+    prefetch_tmap(&maps.out);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -262,52 +277,75 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
+          if (p.nseg == 1 && p.seg_scale == nullptr) {  // plain GEMM: the accumulator IS the result
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fmaf(scale, __uint_as_float(v[i]), sum[c * 32 + i]);
+            for (int i = 0; i < 32; ++i) sum[c * 32 + i] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fmaf(scale, __uint_as_float(v[i]), sum[c * 32 + i]);
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);  // accumulator may be overwritten
       }
-      // ---- finalize: bias, activation, optional row-dot, bf16 store (each element written once) ----
+      // ---- finalize: bias, activation, optional row-dot, bf16 pack; rows staged in shared memory (128B swizzle) and
+      //      written with TMA stores: fully coalesced, asynchronous, M/N tails clipped by the tensor map ----
       const int col0 = n_blk * BN + h * 128;
       const bool row_ok = row < p.M;
       float rowdot = 0.f;
-      __nv_bfloat16* yrow = p.Y + (long long)row * p.ldy;
+      const uint32_t my_box = stage_out_addr + h * OUT_BOX_BYTES;
+      const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * 128u;
+      const uint32_t sw = uint32_t(lane & 7);  // (row & 7): the 16-byte chunk index is XOR-ed with it (SWIZZLE_128B)
+      const bool issuer = (warp == 4 + 4 * h) && lane == 0;
 #pragma unroll
-      for (int c8 = 0; c8 < 16; ++c8) {
-        const int n = col0 + c8 * 8;
-        if (n < p.N) {  // N % 8 == 0 is enforced on the host
-          float b[8];
-          if (p.bias != nullptr) {
-            Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
-          } else if (p.bias_rows != nullptr) {
-            const float4* br = reinterpret_cast<const float4*>(p.bias_rows + (long long)video * p.N + n);
-            const float4 b0 = __ldg(br), b1 = __ldg(br + 1);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-          } else {
+      for (int pass = 0; pass < 2; ++pass) {
+        if (issuer) tma_store_wait_read();  // the previous store has finished reading this staging box
+        named_bar_sync(1 + h, 128);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = 0.f;
-          }
-          float o[8];
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const int cc = pass * 8 + c8;
+          const int n = col0 + cc * 8;
+          uint4 packed = make_uint4(0, 0, 0, 0);
+          if (n < p.N) {  // N % 8 == 0 is enforced on the host
+            float b[8];
+            if (p.bias != nullptr) {
+              Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
+            } else if (p.bias_rows != nullptr) {
+              const float4* br = reinterpret_cast<const float4*>(p.bias_rows + (long long)video * p.N + n);
+              const float4 b0 = __ldg(br), b1 = __ldg(br + 1);
+              b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            o[i] = sum[c8 * 8 + i] + b[i];
-            if (p.act == MERV_ACT_GELU_ERF) o[i] = gelu_erf(o[i]);
+              for (int i = 0; i < 8; ++i) b[i] = 0.f;
+            }
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i] = sum[cc * 8 + i] + b[i];
+              if (p.act == MERV_ACT_GELU_ERF) o[i] = gelu_erf_fast(o[i]);
+            }
+            packed = Vec16<__nv_bfloat16>::pack(o);
+            if (p.rowdot_vec != nullptr) {
+              float r[8];
+              Vec16<__nv_bfloat16>::unpack(packed, r);  // dot with the values as stored
+              const float4* rv = reinterpret_cast<const float4*>(p.rowdot_vec + n);
+              const float4 r0 = __ldg(rv), r1 = __ldg(rv + 1);
+              rowdot += r[0] * r0.x + r[1] * r0.y + r[2] * r0.z + r[3] * r0.w + r[4] * r1.x + r[5] * r1.y + r[6] * r1.z + r[7] * r1.w;
+            }
           }
-          const uint4 packed = Vec16<__nv_bfloat16>::pack(o);
-          if (p.rowdot_vec != nullptr) {
-            float r[8];
-            Vec16<__nv_bfloat16>::unpack(packed, r);  // dot with the values as stored
-            const float4* rv = reinterpret_cast<const float4*>(p.rowdot_vec + n);
-            const float4 r0 = __ldg(rv), r1 = __ldg(rv + 1);
-            rowdot += r[0] * r0.x + r[1] * r0.y + r[2] * r0.z + r[3] * r0.w + r[4] * r1.x + r[5] * r1.y + r[6] * r1.z + r[7] * r1.w;
-          }
-          if (row_ok) *reinterpret_cast<uint4*>(yrow + n) = packed;
+          sts_v4(my_row + ((uint32_t(c8) ^ sw) << 4), packed);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+        named_bar_sync(1 + h, 128);
+        if (issuer && col0 + pass * OUT_BOX_COLS < p.N) {
+          tma_store_2d(&maps.out, my_box, col0 + pass * OUT_BOX_COLS, m_blk * BM);
+          tma_store_commit();
         }
       }
       if (p.rowdot_vec != nullptr && row_ok && col0 < p.N) p.rowdot_out[(long long)row * p.rowdot_nblk + (col0 / MERV_ROWDOT_BLOCK)] = rowdot;
     }
+    if ((warp == 4 || warp == 8) && lane == 0) tma_store_wait_all();  // outstanding stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -337,12 +375,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, 64] with 128-byte swizzle
-static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols = BK) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {BK, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -385,6 +423,7 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     p.kblocks[s] = (g.K + BK - 1) / BK;  // the K tail is zero-filled by TMA
   }
   for (int s = nseg; s < MERV_MAX_SEGMENTS; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
+  if (int rc = make_tmap(&maps.out, Y, M, N, ldy, BM, OUT_BOX_COLS)) return rc;
   p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;
   p.num_videos = (M + rows_per_video - 1) / rows_per_video;
   p.bias = static_cast<const __nv_bfloat16*>(bias); p.act = act;
