@@ -78,7 +78,9 @@ typedef struct {
 
 /* parts[e] = number of score partials per video the pool kernel emits for encoder e (independent of B). */
 int merv_pool3d_score_parts(const merv_pool_desc* enc, int num_encoders, int dtype, int32_t* parts);
-int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, void* stream);
+/* max_ctas: 0 = one persistent CTA per SM; k > 0 caps the grid at k CTAs so the kernel can share the GPU with a
+ * concurrently running kernel on another stream (see merv_fused_linear_mix). */
+int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, int max_ctas, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Projector layer: Y = act(A W^T + bias).  Replaces nn.Linear (+ nn.GELU) inside LinearProjector.forward /
@@ -147,11 +149,13 @@ int merv_softmax_mix(const void* const* V, const int32_t* tokens, const float* s
  * written exactly once.  A_s [M, K_s] (lda[s]) are the pooled features, W_s [N, K_s] (ldw[s]);
  * scale [M / rows_per_video, nseg] fp32 (the mixing weights), bias_mix [M / rows_per_video, N] fp32.
  * Replaces LinearProjector.forward x E + CrossAttentionAdapterLearnableQuery.forward's stack/bmm
- * (nn_utils.py:31-32,503,521).  bf16 only.
+ * (nn_utils.py:31-32,503,521).  bf16 only.  max_ctas: 0 = one CTA per SM; k > 0 caps the persistent grid at k CTAs, leaving
+ * the remaining SMs to a concurrently running HBM-bound kernel (the pool of the next chunk of videos): the GEMM is
+ * tensor-bound and the pool HBM-bound, so running them side by side hides the pool.
  * ------------------------------------------------------------------------------------------------------- */
 int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                           const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
-                          int64_t ldo, int M, int N, int rows_per_video, void* stream);
+                          int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,7 @@ _SIGNATURES = {
     "merv_device_check": (c_int, []),
     "merv_num_sms": (c_int, []),
     "merv_pool3d_score_parts": (c_int, [POINTER(PoolDesc), c_int, c_int, POINTER(c_int32)]),
-    "merv_pool3d": (c_int, [POINTER(PoolDesc), c_int, c_int, c_int, c_void_p]),
+    "merv_pool3d": (c_int, [POINTER(PoolDesc), c_int, c_int, c_int, c_int, c_void_p]),
     "merv_linear_bias_act": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "merv_fusion_query_vec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -58,7 +58,7 @@ _SIGNATURES = {
     "merv_softmax_weights": (c_int, [c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_softmax_mix": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_fused_linear_mix": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
-                                      c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
+                                      c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -87,7 +87,7 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MERV_BF16 && !force_simt()) {
     GemmSegment seg = {A, lda, W, ldw, K};
-    return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, rowdot_vec, rowdot_out, Y, ldy, M, N, s);
+    return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, rowdot_vec, rowdot_out, Y, ldy, M, N, 0, s);
   }
   MERV_REQUIRE(rowdot_vec == nullptr && rowdot_out == nullptr, MERV_E_DTYPE,
                "merv_linear_bias_act: the row-dot epilogue exists only on the bf16 tensor-core path");
@@ -96,7 +96,7 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
 
 extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                                      const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
-                                     int64_t ldo, int M, int N, int rows_per_video, void* stream) {
+                                     int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* stream) {
   MERV_REQUIRE(A && lda && W && ldw && K && scale && out, MERV_E_ARG, "merv_fused_linear_mix: NULL pointer");
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_linear_mix: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M >= 0 && N > 0 && rows_per_video > 0, MERV_E_SHAPE, "merv_fused_linear_mix: M=%d N=%d rows_per_video=%d", M, N, rows_per_video);
@@ -106,5 +106,5 @@ extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, c
   GemmSegment seg[MERV_MAX_SEGMENTS];
   for (int s = 0; s < nseg; ++s) seg[s] = GemmSegment{A[s], lda[s], W[s], ldw[s], K[s]};
   return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, M, N,
-                             static_cast<cudaStream_t>(stream));
+                             max_ctas, static_cast<cudaStream_t>(stream));
 }

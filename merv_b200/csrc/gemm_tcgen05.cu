@@ -392,7 +392,7 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, int M,
-                        int N, cudaStream_t stream) {
+                        int N, int max_ctas, cudaStream_t stream) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -431,7 +431,8 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy;
   p.m_blocks = (M + BM - 1) / BM; p.n_blocks = (N + BN - 1) / BN;
   const long long total = (long long)p.m_blocks * p.n_blocks;
-  const int sms = sm_count();
+  int sms = sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   const int grid = int(total < sms ? total : sms);
   gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(maps, p);
   MERV_CUDA_OK(cudaGetLastError());

@@ -7,11 +7,11 @@
 // GEMM.  HBM-bound: compulsory traffic = input + pooled output (33.75 MB/video at merv-full).
 //
 // Main kernel (pool3d_tma_kernel): persistent, one CTA per SM, warp-specialised.
-//   warp 16 (producer): one lane streams slabs [frames of the temporal window x H x W x 128-byte channel chunk]
+//   warp 12 (producer): one lane streams slabs [frames of the temporal window x H x W x 128-byte channel chunk]
 //                      into a 6-stage shared-memory ring with 5-D TMA (cp.async.bulk.tensor): up to ~190 KB in
 //                      flight per SM, independent of register pressure, which is what saturates HBM3e;
-//   warps 0-15 (consumers): 4 groups of 4 warps; group g owns every 4th slab, so four slabs are reduced
-//                      concurrently and no warp ever waits on another group.  A thread owns (output token,
+//   warps 0-11 (consumers): 3 groups of 4 warps; group g owns every 3rd slab (and ring stages g, g+3), so three
+//                      slabs are reduced concurrently and no warp ever waits on another group.  A thread owns (output token,
 //                      16-byte channel vector) units: up to 9 window taps are fetched with back-to-back 128-bit
 //                      shared loads (conflict-free: 8 lanes cover one 128-byte row), accumulated in fp32,
 //                      scaled and written with one 128-bit store.
@@ -32,6 +32,12 @@
 #include "common.cuh"
 
 namespace merv {
+
+// L2 prefetch of the producer's next batch of slabs: measured SLOWER on B200 (3.9 vs 4.4 TB/s on 16 videos), kept as a
+// compile-time experiment only.
+#ifndef MERV_POOL_L2_PREFETCH
+#define MERV_POOL_L2_PREFETCH 0
+#endif
 
 __device__ __forceinline__ void window(int k, int n_in, int n_out, int& lo, int& hi) {
   lo = (k * n_in) / n_out;                    // floor(k * n_in / n_out)
@@ -57,9 +63,14 @@ __device__ __forceinline__ float group_sum(float v, float* red, int warp, int la
 // ============================================================================================================
 constexpr int PT_STAGES = 6;
 constexpr int PT_STAGE_BYTES = 32768;
-constexpr int PT_CONSUMERS = 512;      // 16 consumer warps
+constexpr int PT_CONSUMERS = 384;      // 12 consumer warps
 constexpr int PT_CWARPS = PT_CONSUMERS / 32;
-constexpr int PT_GROUPS = 4;           // consumer groups working on different slabs concurrently
+constexpr int PT_BATCH = 16;           // items whose coordinates the producer warp computes (and L2-prefetches) at once
+constexpr int PT_GROUPS = 3;           // consumer groups working on different slabs concurrently
+// Each stage must belong to exactly ONE group (slab n -> group n % PT_GROUPS, stage n % PT_STAGES): a group then visits
+// its stages in order, one mbarrier phase at a time.  If a group skipped phases of a stage, a parity wait could be
+// satisfied by a stale phase (mbarrier waits only distinguish the current phase from the previous one).
+static_assert(PT_STAGES % PT_GROUPS == 0, "every ring stage must be owned by one consumer group");
 constexpr int PT_GROUP_THREADS = PT_CONSUMERS / PT_GROUPS;
 constexpr int PT_GROUP_WARPS = PT_GROUP_THREADS / 32;
 constexpr int PT_THREADS = PT_CONSUMERS + 32;
@@ -127,6 +138,11 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// L2 prefetch of a future slab (experiment, see MERV_POOL_L2_PREFETCH).
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   uint4 r;
@@ -196,30 +212,48 @@ pool3d_tma_kernel(const __grid_constant__ PoolTmaMaps maps, const __grid_constan
   __syncthreads();
 
   if (warp == PT_CWARPS) {
-    // ===== producer (one lane): all per-item index arithmetic lives here, consumers read it from smeta =====
-    if (lane == 0) {
+    // ===== producer warp: all per-item index arithmetic lives here, consumers read it from smeta.  The integer
+    //       divisions (~1.5k cycles per item when done serially) are computed for 32 items at once, one per lane;
+    //       the lanes then take turns, in ring order, to wait for a free stage and issue their TMA. =====
+    if (lane == 0)
       for (int e = 0; e < p.n_enc; ++e) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[e]) : "memory");
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-        const int ei = pt_find_encoder(p, item);
+    uint32_t it = 0;
+    const int stride = int(gridDim.x);
+    for (int base_item = blockIdx.x; base_item < p.total_items; base_item += PT_BATCH * stride) {
+      const int item = base_item + lane * stride;
+      int ei = 0, chunk = 0, b = 0, t = 0, f0 = 0, f1 = 1;
+      const bool mine = lane < PT_BATCH && item < p.total_items;
+      if (mine) {
+        ei = pt_find_encoder(p, item);
         const PoolTmaEnc& e = p.enc[ei];
         const int local = item - e.item_begin;
-        const int chunk = local % e.nchunks;
+        chunk = local % e.nchunks;
         const int bt = local / e.nchunks;
-        const int t = bt % e.T;
-        const int b = bt / e.T;
-        int f0, f1;
+        t = bt % e.T;
+        b = bt / e.T;
         window(t, e.F, e.T, f0, f1);
-        const uint32_t stage = it % PT_STAGES, ph = (it / PT_STAGES) & 1u;
-        pt_mbar_wait(empty_bar + 8 * stage, ph ^ 1u);
-        smeta[stage] = make_int4(ei | ((f1 - f0) << 8), chunk, b, t);  // ordered before the consumers' acquire by the arrive below
-        pt_mbar_expect_tx(full_bar + 8 * stage, e.slab_bytes);
-        // the box always spans nf_max frames starting at f0; frames past the window (or past F: zero-filled) are ignored
-        tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, 0, 0, f0, b);
+        if (MERV_POOL_L2_PREFETCH) tma_prefetch_5d(&maps.m[ei], chunk * e.cb, 0, 0, f0, b);  // the whole batch, up front
       }
+      __syncwarp();
+      const int remaining = (p.total_items - base_item + stride - 1) / stride;
+      const int count = remaining < PT_BATCH ? remaining : PT_BATCH;
+      for (int j = 0; j < count; ++j) {
+        if (lane == j) {
+          const uint32_t n = it + uint32_t(j);
+          const uint32_t stage = n % PT_STAGES, ph = (n / PT_STAGES) & 1u;
+          const PoolTmaEnc& e = p.enc[ei];
+          pt_mbar_wait(empty_bar + 8 * stage, ph ^ 1u);
+          smeta[stage] = make_int4(ei | ((f1 - f0) << 8), chunk, b, t);  // ordered before the consumers' acquire by the arrive below
+          pt_mbar_expect_tx(full_bar + 8 * stage, e.slab_bytes);
+          // the box always spans nf_max frames starting at f0; frames past the window (or past F: zero-filled) are ignored
+          tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, 0, 0, f0, b);
+        }
+        __syncwarp();
+      }
+      it += uint32_t(count);
     }
   } else if (blockIdx.x < p.total_items) {
-    // ===== consumers: group g reduces the CTA's slabs g, g + 4, g + 8, ... =====
+    // ===== consumers: group g reduces the CTA's slabs g, g + 3, g + 6, ... =====
     const int group = warp / PT_GROUP_WARPS;
     const int gtid = threadIdx.x - group * PT_GROUP_THREADS;
     const int gwarp = warp - group * PT_GROUP_WARPS;
@@ -482,7 +516,7 @@ static int validate(const merv_pool_desc* enc, int num_encoders, int B, int dtyp
 }
 
 template <typename T>
-static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, cudaStream_t s) {
+static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, int max_ctas, cudaStream_t s) {
   EncodeTiledFn encode = pool_encode_fn();
   if (encode == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int es = sizeof(T);
@@ -515,7 +549,8 @@ static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, cudaSt
   for (int i = n; i < MERV_MAX_ENCODERS; ++i) maps.m[i] = maps.m[0];
   p.total_items = begin;
   MERV_CUDA_OK(cudaFuncSetAttribute(pool3d_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-  const int sms = sm_count();
+  int sms = sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   const int grid = begin < sms ? begin : sms;
   pool3d_tma_kernel<T><<<grid, PT_THREADS, PT_SMEM, s>>>(maps, p);
   MERV_CUDA_OK(cudaGetLastError());
@@ -572,12 +607,12 @@ extern "C" int merv_pool3d_score_parts(const merv_pool_desc* enc, int num_encode
   return MERV_OK;
 }
 
-extern "C" int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, void* stream) {
+extern "C" int merv_pool3d(const merv_pool_desc* enc, int num_encoders, int B, int dtype, int max_ctas, void* stream) {
   if (int rc = validate(enc, num_encoders, B, dtype)) return rc;
   if (int rc = require_sm100()) return rc;
   if (B == 0) return MERV_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (use_tma(enc, num_encoders, dtype))
-    return dtype == MERV_BF16 ? launch_tma<__nv_bfloat16>(enc, num_encoders, B, dtype, s) : launch_tma<float>(enc, num_encoders, B, dtype, s);
+    return dtype == MERV_BF16 ? launch_tma<__nv_bfloat16>(enc, num_encoders, B, dtype, max_ctas, s) : launch_tma<float>(enc, num_encoders, B, dtype, max_ctas, s);
   return launch_direct(enc, num_encoders, B, dtype, s);
 }

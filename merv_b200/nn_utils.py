@@ -414,31 +414,36 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             return False
         return all(len(v.projector.layers()) >= 1 for v in V)
 
+    # ---- fused pipeline ------------------------------------------------------------------------------------
+    def _fused_stage1(self, projs, xs, vcs, dtype, max_ctas: int = 0):
+        """pool (+ hidden layers) -> (A operands of the last layer, score partials)."""
+        frames, size = [p.output_frames for p in projs], projs[0].output_size
+        if all(len(p.layers()) == 1 for p in projs):
+            # scores straight from the pool kernel: u . y = v . pooled + c for the affine projector
+            return ops.pool3d(xs, frames, size, score_vecs=[vc[0] for vc in vcs], max_ctas=max_ctas)
+        pooled, _ = ops.pool3d(xs, frames, size, max_ctas=max_ctas)
+        acts, partials = [], []
+        for p, x, (v, _) in zip(projs, pooled, vcs):
+            h, rd = _run_layers(x, p.layers()[:-1], p._cast_cache, dtype, last_rowdot_vec=v)
+            acts.append(h)
+            partials.append(rd)
+        return acts, partials
+
     def _forward_fused(self, V: Sequence[DeferredProjection]) -> Tuple[torch.Tensor, torch.Tensor]:
         """pool (one launch) -> hidden layers -> scores -> one tcgen05 GEMM with the mix in its epilogue."""
         dtype = torch.bfloat16
         projs = [v.projector for v in V]
         xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
-        B, T = xs[0].shape[0], self.token_length
-        all_linear = all(len(p.layers()) == 1 for p in projs)
+        B, T, K = xs[0].shape[0], self.token_length, self.llm_dim
         lasts = [p.layers()[-1][0] for p in projs]
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
-        frames, size = [p.output_frames for p in projs], projs[0].output_size
-        if all_linear:
-            # scores straight from the pool kernel: u . y = v . pooled + c for the affine projector
-            acts, partials = ops.pool3d(xs, frames, size, score_vecs=[vc[0] for vc in vcs])
-        else:
-            pooled, _ = ops.pool3d(xs, frames, size)
-            acts, partials = [], []
-            for p, x, (v, _) in zip(projs, pooled, vcs):
-                h, rd = _run_layers(x, p.layers()[:-1], p._cast_cache, dtype, last_rowdot_vec=v)
-                acts.append(h)
-                partials.append(rd)
-        scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
         biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
-        weights, bias_mix = ops.softmax_weights(scores, biases, self.llm_dim)
-        out = ops.fused_linear_mix(acts, [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)], weights, bias_mix, T)
-        return out.view(B, T, self.llm_dim), weights.to(dtype)
+        Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
+        acts, partials = self._fused_stage1(projs, xs, vcs, dtype)
+        scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
+        weights, bias_mix = ops.softmax_weights(scores, biases, K)
+        out = ops.fused_linear_mix(acts, Ws, weights, bias_mix, T)
+        return out.view(B, T, K), weights.to(dtype)
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -110,7 +110,7 @@ def _call(name, fn, *args) -> None:
 # ------------------------------------------------------------------------------------------------------------
 def pool3d(
     xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int,
-    score_vecs: Optional[Sequence[torch.Tensor]] = None,
+    score_vecs: Optional[Sequence[torch.Tensor]] = None, max_ctas: int = 0,
 ) -> Tuple[List[torch.Tensor], Optional[List[torch.Tensor]]]:
     """Adaptive 3-D average pooling of every encoder's [B, F, N, C] features in ONE launch -> [B, T*S*S, C].
 
@@ -151,7 +151,7 @@ def pool3d(
                 pt = torch.empty((B, parts[i]), dtype=torch.float32, device=dev)
                 descs[i].score_vec, descs[i].score_partial = sv.data_ptr(), pt.data_ptr()
                 partials.append(pt)
-        _call('merv_pool3d', lib.merv_pool3d, descs, n, B, code, _stream())
+        _call('merv_pool3d', lib.merv_pool3d, descs, n, B, code, max_ctas, _stream())
     return ys, partials
 
 
@@ -248,15 +248,21 @@ def scores_from_partials(partials: Sequence[torch.Tensor], consts: Optional[Sequ
     return scores
 
 
+def num_sms() -> int:
+    return _lib.load().merv_num_sms()
+
+
 def softmax_weights(
-    scores: torch.Tensor, biases: Optional[Sequence[Optional[torch.Tensor]]] = None, N: int = 0
+    scores: torch.Tensor, biases: Optional[Sequence[Optional[torch.Tensor]]] = None, N: int = 0,
+    out: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """weights = softmax(scores, -1) (fp32) and, if `biases` is given, bias_mix[b] = sum_e weights[b,e] * bias_e (fp32 [B, N])."""
     lib = _lib.load()
     dev = _require_cuda(scores)
     B, E = scores.shape
     with torch.cuda.device(dev):
-        weights = torch.empty((B, E), dtype=torch.float32, device=dev)
+        weights = out if out is not None else torch.empty((B, E), dtype=torch.float32, device=dev)
+        assert weights.shape == (B, E) and weights.dtype == torch.float32 and weights.is_contiguous()
         bias_mix, bptr, code = None, None, MERV_F32
         if biases is not None:
             bias_mix = torch.empty((B, N), dtype=torch.float32, device=dev)
@@ -291,7 +297,7 @@ def softmax_mix(
 
 def fused_linear_mix(
     As: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor], scale: torch.Tensor, bias_mix: Optional[torch.Tensor],
-    rows_per_video: int, out: Optional[torch.Tensor] = None,
+    rows_per_video: int, out: Optional[torch.Tensor] = None, max_ctas: int = 0,
 ) -> torch.Tensor:
     """out[m] = sum_s scale[m // rows_per_video, s] * (A_s[m] @ W_s.T) + bias_mix[m // rows_per_video]  (bf16, tcgen05).
 
@@ -312,5 +318,5 @@ def fused_linear_mix(
         _call('merv_fused_linear_mix', lib.merv_fused_linear_mix, ptr_array([a.data_ptr() for a in As]), i64_array([a.stride(0) for a in As]),
                                         ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]),
                                         i32_array([a.shape[1] for a in As]), len(As), scale.data_ptr(), _p(bias_mix), out.data_ptr(),
-                                        out.stride(0), M, N, rows_per_video, _stream())
+                                        out.stride(0), M, N, rows_per_video, max_ctas, _stream())
     return out

@@ -48,7 +48,7 @@ def test_argument_errors_are_reported_not_crashed():
     from merv_b200 import _lib
 
     lib = _lib.load()
-    rc = lib.merv_pool3d(None, 1, 1, _lib.MERV_BF16, None)
+    rc = lib.merv_pool3d(None, 1, 1, _lib.MERV_BF16, 0, None)
     assert rc == -6 and b"NULL" in lib.merv_last_error()
     rc = lib.merv_linear_bias_act(None, 0, None, 0, None, None, 0, 1, 1, 1, 0, 7, None, None, None)
     assert rc == -3 and b"dtype" in lib.merv_last_error()
