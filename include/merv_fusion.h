@@ -71,6 +71,9 @@ typedef struct {
   void* y;
   const float* score_vec; /* [C] or NULL */
   float* score_partial;   /* [B, parts] or NULL (both or neither) */
+  const int32_t* batch_index; /* [B] or NULL: output video b reads input video batch_index[b] (the gather by
+                                 `multimodal_indices` at merv/models/vidlms/merv.py:572 fused into the load) */
+  int32_t src_batch;          /* videos in x when batch_index is given (0 = B) */
   int32_t F, H, W, C, T, S;
   int64_t x_batch_stride, x_frame_stride, x_token_stride;
   int64_t y_batch_stride, y_row_stride;
@@ -131,9 +134,12 @@ int merv_scores_from_partials(const float* const* partial, const int32_t* count,
                               float* scores, int B, int E, int T, void* stream);
 
 /* weights[b,:] = softmax(scores[b,:]) (fp32);  optionally bias_mix[b,n] = sum_e weights[b,e] * bias_e[n]
- * (the per-video bias of the fused affine path; bias_e in `dtype`, may contain NULL entries). */
+ * (the per-video bias of the fused affine path; bias_e in `dtype`, may contain NULL entries).
+ * merv_softmax_weights_ex additionally writes a bf16 copy of the weights (what the modules return in bf16 mode). */
 int merv_softmax_weights(const float* scores, float* weights, const void* const* bias, float* bias_mix, int B,
                          int E, int N, int dtype, void* stream);
+int merv_softmax_weights_ex(const float* scores, float* weights, void* weights_bf16, const void* const* bias,
+                            float* bias_mix, int B, int E, int N, int dtype, void* stream);
 
 /* out[b,t,:] = sum_e weights[b,e] * V_e[b,t,:]   — replaces torch.stack + torch.bmm at nn_utils.py:503,521.
  * Reads every V_e element once, writes every fused token once.  T_e in {T, 1} (broadcast, nn_utils.py:502).
@@ -148,6 +154,9 @@ int merv_softmax_mix(const void* const* V, const int32_t* tokens, const float* s
  * One persistent tcgen05 kernel; per-encoder projected tokens are never written to HBM; each fused token is
  * written exactly once.  A_s [M, K_s] (lda[s]) are the pooled features, W_s [N, K_s] (ldw[s]);
  * scale [M / rows_per_video, nseg] fp32 (the mixing weights), bias_mix [M / rows_per_video, N] fp32.
+ * out_batch_stride (elements): 0 or rows_per_video * ldo = one contiguous [M, N] output; larger = video b's rows start at
+ * out + b * out_batch_stride, i.e. the prefix is written straight into its slot of the [B, bos + T + L_text, N] multimodal
+ * embedding buffer that MERV.forward otherwise builds with torch.cat (merv.py:633-640); needs rows_per_video % 128 == 0.
  * Replaces LinearProjector.forward x E + CrossAttentionAdapterLearnableQuery.forward's stack/bmm
  * (nn_utils.py:31-32,503,521).  bf16 only.  max_ctas: 0 = one CTA per SM; k > 0 caps the persistent grid at k CTAs, leaving
  * the remaining SMs to a concurrently running HBM-bound kernel (the pool of the next chunk of videos): the GEMM is
@@ -155,7 +164,37 @@ int merv_softmax_mix(const void* const* V, const int32_t* tokens, const float* s
  * ------------------------------------------------------------------------------------------------------- */
 int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                           const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
-                          int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* stream);
+                          int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole fused path in ONE call (affine "linear" projectors, bf16): pool -> scores -> softmax -> fused GEMM, i.e.
+ * merv/models/vidlms/merv.py:587-589 + 607-609 for the shipped "3davg+linear" + "cross_attention_avg_lq" configs.
+ * Exists for the small-batch serving case (generate runs the path once per video at B = 1), where host overhead per
+ * launch dominates: 4 kernels are enqueued from one FFI crossing.  All workspaces are caller-provided.
+ *   pool[e]        : as for merv_pool3d; .y is the pooled workspace [B, T*S*S, C_e], .score_vec = v_e (fp32 [C_e]),
+ *                    .score_partial = workspace [B, parts_e] (parts_e from merv_pool3d_score_parts)
+ *   W, ldw, bias, c: last-layer weights [N, C_e], biases [N] (bf16) and score constants c_e (fp32 [1]) per encoder
+ *   scores, weights: workspaces fp32 [B, E]; bias_mix fp32 [B, N]; weights_bf16 (optional) bf16 [B, E] copy of weights
+ *   out            : bf16 [B, rows_per_video, N] with row stride ldo and batch stride out_batch_stride (0 = contiguous)
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t num_encoders, B, N, rows_per_video;
+  merv_pool_desc pool[MERV_MAX_SEGMENTS];
+  int32_t parts[MERV_MAX_SEGMENTS];
+  const void* W[MERV_MAX_SEGMENTS];
+  int64_t ldw[MERV_MAX_SEGMENTS];
+  const void* bias[MERV_MAX_SEGMENTS];
+  const float* c[MERV_MAX_SEGMENTS];
+  float* scores;
+  float* weights;
+  float* bias_mix;
+  void* weights_bf16; /* may be NULL */
+  void* out;
+  int64_t ldo, out_batch_stride;
+} merv_fused_desc;
+
+int merv_fused_forward(const merv_fused_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

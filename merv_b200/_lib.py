@@ -31,10 +31,22 @@ class PoolDesc(C.Structure):
     """merv_pool_desc"""
 
     _fields_ = [
-        ("x", c_void_p), ("y", c_void_p), ("score_vec", c_void_p), ("score_partial", c_void_p),
+        ("x", c_void_p), ("y", c_void_p), ("score_vec", c_void_p), ("score_partial", c_void_p), ("batch_index", c_void_p), ("src_batch", c_int32),
         ("F", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("T", c_int32), ("S", c_int32),
         ("x_batch_stride", c_int64), ("x_frame_stride", c_int64), ("x_token_stride", c_int64),
         ("y_batch_stride", c_int64), ("y_row_stride", c_int64),
+    ]
+
+
+class FusedDesc(C.Structure):
+    """merv_fused_desc"""
+
+    _fields_ = [
+        ("num_encoders", c_int32), ("B", c_int32), ("N", c_int32), ("rows_per_video", c_int32),
+        ("pool", PoolDesc * 4), ("parts", c_int32 * 4),
+        ("W", c_void_p * 4), ("ldw", c_int64 * 4), ("bias", c_void_p * 4), ("c", c_void_p * 4),
+        ("scores", c_void_p), ("weights", c_void_p), ("bias_mix", c_void_p), ("weights_bf16", c_void_p),
+        ("out", c_void_p), ("ldo", c_int64), ("out_batch_stride", c_int64),
     ]
 
 
@@ -56,9 +68,11 @@ _SIGNATURES = {
     "merv_scores_from_tokens_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "merv_scores_from_partials": (c_int, [_PP, POINTER(c_int32), _PP, c_void_p, c_int, c_int, c_int, c_void_p]),
     "merv_softmax_weights": (c_int, [c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "merv_softmax_weights_ex": (c_int, [c_void_p, c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "merv_fused_forward": (c_int, [POINTER(FusedDesc), c_void_p]),
     "merv_softmax_mix": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_fused_linear_mix": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
-                                      c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+                                      c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -87,7 +87,7 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MERV_BF16 && !force_simt()) {
     GemmSegment seg = {A, lda, W, ldw, K};
-    return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, rowdot_vec, rowdot_out, Y, ldy, M, N, 0, s);
+    return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, rowdot_vec, rowdot_out, Y, ldy, 0, M, N, 0, s);
   }
   MERV_REQUIRE(rowdot_vec == nullptr && rowdot_out == nullptr, MERV_E_DTYPE,
                "merv_linear_bias_act: the row-dot epilogue exists only on the bf16 tensor-core path");
@@ -96,7 +96,7 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
 
 extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                                      const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
-                                     int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* stream) {
+                                     int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas, void* stream) {
   MERV_REQUIRE(A && lda && W && ldw && K && scale && out, MERV_E_ARG, "merv_fused_linear_mix: NULL pointer");
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_linear_mix: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M >= 0 && N > 0 && rows_per_video > 0, MERV_E_SHAPE, "merv_fused_linear_mix: M=%d N=%d rows_per_video=%d", M, N, rows_per_video);
@@ -105,6 +105,32 @@ extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, c
   if (M == 0) return MERV_OK;
   GemmSegment seg[MERV_MAX_SEGMENTS];
   for (int s = 0; s < nseg; ++s) seg[s] = GemmSegment{A[s], lda[s], W[s], ldw[s], K[s]};
-  return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, M, N,
-                             max_ctas, static_cast<cudaStream_t>(stream));
+  return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, out_batch_stride,
+                             M, N, max_ctas, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int merv_fused_forward(const merv_fused_desc* d, void* stream) {
+  MERV_REQUIRE(d != nullptr, MERV_E_ARG, "merv_fused_forward: desc is NULL");
+  const int E = d->num_encoders;
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_forward: num_encoders=%d not in [1,%d]", E, MERV_MAX_SEGMENTS);
+  MERV_REQUIRE(d->B >= 0 && d->N > 0 && d->rows_per_video > 0, MERV_E_SHAPE, "merv_fused_forward: B=%d N=%d rows_per_video=%d", d->B, d->N,
+               d->rows_per_video);
+  MERV_REQUIRE(d->scores && d->weights && d->bias_mix && d->out, MERV_E_ARG, "merv_fused_forward: NULL workspace or output");
+  if (d->B == 0) return MERV_OK;
+  const void* A[MERV_MAX_SEGMENTS];
+  int64_t lda[MERV_MAX_SEGMENTS];
+  int32_t K[MERV_MAX_SEGMENTS];
+  const float* partial[MERV_MAX_SEGMENTS];
+  for (int e = 0; e < E; ++e) {
+    const merv_pool_desc& p = d->pool[e];
+    MERV_REQUIRE(p.T * p.S * p.S == d->rows_per_video, MERV_E_SHAPE, "merv_fused_forward: encoder %d emits %d tokens, expected %d", e,
+                 p.T * p.S * p.S, d->rows_per_video);
+    MERV_REQUIRE(p.score_vec && p.score_partial && d->parts[e] > 0, MERV_E_ARG, "merv_fused_forward: encoder %d needs score_vec / score_partial / parts", e);
+    A[e] = p.y; lda[e] = p.y_row_stride; K[e] = p.C; partial[e] = p.score_partial;
+  }
+  if (int rc = merv_pool3d(d->pool, E, d->B, MERV_BF16, 0, stream)) return rc;
+  if (int rc = merv_scores_from_partials(partial, d->parts, d->c, d->scores, d->B, E, d->rows_per_video, stream)) return rc;
+  if (int rc = merv_softmax_weights_ex(d->scores, d->weights, d->weights_bf16, d->bias, d->bias_mix, d->B, E, d->N, MERV_BF16, stream)) return rc;
+  return merv_fused_linear_mix(A, lda, d->W, d->ldw, K, E, d->weights, d->bias_mix, d->out, d->ldo, d->out_batch_stride,
+                               d->B * d->rows_per_video, d->N, d->rows_per_video, 0, stream);
 }

@@ -55,12 +55,13 @@ struct GemmParams {
   __nv_bfloat16* Y;
   long long ldy;
   int m_blocks, n_blocks;
+  int out_flat;  // 1: Y is one contiguous [M, N] matrix (output map = [1, M, N]); 0: [videos, rows_per_video, N] with a batch stride
 };
 
 struct TensorMaps {
   CUtensorMap a[MERV_MAX_SEGMENTS];
   CUtensorMap b[MERV_MAX_SEGMENTS];
-  CUtensorMap out;  // Y as [M, N] boxes of 128 x 64 for the epilogue's TMA stores
+  CUtensorMap out;  // Y as [videos, rows_per_video, N] (batch stride may exceed rows_per_video * ldy), boxes of 128 x 64
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -106,8 +107,9 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -339,7 +341,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
         named_bar_sync(1 + h, 128);
         if (issuer && col0 + pass * OUT_BOX_COLS < p.N) {
-          tma_store_2d(&maps.out, my_box, col0 + pass * OUT_BOX_COLS, m_blk * BM);
+          const int m0 = m_blk * BM;
+          const int v0 = p.out_flat ? 0 : m0 / p.rows_per_video;
+          tma_store_3d(&maps.out, my_box, col0 + pass * OUT_BOX_COLS, m0 - v0 * p.rows_per_video, v0);
           tma_store_commit();
         }
       }
@@ -391,8 +395,8 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
 
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
-                        const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, int M,
-                        int N, int max_ctas, cudaStream_t stream) {
+                        const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
+                        int M, int N, int max_ctas, cudaStream_t stream) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -423,7 +427,23 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     p.kblocks[s] = (g.K + BK - 1) / BK;  // the K tail is zero-filled by TMA
   }
   for (int s = nseg; s < MERV_MAX_SEGMENTS; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
-  if (int rc = make_tmap(&maps.out, Y, M, N, ldy, BM, OUT_BOX_COLS)) return rc;
+  {
+    // output as a 3-D tensor (N, rows, videos): flat when the videos are back to back, otherwise one "video" per
+    // batch-stride step (e.g. the prefix slot of a [B, 1 + T + L_text, N] multimodal embedding buffer, merv.py:633-640)
+    const bool flat = y_batch_stride == 0 || y_batch_stride == (long long)rows_per_video * ldy;
+    MERV_REQUIRE(flat || (rows_per_video % BM == 0 && y_batch_stride % 8 == 0 && y_batch_stride >= (long long)rows_per_video * ldy), MERV_E_SHAPE,
+                 "gemm: a batch-strided output needs rows_per_video %% %d == 0 and a 16-byte aligned batch stride >= rows_per_video * ldo", BM);
+    p.out_flat = flat ? 1 : 0;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)(flat ? M : rows_per_video), (cuuint64_t)(flat ? 1 : (M / rows_per_video))};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldy * 2, (cuuint64_t)(flat ? (long long)M * ldy : y_batch_stride) * 2};
+    const cuuint32_t box[3] = {OUT_BOX_COLS, BM, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled(out) failed with CUresult %d (M=%d N=%d ldy=%lld)", int(r), M, N, ldy);
+  }
   p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;
   p.num_videos = (M + rows_per_video - 1) / rows_per_video;
   p.bias = static_cast<const __nv_bfloat16*>(bias); p.act = act;

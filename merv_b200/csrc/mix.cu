@@ -152,11 +152,15 @@ struct BiasParams {
 // weights[b,:] = softmax(scores[b,:]);  bias_mix[b,n] = sum_e weights[b,e] * bias_e[n]
 template <typename T>
 __global__ void __launch_bounds__(256) softmax_weights_kernel(const float* __restrict__ scores, float* __restrict__ weights,
+                                                              __nv_bfloat16* __restrict__ weights_bf16,
                                                               const __grid_constant__ BiasParams bp, float* __restrict__ bias_mix,
                                                               int E, int N) {
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const float w = warp_softmax_over_encoders(lane < E ? scores[(long long)b * E + lane] : 0.f, lane, E);
-  if (blockIdx.x == 0 && threadIdx.x < E) weights[(long long)b * E + threadIdx.x] = w;
+  if (blockIdx.x == 0 && threadIdx.x < E) {
+    weights[(long long)b * E + threadIdx.x] = w;
+    if (weights_bf16 != nullptr) weights_bf16[(long long)b * E + threadIdx.x] = __float2bfloat16_rn(w);
+  }
   if (bias_mix == nullptr) return;
   const int n = blockIdx.x * 256 + threadIdx.x;
   float acc = 0.f;
@@ -371,8 +375,15 @@ extern "C" int merv_scores_from_partials(const float* const* partial, const int3
   return MERV_OK;
 }
 
+extern "C" int merv_softmax_weights_ex(const float* scores, float* weights, void* weights_bf16, const void* const* bias,
+                                       float* bias_mix, int B, int E, int N, int dtype, void* stream);
 extern "C" int merv_softmax_weights(const float* scores, float* weights, const void* const* bias, float* bias_mix, int B,
                                     int E, int N, int dtype, void* stream) {
+  return merv_softmax_weights_ex(scores, weights, nullptr, bias, bias_mix, B, E, N, dtype, stream);
+}
+
+extern "C" int merv_softmax_weights_ex(const float* scores, float* weights, void* weights_bf16, const void* const* bias,
+                                       float* bias_mix, int B, int E, int N, int dtype, void* stream) {
   MERV_DTYPE_OK("merv_softmax_weights");
   MERV_REQUIRE(scores && weights, MERV_E_ARG, "merv_softmax_weights: NULL pointer");
   MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_softmax_weights: E=%d", E);
@@ -387,9 +398,9 @@ extern "C" int merv_softmax_weights(const float* scores, float* weights, const v
   const int gx = bias_mix ? (N + 255) / 256 : 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MERV_BF16)
-    softmax_weights_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, s>>>(scores, weights, bp, bias_mix, E, N);
+    softmax_weights_kernel<__nv_bfloat16><<<dim3(gx, B), 256, 0, s>>>(scores, weights, static_cast<__nv_bfloat16*>(weights_bf16), bp, bias_mix, E, N);
   else
-    softmax_weights_kernel<float><<<dim3(gx, B), 256, 0, s>>>(scores, weights, bp, bias_mix, E, N);
+    softmax_weights_kernel<float><<<dim3(gx, B), 256, 0, s>>>(scores, weights, static_cast<__nv_bfloat16*>(weights_bf16), bp, bias_mix, E, N);
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }

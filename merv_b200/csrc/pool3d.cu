@@ -82,6 +82,7 @@ struct PoolTmaEnc {
   void* y;
   const float* score_vec;
   float* score_partial;
+  const int* batch_index;
   int F, H, W, C, T, S;
   int cb;        // channels per slab (elements); cb * sizeof(T) <= 128 bytes
   int vpr;       // 16-byte vectors per slab row (1, 2, 4 or 8)
@@ -246,7 +247,8 @@ pool3d_tma_kernel(const __grid_constant__ PoolTmaMaps maps, const __grid_constan
           smeta[stage] = make_int4(ei | ((f1 - f0) << 8), chunk, b, t);  // ordered before the consumers' acquire by the arrive below
           pt_mbar_expect_tx(full_bar + 8 * stage, e.slab_bytes);
           // the box always spans nf_max frames starting at f0; frames past the window (or past F: zero-filled) are ignored
-          tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, 0, 0, f0, b);
+          tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, 0, 0, f0,
+                      e.batch_index ? __ldg(e.batch_index + b) : b);
         }
         __syncwarp();
       }
@@ -347,6 +349,7 @@ struct PoolEnc {
   void* y;
   const float* score_vec;
   float* score_partial;
+  const int* batch_index;
   int F, H, W, C, T, S;
   int rows_per_item, groups;  // output rows handled by one CTA; groups = ceil(S / rows_per_item)
   int items;                  // B * T * groups
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(256) pool3d_direct_kernel(const __grid_constan
   const int i_begin = g * e.rows_per_item;
   const int i_end = min(e.S, i_begin + e.rows_per_item);
   const int nvec = e.C / VEC;
-  const T* __restrict__ xb = static_cast<const T*>(e.x) + (long long)b * e.xbs;
+  const T* __restrict__ xb = static_cast<const T*>(e.x) + (long long)(e.batch_index ? e.batch_index[b] : b) * e.xbs;
   T* __restrict__ yb = static_cast<T*>(e.y) + (long long)b * e.ybs;
   float dot = 0.f;
 
@@ -509,6 +512,7 @@ static int validate(const merv_pool_desc* enc, int num_encoders, int B, int dtyp
                      d.y_batch_stride % vec == 0 && d.y_row_stride % vec == 0 && d.x_token_stride >= d.C &&
                      d.y_row_stride >= d.C,
                  MERV_E_ALIGN, "merv_pool3d: encoder %d: strides must be multiples of %d elements and >= C", i, vec);
+    MERV_REQUIRE(d.batch_index == nullptr || d.src_batch > 0, MERV_E_ARG, "merv_pool3d: encoder %d: batch_index needs src_batch > 0", i);
     MERV_REQUIRE((d.score_vec == nullptr) == (d.score_partial == nullptr), MERV_E_ARG,
                  "merv_pool3d: encoder %d: score_vec and score_partial go together", i);
   }
@@ -528,14 +532,15 @@ static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, int ma
     const merv_pool_desc& d = enc[i];
     const TmaPlan pl = plan_tma(d, dtype);
     PoolTmaEnc& e = p.enc[i];
-    e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial;
+    e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial; e.batch_index = d.batch_index;
     e.F = d.F; e.H = d.H; e.W = d.W; e.C = d.C; e.T = d.T; e.S = d.S;
     e.nf_max = pl.nf_max; e.cb = pl.cb; e.vpr = pl.vpr; e.vshift = pl.vpr == 8 ? 3 : pl.vpr == 4 ? 2 : pl.vpr == 2 ? 1 : 0; e.nchunks = pl.nchunks; e.units = pl.units; e.slab_bytes = pl.slab_bytes;
     e.item_begin = begin; e.items = B * d.T * pl.nchunks;
     begin += e.items;
     e.ybs = d.y_batch_stride; e.yrs = d.y_row_stride;
     // x as a 5-D tensor (C, W, H, F, B), channel innermost; one box = the [nf_max, H, W, cb] slab of one output frame
-    const cuuint64_t dims[5] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.F, (cuuint64_t)B};
+    const cuuint64_t dims[5] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.F,
+                                (cuuint64_t)(d.batch_index && d.src_batch > 0 ? d.src_batch : B)};
     const cuuint64_t strides[4] = {(cuuint64_t)d.x_token_stride * es, (cuuint64_t)d.x_token_stride * d.W * es,
                                    (cuuint64_t)d.x_frame_stride * es, (cuuint64_t)d.x_batch_stride * es};
     const cuuint32_t box[5] = {(cuuint32_t)pl.cb, (cuuint32_t)d.W, (cuuint32_t)d.H, (cuuint32_t)pl.nf_max, 1};
@@ -564,7 +569,7 @@ static int launch_direct(const merv_pool_desc* enc, int n, int B, int dtype, cud
   for (int i = 0; i < n; ++i) {
     const merv_pool_desc& d = enc[i];
     PoolEnc& e = p.enc[i];
-    e.x = d.x; e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial;
+    e.x = d.x; e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial; e.batch_index = d.batch_index;
     e.F = d.F; e.H = d.H; e.W = d.W; e.C = d.C; e.T = d.T; e.S = d.S;
     e.rows_per_item = direct_rows_per_item(d.S);
     e.groups = (d.S + e.rows_per_item - 1) / e.rows_per_item;

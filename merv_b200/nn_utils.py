@@ -377,8 +377,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         return hit[1]
 
     # ---- forward --------------------------------------------------------------------------------------------
-    def forward(self, V):
+    def forward(self, V, out: Optional[torch.Tensor] = None, batch_index: Optional[torch.Tensor] = None):
         # V is a list of tensors with size (B, T, K). T should all be same, or 1.  (nn_utils.py:491-495)
+        # `out` / `batch_index` are extensions of the linked (fused) path only, see _forward_fused.
         for emb in V:
             assert emb.shape[1] == self.token_length or emb.shape[1] == 1, (self.token_length, [e.shape for e in V])
         if not self.averagetoken:
@@ -392,7 +393,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         _no_autograd(self, *[v for v in V if isinstance(v, torch.Tensor)])
 
         if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
-            return self._forward_fused(V)
+            return self._forward_fused(V, out=out, batch_index=batch_index)
+        if out is not None or batch_index is not None:
+            raise NotImplementedError("out= / batch_index= are supported on the linked bf16 path only")
         V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
         return self._forward_tokens(V)
 
@@ -415,13 +418,13 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         return all(len(v.projector.layers()) >= 1 for v in V)
 
     # ---- fused pipeline ------------------------------------------------------------------------------------
-    def _fused_stage1(self, projs, xs, vcs, dtype, max_ctas: int = 0):
+    def _fused_stage1(self, projs, xs, vcs, dtype, max_ctas: int = 0, batch_index=None):
         """pool (+ hidden layers) -> (A operands of the last layer, score partials)."""
         frames, size = [p.output_frames for p in projs], projs[0].output_size
         if all(len(p.layers()) == 1 for p in projs):
             # scores straight from the pool kernel: u . y = v . pooled + c for the affine projector
-            return ops.pool3d(xs, frames, size, score_vecs=[vc[0] for vc in vcs], max_ctas=max_ctas)
-        pooled, _ = ops.pool3d(xs, frames, size, max_ctas=max_ctas)
+            return ops.pool3d(xs, frames, size, score_vecs=[vc[0] for vc in vcs], max_ctas=max_ctas, batch_index=batch_index)
+        pooled, _ = ops.pool3d(xs, frames, size, max_ctas=max_ctas, batch_index=batch_index)
         acts, partials = [], []
         for p, x, (v, _) in zip(projs, pooled, vcs):
             h, rd = _run_layers(x, p.layers()[:-1], p._cast_cache, dtype, last_rowdot_vec=v)
@@ -429,21 +432,50 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             partials.append(rd)
         return acts, partials
 
-    def _forward_fused(self, V: Sequence[DeferredProjection]) -> Tuple[torch.Tensor, torch.Tensor]:
-        """pool (one launch) -> hidden layers -> scores -> one tcgen05 GEMM with the mix in its epilogue."""
+    def _forward_fused(self, V: Sequence[DeferredProjection], out: Optional[torch.Tensor] = None,
+                       batch_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """pool (one launch) -> hidden layers -> scores -> one tcgen05 GEMM with the mix in its epilogue.
+
+        `out`: optional [B, T, K] bf16 view (any batch stride) the prefix is written into, e.g. the prefix slot of the
+        multimodal embedding buffer (merv.py:633-640).  `batch_index`: optional int32 [B'] gather of the input videos
+        (`multimodal_indices`, merv.py:572) fused into the pool kernel's loads.
+        """
         dtype = torch.bfloat16
         projs = [v.projector for v in V]
         xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
-        B, T, K = xs[0].shape[0], self.token_length, self.llm_dim
+        xs = [x if x.stride(3) == 1 and not any(st % 8 for st in x.stride()[:3]) else x.contiguous() for x in xs]
+        B, T, K = (xs[0].shape[0] if batch_index is None else batch_index.numel()), self.token_length, self.llm_dim
         lasts = [p.layers()[-1][0] for p in projs]
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
         biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
         Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
-        acts, partials = self._fused_stage1(projs, xs, vcs, dtype)
+        timer = ops._timer
+        if all(len(p.layers()) == 1 for p in projs) and (timer is None or not timer.timing) and (out is None or out.dim() == 3):
+            return self._fused_plan(projs, xs, vcs, Ws, biases, B).run(xs, out, batch_index)
+        acts, partials = self._fused_stage1(projs, xs, vcs, dtype, batch_index=batch_index)
         scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
         weights, bias_mix = ops.softmax_weights(scores, biases, K)
-        out = ops.fused_linear_mix(acts, Ws, weights, bias_mix, T)
-        return out.view(B, T, K), weights.to(dtype)
+        if out is not None:
+            assert out.shape == (B, T, K), f"out must be [B, T, K] = {(B, T, K)}, got {tuple(out.shape)}"
+            ops.fused_linear_mix(acts, Ws, weights, bias_mix, T, out=out)
+            return out, weights.to(dtype)
+        res = ops.fused_linear_mix(acts, Ws, weights, bias_mix, T)
+        return res.view(B, T, K), weights.to(dtype)
+
+
+    def _fused_plan(self, projs, xs, vcs, Ws, biases, B) -> "ops.FusedLinearPlan":
+        """One cached single-call plan per (shapes, strides, weight versions, stream)."""
+        key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), tuple(id(vc[0]) for vc in vcs),
+               tuple(w.data_ptr() for w in Ws), torch.cuda.current_stream(xs[0].device).cuda_stream)
+        plans = self.__dict__.setdefault("_plans", {})
+        plan = plans.get(key)
+        if plan is None:
+            if len(plans) >= 8:  # shapes rarely change; keep the cache (and its workspaces) small
+                plans.clear()
+            plan = ops.FusedLinearPlan(xs, [p.output_frames for p in projs], projs[0].output_size, [vc[0] for vc in vcs],
+                                       [vc[1] for vc in vcs], Ws, biases, B, xs[0].shape[0])
+            plans[key] = plan
+        return plan
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -491,9 +523,29 @@ class MervFusion(nn.Module):
                                                      averagetoken=True, num_encoder=len(projs))
         return cls(projs, fusion, fused=fused)
 
-    def forward(self, patch_features: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
+                batch_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
-        return self.feature_fusion(projected)
+        if out is None and batch_index is None:
+            return self.feature_fusion(projected)
+        return self.feature_fusion(projected, out=out, batch_index=batch_index)
+
+    def forward_into_embeddings(self, patch_features: Sequence[torch.Tensor], input_embeddings: torch.Tensor,
+                                bos_token_length: int = 1, multimodal_indices: Optional[torch.Tensor] = None):
+        """Build `[BOS | visual prefix | text]` embeddings as MERV.forward does (merv.py:572,633-640) without the
+        concat copy of the prefix: the buffer is allocated once, the text embeddings are copied around the prefix slot
+        and the fused GEMM writes the prefix straight into it.  Returns (multimodal_embeddings, weights)."""
+        ff = self.feature_fusion
+        idx = multimodal_indices
+        emb = input_embeddings if idx is None else input_embeddings[idx]
+        B, L, K = emb.shape
+        T = ff.token_length
+        buf = torch.empty((B, L + T, K), dtype=torch.bfloat16, device=emb.device)
+        buf[:, :bos_token_length].copy_(emb[:, :bos_token_length])
+        buf[:, bos_token_length + T:].copy_(emb[:, bos_token_length:])
+        _, weights = self.forward(patch_features, out=buf[:, bos_token_length:bos_token_length + T],
+                                  batch_index=None if idx is None else idx.to(torch.int32))
+        return buf, weights
 
 
 def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:

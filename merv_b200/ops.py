@@ -54,7 +54,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 KERNELS_PER_CALL = {
     "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
-    "merv_softmax_mix": 1, "merv_fused_linear_mix": 1,
+    "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 4, "merv_softmax_weights_ex": 1,
 }
 
 
@@ -110,16 +110,20 @@ def _call(name, fn, *args) -> None:
 # ------------------------------------------------------------------------------------------------------------
 def pool3d(
     xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int,
-    score_vecs: Optional[Sequence[torch.Tensor]] = None, max_ctas: int = 0,
+    score_vecs: Optional[Sequence[torch.Tensor]] = None, max_ctas: int = 0, batch_index: Optional[torch.Tensor] = None,
 ) -> Tuple[List[torch.Tensor], Optional[List[torch.Tensor]]]:
     """Adaptive 3-D average pooling of every encoder's [B, F, N, C] features in ONE launch -> [B, T*S*S, C].
 
     Reference: AveragePooling3DProjector.forward, merv/util/nn_utils.py:320-329.  With `score_vecs` (fp32 [C_e] each)
-    also returns per-encoder partial dot products [B, parts_e] of the pooled tokens with that vector.
+    also returns per-encoder partial dot products [B, parts_e] of the pooled tokens with that vector.  `batch_index`
+    (int32 [B']) selects/reorders the videos read from every x (the `multimodal_indices` gather of merv.py:572, fused).
     """
     lib = _lib.load()
-    dev = _require_cuda(*xs, *(score_vecs or []))
-    B = xs[0].shape[0]
+    dev = _require_cuda(*xs, *(score_vecs or []), batch_index)
+    src_B = xs[0].shape[0]
+    if batch_index is not None:
+        assert batch_index.dtype == torch.int32 and batch_index.dim() == 1 and batch_index.is_contiguous()
+    B = src_B if batch_index is None else batch_index.numel()
     code = dtype_code(xs[0].dtype)
     n = len(xs)
     descs = (PoolDesc * n)()
@@ -127,7 +131,7 @@ def pool3d(
     with torch.cuda.device(dev):
         for i, (x, T) in enumerate(zip(xs, out_frames)):
             assert x.dim() == 4, f"expected [B, F, N, C] features, got {tuple(x.shape)}"
-            assert x.shape[0] == B and x.dtype == xs[0].dtype
+            assert x.shape[0] == src_B and x.dtype == xs[0].dtype
             if x.stride(3) != 1 or any(s % 8 for s in x.stride()[:3]):
                 x = x.contiguous()
             keep.append(x)
@@ -137,6 +141,7 @@ def pool3d(
             y = torch.empty((B, T * out_size * out_size, Cc), dtype=x.dtype, device=dev)
             d = descs[i]
             d.x, d.y, d.score_vec, d.score_partial = x.data_ptr(), y.data_ptr(), None, None
+            d.batch_index, d.src_batch = _p(batch_index), src_B
             d.F, d.H, d.W, d.C, d.T, d.S = F, H, H, Cc, T, out_size
             d.x_batch_stride, d.x_frame_stride, d.x_token_stride = x.stride(0), x.stride(1), x.stride(2)
             d.y_batch_stride, d.y_row_stride = y.stride(0), y.stride(1)
@@ -301,10 +306,12 @@ def fused_linear_mix(
 ) -> torch.Tensor:
     """out[m] = sum_s scale[m // rows_per_video, s] * (A_s[m] @ W_s.T) + bias_mix[m // rows_per_video]  (bf16, tcgen05).
 
-    `out` may be a preallocated [M, N] view with row stride >= N (e.g. a slice of the multimodal embedding buffer).
+    `out` may be a preallocated [M, N] matrix (row stride >= N) or a [B, rows_per_video, N] view with an arbitrary batch
+    stride, e.g. `embeddings[:, bos:bos + T, :]` of the multimodal embedding buffer (merv.py:633-640): the prefix is then
+    written in place instead of being concatenated afterwards.
     """
     lib = _lib.load()
-    dev = _require_cuda(*As, *Ws, scale, bias_mix)
+    dev = _require_cuda(*As, *Ws, scale, bias_mix, out)
     assert all(a.dtype == torch.bfloat16 for a in As) and all(w.dtype == torch.bfloat16 for w in Ws), "fused path is bf16 only"
     As = [a.reshape(-1, a.shape[-1]) for a in As]
     As = [a if a.stride(1) == 1 else a.contiguous() for a in As]
@@ -314,9 +321,74 @@ def fused_linear_mix(
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
-        assert out.shape == (M, N) and out.stride(1) == 1
+        assert out.dtype == torch.bfloat16 and out.stride(-1) == 1
+        if out.dim() == 3:
+            assert out.shape == (M // rows_per_video, rows_per_video, N)
+            ldo, batch_stride = out.stride(1), out.stride(0)
+        else:
+            assert out.shape == (M, N)
+            ldo, batch_stride = out.stride(0), 0
         _call('merv_fused_linear_mix', lib.merv_fused_linear_mix, ptr_array([a.data_ptr() for a in As]), i64_array([a.stride(0) for a in As]),
-                                        ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]),
-                                        i32_array([a.shape[1] for a in As]), len(As), scale.data_ptr(), _p(bias_mix), out.data_ptr(),
-                                        out.stride(0), M, N, rows_per_video, max_ctas, _stream())
+              ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]), i32_array([a.shape[1] for a in As]), len(As),
+              scale.data_ptr(), _p(bias_mix), out.data_ptr(), ldo, batch_stride, M, N, rows_per_video, max_ctas, _stream())
     return out
+
+
+class FusedLinearPlan:
+    """Pre-built `merv_fused_desc` for the whole affine path (pool -> scores -> softmax -> fused GEMM) at fixed shapes:
+    one FFI crossing per forward instead of ~20 Python-level operations.  Matters at small batch (generate runs the path
+    once per video at B = 1), where host time per launch dominates.  Workspaces are owned by the plan and reused, so a
+    plan is bound to one stream."""
+
+    def __init__(self, xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int, vs: Sequence[torch.Tensor],
+                 cs: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], B: int, src_B: int):
+        lib = _lib.load()
+        dev = _require_cuda(*xs, *vs, *cs, *Ws)
+        E = len(xs)
+        assert 1 <= E <= _lib.MAX_SEGMENTS
+        self.dev, self.E, self.B, self.src_B = dev, E, B, src_B
+        d = self.desc = _lib.FusedDesc()
+        N = Ws[0].shape[0]
+        T_tok = out_frames[0] * out_size * out_size
+        d.num_encoders, d.B, d.N, d.rows_per_video = E, B, N, T_tok
+        self.keep = [vs, cs, Ws, biases]  # the descriptor holds raw pointers into these
+        with torch.cuda.device(dev):
+            self.pooled, self.partials = [], []
+            for e, (x, T) in enumerate(zip(xs, out_frames)):
+                _, F, Np, Cc = x.shape
+                H = int(math.sqrt(Np))
+                assert H * H == Np, f"patch count {Np} is not a perfect square"
+                y = torch.empty((B, T * out_size * out_size, Cc), dtype=torch.bfloat16, device=dev)
+                pd = d.pool[e]
+                pd.y, pd.score_vec = y.data_ptr(), vs[e].data_ptr()
+                pd.F, pd.H, pd.W, pd.C, pd.T, pd.S = F, H, H, Cc, T, out_size
+                pd.x_batch_stride, pd.x_frame_stride, pd.x_token_stride = x.stride(0), x.stride(1), x.stride(2)
+                pd.y_batch_stride, pd.y_row_stride = y.stride(0), y.stride(1)
+                pd.src_batch = src_B
+                self.pooled.append(y)
+                d.W[e], d.ldw[e], d.bias[e], d.c[e] = Ws[e].data_ptr(), Ws[e].stride(0), _p(biases[e]), cs[e].data_ptr()
+            parts = i32_array([0] * E)
+            check(lib.merv_pool3d_score_parts(d.pool, E, MERV_BF16, parts))
+            for e in range(E):
+                pt = torch.empty((B, parts[e]), dtype=torch.float32, device=dev)
+                d.pool[e].score_partial, d.parts[e] = pt.data_ptr(), parts[e]
+                self.partials.append(pt)
+            self.scores = torch.empty((B, E), dtype=torch.float32, device=dev)
+            self.weights = torch.empty((B, E), dtype=torch.float32, device=dev)
+            self.bias_mix = torch.empty((B, N), dtype=torch.float32, device=dev)
+            d.scores, d.weights, d.bias_mix = self.scores.data_ptr(), self.weights.data_ptr(), self.bias_mix.data_ptr()
+        self.N, self.T_tok = N, T_tok
+        self.fn = lib.merv_fused_forward
+
+    def run(self, xs: Sequence[torch.Tensor], out: Optional[torch.Tensor], batch_index: Optional[torch.Tensor]):
+        d = self.desc
+        with torch.cuda.device(self.dev):
+            if out is None:
+                out = torch.empty((self.B, self.T_tok, self.N), dtype=torch.bfloat16, device=self.dev)
+            w16 = torch.empty((self.B, self.E), dtype=torch.bfloat16, device=self.dev)
+            bi = _p(batch_index)
+            for e, x in enumerate(xs):
+                d.pool[e].x, d.pool[e].batch_index = x.data_ptr(), bi
+            d.out, d.ldo, d.out_batch_stride, d.weights_bf16 = out.data_ptr(), out.stride(1), out.stride(0), w16.data_ptr()
+            _call('merv_fused_forward', self.fn, d, _stream())
+        return out, w16

@@ -125,5 +125,27 @@ except Exception as e:
     report["timing_exception"] = repr(e)
     print("timing exception:", e, flush=True)
 
+try:
+    import merv_b200 as M
+
+    mod = M.MervFusion.build([1024, 1024, 768, 768], 4096, [16] * 4, 64, "linear", seed=1024).to(device=dev, dtype=torch.bfloat16).eval().requires_grad_(False)
+    g = torch.Generator(device=dev).manual_seed(3)
+    for Bs in (1, 2, 8):
+        feats = [torch.randn((Bs, 16, n, c), generator=g, device=dev).to(torch.bfloat16) for n, c in zip([256, 256, 196, 196], [1024, 1024, 768, 768])]
+        with torch.inference_mode():
+            dev_ms = timeit(lambda: mod(feats), n=50)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(50):
+                mod(feats)
+            host_issue_ms = (time.perf_counter() - t0) / 50 * 1e3
+            torch.cuda.synchronize()
+        report[f"latency_B{Bs}_ms"] = dev_ms
+        report[f"host_issue_B{Bs}_ms"] = host_issue_ms
+        print(f"fused path B={Bs}: {dev_ms * 1e3:.1f} us per call on the device timeline, host issue time {host_issue_ms * 1e3:.1f} us", flush=True)
+except Exception as e:
+    report["latency_exception"] = repr(e)
+    print("latency exception:", e, flush=True)
+
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
 json.dump(report, open(os.path.join(REPO, "gpurun_out", "diag.json"), "w"), indent=1)

@@ -350,3 +350,42 @@ def test_error_behaviour():
     p.requires_grad_(False)
     with pytest.raises(AssertionError):  # 15 patches: not a square grid
         p(torch.zeros(1, 4, 15, 64, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# prefix written straight into the multimodal embedding buffer; fused batch gather
+# ---------------------------------------------------------------------------------------------------------
+def test_prefix_written_into_embedding_buffer_and_gather():
+    case = C.CASES["mid_linear"]  # T = 128 tokens per video: a multiple of the 128-row GEMM tile
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=True)
+    B0, T, K = case.batch, case.token_length, case.llm_dim
+    # a batch of 5 "examples" of which rows [3, 0, 3] are multimodal (merv.py:572: patch_feature[multimodal_indices])
+    rep = [torch.cat([_t(f, torch.bfloat16)] * 3)[:5].contiguous() for f in feats]  # source batch of 5 videos
+    idx = torch.tensor([3, 0, 3], device=DEV)
+    text = torch.randn(5, 9, K, device=DEV).to(torch.bfloat16)  # [BOS + 8 text tokens] embeddings
+    with torch.inference_mode():
+        want_prefix, want_w = m([f[idx] for f in rep])  # gather done by torch, plain output
+        buf, w = m.forward_into_embeddings(rep, text, bos_token_length=1, multimodal_indices=idx)
+    assert buf.shape == (3, 9 + T, K)
+    assert torch.equal(buf[:, 1:1 + T], want_prefix), "prefix written in place must be bit-identical to the plain output"
+    assert torch.equal(w, want_w)
+    assert torch.equal(buf[:, :1], text[idx][:, :1]) and torch.equal(buf[:, 1 + T:], text[idx][:, 1:])  # merv.py:633-640
+    # and against the reference golden (videos 3 and 0 of the repeated batch are golden videos 1 and 0)
+    scale = float(g["out_abs_max"])
+    idxs = g["sample_idx"]
+    got = torch.stack([buf[1, 1:1 + T], buf[0, 1:1 + T]])  # golden order: video 0, video 1  ->  source videos 0, 3
+    assert np.abs(_np(got).reshape(-1)[idxs] - g["out_samples"]).max() / scale < BF16_TOL
+
+
+def test_strided_output_requires_tile_aligned_videos():
+    from merv_b200 import _lib, ops
+
+    a = torch.randn(2 * 96, 64, device=DEV).to(torch.bfloat16)
+    w = torch.randn(256, 64, device=DEV).to(torch.bfloat16)
+    scale = torch.ones(2, 1, device=DEV)
+    buf = torch.zeros(2, 100, 256, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(_lib.MervError, match="MERV_E_SHAPE"):  # 96 rows per video is not a multiple of the 128-row tile
+        ops.fused_linear_mix([a], [w], scale, None, 96, out=buf[:, 2:98])
+    out = ops.fused_linear_mix([a], [w], scale, None, 96)  # contiguous output has no such restriction
+    assert O.rel_err(_np(out), _np(a) @ _np(w).T) < 6e-3
