@@ -57,14 +57,62 @@ def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
-def _no_autograd(module: nn.Module, *tensors) -> None:
-    if torch.is_grad_enabled() and (
+def _needs_grad(module: nn.Module, *tensors) -> bool:
+    """True when the call must be recorded by autograd (training step: projectors and adapter are trainable in every
+    stage, merv.py:318-320,342-343,363-365)."""
+    return torch.is_grad_enabled() and (
         any(p.requires_grad for p in module.parameters()) or any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
-    ):
-        raise NotImplementedError(
-            f"{type(module).__name__}: the backward of the sm_100a fusion kernels is not implemented yet (SURVEY.md §8 f-1); "
-            "run under torch.no_grad()/inference_mode() or freeze the module (requires_grad_(False))."
-        )
+    )
+
+
+class _LinearProjectFn(torch.autograd.Function):
+    """y = x W^T + b through the sm_100a GEMM, with dW = dY^T x (same GEMM on transposed copies) and db = colsum(dY).
+    No gradient flows into x: the backbones are frozen (merv.py:316,339,361) and pooling has no parameters."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_c, b_c):
+        y, _ = ops.linear_bias_act(x, w_c, b_c, ACT_NONE)
+        ctx.save_for_backward(x)
+        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        wdt, bdt = ctx.meta
+        x2 = x.reshape(-1, x.shape[-1])
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.stride(1) != 1:
+            dy2 = dy2.contiguous()
+        if dy2.dtype != x2.dtype:
+            dy2 = dy2.to(x2.dtype)
+        dW, _ = ops.linear_bias_act(ops.transpose(dy2), ops.transpose(x2), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
+        db = ops.colsum(dy2) if bdt is not None else None
+        return None, dW.to(wdt), (None if db is None else db.to(bdt)), None, None
+
+
+class _MixFn(torch.autograd.Function):
+    """CrossAttentionAdapterLearnableQuery.forward (nn_utils.py:487-521) with its hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, adapter, dtype, Q, Wq, Wk, bias, *V):
+        c = adapter._cast_cache
+        Vc = [v if v.dtype == dtype else v.to(dtype) for v in V]
+        u = adapter.query_vector(dtype)
+        scores = ops.scores_from_tokens(Vc, u, adapter.token_length)
+        out, weights = ops.softmax_mix(Vc, adapter.token_length, scores=scores)
+        ctx.save_for_backward(weights, u, c.get(Q, dtype), c.get(Wq, dtype), c.get(Wk, dtype), c.get(bias, dtype), *Vc)
+        ctx.meta = (dtype, [p.dtype for p in (Q, Wq, Wk, bias)], [v.dtype for v in V])
+        return out, weights.to(dtype)
+
+    @staticmethod
+    def backward(ctx, dout, dweights):
+        weights, u, Qc, Wqc, Wkc, bc, *Vc = ctx.saved_tensors
+        dtype, pdt, vdt = ctx.meta
+        dw = None if dweights is None else dweights.float().contiguous()
+        dVs, dQ, dWq, dWk, dbias = ops.mix_backward(Vc, dout.to(dtype), weights, dw, u, Qc, Wqc, Wkc, bc)
+        grads = [g.to(t) for g, t in zip((dQ, dWq, dWk, dbias), pdt)]
+        return (None, None, *grads, *[g.to(t) for g, t in zip(dVs, vdt)])
 
 
 def _version(p: torch.Tensor) -> int:
@@ -113,8 +161,16 @@ def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
     raise TypeError(f"unsupported projector module {type(projector).__name__}")
 
 
-def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None):
+def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None, train: bool = False):
     rd = None
+    if train:
+        if len(layers) != 1 or layers[0][1] != ACT_NONE:
+            raise NotImplementedError(
+                "the backward is implemented for the 'linear' projector (every shipped config, conf/models.py:103,154); "
+                "gelu-mlp / fused-gelu-mlp train-time gradients are not built yet (SURVEY.md §8 f-1)"
+            )
+        lin = layers[0][0]
+        return _LinearProjectFn.apply(x, lin.weight, lin.bias, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype)), None
     for i, (lin, act) in enumerate(layers):
         rv = last_rowdot_vec if i == len(layers) - 1 else None
         x, rd = ops.linear_bias_act(x, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), act, rv)
@@ -131,12 +187,14 @@ class _ProjectorBase(nn.Module):
 
     def forward(self, img_patches: torch.Tensor) -> torch.Tensor:
         self._check_ln()
-        _no_autograd(self, img_patches)
+        train = _needs_grad(self, img_patches)
+        if train and img_patches.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the projector input are not implemented (frozen backbones, merv.py:316)")
         dtype = _compute_dtype(img_patches)
         if not hasattr(self, "_cast_cache"):
             self._cast_cache = _CastCache()
         x = img_patches if img_patches.dtype == dtype else img_patches.to(dtype)
-        y, _ = _run_layers(x, _projector_layers(self), self._cast_cache, dtype)
+        y, _ = _run_layers(x, _projector_layers(self), self._cast_cache, dtype, train=train)
         return y
 
 
@@ -283,14 +341,17 @@ class AveragePooling3DProjector(TokenResampler):
 
     def _forward_unfused(self, fused_img_patches: torch.Tensor, rowdot_vec: Optional[torch.Tensor] = None):
         dtype = _compute_dtype(fused_img_patches)
-        x = fused_img_patches if fused_img_patches.dtype == dtype else fused_img_patches.to(dtype)
+        train = _needs_grad(self, fused_img_patches)
+        if train and fused_img_patches.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the patch features are not implemented (frozen backbones, merv.py:316)")
+        x = fused_img_patches.detach()
+        x = x if x.dtype == dtype else x.to(dtype)
         (pooled,), _ = ops.pool3d([x], [self.output_frames], self.output_size)
-        y, rd = _run_layers(pooled, self.layers(), self._cast_cache, dtype, rowdot_vec)
+        y, rd = _run_layers(pooled, self.layers(), self._cast_cache, dtype, rowdot_vec, train=train)
         return (y, rd) if rowdot_vec is not None else y
 
     def forward(self, fused_img_patches: torch.Tensor) -> Union[torch.Tensor, DeferredProjection]:
         assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
-        _no_autograd(self, fused_img_patches)
         if not fused_img_patches.is_cuda:
             raise RuntimeError("merv_b200 runs only on CUDA (sm_100a) tensors; there is deliberately no CPU fallback.")
         fusion = self._linked_fusion() if self._linked_fusion is not None else None
@@ -390,13 +451,17 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         if self.positional_embedding:
             raise NotImplementedError("positional_embedding=True is outside the accelerated hot path (default False)")
         assert 1 <= len(V) <= 8, f"1..8 encoders supported, got {len(V)}"
-        _no_autograd(self, *[v for v in V if isinstance(v, torch.Tensor)])
 
         if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
             return self._forward_fused(V, out=out, batch_index=batch_index)
         if out is not None or batch_index is not None:
             raise NotImplementedError("out= / batch_index= are supported on the linked bf16 path only")
         V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
+        if _needs_grad(self, *V):
+            if any(v.shape[1] != self.token_length for v in V):
+                raise NotImplementedError("the backward does not cover single-token (broadcast) encoders")
+            att = self.attention
+            return _MixFn.apply(self, _compute_dtype(V[0]), self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias, *V)
         return self._forward_tokens(V)
 
     def _forward_tokens(self, V: Sequence[torch.Tensor], rowdots=None) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -55,6 +55,7 @@ KERNELS_PER_CALL = {
     "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 4, "merv_softmax_weights_ex": 1,
+    "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10,
 }
 
 
@@ -392,3 +393,56 @@ class FusedLinearPlan:
             d.out, d.ldo, d.out_batch_stride, d.weights_bf16 = out.data_ptr(), out.stride(1), out.stride(0), w16.data_ptr()
             _call('merv_fused_forward', self.fn, d, _stream())
         return out, w16
+
+
+# ---- backward building blocks (SURVEY.md §8 f-1) ------------------------------------------------------------------
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    """[R, C] -> contiguous [C, R]."""
+    lib = _lib.load()
+    dev = _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    R, Cc = x.shape
+    with torch.cuda.device(dev):
+        y = torch.empty((Cc, R), dtype=x.dtype, device=dev)
+        _call('merv_transpose', lib.merv_transpose, x.data_ptr(), y.data_ptr(), R, Cc, x.stride(0), y.stride(0), dtype_code(x.dtype), _stream())
+    return y
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """sum over rows of [M, N] -> [N] in x.dtype (fp32 accumulation, fixed order)."""
+    lib = _lib.load()
+    dev = _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, N = x.shape
+    with torch.cuda.device(dev):
+        out = torch.empty(N, dtype=x.dtype, device=dev)
+        ws = torch.empty(max(1, lib.merv_colsum_workspace(M, N)), dtype=torch.float32, device=dev)
+        _call('merv_colsum', lib.merv_colsum, x.data_ptr(), out.data_ptr(), ws.data_ptr(), M, N, x.stride(0), dtype_code(x.dtype), _stream())
+    return out
+
+
+def mix_backward(Vs: Sequence[torch.Tensor], dout: torch.Tensor, weights: torch.Tensor, dweights: Optional[torch.Tensor], u: torch.Tensor,
+                 Q: torch.Tensor, Wq: torch.Tensor, Wk: torch.Tensor, in_proj_bias: torch.Tensor):
+    """Gradients of the adapter: returns (dV list, dQ [1, embed], dWq, dWk, d in_proj_bias) in the compute dtype."""
+    lib = _lib.load()
+    dev = _require_cuda(*Vs, dout, weights, dweights, u, Q, Wq, Wk, in_proj_bias)
+    B, T, K = Vs[0].shape
+    E, embed = len(Vs), Wk.shape[0]
+    dt = Vs[0].dtype
+    Vs = [v.contiguous() for v in Vs]
+    dout = dout.contiguous()
+    assert all(v.shape == (B, T, K) and v.dtype == dt for v in Vs) and dout.shape == (B, T, K) and dout.dtype == dt
+    assert weights.dtype == torch.float32 and weights.is_contiguous() and (dweights is None or (dweights.dtype == torch.float32 and dweights.is_contiguous()))
+    with torch.cuda.device(dev):
+        dVs = [torch.empty_like(v) for v in Vs]
+        dQ = torch.empty((1, embed), dtype=dt, device=dev)
+        dWq = torch.empty((embed, embed), dtype=dt, device=dev)
+        dWk = torch.empty((embed, K), dtype=dt, device=dev)
+        dbias = torch.empty(3 * embed, dtype=dt, device=dev)
+        n = lib.merv_mix_backward_workspace(B, E, T, K, embed)
+        ws = torch.empty(n, dtype=torch.float32, device=dev)
+        _call('merv_mix_backward', lib.merv_mix_backward, ptr_array([v.data_ptr() for v in Vs]), dout.data_ptr(), weights.data_ptr(), _p(dweights),
+              u.data_ptr(), Q.contiguous().data_ptr(), Wq.contiguous().data_ptr(), Wk.contiguous().data_ptr(), in_proj_bias.data_ptr(),
+              ptr_array([d.data_ptr() for d in dVs]), dQ.data_ptr(), dWq.data_ptr(), dWk.data_ptr(), dbias.data_ptr(), ws.data_ptr(), n,
+              B, E, T, K, embed, dtype_code(dt), _stream())
+    return dVs, dQ, dWq, dWk, dbias

@@ -33,8 +33,7 @@ def _project(x: torch.Tensor, p: Dict[str, torch.Tensor], mlp_type: str) -> torc
     raise ValueError(f"Projector with `{mlp_type = }` is not supported!")
 
 
-@torch.no_grad()
-def fusion_forward(
+def fusion_forward_autograd(
     features: Sequence[torch.Tensor], projector_params: Sequence[Dict[str, torch.Tensor]], fusion_params: Dict[str, torch.Tensor],
     out_frames: Sequence[int], out_size: int, mlp_type: str, token_length: int,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -64,3 +63,9 @@ def fusion_forward(
     K = V.shape[-1]
     out = torch.bmm(weights, V.reshape(B, E, K * token_length)).reshape(B, token_length, K)
     return out, weights[:, 0]
+
+
+@torch.no_grad()
+def fusion_forward(*args, **kwargs):
+    """The timed CPU baseline / forward checker (no autograd graph)."""
+    return fusion_forward_autograd(*args, **kwargs)

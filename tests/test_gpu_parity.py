@@ -344,10 +344,7 @@ def test_error_behaviour():
         ops.linear_bias_act(torch.zeros(4, 8, device=DEV, dtype=torch.float16), torch.zeros(8, 8, device=DEV, dtype=torch.float16), None)
     with pytest.raises(_lib.MervError, match="MERV_E_ALIGN|MERV_E_SHAPE"):
         ops.linear_bias_act(torch.zeros(4, 12, device=DEV, dtype=torch.bfloat16), torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16), None)
-    p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(DEV)
-    with pytest.raises(NotImplementedError, match="backward"):
-        p(torch.zeros(1, 4, 16, 64, device=DEV))
-    p.requires_grad_(False)
+    p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(DEV).requires_grad_(False)
     with pytest.raises(AssertionError):  # 15 patches: not a square grid
         p(torch.zeros(1, 4, 15, 64, device=DEV))
 
@@ -389,3 +386,70 @@ def test_strided_output_requires_tile_aligned_videos():
         ops.fused_linear_mix([a], [w], scale, None, 96, out=buf[:, 2:98])
     out = ops.fused_linear_mix([a], [w], scale, None, 96)  # contiguous output has no such restriction
     assert O.rel_err(_np(out), _np(a) @ _np(w).T) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward of the module-by-module path vs torch autograd through the reference's op sequence
+# ---------------------------------------------------------------------------------------------------------
+def _reference_grads(case, feats, pp, fp, G, H):
+    from oracle import torch_port
+
+    tt = lambda d: {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in d.items()}  # noqa: E731
+    ppt, fpt = [tt(p) for p in pp], tt(fp)
+    out, w = torch_port.fusion_forward_autograd([torch.from_numpy(f).double() for f in feats], ppt, fpt, case.out_frames, case.out_size,
+                                                case.mlp_type, case.token_length)
+    loss = (out * torch.from_numpy(G).double()).sum() + (w * torch.from_numpy(H).double()).sum()
+    loss.backward()
+    return [{k: v.grad.numpy() for k, v in p.items()} for p in ppt], {k: (None if v.grad is None else v.grad.numpy()) for k, v in fpt.items()}
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_backward_matches_reference_autograd(dtype, tol):
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((case.batch, case.token_length, case.llm_dim)).astype(np.float32)
+    H = rng.standard_normal((case.batch, case.num_encoders)).astype(np.float32)
+    if dtype == torch.bfloat16:  # compare like with like: reference gradients at the bf16-rounded operating point
+        feats = [_bf16_round(f) for f in feats]
+        pp = [{k: _bf16_round(v) for k, v in p.items()} for p in pp]
+        fp = {k: _bf16_round(v) for k, v in fp.items()}
+    want_p, want_f = _reference_grads(case, feats, pp, fp, G, H)
+
+    import merv_b200 as M
+
+    m = M.MervFusion.build(case.dims, case.llm_dim, case.out_frames, case.out_size**2, case.mlp_type, text_embedding_dim=case.embed_dim, fused=True)
+    for proj, p in zip(m.projectors, pp):
+        proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    m.feature_fusion.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()})
+    m = m.to(device=DEV, dtype=dtype).train()
+    out, w = m([_t(f, dtype) for f in feats])  # grad mode: module-by-module path through the autograd Functions
+    assert out.requires_grad and w.requires_grad
+    loss = (out.float() * _t(G)).sum() + (w.float() * _t(H)).sum()
+    loss.backward()
+    for i, proj in enumerate(m.projectors):
+        lin = proj.projector.projector
+        assert O.rel_err(_np(lin.weight.grad), want_p[i]["projector.weight"]) < tol, f"dW of projector {i}"
+        assert O.rel_err(_np(lin.bias.grad), want_p[i]["projector.bias"]) < tol, f"db of projector {i}"
+    ff = m.feature_fusion
+    E = case.embed_dim
+    assert O.rel_err(_np(ff.Q.grad), want_f["Q"]) < tol
+    assert O.rel_err(_np(ff.attention.q_proj_weight.grad), want_f["attention.q_proj_weight"]) < tol
+    assert O.rel_err(_np(ff.attention.k_proj_weight.grad), want_f["attention.k_proj_weight"]) < tol
+    got_b, want_b = _np(ff.attention.in_proj_bias.grad), want_f["attention.in_proj_bias"]
+    assert O.rel_err(got_b[:E], want_b[:E]) < tol
+    assert np.abs(want_b[E:]).max() < 1e-6 * np.abs(want_b[:E]).max() and np.abs(got_b[E:]).max() == 0.0  # b_k cancels, b_v is dead
+    # exactly like the reference: the discarded attention output leaves v_proj / out_proj without gradient
+    assert want_f["attention.v_proj_weight"] is None and ff.attention.v_proj_weight.grad is None
+    assert ff.attention.out_proj.weight.grad is None
+
+
+def test_backward_unsupported_cases_raise():
+    import merv_b200 as M
+
+    p = M.AveragePooling3DProjector(64, 128, 4, 4, "gelu-mlp").to(DEV)
+    with pytest.raises(NotImplementedError, match="linear"):
+        p(torch.zeros(1, 4, 16, 64, device=DEV))
+    p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(DEV)
+    with pytest.raises(NotImplementedError, match="frozen backbones"):
+        p(torch.zeros(1, 4, 16, 64, device=DEV, requires_grad=True))
