@@ -368,6 +368,36 @@ class AveragePooling3DProjector(TokenResampler):
         return self.output_frames
 
 
+class AveragePoolingProjector(AveragePooling3DProjector):
+    """Emu-2 style projector: n x n average pooling of every frame, then the projector (nn_utils.py:136-174).
+
+    Same kernels as the 3-D resampler with an identity temporal window (the reference asserts num_frames ==
+    output_frames, nn_utils.py:155); state-dict keys and constructor signature are the reference's (note the argument
+    order: output_size before output_frames, and the ``avg_pool`` attribute name)."""
+
+    def __init__(
+        self, fused_vision_dim: int, llm_dim: int, output_size: int, output_frames: int = 8, mlp_type: str = "gelu-mlp"
+    ) -> None:
+        super().__init__(fused_vision_dim, llm_dim, output_frames, output_size, mlp_type)
+        del self.avg_pooling
+        self.avg_pool = nn.AdaptiveAvgPool2d((output_size, output_size))
+
+    @classmethod
+    def from_reference(cls, ref_module: nn.Module) -> "AveragePoolingProjector":
+        lins = [m for m in ref_module.projector.modules() if isinstance(m, nn.Linear)]
+        if not lins:
+            raise ValueError("reference projector has no Linear layer (mlp_type 'none' has nothing to accelerate)")
+        mlp_type = {1: "linear", 2: "gelu-mlp", 3: "fused-gelu-mlp"}[len(lins)]
+        new = cls(lins[0].in_features, lins[-1].out_features, ref_module.output_size, ref_module.output_frames, mlp_type)
+        new.projector.projector = ref_module.projector.projector
+        return new
+
+    def forward(self, fused_img_patches: torch.Tensor):
+        assert fused_img_patches.dim() == 4
+        assert fused_img_patches.shape[1] == self.output_frames  # nn_utils.py:154-155
+        return super().forward(fused_img_patches)
+
+
 # Adapters here
 class CrossAttentionAdapterLearnableQuery(nn.Module):
     def __init__(
@@ -543,6 +573,42 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         return plan
 
 
+class ScalarAdapter(nn.Module):
+    """One learnable scalar per encoder, softmax-normalised, the same mix for every video (nn_utils.py:524-537;
+    feature_fusion == "scalar", merv.py:224-225).  Like the reference it always holds 4 scalars."""
+
+    def __init__(self, num_encoder=4) -> None:
+        super().__init__()
+        self.scalar = torch.nn.Parameter(torch.randn(4))
+
+    def forward(self, projected_patch_embeddings):
+        V = projected_patch_embeddings
+        E = len(V)
+        assert E == self.scalar.numel(), f"ScalarAdapter holds {self.scalar.numel()} scalars, got {E} encoders (nn_utils.py:527,535)"
+        if _needs_grad(self, *[v for v in V if isinstance(v, torch.Tensor)]):
+            raise NotImplementedError("the backward of ScalarAdapter is not implemented (SURVEY.md §8 f-4)")
+        linked = all(isinstance(v, DeferredProjection) for v in V)
+        first = V[0].features if linked else V[0]
+        B = first.shape[0]
+        scores = self.scalar.detach().float().reshape(1, E).expand(B, E).contiguous()  # softmax happens in the kernels
+        if linked and all(v.dtype == torch.bfloat16 and len(v.projector.layers()) == 1 for v in V):
+            # affine projectors: out = sum_e w_e (P_e W_e^T + b_e) in one tcgen05 GEMM, Y_e never written
+            dtype = torch.bfloat16
+            projs = [v.projector for v in V]
+            xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
+            pooled, _ = ops.pool3d(xs, [p.output_frames for p in projs], projs[0].output_size)
+            lasts = [p.layers()[-1][0] for p in projs]
+            weights, bias_mix = ops.softmax_weights(scores, [p._cast_cache.get(l.bias, dtype) for l, p in zip(lasts, projs)], lasts[0].out_features)
+            T = V[0].shape[1]
+            out = ops.fused_linear_mix(pooled, [p._cast_cache.get(l.weight, dtype) for l, p in zip(lasts, projs)], weights, bias_mix, T)
+            return out.view(B, T, -1), weights[:1].to(dtype)
+        V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
+        dtype = _compute_dtype(V[0])
+        V = [v if v.dtype == dtype else v.to(dtype) for v in V]
+        out, weights = ops.softmax_mix(V, V[0].shape[1], scores=scores)
+        return out, weights[:1].to(dtype)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # linking: the fused pipeline behind the unchanged MERV.forward glue
 # ------------------------------------------------------------------------------------------------------------
@@ -620,15 +686,21 @@ def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
     CrossAttentionAdapterLearnableQuery) keep their names, so checkpoints, ``all_module_keys`` (merv.py:235) and the
     FSDP wrap policy (merv.py:473-497, extended via isinstance on these classes) keep working.
     """
+    proj_classes = {"AveragePooling3DProjector": AveragePooling3DProjector, "AveragePoolingProjector": AveragePoolingProjector}
     new_projs = []
     for p in vidlm.projectors:
-        if type(p).__name__ != "AveragePooling3DProjector":
-            raise TypeError(f"patch_merv supports 3davg arch_specifiers only, found projector {type(p).__name__}")
-        new_projs.append(p if isinstance(p, AveragePooling3DProjector) else AveragePooling3DProjector.from_reference(p))
+        cls = proj_classes.get(type(p).__name__)
+        if cls is None:
+            raise TypeError(f"patch_merv supports the 3davg / avg arch_specifiers only, found projector {type(p).__name__}")
+        new_projs.append(p if isinstance(p, AveragePooling3DProjector) else cls.from_reference(p))
     ff = vidlm.feature_fusion
-    if type(ff).__name__ != "CrossAttentionAdapterLearnableQuery":
-        raise TypeError(f"patch_merv supports feature_fusion='cross_attention_avg_lq' only, found {type(ff).__name__}")
-    new_ff = ff if isinstance(ff, CrossAttentionAdapterLearnableQuery) else CrossAttentionAdapterLearnableQuery.from_reference(ff)
+    if type(ff).__name__ == "CrossAttentionAdapterLearnableQuery":
+        new_ff = ff if isinstance(ff, CrossAttentionAdapterLearnableQuery) else CrossAttentionAdapterLearnableQuery.from_reference(ff)
+    elif type(ff).__name__ == "ScalarAdapter":
+        new_ff = ff if isinstance(ff, ScalarAdapter) else ScalarAdapter()
+        new_ff.scalar = ff.scalar
+    else:
+        raise TypeError(f"patch_merv supports feature_fusion in {{'cross_attention_avg_lq', 'scalar'}}, found {type(ff).__name__}")
     vidlm.projectors = nn.ModuleList(new_projs)
     vidlm.feature_fusion = new_ff
     if fused:

@@ -32,6 +32,8 @@ class Case:
     q_scale: float = 8.0
     offsets: Tuple[float, ...] = (0.0, 0.5, -0.5, 0.25)
     seed: int = 7
+    resampler: str = "3davg"  # "3davg" (AveragePooling3DProjector) | "avg" (AveragePoolingProjector, 2-D per frame)
+    fusion: str = "cross_attention_avg_lq"  # | "scalar" (ScalarAdapter)
 
     @property
     def num_encoders(self) -> int:
@@ -84,6 +86,11 @@ CASES: Dict[str, Case] = {
             llm_dim=512, embed_dim=384, out_frames=(8, 8, 8, 8), out_size=4, mlp_type="linear"),
         _mk("mid_gelu", batch=2, frames=(8, 8, 8, 8), patches=(64, 64, 49, 49), dims=(256, 256, 192, 192),
             llm_dim=512, embed_dim=384, out_frames=(8, 8, 8, 8), out_size=4, mlp_type="gelu-mlp"),
+        # the 2-D per-frame resampler ("avg", nn_utils.py:136-174) and the scalar mixer (nn_utils.py:524-537)
+        _mk("avg2d_linear", batch=2, frames=(4, 4, 4, 4), patches=(64, 64, 49, 49), dims=(64, 64, 48, 48),
+            llm_dim=128, embed_dim=96, out_frames=(4, 4, 4, 4), out_size=4, mlp_type="linear", resampler="avg"),
+        _mk("scalar_mixer", batch=2, frames=(4, 4, 4, 4), patches=(16, 16, 49, 49), dims=(64, 64, 48, 48),
+            llm_dim=128, embed_dim=96, out_frames=(4, 4, 4, 4), out_size=4, mlp_type="linear", fusion="scalar"),
         # full size, one video: stored as a digest (weights, sums, sampled elements), not in full
         _mk("merv_full_b1", batch=1, mlp_type="linear", q_scale=64.0, **MERV_FULL),
         _mk("merv_full_b1_gelu", batch=1, mlp_type="gelu-mlp", q_scale=64.0, **MERV_FULL),
@@ -134,8 +141,11 @@ def make_projector_params(case: Case, seed: int = 1024) -> List[Dict[str, np.nda
 
 
 def make_fusion_params(case: Case, seed: int = 2048) -> Dict[str, np.ndarray]:
-    """State dict of ``CrossAttentionAdapterLearnableQuery`` (nn_utils.py:456-485), keys as in SURVEY.md §8b."""
+    """State dict of ``CrossAttentionAdapterLearnableQuery`` (nn_utils.py:456-485), keys as in SURVEY.md §8b
+    (or of ``ScalarAdapter``, nn_utils.py:524-527)."""
     rng = np.random.default_rng(seed)
+    if case.fusion == "scalar":
+        return {"scalar": rng.standard_normal(4).astype(np.float32)}
     E, K = case.embed_dim, case.llm_dim
     xav = lambda fo, fi: math.sqrt(6.0 / (fi + fo))  # noqa: E731
     return {

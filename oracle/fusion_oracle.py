@@ -156,6 +156,14 @@ def cross_attention_fusion_forward(
     return out.astype(stacked.dtype), w.astype(stacked.dtype)
 
 
+def scalar_adapter_forward(V: Sequence[np.ndarray], params: Dict[str, np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """``ScalarAdapter.forward`` (merv/util/nn_utils.py:529-537): softmax over a learnable 4-vector, the same weights for
+    every video; returns (sum_e w_e V_e, weights [1, E])."""
+    w = _softmax_last(params["scalar"][None, :])
+    out = np.einsum("e,ebtk->btk", w[0], np.stack(V, axis=0))
+    return out.astype(V[0].dtype), w.astype(V[0].dtype)
+
+
 # --------------------------------------------------------------------------------------------
 # whole path, as MERV.forward glues it
 # --------------------------------------------------------------------------------------------
@@ -177,7 +185,10 @@ def merv_fusion_forward(
         avgpool3d_projector_forward(x, p, t, out_size, mlp_type)
         for x, p, t in zip(features, projector_params, out_frames)
     ]
-    out, w = cross_attention_fusion_forward(ys, fusion_params, token_length)
+    if "scalar" in fusion_params:  # feature_fusion == "scalar" (merv.py:224-225)
+        out, w = scalar_adapter_forward(ys, fusion_params)
+    else:
+        out, w = cross_attention_fusion_forward(ys, fusion_params, token_length)
     return out, w, ys
 
 

@@ -31,16 +31,20 @@ GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 
 
 def build_reference(ref, case: C.Case, dtype=torch.float32):
+    Proj = ref.AveragePooling3DProjector if case.resampler == "3davg" else ref.AveragePoolingProjector  # merv.py:116-141
     projs = torch.nn.ModuleList(
         [
-            ref.AveragePooling3DProjector(c, case.llm_dim, output_frames=t, output_size=case.out_size, mlp_type=case.mlp_type)
+            Proj(c, case.llm_dim, output_frames=t, output_size=case.out_size, mlp_type=case.mlp_type)
             for c, t in zip(case.dims, case.out_frames)
         ]
     )
-    fusion = ref.CrossAttentionAdapterLearnableQuery(
-        embed_dim=case.embed_dim, llm_dim=case.llm_dim, token_length=case.token_length, averagetoken=True,
-        num_encoder=case.num_encoders,
-    )
+    if case.fusion == "scalar":
+        fusion = ref.ScalarAdapter(case.num_encoders)  # merv.py:224-225
+    else:
+        fusion = ref.CrossAttentionAdapterLearnableQuery(
+            embed_dim=case.embed_dim, llm_dim=case.llm_dim, token_length=case.token_length, averagetoken=True,
+            num_encoder=case.num_encoders,
+        )
     pp, fp = C.make_projector_params(case), C.make_fusion_params(case)
     for proj, p in zip(projs, pp):
         proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
@@ -57,8 +61,12 @@ def run_reference(projs, fusion, feats, dtype=torch.float32):
     for p, x in zip(projs, xs):  # the intermediate of nn_utils.py:328-329, for the pool-kernel parity test
         import einops
         H = int(x.shape[2] ** 0.5)
-        v = einops.rearrange(x, "B F (H W) C -> B C F H W", H=H)
-        pooled.append(einops.rearrange(p.avg_pooling(v), "B C F H W -> B (F H W) C").contiguous())
+        if hasattr(p, "avg_pooling"):
+            v = einops.rearrange(x, "B F (H W) C -> B C F H W", H=H)
+            pooled.append(einops.rearrange(p.avg_pooling(v), "B C F H W -> B (F H W) C").contiguous())
+        else:  # 2-D per-frame resampler, nn_utils.py:157-164
+            v = einops.rearrange(x, "B F (H W) C -> (B F) C H W", H=H)
+            pooled.append(einops.rearrange(p.avg_pool(v), "(B F) C H W -> B (F H W) C", F=x.shape[1]).contiguous())
     return out, w, ys, pooled
 
 

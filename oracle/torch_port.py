@@ -45,6 +45,10 @@ def fusion_forward_autograd(
         pooled = F.adaptive_avg_pool3d(v, (t, out_size, out_size))
         pooled = pooled.permute(0, 2, 3, 4, 1).reshape(B, t * out_size * out_size, Cc)  # "B C F H W -> B (F H W) C"
         ys.append(_project(pooled, p, mlp_type))
+    if "scalar" in fusion_params:  # ScalarAdapter, nn_utils.py:529-537
+        stacked = torch.stack(ys, 0)
+        w = fusion_params["scalar"].softmax(0)
+        return (stacked * w.view(-1, 1, 1, 1)).sum(0), w.unsqueeze(0)
     for emb in ys:
         assert emb.shape[1] == token_length or emb.shape[1] == 1
     B, E = ys[0].shape[0], len(ys)

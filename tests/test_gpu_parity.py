@@ -34,8 +34,15 @@ def _bf16_round(a):
 def build_module(case, pp, fp, dtype, fused):
     import merv_b200 as M
 
-    m = M.MervFusion.build(case.dims, case.llm_dim, case.out_frames, case.out_size**2, case.mlp_type,
-                           text_embedding_dim=case.embed_dim, fused=fused)
+    if case.resampler == "avg":  # 2-D per-frame resampler (merv.py:116-122)
+        projs = [M.AveragePoolingProjector(c, case.llm_dim, case.out_size, t, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
+    else:
+        projs = [M.AveragePooling3DProjector(c, case.llm_dim, t, case.out_size, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
+    if case.fusion == "scalar":
+        fusion = M.ScalarAdapter(case.num_encoders)
+    else:
+        fusion = M.CrossAttentionAdapterLearnableQuery(case.embed_dim, case.llm_dim, case.token_length, averagetoken=True, num_encoder=case.num_encoders)
+    m = M.MervFusion(projs, fusion, fused=fused)
     for proj, p in zip(m.projectors, pp):
         proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
     m.feature_fusion.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()})
@@ -181,13 +188,14 @@ def test_mix_kernels_match_oracle_incl_broadcast(dtype):
 # ---------------------------------------------------------------------------------------------------------
 # module paths vs the reference goldens
 # ---------------------------------------------------------------------------------------------------------
-SMALL = ["tiny_linear", "tiny_gelu", "tiny_fused_gelu", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear", "mid_gelu"]
+SMALL = ["tiny_linear", "tiny_gelu", "tiny_fused_gelu", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear", "mid_gelu",
+         "avg2d_linear", "scalar_mixer"]
 
 
 def _check_against_golden(case, g, out, w, tol, wtol):
     out_np, w_np = _np(out), _np(w)
     assert out.shape == (case.batch, case.token_length, case.llm_dim)
-    assert w.shape == (case.batch, case.num_encoders)
+    assert w.shape == ((1 if case.fusion == "scalar" else case.batch), case.num_encoders)  # ScalarAdapter returns [1, E] (nn_utils.py:537)
     assert np.allclose(w_np.sum(-1), 1.0, atol=1e-2 if wtol > 1e-4 else 1e-5)
     scale = float(g["out_abs_max"])
     idx = g["sample_idx"]

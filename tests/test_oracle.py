@@ -38,7 +38,7 @@ def test_oracle_matches_reference_golden(name):
     g, feats, pp, fp = regenerate(case)
     out, w, ys = O.merv_fusion_forward(feats, pp, fp, case.out_frames, case.out_size, case.mlp_type, case.token_length)
     assert out.shape == (case.batch, case.token_length, case.llm_dim)
-    assert w.shape == (case.batch, case.num_encoders)
+    assert w.shape == ((1 if case.fusion == "scalar" else case.batch), case.num_encoders)  # ScalarAdapter returns [1, E]
     assert np.allclose(w.sum(-1), 1.0, atol=1e-5)
     scale = float(g["out_abs_max"])
     assert np.abs(w - g["weights"]).max() < 2e-5
