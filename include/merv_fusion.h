@@ -42,7 +42,7 @@ enum {
 
 #define MERV_MAX_ENCODERS 8
 #define MERV_MAX_SEGMENTS 4
-#define MERV_ROWDOT_BLOCK 128 /* column-block width of the row-dot partials emitted by the GEMM epilogue */
+#define MERV_ROWDOT_BLOCK 64 /* column-block width of the row-dot partials emitted by the GEMM epilogue */
 
 int merv_abi_version(void);
 const char* merv_last_error(void);

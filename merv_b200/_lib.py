@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
 
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1
-MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 128
+MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 64
 ABI_VERSION = 1
 
 ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}

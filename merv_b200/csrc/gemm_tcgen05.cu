@@ -9,7 +9,7 @@
 //
 // Tile 128 x 256 x 64 per CTA (cta_group::1, UMMA 128x256x16), 4-stage TMA->smem ring (128B swizzle, K-major
 // A and W), two 256-column TMEM accumulators.  A "segment" is one (A_s, W_s, K_s) product; the MMA warp
-// alternates accumulators per segment, the 8 epilogue warps drain each finished accumulator into fp32
+// alternates accumulators per segment, the 16 epilogue warps drain each finished accumulator into fp32
 // registers scaled by the segment's mixing weight while the next segment (or next tile) is being multiplied,
 // and after the last segment apply bias / erf-GELU / optional row-dot, stage the bf16 rows in shared memory and
 // write them with TMA stores — each output element is written exactly once.
@@ -18,7 +18,7 @@
 //   warp 1      tcgen05.mma issuer (one elected lane)
 //   warp 2      TMEM allocator
 //   warp 3      idle
-//   warps 4-11  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 and columns 128*((w-4)/4)..+127 of the tile
+//   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 and columns 64*((w-4)/4)..+63 of the tile
 #include <cuda.h>
 
 #include <mutex>
@@ -32,12 +32,18 @@ constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int GEMM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
-constexpr int OUT_BOX_COLS = 64;                       // one staged output box: 128 rows x 64 bf16 (128-byte rows, 128B swizzle)
-constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;   // 16 KB per column half
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * OUT_BOX_BYTES + 256 /*barriers*/;
+constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the epilogue (erf-GELU, bias, row-dot) is issue/latency bound
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;    // 640
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);         // 64 accumulator columns per epilogue warp
+constexpr int OUT_BOX_COLS = 32;                       // one staged output box: 128 rows x 32 bf16 (64-byte rows, 64B swizzle)
+constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;   // 8 KB per column group
+constexpr int OUT_GROUPS = EPI_WARPS / 4;              // 4 groups of 4 warps, one staging box each
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
+static_assert(MERV_ROWDOT_BLOCK == EPI_COLS, "one row-dot partial per epilogue warp slice");
 constexpr int TMEM_COLS = 512;
+constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 40, EPILOGUE_REGS = 104;  // see setmaxnreg below
+static_assert(GEMM_THREADS * KERNEL_REGS <= 65536, "register file");
+static_assert(128 * PRODUCER_REGS + EPI_WARPS * 32 * EPILOGUE_REGS <= GEMM_THREADS * KERNEL_REGS, "setmaxnreg.inc must fit in what setmaxnreg.dec released");
 
 struct GemmParams {
   int M, N;
@@ -103,9 +109,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+// L2 eviction-priority policies (the encodings createpolicy.fractional.L2::evict_{normal,last} produce for fraction 1.0)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -170,8 +179,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
-  const uint32_t stage_out_addr = tiles_addr + STAGES * STAGE_BYTES;  // 2 x 16 KB, 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + 2 * OUT_BOX_BYTES);
+  const uint32_t stage_out_addr = tiles_addr + STAGES * STAGE_BYTES;  // 4 x 8 KB, 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + OUT_GROUPS * OUT_BOX_BYTES);
   const uint32_t full_bar = smem_u32(bars);                  // [STAGES]
   const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
   const uint32_t tfull_bar = empty_bar + 8 * STAGES;         // [2]
@@ -223,8 +232,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             mbar_wait(empty_bar + 8 * stage, ph ^ 1u);
             mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
-            tma_load_2d(&maps.a[s], full_bar + 8 * stage, sa, kb * BK, m_blk * BM);
-            tma_load_2d(&maps.b[s], full_bar + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN);
+            // activations stream through once per wave of tiles; the weights are re-read by every M block, so they
+            // are kept in L2 preferentially (for the 4096 x 16384 second MLP layer they barely fit: 134 of 126 MB)
+            tma_load_2d(&maps.a[s], full_bar + 8 * stage, sa, kb * BK, m_blk * BM, L2_EVICT_NORMAL);
+            tma_load_2d(&maps.b[s], full_bar + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN, L2_EVICT_LAST);
           }
         }
       }
@@ -255,27 +266,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // Register redistribution happens INSIDE the CTA's launch-time allocation (640 threads x 96 = 61440): warps 0-3 give
+    // back 128 x (96 - 40) = 7168, so the 512 epilogue threads can grow by at most 14 each -> 104 (a larger request
+    // would block forever in setmaxnreg.inc).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     // ===== epilogue =====
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int h = (warp - 4) >> 2;   // column half of the tile
+    const int h = (warp - 4) >> 2;   // column group of the tile: columns 64 h .. 64 h + 63
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
       const int row = m_blk * BM + q * 32 + lane;
       int video = row / p.rows_per_video;
       if (video >= p.num_videos) video = p.num_videos - 1;
-      float sum[128];
+      float sum[EPI_COLS];
 #pragma unroll
-      for (int i = 0; i < 128; ++i) sum[i] = 0.f;
+      for (int i = 0; i < EPI_COLS; ++i) sum[i] = 0.f;
       for (int s = 0; s < p.nseg; ++s, ++acc_it) {
         const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         const float scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
         mbar_wait(tfull_bar + 8 * buf, aph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * 128;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < EPI_COLS / 32; ++c) {
           uint32_t v[32];
           tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
@@ -293,20 +307,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       }
       // ---- finalize: bias, activation, optional row-dot, bf16 pack; rows staged in shared memory (128B swizzle) and
       //      written with TMA stores: fully coalesced, asynchronous, M/N tails clipped by the tensor map ----
-      const int col0 = n_blk * BN + h * 128;
+      const int col0 = n_blk * BN + h * EPI_COLS;
       const bool row_ok = row < p.M;
-      float rowdot = 0.f;
+      float rd[8];  // 8 independent partial sums: no serial dependency chain through the 128 columns
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rd[i] = 0.f;
       const uint32_t my_box = stage_out_addr + h * OUT_BOX_BYTES;
-      const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * 128u;
-      const uint32_t sw = uint32_t(lane & 7);  // (row & 7): the 16-byte chunk index is XOR-ed with it (SWIZZLE_128B)
+      const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * 64u;
+      const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3
       const bool issuer = (warp == 4 + 4 * h) && lane == 0;
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         if (issuer) tma_store_wait_read();  // the previous store has finished reading this staging box
         named_bar_sync(1 + h, 128);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const int cc = pass * 8 + c8;
+        for (int c8 = 0; c8 < 4; ++c8) {
+          const int cc = pass * 4 + c8;
           const int n = col0 + cc * 8;
           uint4 packed = make_uint4(0, 0, 0, 0);
           if (n < p.N) {  // N % 8 == 0 is enforced on the host
@@ -333,7 +349,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
               Vec16<__nv_bfloat16>::unpack(packed, r);  // dot with the values as stored
               const float4* rv = reinterpret_cast<const float4*>(p.rowdot_vec + n);
               const float4 r0 = __ldg(rv), r1 = __ldg(rv + 1);
-              rowdot += r[0] * r0.x + r[1] * r0.y + r[2] * r0.z + r[3] * r0.w + r[4] * r1.x + r[5] * r1.y + r[6] * r1.z + r[7] * r1.w;
+              rd[0] = fmaf(r[0], r0.x, rd[0]); rd[1] = fmaf(r[1], r0.y, rd[1]); rd[2] = fmaf(r[2], r0.z, rd[2]); rd[3] = fmaf(r[3], r0.w, rd[3]);
+              rd[4] = fmaf(r[4], r1.x, rd[4]); rd[5] = fmaf(r[5], r1.y, rd[5]); rd[6] = fmaf(r[6], r1.z, rd[6]); rd[7] = fmaf(r[7], r1.w, rd[7]);
             }
           }
           sts_v4(my_row + ((uint32_t(c8) ^ sw) << 4), packed);
@@ -347,9 +364,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
           tma_store_commit();
         }
       }
-      if (p.rowdot_vec != nullptr && row_ok && col0 < p.N) p.rowdot_out[(long long)row * p.rowdot_nblk + (col0 / MERV_ROWDOT_BLOCK)] = rowdot;
+      if (p.rowdot_vec != nullptr && row_ok && col0 < p.N)
+        p.rowdot_out[(long long)row * p.rowdot_nblk + (col0 / MERV_ROWDOT_BLOCK)] = ((rd[0] + rd[1]) + (rd[2] + rd[3])) + ((rd[4] + rd[5]) + (rd[6] + rd[7]));
     }
-    if ((warp == 4 || warp == 8) && lane == 0) tma_store_wait_all();  // outstanding stores complete before the CTA retires
+    if (((warp - 4) & 3) == 0 && lane == 0) tma_store_wait_all();  // outstanding stores complete before the CTA retires
   }
 
   tc_fence_before();
@@ -441,7 +459,7 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     const cuuint32_t box[3] = {OUT_BOX_COLS, BM, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled(out) failed with CUresult %d (M=%d N=%d ldy=%lld)", int(r), M, N, ldy);
   }
   p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;

@@ -118,6 +118,10 @@ try:
         report[f"gemm_65536x4096x1024_act{act}_ms"] = t
         report[f"gemm_65536x4096x1024_act{act}_TFLOPs"] = tf
         print(f"tcgen05 GEMM 65536x4096x1024 act={act}: {t:.3f} ms = {tf:.0f} TFLOP/s", flush=True)
+    rv = torch.randn(4096, device=dev)
+    t = timeit(lambda: ops.linear_bias_act(a, w, bias, 1, rowdot_vec=rv), n=5)
+    report["gemm_65536x4096x1024_gelu_rowdot_ms"] = t
+    print(f"tcgen05 GEMM 65536x4096x1024 act=1 + row-dot: {t:.3f} ms = {2 * B * 1024 * 4096 * 1024 / t / 1e9:.0f} TFLOP/s", flush=True)
     ref_t = timeit(lambda: torch.nn.functional.linear(a, w, bias), n=5)
     report["cublas_65536x4096x1024_TFLOPs"] = 2 * B * 1024 * 4096 * 1024 / ref_t / 1e9
     print(f"cuBLAS (torch F.linear) same shape: {ref_t:.3f} ms = {report['cublas_65536x4096x1024_TFLOPs']:.0f} TFLOP/s", flush=True)

@@ -123,10 +123,12 @@ def test_tcgen05_linear_matches_oracle(M, N, K, act):
         want = O.gelu_erf(want)
     assert y.shape == (M, N)
     assert O.rel_err(_np(y), want) < 6e-3  # fp32 accumulate, one bf16 rounding of the output
-    # row-dot partials: dot of the STORED row with rv, per 128-column block
-    nblk = (N + 127) // 128
+    # row-dot partials: dot of the STORED row with rv, per MERV_ROWDOT_BLOCK-column block
+    from merv_b200._lib import ROWDOT_BLOCK as RB
+
+    nblk = (N + RB - 1) // RB
     yy = _np(y).astype(np.float64)
-    want_rd = np.stack([(yy[:, j * 128:(j + 1) * 128] * rv[j * 128:(j + 1) * 128]).sum(1) for j in range(nblk)], 1)
+    want_rd = np.stack([(yy[:, j * RB:(j + 1) * RB] * rv[j * RB:(j + 1) * RB]).sum(1) for j in range(nblk)], 1)
     assert rd.shape == (M, nblk)
     assert np.abs(_np(rd) - want_rd).max() < 1e-3 * max(1.0, np.abs(want_rd).max())
 
@@ -461,3 +463,32 @@ def test_backward_unsupported_cases_raise():
     p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(DEV)
     with pytest.raises(NotImplementedError, match="frozen backbones"):
         p(torch.zeros(1, 4, 16, 64, device=DEV, requires_grad=True))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# boundary contract: stream-ordered, no host sync -> CUDA-graph capturable (SURVEY.md §8b "Threading / streams")
+# ---------------------------------------------------------------------------------------------------------
+def test_fused_forward_is_cuda_graph_capturable():
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=True)
+    xs = [_t(f, torch.bfloat16) for f in feats]
+    with torch.inference_mode():
+        want, want_w = m(xs)  # also builds the cached plan and the input-independent vectors outside the capture
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(xs)  # warm the plan for this stream
+            with torch.cuda.graph(graph, stream=side):
+                out, w = m(xs)
+        torch.cuda.synchronize()
+        out.zero_()
+        for x, f in zip(xs, feats):  # new inputs in the captured buffers, then replay
+            x.copy_(_t(f[::-1].copy(), torch.bfloat16))
+        graph.replay()
+        torch.cuda.synchronize()
+        want2, _ = m([_t(f[::-1].copy(), torch.bfloat16) for f in feats])
+    assert torch.equal(out, want2), "graph replay must recompute from the captured input buffers"
+    assert not torch.equal(want, want2)
