@@ -42,6 +42,17 @@ FLOPS_LINEAR = 2 * OUT_TOKENS * LLM_DIM * sum(DIMS)  # 30.065 GFLOP
 FLOPS_GELU = FLOPS_LINEAR + 4 * 2 * OUT_TOKENS * LLM_DIM * LLM_DIM  # 167.5 GFLOP
 
 
+def ncu_traffic_bytes(profile_txt: str):
+    """dram read + write bytes per launch from the committed `ncu --set full` summary under profiles/ (None if absent)."""
+    path = os.path.join(REPO, "profiles", profile_txt)
+    if not os.path.isfile(path):
+        return None
+    for line in open(path):
+        if line.strip().startswith("traffic (dram read + write)"):
+            return float(line.split()[-2]) * 1e6
+    return None
+
+
 def load_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -297,7 +308,9 @@ def main():
     pool_ms = (sum(pool_calls) / args.steps) if pool_calls else None  # per step (module-by-module mode pools each encoder separately)
     if pool_ms:
         gbs = (BYTES_IN + BYTES_POOLED) * B / (pool_ms * 1e-3) / 1e9
-        kernels["merv_pool3d"] = {"bound": "hbm", "ms": pool_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
+        kernels["merv_pool3d"] = {"bound": "hbm", "ms": pool_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                  "algorithmic_bytes": (BYTES_IN + BYTES_POOLED) * B,
+                                  "traffic": ncu_traffic_bytes("r1f_prof_pool3d_tma.txt") if B == 64 else None}
     flops = FLOPS_LINEAR if args.projector == "linear" else FLOPS_GELU
     if args.mode == "fused":
         gemm_name = "merv_fused_linear_mix"
@@ -311,7 +324,11 @@ def main():
         tf = gemm_flops / (g_ms * 1e-3) / 1e12
         roofline = {"kernel": "gemm_bf16_tcgen05_kernel (merv_fused_linear_mix)", "bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"],
                     "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"], "frac_of_burst_peak": tf / peaks["tf_burst"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                    "ms_per_launch": g_ms, "traffic": None}
+                    "ms_per_launch": g_ms,
+                    # ncu capture of this kernel at this exact configuration (B=64, linear, fused), committed under profiles/
+                    "traffic": ncu_traffic_bytes("r1f_prof_gemm_bf16_tcgen05.txt") if (args.projector == "linear" and B == 64) else None,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                    "algorithmic_bytes": (BYTES_POOLED + BYTES_OUT) * B + sum(LLM_DIM * c * 2 for c in DIMS)}
         kernels[gemm_name] = roofline
     elif args.mode == "unfused":
         d = durations.get("merv_linear_bias_act", [])
