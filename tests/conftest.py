@@ -8,8 +8,23 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 
+def _ensure_library_built():
+    """The CUDA library is a build artefact (git-ignored): build it with nvcc if this checkout has none yet.
+    This is the same step as __graft_entry__.build(); there is still no fallback if nvcc is missing."""
+    lib = os.path.join(REPO, "merv_b200", "libmerv_fusion.so")
+    if os.path.isfile(lib):
+        return
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("merv_b200_build", os.path.join(REPO, "merv_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) and the built libmerv_fusion.so")
+    _ensure_library_built()
 
 
 def pytest_collection_modifyitems(config, items):

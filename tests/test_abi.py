@@ -137,3 +137,22 @@ def test_adopts_reference_modules_in_place():
     assert before == after, "patch_merv must keep state-dict keys and share (not copy) the parameters"
     assert isinstance(v.projectors[0], M.AveragePooling3DProjector)
     assert isinstance(v.feature_fusion, M.CrossAttentionAdapterLearnableQuery)
+
+
+def test_product_never_touches_the_oracle_or_a_cpu_path():
+    # The oracle is test infrastructure: nothing under merv_b200/ may import it (or the reference), and the compute
+    # functions must not have a torch fallback branch for CPU tensors.
+    import pathlib
+
+    pkg = pathlib.Path(REPO) / "merv_b200"
+    for path in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*.cu*")):
+        text = path.read_text()
+        for needle in ("import oracle", "from oracle", "/root/reference", "ref_loader", "torch_port"):
+            assert needle not in text, f"{path.name} references {needle!r}"
+    import ast
+
+    tree = ast.parse((pkg / "ops.py").read_text())  # code only: docstrings cite the reference ops they replace
+    called = {ast.unparse(n.func) for n in ast.walk(tree) if isinstance(n, ast.Call)}
+    for needle in ("torch.matmul", "torch.mm", "torch.bmm", "F.linear", "torch.nn.functional.linear", "F.adaptive_avg_pool3d",
+                   "torch.softmax", "F.softmax", "F.gelu", "torch.einsum", "torch.stack"):
+        assert needle not in called, f"ops.py calls a torch compute op: {needle}"
