@@ -21,24 +21,32 @@
 //   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 and columns 64*((w-4)/4)..+63 of the tile
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
 
 namespace merv {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;  // BM = rows per CTA; a CTA pair (cta_group::2) computes 256 x 256
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+// per-CTA stage: its 128 rows of A and, for a CTA pair, its half (128 rows) of the W tile
+template <int kCtas> struct Cfg {
+  static constexpr int STAGES = kCtas == 1 ? 4 : 6;
+  static constexpr int B_ROWS = BN / kCtas;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(STAGES * STAGE_BYTES == 4 * (A_BYTES + BN * BK * 2), "both variants use the same 192 KB ring");
+};
+constexpr int RING_BYTES = 4 * (A_BYTES + BN * BK * 2);
 constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the epilogue (erf-GELU, bias, row-dot) is issue/latency bound
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;    // 640
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);         // 64 accumulator columns per epilogue warp
 constexpr int OUT_BOX_COLS = 32;                       // one staged output box: 128 rows x 32 bf16 (64-byte rows, 64B swizzle)
 constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;   // 8 KB per column group
 constexpr int OUT_GROUPS = EPI_WARPS / 4;              // 4 groups of 4 warps, one staging box each
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
 static_assert(MERV_ROWDOT_BLOCK == EPI_COLS, "one row-dot partial per epilogue warp slice");
 constexpr int TMEM_COLS = 512;
 constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 40, EPILOGUE_REGS = 104;  // see setmaxnreg below
@@ -127,6 +135,42 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completes its bytes on the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int x, int y, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(x), "r"(y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the pair's MMAs so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -173,14 +217,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel -------------------------------------------------------------------------------------------
+// kCtas == 1: one CTA per 128 x 256 tile.  kCtas == 2: a CTA pair (cluster 2x1, cta_group::2) per 256 x 256 tile — each CTA
+// holds its 128 rows of A and HALF of the W tile, the leader's single thread issues UMMA 256x256x16 for both SMs, each
+// CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
+template <int kCtas>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
+  constexpr int STAGES = Cfg<kCtas>::STAGES, STAGE_BYTES = Cfg<kCtas>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
-  const uint32_t stage_out_addr = tiles_addr + STAGES * STAGE_BYTES;  // 4 x 8 KB, 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + OUT_GROUPS * OUT_BOX_BYTES);
+  const uint32_t stage_out_addr = tiles_addr + RING_BYTES;  // 4 x 8 KB, 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES);
   const uint32_t full_bar = smem_u32(bars);                  // [STAGES]
   const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
   const uint32_t tfull_bar = empty_bar + 8 * STAGES;         // [2]
@@ -188,7 +237,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_blocks * p.n_blocks;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
+  const int unit = kCtas == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);  // tile-processing unit: a CTA or a CTA pair
+  const int num_units = int(gridDim.x) / kCtas;
+  const int total_tiles = p.m_blocks * p.n_blocks;  // m_blocks counts (128 * kCtas)-row blocks
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -204,17 +256,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, EPI_WARPS);
+      mbar_init(tempty_bar + 8 * i, EPI_WARPS * kCtas);  // in a pair, both CTAs' epilogue warps arrive on the leader's barrier
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kCtas == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {  // the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // the peer's barriers are initialised before anything remote touches them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -223,15 +281,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     if (warp == 0 && lane == 0) {
       // ===== TMA producer =====
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t leader_full = kCtas == 2 ? mapa_rank(full_bar, 0) : full_bar;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
         for (int s = 0; s < p.nseg; ++s) {
           const int nkb = p.kblocks[s];
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
-            mbar_wait(empty_bar + 8 * stage, ph ^ 1u);
-            mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+            mbar_wait(empty_bar + 8 * stage, ph ^ 1u);  // own barrier: the pair's MMA commit is multicast to both CTAs
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
+            if constexpr (kCtas == 2) {
+              // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
+              if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * STAGE_BYTES);
+              tma_load_2d_pair(&maps.a[s], leader_full + 8 * stage, sa, kb * BK, (m_blk * 2 + int(rank)) * BM, L2_EVICT_NORMAL);
+              tma_load_2d_pair(&maps.b[s], leader_full + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN + int(rank) * (BN / 2), L2_EVICT_LAST);
+              continue;
+            }
+            mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
             // activations stream through once per wave of tiles; the weights are re-read by every M block, so they
             // are kept in L2 preferentially (for the 4096 x 16384 second MLP layer they barely fit: 134 of 126 MB)
             tma_load_2d(&maps.a[s], full_bar + 8 * stage, sa, kb * BK, m_blk * BM, L2_EVICT_NORMAL);
@@ -239,11 +305,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
           }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ===== MMA issuer (the leader CTA's single thread drives both SMs of a pair) =====
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN);
       uint32_t it = 0, acc_it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         for (int s = 0; s < p.nseg; ++s, ++acc_it) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           mbar_wait(tempty_bar + 8 * buf, aph ^ 1u);  // epilogue has drained this accumulator
@@ -257,11 +323,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
             const uint64_t a_desc = umma_desc_sw128(sa), b_desc = umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the address field
-              umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(empty_bar + 8 * stage);  // frees the smem stage once these MMAs have read it
+            for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle atom = +2 in the address field
+              if constexpr (kCtas == 2) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+            if constexpr (kCtas == 2) umma_commit_pair(empty_bar + 8 * stage);
+            else umma_commit(empty_bar + 8 * stage);
           }
-          umma_commit(tfull_bar + 8 * buf);  // accumulator complete -> epilogue
+          // accumulator complete -> epilogue (of both CTAs)
+          if constexpr (kCtas == 2) umma_commit_pair(tfull_bar + 8 * buf);
+          else umma_commit(tfull_bar + 8 * buf);
         }
       }
     }
@@ -274,9 +346,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int h = (warp - 4) >> 2;   // column group of the tile: columns 64 h .. 64 h + 63
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t leader_tempty = kCtas == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
+    for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
-      const int row = m_blk * BM + q * 32 + lane;
+      const int m_base = (m_blk * kCtas + int(rank)) * BM;  // first output row of THIS CTA's half of the tile
+      const int row = m_base + q * 32 + lane;
       int video = row / p.rows_per_video;
       if (video >= p.num_videos) video = p.num_videos - 1;
       float sum[EPI_COLS];
@@ -303,7 +377,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar + 8 * buf);  // accumulator may be overwritten
+        if (lane == 0) {  // accumulator may be overwritten (the MMA issuer lives in the leader CTA)
+          if constexpr (kCtas == 2) mbar_arrive_cluster(leader_tempty + 8 * buf);
+          else mbar_arrive(tempty_bar + 8 * buf);
+        }
       }
       // ---- finalize: bias, activation, optional row-dot, bf16 pack; rows staged in shared memory (128B swizzle) and
       //      written with TMA stores: fully coalesced, asynchronous, M/N tails clipped by the tensor map ----
@@ -358,7 +435,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
         named_bar_sync(1 + h, 128);
         if (issuer && col0 + pass * OUT_BOX_COLS < p.N) {
-          const int m0 = m_blk * BM;
+          const int m0 = m_base;
           const int v0 = p.out_flat ? 0 : m0 / p.rows_per_video;
           tma_store_3d(&maps.out, my_box, col0 + pass * OUT_BOX_COLS, m0 - v0 * p.rows_per_video, v0);
           tma_store_commit();
@@ -371,14 +448,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all();  // the peer may still read this CTA's operands / arrive on its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (kCtas == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
+// Which variant runs.  Measured on B200 (65536 x 4096, bf16): the CTA pair is 5 % faster for a plain K = 1024 GEMM
+// (1288 vs 1229 TFLOP/s: less L2->SM and shared-memory operand traffic) but 2 % slower for the fused 4-segment
+// K = 3584 GEMM (1393 vs 1421), which is power-bound, not operand-bound.  So: pair for plain un-activated GEMMs,
+// single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
+static int gemm_cta_group(int nseg, int act) {
+  const char* e = getenv("MERV_GEMM_CTA_GROUP");
+  if (e != nullptr && e[0] == '1') return 1;
+  if (e != nullptr && e[0] == '2') return 2;
+  return (nseg == 1 && act == MERV_ACT_NONE) ? 2 : 1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -423,13 +515,13 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
                MERV_E_ALIGN, "gemm: Y / bias / rowdot_vec must be 16-byte aligned");
   MERV_REQUIRE(rows_per_video > 0, MERV_E_SHAPE, "gemm: rows_per_video=%d", rows_per_video);
   MERV_REQUIRE((rowdot_vec == nullptr) == (rowdot_out == nullptr), MERV_E_ARG, "gemm: rowdot_vec and rowdot_out go together");
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  // (per-device attribute; cheap enough to set on every call, but once per process per device is enough)
-  attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  (void)attr_once;
-  MERV_REQUIRE(attr_err == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", SMEM_BYTES,
-               cudaGetErrorString(attr_err));
+  const int ctas = gemm_cta_group(nseg, act);
+  {
+    const cudaError_t e1 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    const cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    MERV_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", SMEM_BYTES,
+                 cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  }
 
   TensorMaps maps;
   GemmParams p = {};
@@ -441,7 +533,7 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
                  "gemm: segment %d: K=%d lda=%lld ldw=%lld must be multiples of 8 with ld >= K", s, g.K, g.lda, g.ldw);
     MERV_REQUIRE(aligned16(g.A) && aligned16(g.W), MERV_E_ALIGN, "gemm: segment %d: operands must be 16-byte aligned", s);
     if (int rc = make_tmap(&maps.a[s], g.A, M, g.K, g.lda, BM)) return rc;
-    if (int rc = make_tmap(&maps.b[s], g.W, N, g.K, g.ldw, BN)) return rc;
+    if (int rc = make_tmap(&maps.b[s], g.W, N, g.K, g.ldw, BN / ctas)) return rc;  // a CTA of a pair loads half of the W tile
     p.kblocks[s] = (g.K + BK - 1) / BK;  // the K tail is zero-filled by TMA
   }
   for (int s = nseg; s < MERV_MAX_SEGMENTS; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }
@@ -467,12 +559,29 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   p.bias = static_cast<const __nv_bfloat16*>(bias); p.act = act;
   p.rowdot_vec = rowdot_vec; p.rowdot_out = rowdot_out; p.rowdot_nblk = (N + MERV_ROWDOT_BLOCK - 1) / MERV_ROWDOT_BLOCK;
   p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy;
-  p.m_blocks = (M + BM - 1) / BM; p.n_blocks = (N + BN - 1) / BN;
+  p.m_blocks = (M + BM * ctas - 1) / (BM * ctas); p.n_blocks = (N + BN - 1) / BN;
   const long long total = (long long)p.m_blocks * p.n_blocks;
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
-  const int grid = int(total < sms ? total : sms);
-  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(maps, p);
+  long long units = sms / ctas;  // persistent: one CTA (or CTA pair) per SM (pair)
+  if (units > total) units = total;
+  if (units < 1) units = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(units * ctas));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = unsigned(ctas);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (ctas == 2)
+    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, maps, p));
+  else
+    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1>, maps, p));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }

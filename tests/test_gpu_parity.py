@@ -108,8 +108,11 @@ GEMM_SHAPES = [
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("act", [0, 1])
-def test_tcgen05_linear_matches_oracle(M, N, K, act):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tcgen05_linear_matches_oracle(M, N, K, act, cta_group, monkeypatch):
     from merv_b200 import ops
+
+    monkeypatch.setenv("MERV_GEMM_CTA_GROUP", str(cta_group))  # single-CTA kernel / CTA-pair (cta_group::2) kernel
 
     rng = np.random.default_rng(M + N + K)
     a = _bf16_round(rng.standard_normal((M, K), dtype=np.float32))
@@ -246,6 +249,18 @@ def test_autocast_fp32_master_weights(name):
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
         out, w = m([_t(f, torch.bfloat16) for f in feats])
     assert out.dtype == torch.bfloat16
+    _check_against_golden(case, g, out, w, BF16_TOL, 2e-2)
+
+
+@pytest.mark.parametrize("name", ["mid_linear", "mid_gelu", "merv_full_b1"])
+def test_cta_pair_kernel_through_the_modules(name, monkeypatch):
+    # the whole fused path with every GEMM forced onto the cta_group::2 kernel
+    monkeypatch.setenv("MERV_GEMM_CTA_GROUP", "2")
+    case = C.CASES[name]
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=True)
+    with torch.inference_mode():
+        out, w = m([_t(f, torch.bfloat16) for f in feats])
     _check_against_golden(case, g, out, w, BF16_TOL, 2e-2)
 
 
