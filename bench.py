@@ -105,6 +105,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def make_cpu_inputs(batch: int, seed: int = 7):
     import torch
 
@@ -148,7 +158,7 @@ def reference_arm(args, rank: int, world: int):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, world, note=f"reference CPU path (torch ATen ops of merv/util/nn_utils.py via oracle/torch_port.py), {sample} videos per step"),
-        "cpu_baseline": {"value": value, "unit": "videos/s", "cores": cores, "kind": "port", "sample": f"{sample} merv-full videos per step, bf16, {args.steps} steps after {args.warmup} warm-up"},
+        "cpu_baseline": {"value": value, "unit": "videos/s", "cores": cores, "cpu": cpu_model(), "kind": "port", "sample": f"{sample} merv-full videos per step, bf16, {args.steps} steps after {args.warmup} warm-up"},
         "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fused_tokens_per_s": value * OUT_TOKENS, "gpu_launches": 0,
     }
@@ -171,7 +181,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="videos per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="videos per GPU per step (weak scaling, the default)")
+    ap.add_argument("--global-batch", type=int, default=0, help="if > 0: strong scaling, this many videos per step split over the ranks (SURVEY.md §8d config 3: 64)")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip timing the reference's op sequence in torch eager on the same GPU")
     ap.add_argument("--projector", default="linear", choices=["linear", "gelu-mlp"])
     ap.add_argument("--mode", default="fused", choices=["fused", "unfused"])
     ap.add_argument("--input-sets", type=int, default=3)
@@ -185,6 +197,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    scaling = "weak"
+    if args.global_batch > 0:
+        assert args.global_batch % world == 0, "--global-batch must be a multiple of the number of ranks"
+        args.batch, scaling = args.global_batch // world, "strong"
     if args.impl == "reference":
         return reference_arm(args, rank, world)
     if args.warmup < 3:
@@ -346,20 +362,49 @@ def main():
         kernels.setdefault(name, {"ms": sum(d) / len(d)})
         kernels[name]["calls_per_step"] = len(d) / args.steps
 
+    # second comparator (SURVEY.md §8d "the real bar"): the reference's op sequence in PyTorch eager on this same B200
+    torch_eager = None
+    if world == 1 and not args.no_torch_eager:
+        try:
+            from oracle import torch_port
+
+            pp = [{k: v for k, v in p.projector.state_dict().items()} for p in module.projectors]
+            fp = dict(module.feature_fusion.state_dict())
+            run = lambda i: torch_port.fusion_forward(sets[i % len(sets)], pp, fp, TOKENS_T, 8, args.projector, OUT_TOKENS)  # noqa: E731
+            for i in range(3):
+                ref_out, _ = run(i)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for i in range(5):
+                ref_out, _ = run(i)
+            t1.record()
+            torch.cuda.synchronize()
+            ms_ref = t0.elapsed_time(t1) / 5
+            with torch.inference_mode():
+                ours_out, _ = module(sets[4 % len(sets)])
+            diff = float((ours_out.float() - ref_out.float()).abs().max() / ref_out.float().abs().max())
+            torch_eager = {"value": B / (ms_ref * 1e-3), "unit": "videos/s", "ms_per_step": ms_ref, "speedup_of_this_repo": ms_ref / ms_step,
+                           "max_rel_diff_vs_this_repo": diff,
+                           "what": "oracle/torch_port.py (the reference's ATen op sequence: permute, adaptive_avg_pool3d, F.linear, stack, mean, MHA, bmm) in torch eager bf16 on the same GPU, same inputs"}
+            del ref_out, ours_out
+        except Exception as e:  # a comparator, never a dependency
+            torch_eager = {"error": repr(e)[:200]}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         v, ms, cores = cpu_reference_run(args.projector, args.cpu_sample_videos, 3, 1)
-        cpu_baseline = {"value": v, "unit": "videos/s", "cores": cores, "kind": "port", "ms_per_video": 1e3 / v,
+        cpu_baseline = {"value": v, "unit": "videos/s", "cores": cores, "cpu": cpu_model(), "kind": "port", "ms_per_video": 1e3 / v,
                         "sample": f"{args.cpu_sample_videos} merv-full videos per pass (bf16), 3 passes after 1 warm-up, torch ATen op sequence of the reference (oracle/torch_port.py)"}
 
     line = {
         "metric": "merv-full fusion videos/sec", "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": workload_config(args, world),
         "fused_tokens_per_s": value * OUT_TOKENS,
         "path_effective_GBps_per_gpu": (BYTES_IN + BYTES_OUT) * B / (ms_step * 1e-3) / 1e9,
         "path_TFLOPs_per_gpu": flops * B / (ms_step * 1e-3) / 1e12,
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "torch_eager_same_gpu": torch_eager, "e2e": e2e, "gpu_launches": launches,
         "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "allgather_ms": gather_ms, "output_abs_mean": checksum,
         "peaks": peaks,
     }
