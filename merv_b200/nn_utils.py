@@ -561,7 +561,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
     def _fused_plan(self, projs, xs, vcs, Ws, biases, B) -> "ops.FusedLinearPlan":
         """One cached single-call plan per (shapes, strides, weight versions, stream)."""
         key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), tuple(id(vc[0]) for vc in vcs),
-               tuple(w.data_ptr() for w in Ws), torch.cuda.current_stream(xs[0].device).cuda_stream)
+               tuple(w.data_ptr() for w in Ws), xs[0].device.index, torch.cuda.current_stream(xs[0].device).cuda_stream)
         plans = self.__dict__.setdefault("_plans", {})
         plan = plans.get(key)
         if plan is None:
