@@ -133,13 +133,15 @@ class _CastCache:
     def get(self, p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
         if p is None:
             return None
-        if p.dtype == dtype:
+        if p.dtype == dtype and p.data_ptr() % 16 == 0 and p.is_contiguous():
             return p.detach()
+        # (a same-dtype parameter that is a misaligned / strided view — e.g. FSDP's use_orig_params views into a flat
+        #  buffer, fsdp.py:240 — is copied once per version: TMA and the 128-bit loads need 16-byte aligned rows)
         key = (id(p), dtype)
         tag = (p.data_ptr(), _version(p), tuple(p.shape))
         hit = self._store.get(key)
         if hit is None or hit[0] != tag:
-            hit = (tag, p.detach().to(dtype))
+            hit = (tag, p.detach().to(dtype).contiguous().clone() if p.dtype == dtype else p.detach().to(dtype).contiguous())
             self._store[key] = hit
         return hit[1]
 

@@ -304,9 +304,8 @@ def _full_features(B, seed=7):
     return [(torch.randn(s, generator=g, device=DEV) + mu).to(torch.bfloat16) for s, mu in zip(shapes, mus)]
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_full_size_batch_properties(fused):
-    B = 16
+@pytest.mark.parametrize("fused,B", [(True, 64), (False, 16)])  # B = 64 is BASELINE.json's benchmark batch
+def test_full_size_batch_properties(fused, B):
     m = _full_module(fused)
     feats = _full_features(B)
     with torch.inference_mode():
@@ -507,3 +506,20 @@ def test_fused_forward_is_cuda_graph_capturable():
         want2, _ = m([_t(f[::-1].copy(), torch.bfloat16) for f in feats])
     assert torch.equal(out, want2), "graph replay must recompute from the captured input buffers"
     assert not torch.equal(want, want2)
+
+
+def test_misaligned_parameter_views_are_handled():
+    # FSDP's use_orig_params=True (fsdp.py:240) hands out parameter views at arbitrary element offsets of a flat buffer
+    import merv_b200 as M
+
+    p = M.AveragePooling3DProjector(64, 128, 4, 4, "linear").to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+    lin = p.projector.projector
+    flat = torch.zeros(lin.weight.numel() + 3, device=DEV, dtype=torch.bfloat16)
+    flat[3:].copy_(lin.weight.reshape(-1))
+    x = torch.randn(2, 4, 16, 64, device=DEV).to(torch.bfloat16)
+    with torch.inference_mode():
+        want = p(x)
+        lin.weight.data = flat[3:].view_as(lin.weight)  # 6-byte offset: not 16-byte aligned
+        assert lin.weight.data_ptr() % 16 != 0
+        got = p(x)
+    assert torch.equal(got, want)
