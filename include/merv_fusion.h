@@ -201,11 +201,14 @@ int merv_fused_forward(const merv_fused_desc* d, void* stream);
  * merv/models/vidlms/merv.py:318-320,342-343,363-365; backbones are frozen so nothing flows into the features).
  *   merv_transpose : y[c, r] = x[r, c]           (operands of dW = dY^T P for the K-major tcgen05 GEMM)
  *   merv_colsum    : out[n] = sum_m x[m, n]      (bias gradient), workspace merv_colsum_workspace(M, N) floats
+ *   merv_gelu      : elementwise erf-GELU forward / backward (the training path keeps the pre-activations)
  *   merv_mix_backward : gradients of CrossAttentionAdapterLearnableQuery.forward (nn_utils.py:487-521) w.r.t. every
  *       V_e and Q / q_proj_weight / k_proj_weight / in_proj_bias; v_proj_weight and out_proj get none (the attention
  *       output is discarded in the reference as well).  weights = forward output (fp32), u = merv_fusion_query_vec.
  * ------------------------------------------------------------------------------------------------------- */
 int merv_transpose(const void* x, void* y, int R, int C, int64_t ldx, int64_t ldy, int dtype, void* stream);
+/* out = gelu(z) when dy == NULL, else out = dy * gelu'(z)  (exact erf GELU; MLP projectors in the training step) */
+int merv_gelu(const void* z, const void* dy, void* out, int64_t n, int dtype, void* stream);
 size_t merv_colsum_workspace(int M, int N);
 int merv_colsum(const void* x, void* out, float* workspace, int M, int N, int64_t ld, int dtype, void* stream);
 size_t merv_mix_backward_workspace(int B, int E, int T, int K, int embed);

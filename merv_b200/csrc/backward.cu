@@ -208,6 +208,27 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   if (i < 3 * embed) dbias[i] = from_float<T>(i < embed ? dq[i] : 0.f);  // b_k cancels in the softmax, b_v is dead
 }
 
+// ---- elementwise erf-GELU forward / backward for the MLP projectors' training path (nn.GELU(), nn_utils.py:48) --------
+// y = gelu(z);  dz = dy * gelu'(z),  gelu'(z) = 0.5 (1 + erf(z / sqrt 2)) + z exp(-z^2 / 2) / sqrt(2 pi)
+template <typename T, bool kBackward>
+__global__ void __launch_bounds__(256) gelu_kernel(const T* __restrict__ z, const T* __restrict__ dy, T* __restrict__ out, long long nvec) {
+  constexpr int VEC = Vec16<T>::kN;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (long long)gridDim.x * 256) {
+    float a[VEC], g[VEC], o[VEC];
+    Vec16<T>::unpack(ldg_nc_v4(z + i * VEC), a);
+    if (kBackward) Vec16<T>::unpack(ldg_nc_v4(dy + i * VEC), g);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+      const float cdf = 0.5f * (1.0f + erff(a[c] * 0.70710678118654752440f));
+      if (kBackward)
+        o[c] = g[c] * (cdf + a[c] * 0.3989422804014327f * expf(-0.5f * a[c] * a[c]));
+      else
+        o[c] = a[c] * cdf;
+    }
+    stg_na_v4(out + i * VEC, Vec16<T>::pack(o));
+  }
+}
+
 template <typename T>
 static int launch_mix_dv(const BwdPtrs& p, const void* dOut, const float* weights, const float* ds, const float* u, int B, int E, int Ttok, int K,
                          cudaStream_t s) {
@@ -332,6 +353,32 @@ extern "C" int merv_mix_backward(const void* const* V, const void* dOut, const f
     outer_kernel<T_, T_><<<(unsigned)((nWq + 255) / 256), 256, 0, s>>>(dq, (const T_*)Q, (T_*)dWq, embed, embed, 1.0f);
     gemv_tf_kernel<T_><<<(embed + 31) / 32, 256, 0, s>>>((const T_*)Wq, dq, (T_*)dQ, embed, embed);
     bias_grad_kernel<T_><<<(3 * embed + 255) / 256, 256, 0, s>>>(dq, (T_*)dbias, embed);
+  }
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+// out = gelu(z) (dy == NULL) or out = dy * gelu'(z); n elements, contiguous, n % (16 / sizeof) == 0
+extern "C" int merv_gelu(const void* z, const void* dy, void* out, int64_t n, int dtype, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_gelu: unknown dtype %d", dtype);
+  MERV_REQUIRE(z && out, MERV_E_ARG, "merv_gelu: NULL pointer");
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(n >= 0 && n % vec == 0, MERV_E_SHAPE, "merv_gelu: n=%lld must be a multiple of %d", (long long)n, vec);
+  MERV_REQUIRE(aligned16(z) && aligned16(out) && (dy == nullptr || aligned16(dy)), MERV_E_ALIGN, "merv_gelu: pointers must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  if (n == 0) return MERV_OK;
+  const long long nvec = n / vec;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16) {
+    using T_ = __nv_bfloat16;
+    if (dy) gelu_kernel<T_, true><<<(unsigned)blocks, 256, 0, s>>>((const T_*)z, (const T_*)dy, (T_*)out, nvec);
+    else gelu_kernel<T_, false><<<(unsigned)blocks, 256, 0, s>>>((const T_*)z, nullptr, (T_*)out, nvec);
+  } else {
+    if (dy) gelu_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)z, (const float*)dy, (float*)out, nvec);
+    else gelu_kernel<float, false><<<(unsigned)blocks, 256, 0, s>>>((const float*)z, nullptr, (float*)out, nvec);
   }
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;

@@ -65,30 +65,61 @@ def _needs_grad(module: nn.Module, *tensors) -> bool:
     )
 
 
-class _LinearProjectFn(torch.autograd.Function):
-    """y = x W^T + b through the sm_100a GEMM, with dW = dY^T x (same GEMM on transposed copies) and db = colsum(dY).
-    No gradient flows into x: the backbones are frozen (merv.py:316,339,361) and pooling has no parameters."""
+class _ProjectorFn(torch.autograd.Function):
+    """Linear / gelu-mlp / fused-gelu-mlp projector (nn_utils.py:22-59,86-108) with a hand-written backward.
+
+    forward : Z_i = X_i W_i^T + b_i on the sm_100a GEMM (pre-activations kept), X_{i+1} = gelu(Z_i)
+    backward: dZ_i = dX_{i+1} * gelu'(Z_i);  dW_i = dZ_i^T X_i and dX_i = dZ_i W_i (same GEMM on transposed copies — the
+              kernel is K-major);  db_i = colsum(dZ_i)
+    No gradient flows into the projector input: the backbones are frozen (merv.py:316,339,361) and pooling has no parameters.
+    """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w_c, b_c):
-        y, _ = ops.linear_bias_act(x, w_c, b_c, ACT_NONE)
-        ctx.save_for_backward(x)
-        ctx.meta = (weight.dtype, None if bias is None else bias.dtype)
-        return y
+    def forward(ctx, x, acts, dtype, cache, *params):
+        # params = (W_0, b_0, W_1, b_1, ...) — the nn.Parameters, so autograd routes the gradients; compute-dtype copies from `cache`
+        n = len(acts)
+        xs, zs, ws = [x], [], []
+        for i in range(n):
+            w_c, b_c = cache.get(params[2 * i], dtype), cache.get(params[2 * i + 1], dtype)
+            z, _ = ops.linear_bias_act(xs[-1], w_c, b_c, ACT_NONE)
+            ws.append(w_c)
+            if acts[i] == ACT_GELU_ERF:
+                zs.append(z)
+                xs.append(ops.gelu(z))
+            else:
+                zs.append(None)
+                xs.append(z)
+        ctx.acts = acts
+        ctx.param_dtypes = [p.dtype for p in params]
+        ctx.nz = [z is not None for z in zs]
+        ctx.save_for_backward(*xs[:-1], *[z for z in zs if z is not None], *ws)
+        return xs[-1]
 
     @staticmethod
     def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        wdt, bdt = ctx.meta
-        x2 = x.reshape(-1, x.shape[-1])
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        if dy2.stride(1) != 1:
-            dy2 = dy2.contiguous()
-        if dy2.dtype != x2.dtype:
-            dy2 = dy2.to(x2.dtype)
-        dW, _ = ops.linear_bias_act(ops.transpose(dy2), ops.transpose(x2), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
-        db = ops.colsum(dy2) if bdt is not None else None
-        return None, dW.to(wdt), (None if db is None else db.to(bdt)), None, None
+        n = len(ctx.acts)
+        saved = list(ctx.saved_tensors)
+        xs = saved[:n]
+        nz = sum(ctx.nz)
+        z_it = iter(saved[n:n + nz])
+        zs = [next(z_it) if has else None for has in ctx.nz]
+        ws = saved[n + nz:]
+        g = dy.reshape(-1, dy.shape[-1])
+        if g.dtype != xs[0].dtype:
+            g = g.to(xs[0].dtype)
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        grads = [None] * (2 * n)
+        for i in reversed(range(n)):
+            if zs[i] is not None:
+                g = ops.gelu(zs[i].reshape(g.shape), g)  # dZ_i
+            x2 = xs[i].reshape(-1, xs[i].shape[-1])
+            dW, _ = ops.linear_bias_act(ops.transpose(g), ops.transpose(x2), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
+            grads[2 * i] = dW.to(ctx.param_dtypes[2 * i])
+            grads[2 * i + 1] = ops.colsum(g).to(ctx.param_dtypes[2 * i + 1])
+            if i > 0:
+                g, _ = ops.linear_bias_act(g, ops.transpose(ws[i]), None, ACT_NONE)  # dX_i = dZ_i W_i: [M, N] x [K, N]^T -> [M, K]
+        return (None, None, None, None, *grads)
 
 
 class _MixFn(torch.autograd.Function):
@@ -166,13 +197,10 @@ def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
 def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None, train: bool = False):
     rd = None
     if train:
-        if len(layers) != 1 or layers[0][1] != ACT_NONE:
-            raise NotImplementedError(
-                "the backward is implemented for the 'linear' projector (every shipped config, conf/models.py:103,154); "
-                "gelu-mlp / fused-gelu-mlp train-time gradients are not built yet (SURVEY.md §8 f-1)"
-            )
-        lin = layers[0][0]
-        return _LinearProjectFn.apply(x, lin.weight, lin.bias, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype)), None
+        if any(lin.bias is None for lin, _ in layers):
+            raise NotImplementedError("bias-free projector layers are not covered by the backward")
+        params = [t for lin, _ in layers for t in (lin.weight, lin.bias)]
+        return _ProjectorFn.apply(x, tuple(act for _, act in layers), dtype, cache, *params), None
     for i, (lin, act) in enumerate(layers):
         rv = last_rowdot_vec if i == len(layers) - 1 else None
         x, rd = ops.linear_bias_act(x, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), act, rv)

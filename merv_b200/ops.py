@@ -55,7 +55,7 @@ KERNELS_PER_CALL = {
     "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 4, "merv_softmax_weights_ex": 1,
-    "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10,
+    "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
 }
 
 
@@ -406,6 +406,18 @@ def transpose(x: torch.Tensor) -> torch.Tensor:
         y = torch.empty((Cc, R), dtype=x.dtype, device=dev)
         _call('merv_transpose', lib.merv_transpose, x.data_ptr(), y.data_ptr(), R, Cc, x.stride(0), y.stride(0), dtype_code(x.dtype), _stream())
     return y
+
+
+def gelu(z: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """gelu(z) (exact erf), or dy * gelu'(z) when `dy` is given."""
+    lib = _lib.load()
+    dev = _require_cuda(z, dy)
+    z = z.contiguous()
+    dy = None if dy is None else dy.contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty_like(z)
+        _call('merv_gelu', lib.merv_gelu, z.data_ptr(), _p(dy), out.data_ptr(), z.numel(), dtype_code(z.dtype), _stream())
+    return out
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:
