@@ -376,6 +376,9 @@ class AveragePooling3DProjector(TokenResampler):
             raise NotImplementedError("gradients w.r.t. the patch features are not implemented (frozen backbones, merv.py:316)")
         x = fused_img_patches.detach()
         x = x if x.dtype == dtype else x.to(dtype)
+        if x.shape[0] == 0:
+            y = torch.empty((0, self.output_frames * self.output_size**2, self.llm_dim), dtype=dtype, device=x.device)
+            return (y, None) if rowdot_vec is not None else y
         (pooled,), _ = ops.pool3d([x], [self.output_frames], self.output_size)
         y, rd = _run_layers(pooled, self.layers(), self._cast_cache, dtype, rowdot_vec, train=train)
         return (y, rd) if rowdot_vec is not None else y
@@ -511,6 +514,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         if self.positional_embedding:
             raise NotImplementedError("positional_embedding=True is outside the accelerated hot path (default False)")
         assert 1 <= len(V) <= 8, f"1..8 encoders supported, got {len(V)}"
+        if V[0].shape[0] == 0:  # a rank that owns no videos (merv_b200/parallel.py): nothing to launch
+            dt, dev = (V[0].dtype, V[0].device)
+            return torch.empty((0, self.token_length, self.llm_dim), dtype=dt, device=dev), torch.empty((0, len(V)), dtype=dt, device=dev)
 
         if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
             return self._forward_fused(V, out=out, batch_index=batch_index)

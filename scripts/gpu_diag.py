@@ -151,5 +151,38 @@ except Exception as e:
     report["latency_exception"] = repr(e)
     print("latency exception:", e, flush=True)
 
+try:  # training-shaped call: forward + backward at the reference's per-device batch (conf/models.py:125: 16)
+    import merv_b200 as M
+    from oracle import torch_port
+
+    Bt = 16
+    mod = M.MervFusion.build([1024, 1024, 768, 768], 4096, [16] * 4, 64, "linear", seed=1024).to(device=dev, dtype=torch.bfloat16).train()
+    g = torch.Generator(device=dev).manual_seed(5)
+    feats = [torch.randn((Bt, 16, n, c), generator=g, device=dev).to(torch.bfloat16) for n, c in zip([256, 256, 196, 196], [1024, 1024, 768, 768])]
+    G = torch.randn((Bt, 1024, 4096), generator=g, device=dev).to(torch.bfloat16)
+
+    def ours_step():
+        out, w = mod(feats)
+        out.backward(G)
+        mod.zero_grad(set_to_none=True)
+
+    pp = [{k: v.detach().clone().requires_grad_(True) for k, v in p.projector.state_dict().items()} for p in mod.projectors]
+    fp = {k: v.detach().clone().requires_grad_(True) for k, v in mod.feature_fusion.state_dict().items()}
+
+    def eager_step():
+        out, w = torch_port.fusion_forward_autograd(feats, pp, fp, [16] * 4, 8, "linear", 1024)
+        out.backward(G)
+        for d in pp + [fp]:
+            for t in d.values():
+                t.grad = None
+
+    t_ours = timeit(ours_step, n=10)
+    t_eager = timeit(eager_step, n=10)
+    report["train_step_B16_ms"] = {"ours": t_ours, "torch_eager_reference_ops": t_eager}
+    print(f"training-shaped fwd+bwd B=16 (bf16, linear): ours {t_ours:.3f} ms vs reference op sequence in torch eager {t_eager:.3f} ms", flush=True)
+except Exception as e:
+    report["train_exception"] = repr(e)
+    print("train-step exception:", e, flush=True)
+
 os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
 json.dump(report, open(os.path.join(REPO, "gpurun_out", "diag.json"), "w"), indent=1)

@@ -525,3 +525,34 @@ def test_misaligned_parameter_views_are_handled():
         assert lin.weight.data_ptr() % 16 != 0
         got = p(x)
     assert torch.equal(got, want)
+
+
+def test_empty_batch_and_more_than_four_encoders():
+    import merv_b200 as M
+
+    # (a) an empty batch flows through both paths (a rank that owns no videos, merv_b200/parallel.py)
+    case = C.CASES["tiny_linear"]
+    g, feats, pp, fp = regenerate(case)
+    for fused in (True, False):
+        m = build_module(case, pp, fp, torch.bfloat16, fused=fused)
+        with torch.inference_mode():
+            out, w = m([_t(f[:0], torch.bfloat16) for f in feats])
+        assert out.shape == (0, case.token_length, case.llm_dim) and w.shape == (0, case.num_encoders)
+    # (b) five encoders: beyond the 4 K-segments of the fused GEMM -> the linked module falls back to the module-by-module
+    #     kernels (still sm_100a code, never torch) and must agree with the oracle
+    rng = np.random.default_rng(21)
+    dims, T, S, K, Eb = (64, 64, 48, 48, 32), 4, 4, 128, 96
+    feats5 = [rng.standard_normal((2, T, 16, c), dtype=np.float32) + 0.1 * i for i, c in enumerate(dims)]
+    pp5 = [{"projector.weight": rng.uniform(-0.1, 0.1, (K, c)).astype(np.float32), "projector.bias": rng.uniform(-0.1, 0.1, K).astype(np.float32)} for c in dims]
+    fp5 = C.make_fusion_params(C.Case("five", 2, (T,) * 5, (16,) * 5, dims, K, Eb, (T,) * 5, S))
+    projs = [M.AveragePooling3DProjector(c, K, T, S, "linear") for c in dims]
+    ff = M.CrossAttentionAdapterLearnableQuery(Eb, K, T * S * S, averagetoken=True, num_encoder=5)
+    m5 = M.MervFusion(projs, ff, fused=True)
+    for proj, p in zip(m5.projectors, pp5):
+        proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    ff.load_state_dict({k: torch.from_numpy(v) for k, v in fp5.items()})
+    m5 = m5.to(device=DEV, dtype=torch.float32).eval().requires_grad_(False)
+    with torch.inference_mode():
+        out, w = m5([_t(f) for f in feats5])
+    want, want_w, _ = O.merv_fusion_forward(feats5, pp5, fp5, (T,) * 5, S, "linear", T * S * S)
+    assert O.rel_err(_np(out), want) < FP32_TOL and np.abs(_np(w) - want_w).max() < 2e-5
