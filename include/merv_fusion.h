@@ -141,6 +141,11 @@ int merv_softmax_weights(const float* scores, float* weights, const void* const*
 int merv_softmax_weights_ex(const float* scores, float* weights, void* weights_bf16, const void* const* bias,
                             float* bias_mix, int B, int E, int N, int dtype, void* stream);
 
+/* merv_scores_from_partials + merv_softmax_weights_ex in one launch (bf16 biases), bit-identical to the pair. */
+int merv_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c,
+                                const void* const* bias, float* scores, float* weights, void* weights_bf16,
+                                float* bias_mix, int B, int E, int T, int N, void* stream);
+
 /* out[b,t,:] = sum_e weights[b,e] * V_e[b,t,:]   — replaces torch.stack + torch.bmm at nn_utils.py:503,521.
  * Reads every V_e element once, writes every fused token once.  T_e in {T, 1} (broadcast, nn_utils.py:502).
  * If `scores` is non-NULL the softmax is done in-kernel (warp shuffles over the E lanes) and `weights` is an
@@ -171,7 +176,7 @@ int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* 
  * Whole fused path in ONE call (affine "linear" projectors, bf16): pool -> scores -> softmax -> fused GEMM, i.e.
  * merv/models/vidlms/merv.py:587-589 + 607-609 for the shipped "3davg+linear" + "cross_attention_avg_lq" configs.
  * Exists for the small-batch serving case (generate runs the path once per video at B = 1), where host overhead per
- * launch dominates: 4 kernels are enqueued from one FFI crossing.  All workspaces are caller-provided.
+ * launch dominates: 3 kernels are enqueued from one FFI crossing.  All workspaces are caller-provided.
  *   pool[e]        : as for merv_pool3d; .y is the pooled workspace [B, T*S*S, C_e], .score_vec = v_e (fp32 [C_e]),
  *                    .score_partial = workspace [B, parts_e] (parts_e from merv_pool3d_score_parts)
  *   W, ldw, bias, c: last-layer weights [N, C_e], biases [N] (bf16) and score constants c_e (fp32 [1]) per encoder

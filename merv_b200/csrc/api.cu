@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace merv {
 
@@ -51,6 +52,63 @@ int sm_count() {
     g_dev_sms[dev] = sms;
   }
   return g_dev_sms[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+constexpr int kTmapCacheSize = 128;
+static TmapKey g_tmap_keys[kTmapCacheSize];
+static CUtensorMap g_tmap_vals[kTmapCacheSize];
+static int g_tmap_used = 0, g_tmap_next = 0;
+static std::mutex g_tmap_mutex;
+
+int encode_tmap_cached(CUtensorMap* out, int dtype, int rank, const void* base, const unsigned long long* dims,
+                       const unsigned long long* strides_bytes, const unsigned* box, int swizzle) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));  // padding participates in the memcmp
+  key.base = base; key.dtype = dtype; key.rank = rank; key.swizzle = swizzle;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    for (int i = 0; i < g_tmap_used; ++i)
+      if (g_tmap_keys[i] == key) {
+        *out = g_tmap_vals[i];
+        return MERV_OK;
+      }
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  const CUresult r = enc(out, static_cast<CUtensorMapDataType>(dtype), rank, const_cast<void*>(base), d, st, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, static_cast<CUtensorMapSwizzle>(swizzle), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", int(r), rank, dims[0],
+                rank > 1 ? dims[1] : 1ull, box[0], rank > 1 ? box[1] : 1u);
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  const int slot = g_tmap_used < kTmapCacheSize ? g_tmap_used++ : (g_tmap_next++ % kTmapCacheSize);
+  g_tmap_keys[slot] = key;
+  g_tmap_vals[slot] = *out;
+  return MERV_OK;
 }
 
 }  // namespace merv
@@ -129,8 +187,9 @@ extern "C" int merv_fused_forward(const merv_fused_desc* d, void* stream) {
     A[e] = p.y; lda[e] = p.y_row_stride; K[e] = p.C; partial[e] = p.score_partial;
   }
   if (int rc = merv_pool3d(d->pool, E, d->B, MERV_BF16, 0, stream)) return rc;
-  if (int rc = merv_scores_from_partials(partial, d->parts, d->c, d->scores, d->B, E, d->rows_per_video, stream)) return rc;
-  if (int rc = merv_softmax_weights_ex(d->scores, d->weights, d->weights_bf16, d->bias, d->bias_mix, d->B, E, d->N, MERV_BF16, stream)) return rc;
+  if (int rc = merv_scores_softmax_weights(partial, d->parts, d->c, d->bias, d->scores, d->weights, d->weights_bf16, d->bias_mix, d->B, E,
+                                           d->rows_per_video, d->N, stream))
+    return rc;
   return merv_fused_linear_mix(A, lda, d->W, d->ldw, K, E, d->weights, d->bias_mix, d->out, d->ldo, d->out_batch_stride,
                                d->B * d->rows_per_video, d->N, d->rows_per_video, 0, stream);
 }

@@ -25,6 +25,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace merv {
 
@@ -471,38 +472,13 @@ static int gemm_cta_group(int nseg, int act) {
   return (nseg == 1 && act == MERV_ACT_NONE) ? 2 : 1;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  });
-  return fn;
-}
-
-// 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, 64] with 128-byte swizzle
+// 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
 static int make_tmap(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows, int box_cols = BK) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", int(r), rows, cols, ld);
-  return MERV_OK;
+  const unsigned long long dims[2] = {(unsigned long long)cols, (unsigned long long)rows};
+  const unsigned long long strides[1] = {(unsigned long long)ld * 2};
+  const unsigned box[2] = {(unsigned)box_cols, (unsigned)box_rows};
+  return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
-
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
@@ -544,15 +520,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     MERV_REQUIRE(flat || (rows_per_video % BM == 0 && y_batch_stride % 8 == 0 && y_batch_stride >= (long long)rows_per_video * ldy), MERV_E_SHAPE,
                  "gemm: a batch-strided output needs rows_per_video %% %d == 0 and a 16-byte aligned batch stride >= rows_per_video * ldo", BM);
     p.out_flat = flat ? 1 : 0;
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)(flat ? M : rows_per_video), (cuuint64_t)(flat ? 1 : (M / rows_per_video))};
-    const cuuint64_t strides[2] = {(cuuint64_t)ldy * 2, (cuuint64_t)(flat ? (long long)M * ldy : y_batch_stride) * 2};
-    const cuuint32_t box[3] = {OUT_BOX_COLS, BM, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled(out) failed with CUresult %d (M=%d N=%d ldy=%lld)", int(r), M, N, ldy);
+    const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)(flat ? M : rows_per_video), (unsigned long long)(flat ? 1 : (M / rows_per_video))};
+    const unsigned long long strides[2] = {(unsigned long long)ldy * 2, (unsigned long long)(flat ? (long long)M * ldy : y_batch_stride) * 2};
+    const unsigned box[3] = {OUT_BOX_COLS, BM, 1};
+    if (int rc = encode_tmap_cached(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
   p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;
   p.num_videos = (M + rows_per_video - 1) / rows_per_video;

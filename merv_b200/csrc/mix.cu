@@ -172,6 +172,42 @@ __global__ void __launch_bounds__(256) softmax_weights_kernel(const float* __res
   if (n < N) bias_mix[(long long)b * N + n] = acc;
 }
 
+// scores -> softmax -> weights (+ bf16 copy) -> bias_mix in ONE launch (small-batch latency: merv_fused_forward).  The
+// score reduction repeats partial_score_kernel's exact summation order in every block, so the results are bit-identical
+// to the two-kernel sequence.
+template <typename T>
+__global__ void __launch_bounds__(256) scores_softmax_kernel(const __grid_constant__ PartialParams pp, const __grid_constant__ BiasParams bp,
+                                                             float* __restrict__ scores, float* __restrict__ weights,
+                                                             __nv_bfloat16* __restrict__ weights_bf16, float* __restrict__ bias_mix, int E,
+                                                             int Ttok, int N) {
+  __shared__ float red[32];
+  __shared__ float sc[MERV_MAX_ENCODERS];
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  for (int e = 0; e < E; ++e) {
+    const int n = pp.count[e];
+    const float* src = pp.p[e] + (long long)b * n;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) acc += src[i];
+    acc = block_sum<256>(acc, red);
+    if (threadIdx.x == 0) sc[e] = acc / float(Ttok) + (pp.c[e] ? *pp.c[e] : 0.f);
+  }
+  __syncthreads();
+  const float w = warp_softmax_over_encoders(lane < E ? sc[lane] : 0.f, lane, E);
+  if (blockIdx.x == 0 && threadIdx.x < E) {
+    scores[(long long)b * E + threadIdx.x] = sc[threadIdx.x];
+    weights[(long long)b * E + threadIdx.x] = w;
+    if (weights_bf16 != nullptr) weights_bf16[(long long)b * E + threadIdx.x] = __float2bfloat16_rn(w);
+  }
+  const int nn = blockIdx.x * 256 + threadIdx.x;
+  float acc = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const float we = __shfl_sync(0xffffffffu, w, e);
+    const T* be = static_cast<const T*>(bp.bias[e]);
+    if (be != nullptr && nn < N) acc += we * to_float(be[nn]);
+  }
+  if (nn < N) bias_mix[(long long)b * N + nn] = acc;
+}
+
 // ---- out[b,t,:] = sum_e w[b,e] * V_e[b,t,:]  (HBM-bound: E reads + 1 write per element, each exactly once) --
 struct MixParams {
   const void* V[MERV_MAX_ENCODERS];
@@ -427,4 +463,28 @@ extern "C" int merv_softmax_mix(const void* const* V, const int32_t* tokens, con
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MERV_BF16) return launch_mix<__nv_bfloat16>(p, scores, weights, out, B, E, T, K, s);
   return launch_mix<float>(p, scores, weights, out, B, E, T, K, s);
+}
+
+// merv_scores_from_partials + merv_softmax_weights_ex in one launch (bf16 biases); used by merv_fused_forward
+extern "C" int merv_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
+                                           float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
+                                           void* stream) {
+  MERV_REQUIRE(partial && count && bias && scores && weights && bias_mix, MERV_E_ARG, "merv_scores_softmax_weights: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_softmax_weights: E=%d", E);
+  MERV_REQUIRE(B >= 0 && T > 0 && N > 0, MERV_E_SHAPE, "merv_scores_softmax_weights: B=%d T=%d N=%d", B, T, N);
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  PartialParams pp = {};
+  BiasParams bp = {};
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(partial[e] && count[e] > 0, MERV_E_ARG, "merv_scores_softmax_weights: encoder %d: NULL partials or count=%d", e, count[e]);
+    pp.p[e] = partial[e];
+    pp.c[e] = c ? c[e] : nullptr;
+    pp.count[e] = count[e];
+    bp.bias[e] = bias[e];
+  }
+  scores_softmax_kernel<__nv_bfloat16><<<dim3((N + 255) / 256, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pp, bp, scores, weights, static_cast<__nv_bfloat16*>(weights_bf16), bias_mix, E, T, N);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
 }

@@ -30,6 +30,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tmap.cuh"
 
 namespace merv {
 
@@ -476,22 +477,6 @@ static bool use_tma(const merv_pool_desc* enc, int n, int dtype) {
   return true;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn pool_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  });
-  return fn;
-}
-
 static int validate(const merv_pool_desc* enc, int num_encoders, int B, int dtype) {
   MERV_REQUIRE(enc != nullptr, MERV_E_ARG, "merv_pool3d: enc is NULL");
   MERV_REQUIRE(num_encoders >= 1 && num_encoders <= MERV_MAX_ENCODERS, MERV_E_ARG,
@@ -521,8 +506,6 @@ static int validate(const merv_pool_desc* enc, int num_encoders, int B, int dtyp
 
 template <typename T>
 static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, int max_ctas, cudaStream_t s) {
-  EncodeTiledFn encode = pool_encode_fn();
-  if (encode == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int es = sizeof(T);
   PoolTmaMaps maps;
   PoolTmaParams p = {};
@@ -539,17 +522,14 @@ static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, int ma
     begin += e.items;
     e.ybs = d.y_batch_stride; e.yrs = d.y_row_stride;
     // x as a 5-D tensor (C, W, H, F, B), channel innermost; one box = the [nf_max, H, W, cb] slab of one output frame
-    const cuuint64_t dims[5] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.F,
-                                (cuuint64_t)(d.batch_index && d.src_batch > 0 ? d.src_batch : B)};
-    const cuuint64_t strides[4] = {(cuuint64_t)d.x_token_stride * es, (cuuint64_t)d.x_token_stride * d.W * es,
-                                   (cuuint64_t)d.x_frame_stride * es, (cuuint64_t)d.x_batch_stride * es};
-    const cuuint32_t box[5] = {(cuuint32_t)pl.cb, (cuuint32_t)d.W, (cuuint32_t)d.H, (cuuint32_t)pl.nf_max, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = encode(&maps.m[i], es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
-                              const_cast<void*>(d.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-      return fail(MERV_E_CUDA, "merv_pool3d: cuTensorMapEncodeTiled failed with CUresult %d for encoder %d (F=%d H=%d W=%d C=%d)", int(r), i, d.F, d.H, d.W, d.C);
+    const unsigned long long dims[5] = {(unsigned long long)d.C, (unsigned long long)d.W, (unsigned long long)d.H, (unsigned long long)d.F,
+                                        (unsigned long long)(d.batch_index && d.src_batch > 0 ? d.src_batch : B)};
+    const unsigned long long strides[4] = {(unsigned long long)d.x_token_stride * es, (unsigned long long)d.x_token_stride * d.W * es,
+                                           (unsigned long long)d.x_frame_stride * es, (unsigned long long)d.x_batch_stride * es};
+    const unsigned box[5] = {(unsigned)pl.cb, (unsigned)d.W, (unsigned)d.H, (unsigned)pl.nf_max, 1};
+    if (int rc = encode_tmap_cached(&maps.m[i], es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, d.x, dims, strides,
+                                    box, CU_TENSOR_MAP_SWIZZLE_NONE))
+      return rc;
   }
   for (int i = n; i < MERV_MAX_ENCODERS; ++i) maps.m[i] = maps.m[0];
   p.total_items = begin;

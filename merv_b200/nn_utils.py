@@ -582,7 +582,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
         timer = ops._timer
         if all(len(p.layers()) == 1 for p in projs) and (timer is None or not timer.timing) and (out is None or out.dim() == 3):
-            return self._fused_plan(projs, xs, vcs, Ws, biases, B).run(xs, out, batch_index)
+            plan = self._fused_plan(projs, xs, vcs, Ws, biases, B)
+            self.__dict__["_last_plan"] = plan
+            return plan.run(xs, out, batch_index)
         acts, partials = self._fused_stage1(projs, xs, vcs, dtype, batch_index=batch_index)
         scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
         weights, bias_mix = ops.softmax_weights(scores, biases, K)
@@ -690,8 +692,49 @@ class MervFusion(nn.Module):
                                                      averagetoken=True, num_encoder=len(projs))
         return cls(projs, fusion, fused=fused)
 
+    # ---- small-batch fast path: skip the per-module Python glue when nothing changed since the last call -------------
+    def _param_tag(self):
+        ff = self.feature_fusion
+        ps = [ff.Q, ff.attention.q_proj_weight, ff.attention.k_proj_weight, ff.attention.in_proj_bias]
+        for p in self.projectors:
+            lin = p.projector.projector
+            ps += [lin.weight, lin.bias]
+        return tuple((t.data_ptr(), _version(t)) for t in ps)
+
+    def _fast_forward(self, xs, out, batch_index):
+        """Re-run the cached single-call plan (ops.FusedLinearPlan) if shapes, strides, stream and every parameter version
+        are unchanged; returns None when the general path has to (re)build it.  Saves ~50 us of Python per call, which is
+        most of the cost at B = 1."""
+        ff = self.feature_fusion
+        timer = ops._timer
+        if (timer is not None and timer.timing) or not isinstance(ff, CrossAttentionAdapterLearnableQuery):
+            return None
+        x0 = xs[0]
+        if not x0.is_cuda or x0.shape[0] == 0 or any(x.dtype != torch.bfloat16 for x in xs) or (out is not None and out.dim() != 3):
+            return None
+        key = (tuple((x.shape, x.stride()) for x in xs), None if batch_index is None else batch_index.numel(), x0.device.index,
+               torch.cuda.current_stream(x0.device).cuda_stream)
+        cache = self.__dict__.setdefault("_fast", {})
+        hit = cache.get(key)
+        if hit is not None and hit[0] == self._param_tag():
+            return hit[1].run(xs, out, batch_index)
+        # general path once; remember the plan it used (if it took the single-call route)
+        ff.__dict__["_last_plan"] = None
+        projected = [proj(x) for proj, x in zip(self.projectors, xs)]
+        res = ff(projected, out=out, batch_index=batch_index) if (out is not None or batch_index is not None) else ff(projected)
+        plan = ff.__dict__.get("_last_plan")
+        if plan is not None and all(isinstance(p.projector, LinearProjector) for p in self.projectors):
+            if len(cache) >= 8:
+                cache.clear()
+            cache[key] = (self._param_tag(), plan)
+        return res
+
     def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
                 batch_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if not torch.is_grad_enabled() and len(self.projectors) and self.projectors[0]._linked_fusion is not None:
+            res = self._fast_forward(patch_features, out, batch_index)
+            if res is not None:
+                return res
         projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
         if out is None and batch_index is None:
             return self.feature_fusion(projected)

@@ -54,7 +54,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 KERNELS_PER_CALL = {
     "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
-    "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 4, "merv_softmax_weights_ex": 1,
+    "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
 }
 
