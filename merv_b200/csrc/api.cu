@@ -1,5 +1,6 @@
 // extern "C" surface shared by all kernels: error state, device checks, GEMM entry points.
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "tmap.cuh"
@@ -7,13 +8,6 @@
 namespace merv {
 
 static thread_local char g_error[512] = "";
-
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_error, sizeof(g_error), fmt, ap);
-  va_end(ap);
-}
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;

@@ -13,7 +13,6 @@
 namespace merv {
 
 // ---- host-side error plumbing -----------------------------------------------------------------------------
-void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 
 #define MERV_CUDA_OK(expr)                                                                            \

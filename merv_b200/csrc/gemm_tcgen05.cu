@@ -22,7 +22,6 @@
 #include <cuda.h>
 
 #include <cstdlib>
-#include <mutex>
 
 #include "common.cuh"
 #include "tmap.cuh"

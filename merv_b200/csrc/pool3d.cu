@@ -27,7 +27,6 @@
 
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 
 #include "common.cuh"
 #include "tmap.cuh"
