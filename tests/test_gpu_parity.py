@@ -556,3 +556,23 @@ def test_empty_batch_and_more_than_four_encoders():
         out, w = m5([_t(f) for f in feats5])
     want, want_w, _ = O.merv_fusion_forward(feats5, pp5, fp5, (T,) * 5, S, "linear", T * S * S)
     assert O.rel_err(_np(out), want) < FP32_TOL and np.abs(_np(w) - want_w).max() < 2e-5
+
+
+def test_backbone_output_layouts_are_read_in_place():
+    # the backbones' native outputs are strided views, not fresh tensors:
+    #   LanguageBind  [B, 16, 257, C] with a CLS token in front of every frame  (languagebind/__init__.py:85-101)
+    #   ViViT         [B, 1 + 16*196, C] with one leading CLS token             (vivit.py:105-114)
+    # both must flow through the fused path without a copy and give the same result as their contiguous twins
+    import merv_b200 as M
+
+    m = M.MervFusion.build([64, 48], 128, [4, 4], 16, "linear", text_embedding_dim=96, seed=3).to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    lb_full = torch.randn((3, 4, 17, 64), generator=g, device=DEV).to(torch.bfloat16)       # 16 patches + CLS per frame
+    vv_full = torch.randn((3, 1 + 4 * 49, 48), generator=g, device=DEV).to(torch.bfloat16)  # CLS + 4 frames x 49 patches
+    lb = lb_full[:, :, 1:, :]
+    vv = vv_full[:, 1:, :].reshape(3, 4, 49, 48)  # merv.py:576-585 reshape: still a view
+    assert not lb.is_contiguous() and not vv.is_contiguous() and vv.data_ptr() == vv_full.data_ptr() + 48 * 2
+    with torch.inference_mode():
+        out_v, w_v = m([lb, vv])
+        out_c, w_c = m([lb.contiguous(), vv.contiguous()])
+    assert torch.equal(out_v, out_c) and torch.equal(w_v, w_c)
