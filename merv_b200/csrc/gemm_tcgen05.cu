@@ -462,13 +462,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 // ---- host side ---------------------------------------------------------------------------------------------
 // Which variant runs.  Measured on B200 (65536 x 4096, bf16): the CTA pair is 5 % faster for a plain K = 1024 GEMM
 // (1288 vs 1229 TFLOP/s: less L2->SM and shared-memory operand traffic) but 2 % slower for the fused 4-segment
-// K = 3584 GEMM (1393 vs 1421), which is power-bound, not operand-bound.  So: pair for plain un-activated GEMMs,
-// single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
-static int gemm_cta_group(int nseg, int act) {
+// K = 3584 GEMM (1393 vs 1421), which is power-bound, not operand-bound; for the fused K = 16384 GEMM it is 3 % faster
+// again.  So: pair for plain un-activated GEMMs and very deep fused ones, single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
+static int gemm_cta_group(int nseg, int act, long long total_k) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
-  return (nseg == 1 && act == MERV_ACT_NONE) ? 2 : 1;
+  if (nseg == 1) return act == MERV_ACT_NONE ? 2 : 1;  // the GELU epilogue, not the operands, bounds the activated GEMM
+  return total_k >= 8192 ? 2 : 1;  // fused K = 4 x 4096 (second MLP layer): pair 6.30 ms vs 6.47; fused K = 3584: single wins
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
@@ -490,7 +491,9 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
                MERV_E_ALIGN, "gemm: Y / bias / rowdot_vec must be 16-byte aligned");
   MERV_REQUIRE(rows_per_video > 0, MERV_E_SHAPE, "gemm: rows_per_video=%d", rows_per_video);
   MERV_REQUIRE((rowdot_vec == nullptr) == (rowdot_out == nullptr), MERV_E_ARG, "gemm: rowdot_vec and rowdot_out go together");
-  const int ctas = gemm_cta_group(nseg, act);
+  long long total_k = 0;
+  for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
+  const int ctas = gemm_cta_group(nseg, act, total_k);
   {
     const cudaError_t e1 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     const cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
