@@ -172,6 +172,16 @@ int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* 
                           int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
                           void* stream);
 
+/* Fused GEMM + all-gather over NVLink peer memory: as merv_fused_linear_mix, and every finished output tile is ALSO stored
+ * (TMA stores to peer-mapped addresses) to the same rows of `peer_out[0..num_peers)` — the other ranks' symmetric prefix
+ * buffers, already offset to this rank's block of videos.  The transfer overlaps the tensor-core work tile by tile; the
+ * caller synchronises the ranks afterwards (e.g. the symmetric-memory barrier).  Replaces "compute, then ncclAllGather"
+ * for consumers that want the whole batch's prefixes on every rank.  num_peers <= 7. */
+int merv_fused_linear_mix_gather(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                 const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                 int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
+                                 void* const* peer_out, int num_peers, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Whole fused path in ONE call (affine "linear" projectors, bf16): pool -> scores -> softmax -> fused GEMM, i.e.
  * merv/models/vidlms/merv.py:587-589 + 607-609 for the shipped "3davg+linear" + "cross_attention_avg_lq" configs.

@@ -146,9 +146,10 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
   return launch_gemm_simt(A, lda, W, ldw, bias, Y, ldy, M, N, K, act, dtype, s);
 }
 
-extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
-                                     const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
-                                     int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas, void* stream) {
+extern "C" int merv_fused_linear_mix_gather(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                            const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                            int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
+                                            void* const* peer_out, int num_peers, void* stream) {
   MERV_REQUIRE(A && lda && W && ldw && K && scale && out, MERV_E_ARG, "merv_fused_linear_mix: NULL pointer");
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_linear_mix: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M >= 0 && N > 0 && rows_per_video > 0, MERV_E_SHAPE, "merv_fused_linear_mix: M=%d N=%d rows_per_video=%d", M, N, rows_per_video);
@@ -158,7 +159,14 @@ extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, c
   GemmSegment seg[MERV_MAX_SEGMENTS];
   for (int s = 0; s < nseg; ++s) seg[s] = GemmSegment{A[s], lda[s], W[s], ldw[s], K[s]};
   return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, out_batch_stride,
-                             M, N, max_ctas, static_cast<cudaStream_t>(stream));
+                             M, N, max_ctas, static_cast<cudaStream_t>(stream), peer_out, num_peers);
+}
+
+extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                     const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                     int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas, void* stream) {
+  return merv_fused_linear_mix_gather(A, lda, W, ldw, K, nseg, scale, bias_mix, out, ldo, out_batch_stride, M, N, rows_per_video, max_ctas,
+                                      nullptr, 0, stream);
 }
 
 extern "C" int merv_fused_forward(const merv_fused_desc* d, void* stream) {

@@ -40,7 +40,7 @@ struct GemmSegment {
 };
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream);
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out = nullptr, int num_extra = 0);
 int launch_gemm_simt(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* Y, long long ldy,
                      int M, int N, int K, int act, int dtype, cudaStream_t s);
 

@@ -69,13 +69,16 @@ struct GemmParams {
   __nv_bfloat16* Y;
   long long ldy;
   int m_blocks, n_blocks;
+  int num_out;   // destinations of every output tile: 1 (local) + peers' buffers over NVLink (fused all-gather)
   int out_flat;  // 1: Y is one contiguous [M, N] matrix (output map = [1, M, N]); 0: [videos, rows_per_video, N] with a batch stride
 };
 
 struct TensorMaps {
   CUtensorMap a[MERV_MAX_SEGMENTS];
   CUtensorMap b[MERV_MAX_SEGMENTS];
-  CUtensorMap out;  // Y as [videos, rows_per_video, N] (batch stride may exceed rows_per_video * ldy), boxes of 128 x 64
+  // Y as [videos, rows_per_video, N] (batch stride may exceed rows_per_video * ldy), boxes of 128 x 32; out[0] is the local
+  // destination, out[1..] the same rows of the peers' symmetric buffers (peer-mapped addresses)
+  CUtensorMap out[MERV_MAX_ENCODERS];
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------
@@ -247,7 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       prefetch_tmap(&maps.a[s]);
       prefetch_tmap(&maps.b[s]);
     }
-    prefetch_tmap(&maps.out);
+    for (int d = 0; d < p.num_out; ++d) prefetch_tmap(&maps.out[d]);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -437,7 +440,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         if (issuer && col0 + pass * OUT_BOX_COLS < p.N) {
           const int m0 = m_base;
           const int v0 = p.out_flat ? 0 : m0 / p.rows_per_video;
-          tma_store_3d(&maps.out, my_box, col0 + pass * OUT_BOX_COLS, m0 - v0 * p.rows_per_video, v0);
+          for (int d = 0; d < p.num_out; ++d)  // fused all-gather: the same box goes to every rank's buffer
+            tma_store_3d(&maps.out[d], my_box, col0 + pass * OUT_BOX_COLS, m0 - v0 * p.rows_per_video, v0);
           tma_store_commit();
         }
       }
@@ -482,7 +486,7 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream) {
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -525,7 +529,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)(flat ? M : rows_per_video), (unsigned long long)(flat ? 1 : (M / rows_per_video))};
     const unsigned long long strides[2] = {(unsigned long long)ldy * 2, (unsigned long long)(flat ? (long long)M * ldy : y_batch_stride) * 2};
     const unsigned box[3] = {OUT_BOX_COLS, BM, 1};
-    if (int rc = encode_tmap_cached(&maps.out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, Y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    MERV_REQUIRE(num_extra >= 0 && num_extra < MERV_MAX_ENCODERS && (num_extra == 0 || extra_out != nullptr), MERV_E_ARG,
+                 "gemm: %d extra output destinations (at most %d)", num_extra, MERV_MAX_ENCODERS - 1);
+    p.num_out = 1 + num_extra;
+    for (int d = 0; d < p.num_out; ++d) {
+      void* base = d == 0 ? Y : extra_out[d - 1];
+      MERV_REQUIRE(base != nullptr && aligned16(base), MERV_E_ALIGN, "gemm: output destination %d is NULL or not 16-byte aligned", d);
+      if (int rc = encode_tmap_cached(&maps.out[d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    }
+    for (int d = p.num_out; d < MERV_MAX_ENCODERS; ++d) maps.out[d] = maps.out[0];
   }
   p.seg_scale = seg_scale; p.bias_rows = bias_rows; p.rows_per_video = rows_per_video;
   p.num_videos = (M + rows_per_video - 1) / rows_per_video;

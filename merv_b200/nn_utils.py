@@ -501,7 +501,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         return hit[1]
 
     # ---- forward --------------------------------------------------------------------------------------------
-    def forward(self, V, out: Optional[torch.Tensor] = None, batch_index: Optional[torch.Tensor] = None):
+    def forward(self, V, out: Optional[torch.Tensor] = None, batch_index: Optional[torch.Tensor] = None, gather=None):
         # V is a list of tensors with size (B, T, K). T should all be same, or 1.  (nn_utils.py:491-495)
         # `out` / `batch_index` are extensions of the linked (fused) path only, see _forward_fused.
         for emb in V:
@@ -519,9 +519,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             return torch.empty((0, self.token_length, self.llm_dim), dtype=dt, device=dev), torch.empty((0, len(V)), dtype=dt, device=dev)
 
         if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
-            return self._forward_fused(V, out=out, batch_index=batch_index)
-        if out is not None or batch_index is not None:
-            raise NotImplementedError("out= / batch_index= are supported on the linked bf16 path only")
+            return self._forward_fused(V, out=out, batch_index=batch_index, gather=gather)
+        if out is not None or batch_index is not None or gather is not None:
+            raise NotImplementedError("out= / batch_index= / gather= are supported on the linked bf16 path only")
         V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
         if _needs_grad(self, *V):
             if any(v.shape[1] != self.token_length for v in V):
@@ -564,7 +564,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         return acts, partials
 
     def _forward_fused(self, V: Sequence[DeferredProjection], out: Optional[torch.Tensor] = None,
-                       batch_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       batch_index: Optional[torch.Tensor] = None, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """pool (one launch) -> hidden layers -> scores -> one tcgen05 GEMM with the mix in its epilogue.
 
         `out`: optional [B, T, K] bf16 view (any batch stride) the prefix is written into, e.g. the prefix slot of the
@@ -580,6 +580,17 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
         biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
         Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
+        if gather is not None:
+            # fused all-gather (merv_b200.parallel.SymmetricPrefixBuffer): every output tile is also stored into this rank's
+            # block of the other ranks' buffers over NVLink while the GEMM is still running; returns the WHOLE batch's prefixes
+            assert out is None and B == gather.batch_per_rank and T * K * 2 * B == gather.block_bytes
+            acts, partials = self._fused_stage1(projs, xs, vcs, dtype, batch_index=batch_index)
+            scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
+            weights, bias_mix = ops.softmax_weights(scores, biases, K)
+            gather.barrier()  # every rank has finished reading the previous contents of the buffers
+            ops.fused_linear_mix(acts, Ws, weights, bias_mix, T, out=gather.local_block(), peer_out_ptrs=gather.peer_block_ptrs())
+            gather.barrier()  # every rank's stores have landed
+            return gather.buf, weights.to(dtype)
         timer = ops._timer
         if all(len(p.layers()) == 1 for p in projs) and (timer is None or not timer.timing) and (out is None or out.dim() == 3):
             plan = self._fused_plan(projs, xs, vcs, Ws, biases, B)
@@ -730,7 +741,10 @@ class MervFusion(nn.Module):
         return res
 
     def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
-                batch_index: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                batch_index: Optional[torch.Tensor] = None, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if gather is not None:  # fused all-gather of the prefixes over NVLink (parallel.SymmetricPrefixBuffer)
+            projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
+            return self.feature_fusion(projected, batch_index=batch_index, gather=gather)
         if not torch.is_grad_enabled() and len(self.projectors) and self.projectors[0]._linked_fusion is not None:
             res = self._fast_forward(patch_features, out, batch_index)
             if res is not None:

@@ -68,3 +68,39 @@ def fusion_forward_sharded(module, features: Sequence[torch.Tensor], gather: boo
         return prefix, weights
     w3 = all_gather_prefix(weights.unsqueeze(-1), batch, group).squeeze(-1)
     return all_gather_prefix(prefix, batch, group), w3
+
+
+class SymmetricPrefixBuffer:
+    """The whole batch's fused prefixes `[world * batch_per_rank, T, K]` (bf16) in NVLink peer-mapped symmetric memory.
+
+    Passed as `gather=` to a linked `MervFusion` / adapter call, the fused projector+mix GEMM stores every finished output
+    tile into this rank's block of EVERY rank's buffer with TMA stores to peer addresses (`merv_fused_linear_mix_gather`):
+    the all-gather rides on the GEMM's epilogue, tile by tile, instead of running as a separate NCCL collective afterwards.
+    Memory comes from `torch.distributed._symmetric_memory` (plumbing: allocation, rendezvous, barriers).
+    """
+
+    def __init__(self, batch_per_rank: int, tokens: int, width: int, group: Optional[dist.ProcessGroup] = None,
+                 device: Optional[torch.device] = None) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world <= 8, "the fused GEMM stores to at most 7 peers"
+        self.batch_per_rank = batch_per_rank
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty((self.world * batch_per_rank, tokens, width), dtype=torch.bfloat16, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.block_bytes = batch_per_rank * tokens * width * 2
+
+    def local_block(self) -> torch.Tensor:
+        lo = self.rank * self.batch_per_rank
+        return self.buf[lo:lo + self.batch_per_rank]
+
+    def peer_block_ptrs(self) -> List[int]:
+        """Addresses of THIS rank's block inside every other rank's buffer (peer-mapped device pointers)."""
+        ptrs = self.handle.buffer_ptrs
+        return [int(ptrs[p]) + self.rank * self.block_bytes for p in range(self.world) if p != self.rank]
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier across the ranks (device-side signals; no host synchronisation)."""
+        self.handle.barrier()
