@@ -32,21 +32,24 @@ constexpr int BM = 128, BN = 256, BK = 64;  // BM = rows per CTA; a CTA pair (ct
 constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 // per-CTA stage: its 128 rows of A and, for a CTA pair, its half (128 rows) of the W tile
-template <int kCtas> struct Cfg {
-  static constexpr int STAGES = kCtas == 1 ? 4 : 6;
+constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the epilogue (erf-GELU, bias, row-dot) is issue/latency bound
+constexpr int OUT_GROUPS = EPI_WARPS / 4;              // 4 groups of 4 warps, one staging box each
+// kWide (the fused all-gather variant): output boxes of 128-byte rows instead of 64-byte rows — NVLink peer writes are
+// packetised per box row, and 64-byte payloads only reach ~380 GB/s of egress — paid for with one ring stage.
+template <int kCtas, bool kWide> struct Cfg {
+  static constexpr int STAGES = (kCtas == 1 ? 4 : 6) - (kWide ? 1 : 0);
   static constexpr int B_ROWS = BN / kCtas;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static_assert(STAGES * STAGE_BYTES == 4 * (A_BYTES + BN * BK * 2), "both variants use the same 192 KB ring");
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;  // 192 KB (144 / 160 KB when wide)
+  static constexpr int OUT_BOX_COLS = kWide ? 64 : 32;      // one staged output box: 128 rows x 32 (64) bf16, 64B (128B) swizzle
+  static constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
+  static_assert(RING_BYTES % 1024 == 0 && OUT_BOX_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned boxes");
+  static_assert(SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 };
-constexpr int RING_BYTES = 4 * (A_BYTES + BN * BK * 2);
-constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the epilogue (erf-GELU, bias, row-dot) is issue/latency bound
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;    // 640
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);         // 64 accumulator columns per epilogue warp
-constexpr int OUT_BOX_COLS = 32;                       // one staged output box: 128 rows x 32 bf16 (64-byte rows, 64B swizzle)
-constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;   // 8 KB per column group
-constexpr int OUT_GROUPS = EPI_WARPS / 4;              // 4 groups of 4 warps, one staging box each
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
 static_assert(MERV_ROWDOT_BLOCK == EPI_COLS, "one row-dot partial per epilogue warp slice");
 constexpr int TMEM_COLS = 512;
 constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 40, EPILOGUE_REGS = 104;  // see setmaxnreg below
@@ -223,10 +226,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kCtas == 1: one CTA per 128 x 256 tile.  kCtas == 2: a CTA pair (cluster 2x1, cta_group::2) per 256 x 256 tile — each CTA
 // holds its 128 rows of A and HALF of the W tile, the leader's single thread issues UMMA 256x256x16 for both SMs, each
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
-template <int kCtas>
+template <int kCtas, bool kWide>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
-  constexpr int STAGES = Cfg<kCtas>::STAGES, STAGE_BYTES = Cfg<kCtas>::STAGE_BYTES;
+  using C = Cfg<kCtas, kWide>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RING_BYTES = C::RING_BYTES;
+  constexpr int OUT_BOX_COLS = C::OUT_BOX_COLS, OUT_BOX_BYTES = C::OUT_BOX_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -393,16 +398,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 #pragma unroll
       for (int i = 0; i < 8; ++i) rd[i] = 0.f;
       const uint32_t my_box = stage_out_addr + h * OUT_BOX_BYTES;
-      const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * 64u;
-      const uint32_t sw = uint32_t(lane >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index XOR address bits [7,9) = (row >> 1) & 3
+      const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * uint32_t(OUT_BOX_COLS * 2);
+      // 16-byte chunk index XOR address bits [7,..): SWIZZLE_64B (64-byte rows) -> (row >> 1) & 3; SWIZZLE_128B -> row & 7
+      const uint32_t sw = kWide ? (uint32_t(lane) & 7u) : (uint32_t(lane >> 1) & 3u);
+      constexpr int PASSES = EPI_COLS / OUT_BOX_COLS, CHUNKS = OUT_BOX_COLS / 8;
       const bool issuer = (warp == 4 + 4 * h) && lane == 0;
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
+      for (int pass = 0; pass < PASSES; ++pass) {
         if (issuer) tma_store_wait_read();  // the previous store has finished reading this staging box
         named_bar_sync(1 + h, 128);
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const int cc = pass * 4 + c8;
+        for (int c8 = 0; c8 < CHUNKS; ++c8) {
+          const int cc = pass * CHUNKS + c8;
           const int n = col0 + cc * 8;
           uint4 packed = make_uint4(0, 0, 0, 0);
           if (n < p.N) {  // N % 8 == 0 is enforced on the host
@@ -484,6 +491,18 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+template <int kCtas, bool kWide>
+static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const GemmParams& p) {
+  constexpr int smem = Cfg<kCtas, kWide>::SMEM_BYTES;
+  static const cudaError_t attr_rc =  // once per variant (thread-safe static init)
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
+  cfg.dynamicSmemBytes = smem;
+  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide>, maps, p));
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
                         int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra) {
@@ -498,12 +517,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
   const int ctas = gemm_cta_group(nseg, act, total_k);
-  {
-    const cudaError_t e1 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    const cudaError_t e2 = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    MERV_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", SMEM_BYTES,
-                 cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-  }
+  // wide output boxes only pay when the boxes cross NVLink (MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests)
+  bool wide = num_extra > 0;
+  if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
+  const int out_box_cols = wide ? Cfg<1, true>::OUT_BOX_COLS : Cfg<1, false>::OUT_BOX_COLS;
 
   TensorMaps maps;
   GemmParams p = {};
@@ -528,14 +545,16 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     p.out_flat = flat ? 1 : 0;
     const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)(flat ? M : rows_per_video), (unsigned long long)(flat ? 1 : (M / rows_per_video))};
     const unsigned long long strides[2] = {(unsigned long long)ldy * 2, (unsigned long long)(flat ? (long long)M * ldy : y_batch_stride) * 2};
-    const unsigned box[3] = {OUT_BOX_COLS, BM, 1};
+    const unsigned box[3] = {(unsigned)out_box_cols, BM, 1};
     MERV_REQUIRE(num_extra >= 0 && num_extra < MERV_MAX_ENCODERS && (num_extra == 0 || extra_out != nullptr), MERV_E_ARG,
                  "gemm: %d extra output destinations (at most %d)", num_extra, MERV_MAX_ENCODERS - 1);
     p.num_out = 1 + num_extra;
     for (int d = 0; d < p.num_out; ++d) {
       void* base = d == 0 ? Y : extra_out[d - 1];
       MERV_REQUIRE(base != nullptr && aligned16(base), MERV_E_ALIGN, "gemm: output destination %d is NULL or not 16-byte aligned", d);
-      if (int rc = encode_tmap_cached(&maps.out[d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+      if (int rc = encode_tmap_cached(&maps.out[d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box,
+                                      wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))
+        return rc;
     }
     for (int d = p.num_out; d < MERV_MAX_ENCODERS; ++d) maps.out[d] = maps.out[0];
   }
@@ -554,7 +573,6 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(units * ctas));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -563,12 +581,8 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (ctas == 2)
-    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, maps, p));
-  else
-    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1>, maps, p));
-  MERV_CUDA_OK(cudaGetLastError());
-  return MERV_OK;
+  if (ctas == 2) return wide ? launch_variant<2, true>(cfg, maps, p) : launch_variant<2, false>(cfg, maps, p);
+  return wide ? launch_variant<1, true>(cfg, maps, p) : launch_variant<1, false>(cfg, maps, p);
 }
 
 }  // namespace merv

@@ -52,8 +52,8 @@ with torch.inference_mode():
     t_fused = timeit(lambda: m(feats, gather=buf))
 if rank == 0:
     res = {"world": world, "batch_per_gpu": B, "gathered_bit_identical_on_all_ranks": bool(flag.item()), "compute_only_ms": t_compute,
-           "compute_then_nccl_allgather_ms": t_nccl, "fused_gemm_allgather_ms": t_fused, "gathered_bytes_per_rank": (world - 1) * B * 1024 * 4096 * 2}
+           "compute_then_nccl_allgather_ms": t_nccl, "fused_gemm_allgather_ms": t_fused, "wide_out_env": os.environ.get("MERV_GEMM_WIDE_OUT"), "gathered_bytes_per_rank": (world - 1) * B * 1024 * 4096 * 2}
     print(json.dumps(res), flush=True)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
-    json.dump(res, open(os.path.join(REPO, "gpurun_out", f"fused_gather_{world}gpu.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(REPO, "gpurun_out", f"fused_gather_{world}gpu{os.environ.get('MERV_TAG', '')}.json"), "w"), indent=1)
 dist.destroy_process_group()
