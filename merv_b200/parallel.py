@@ -97,9 +97,10 @@ class SymmetricPrefixBuffer:
         return self.buf[lo:lo + self.batch_per_rank]
 
     def peer_block_ptrs(self) -> List[int]:
-        """Addresses of THIS rank's block inside every other rank's buffer (peer-mapped device pointers)."""
+        """Addresses of THIS rank's block inside every other rank's buffer (peer-mapped device pointers), in ring order
+        starting at the next rank so that at any moment the ranks target different peers."""
         ptrs = self.handle.buffer_ptrs
-        return [int(ptrs[p]) + self.rank * self.block_bytes for p in range(self.world) if p != self.rank]
+        return [int(ptrs[(self.rank + k) % self.world]) + self.rank * self.block_bytes for k in range(1, self.world)]
 
     def barrier(self) -> None:
         """Stream-ordered barrier across the ranks (device-side signals; no host synchronisation)."""
