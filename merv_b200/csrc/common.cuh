@@ -131,4 +131,57 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, z));
 }
 
+// Two erf-GELUs at once on Blackwell's packed fp32 pipe (FFMA2): the same A&S 7.1.26 evaluation as gelu_erf_fast with
+// the 12 multiply-add steps done as f32x2 instructions; only |z|, the two MUFU ops and copysign stay scalar.  The tensor
+// -core GEMM's activated epilogue is issue-bound, so instruction count is what matters here.
+__device__ __forceinline__ unsigned long long f32x2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+#define MERV_C2(v) f32x2_pack(v, v)
+  const unsigned long long x = f32x2_pack(x0, x1);
+  const unsigned long long z = f32x2_mul(x, MERV_C2(0.70710678118654752440f));
+  float z0, z1;
+  f32x2_unpack(z, z0, z1);
+  const unsigned long long den = f32x2_fma(MERV_C2(0.3275911f), f32x2_pack(fabsf(z0), fabsf(z1)), MERV_C2(1.0f));
+  float d0, d1, t0, t1;
+  f32x2_unpack(den, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const unsigned long long t = f32x2_pack(t0, t1);
+  // -poly(t): the coefficients carry the sign so that erf = 1 + (-poly) * exp(-z^2) is one FFMA2
+  unsigned long long np = f32x2_fma(MERV_C2(-1.061405429f), t, MERV_C2(1.453152027f));
+  np = f32x2_fma(np, t, MERV_C2(-1.421413741f));
+  np = f32x2_fma(np, t, MERV_C2(0.284496736f));
+  np = f32x2_fma(np, t, MERV_C2(-0.254829592f));
+  np = f32x2_mul(np, t);
+  const unsigned long long arg = f32x2_mul(f32x2_mul(z, MERV_C2(-1.4426950408889634f)), z);  // -z^2 log2(e)
+  float a0, a1, e0, e1;
+  f32x2_unpack(arg, a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const unsigned long long erf_abs = f32x2_fma(np, f32x2_pack(e0, e1), MERV_C2(1.0f));
+  float r0, r1;
+  f32x2_unpack(erf_abs, r0, r1);
+  const unsigned long long hx = f32x2_mul(x, MERV_C2(0.5f));
+  const unsigned long long out = f32x2_fma(hx, f32x2_pack(copysignf(r0, z0), copysignf(r1, z1)), hx);
+  f32x2_unpack(out, x0, x1);
+#undef MERV_C2
+}
+
 }  // namespace merv

@@ -226,7 +226,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // kCtas == 1: one CTA per 128 x 256 tile.  kCtas == 2: a CTA pair (cluster 2x1, cta_group::2) per 256 x 256 tile — each CTA
 // holds its 128 rows of A and HALF of the W tile, the leader's single thread issues UMMA 256x256x16 for both SMs, each
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
-template <int kCtas, bool kWide>
+template <int kCtas, bool kWide, bool kGelu>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
   using C = Cfg<kCtas, kWide>;
@@ -361,56 +361,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       const int row = m_base + q * 32 + lane;
       int video = row / p.rows_per_video;
       if (video >= p.num_videos) video = p.num_videos - 1;
-      float sum[EPI_COLS];
-#pragma unroll
-      for (int i = 0; i < EPI_COLS; ++i) sum[i] = 0.f;
-      for (int s = 0; s < p.nseg; ++s, ++acc_it) {
-        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-        const float scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
-        mbar_wait(tfull_bar + 8 * buf, aph);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
-#pragma unroll
-        for (int c = 0; c < EPI_COLS / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
-          if (p.nseg == 1 && p.seg_scale == nullptr) {  // plain GEMM: the accumulator IS the result
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[c * 32 + i] = __uint_as_float(v[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fmaf(scale, __uint_as_float(v[i]), sum[c * 32 + i]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {  // accumulator may be overwritten (the MMA issuer lives in the leader CTA)
-          if constexpr (kCtas == 2) mbar_arrive_cluster(leader_tempty + 8 * buf);
-          else mbar_arrive(tempty_bar + 8 * buf);
-        }
-      }
-      // ---- finalize: bias, activation, optional row-dot, bf16 pack; rows staged in shared memory (128B swizzle) and
-      //      written with TMA stores: fully coalesced, asynchronous, M/N tails clipped by the tensor map ----
+      // ---- finalize of one staged box: bias, activation, optional row-dot, bf16 pack; rows staged in shared memory
+      //      (swizzled) and written with TMA stores: fully coalesced, asynchronous, M/N tails clipped by the tensor map ----
       const int col0 = n_blk * BN + h * EPI_COLS;
       const bool row_ok = row < p.M;
-      float rd[8];  // 8 independent partial sums: no serial dependency chain through the 128 columns
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rd[i] = 0.f;
+      float rd[8];  // 8 independent partial sums: no serial dependency chain through the 128 columns (zeroed right before the first pass)
       const uint32_t my_box = stage_out_addr + h * OUT_BOX_BYTES;
       const uint32_t my_row = my_box + uint32_t(q * 32 + lane) * uint32_t(OUT_BOX_COLS * 2);
       // 16-byte chunk index XOR address bits [7,..): SWIZZLE_64B (64-byte rows) -> (row >> 1) & 3; SWIZZLE_128B -> row & 7
       const uint32_t sw = kWide ? (uint32_t(lane) & 7u) : (uint32_t(lane >> 1) & 3u);
       constexpr int PASSES = EPI_COLS / OUT_BOX_COLS, CHUNKS = OUT_BOX_COLS / 8;
       const bool issuer = (warp == 4 + 4 * h) && lane == 0;
-#pragma unroll
-      for (int pass = 0; pass < PASSES; ++pass) {
+      auto emit_pass = [&](const int pass, const float* val) {  // val: this row's OUT_BOX_COLS accumulator values of the pass
         if (issuer) tma_store_wait_read();  // the previous store has finished reading this staging box
         named_bar_sync(1 + h, 128);
 #pragma unroll
         for (int c8 = 0; c8 < CHUNKS; ++c8) {
-          const int cc = pass * CHUNKS + c8;
-          const int n = col0 + cc * 8;
+          const int n = col0 + (pass * CHUNKS + c8) * 8;
           uint4 packed = make_uint4(0, 0, 0, 0);
           if (n < p.N) {  // N % 8 == 0 is enforced on the host
             float b[8];
@@ -426,9 +393,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             }
             float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              o[i] = sum[cc * 8 + i] + b[i];
-              if (p.act == MERV_ACT_GELU_ERF) o[i] = gelu_erf_fast(o[i]);
+            for (int i = 0; i < 8; ++i) o[i] = val[c8 * 8 + i] + b[i];
+            if constexpr (kGelu) {  // compile-time: the un-activated kernels carry none of this (registers, code size)
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) gelu_erf_fast2(o[i], o[i + 1]);
             }
             packed = Vec16<__nv_bfloat16>::pack(o);
             if (p.rowdot_vec != nullptr) {
@@ -451,6 +419,67 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             tma_store_3d(&maps.out[d], my_box, col0 + pass * OUT_BOX_COLS, m0 - v0 * p.rows_per_video, v0);
           tma_store_commit();
         }
+      };
+      auto release_accumulator = [&](const uint32_t buf) {  // the MMA issuer (in the leader CTA) may overwrite this TMEM buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtas == 2) mbar_arrive_cluster(leader_tempty + 8 * buf);
+          else mbar_arrive(tempty_bar + 8 * buf);
+        }
+      };
+
+      if constexpr (kGelu) {
+        // activated GEMM (always one segment, no per-video scale): finalize straight out of TMEM, 32 columns at a time,
+        // so only 32 accumulator values are live next to the packed-math constants of the GELU
+        static_assert(!kGelu || (OUT_BOX_COLS == 32 && PASSES == 2), "one tcgen05.ld.x32 per staged box");
+        const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        ++acc_it;
+        mbar_wait(tfull_bar + 8 * buf, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rd[i] = 0.f;
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+          uint32_t v[32];
+          tmem_ld32(taddr + pass * 32, v);
+          tmem_ld_wait();
+          if (pass == PASSES - 1) release_accumulator(buf);
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) val[i] = __uint_as_float(v[i]);
+          emit_pass(pass, val);
+        }
+      } else {
+        float sum[EPI_COLS];
+#pragma unroll
+        for (int i = 0; i < EPI_COLS; ++i) sum[i] = 0.f;
+        for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+          const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          const float scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
+          mbar_wait(tfull_bar + 8 * buf, aph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
+#pragma unroll
+          for (int c = 0; c < EPI_COLS / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (p.nseg == 1 && p.seg_scale == nullptr) {  // plain GEMM: the accumulator IS the result
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[c * 32 + i] = __uint_as_float(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[c * 32 + i] = fmaf(scale, __uint_as_float(v[i]), sum[c * 32 + i]);
+            }
+          }
+          release_accumulator(buf);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rd[i] = 0.f;
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) emit_pass(pass, sum + pass * OUT_BOX_COLS);
       }
       if (p.rowdot_vec != nullptr && row_ok && col0 < p.N)
         p.rowdot_out[(long long)row * p.rowdot_nblk + (col0 / MERV_ROWDOT_BLOCK)] = ((rd[0] + rd[1]) + (rd[2] + rd[3])) + ((rd[4] + rd[5]) + (rd[6] + rd[7]));
@@ -491,14 +520,14 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int kCtas, bool kWide>
+template <int kCtas, bool kWide, bool kGelu>
 static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const GemmParams& p) {
   constexpr int smem = Cfg<kCtas, kWide>::SMEM_BYTES;
   static const cudaError_t attr_rc =  // once per variant (thread-safe static init)
-      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
   cfg.dynamicSmemBytes = smem;
-  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide>, maps, p));
+  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu>, maps, p));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }
@@ -520,6 +549,12 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   // wide output boxes only pay when the boxes cross NVLink (MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests)
   bool wide = num_extra > 0;
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
+  MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
+  if (act != MERV_ACT_NONE) {
+    MERV_REQUIRE(nseg == 1 && seg_scale == nullptr, MERV_E_ARG, "gemm: an activation needs a single segment without per-video scales");
+    MERV_REQUIRE(num_extra == 0, MERV_E_ARG, "gemm: extra output destinations are only supported without an activation");
+    wide = false;
+  }
   const int out_box_cols = wide ? Cfg<1, true>::OUT_BOX_COLS : Cfg<1, false>::OUT_BOX_COLS;
 
   TensorMaps maps;
@@ -581,8 +616,9 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (ctas == 2) return wide ? launch_variant<2, true>(cfg, maps, p) : launch_variant<2, false>(cfg, maps, p);
-  return wide ? launch_variant<1, true>(cfg, maps, p) : launch_variant<1, false>(cfg, maps, p);
+  if (act == MERV_ACT_GELU_ERF) return ctas == 2 ? launch_variant<2, false, true>(cfg, maps, p) : launch_variant<1, false, true>(cfg, maps, p);
+  if (ctas == 2) return wide ? launch_variant<2, true, false>(cfg, maps, p) : launch_variant<2, false, false>(cfg, maps, p);
+  return wide ? launch_variant<1, true, false>(cfg, maps, p) : launch_variant<1, false, false>(cfg, maps, p);
 }
 
 }  // namespace merv
