@@ -306,7 +306,7 @@ def main():
                 dt = float(t.item())
             e2e = {"value": world * B * args.e2e_steps / dt, "unit": "videos/s", "h2d_bytes_per_step": BYTES_IN * B,
                    "d2h_bytes_per_step": BYTES_OUT * B + B * len(DIMS) * 2, "ms_per_step": dt / args.e2e_steps * 1e3,
-                   "steps": args.e2e_steps, "api": "merv_b200.pipeline.HostPipeline (pinned host tensors, 8-video chunks, copy/compute overlap)"}
+                   "steps": args.e2e_steps, "api": "merv_b200.pipeline.HostPipeline (pinned host tensors, 8-video chunks with ramp-up/-down, copy/compute overlap)"}
             # what the bus alone allows for the same bytes (not part of any reported throughput): explains e2e
             c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             dev_out = torch.empty((B, OUT_TOKENS, LLM_DIM), dtype=torch.bfloat16, device=dev)

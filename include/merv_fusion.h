@@ -172,6 +172,14 @@ int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* 
                           int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
                           void* stream);
 
+/* Channel-concat fusion (feature_fusion == "concat_channel"): out = concat_s(A_s, dim=-1) W^T + bias as ONE K-segmented
+ * tcgen05 GEMM, out[m,:] = sum_s A_s[m,:] W[:, k_s : k_s + K_s]^T + bias — the [M, sum K_s] concatenation the reference
+ * builds with torch.concat (merv.py:603-605) before its LinearProjector(E * llm_dim, llm_dim) (merv.py:217-218,606) is
+ * never materialised.  A_s [M, K_s] (lda[s]) are the per-encoder projected tokens, W [N, sum K_s] (ldw) row-major
+ * (nn.Linear layout), bias [N] bf16 or NULL.  bf16 only, nseg <= MERV_MAX_SEGMENTS. */
+int merv_concat_linear(const void* const* A, const int64_t* lda, const void* W, int64_t ldw, const int32_t* K, int nseg,
+                       const void* bias, void* out, int64_t ldo, int M, int N, void* stream);
+
 /* Fused GEMM + all-gather over NVLink peer memory: as merv_fused_linear_mix, and every finished output tile is ALSO stored
  * (TMA stores to peer-mapped addresses) to the same rows of `peer_out[0..num_peers)` — the other ranks' symmetric prefix
  * buffers, already offset to this rank's block of videos.  The transfer overlaps the tensor-core work tile by tile; the

@@ -16,6 +16,7 @@ _lib.load()  # fail loudly at import time if the CUDA library has not been built
 from .nn_utils import (  # noqa: E402
     AveragePooling3DProjector,
     AveragePoolingProjector,
+    ConcatChannelFusion,
     CrossAttentionAdapterLearnableQuery,
     DeferredProjection,
     FusedMLPProjector,
@@ -31,6 +32,6 @@ from .nn_utils import (  # noqa: E402
 )
 
 __all__ = [
-    "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
+    "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
     "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
 ]

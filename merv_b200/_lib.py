@@ -71,6 +71,8 @@ _SIGNATURES = {
     "merv_softmax_weights_ex": (c_int, [c_void_p, c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_fused_linear_mix_gather": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
                                              c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, _PP, c_int, c_void_p]),
+    "merv_concat_linear": (c_int, [_PP, POINTER(c_int64), c_void_p, c_int64, POINTER(c_int32), c_int, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                   c_void_p]),
     "merv_fused_forward": (c_int, [POINTER(FusedDesc), c_void_p]),
     "merv_scores_softmax_weights": (c_int, [_PP, POINTER(c_int32), _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p]),

@@ -169,6 +169,25 @@ extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, c
                                       nullptr, 0, stream);
 }
 
+extern "C" int merv_concat_linear(const void* const* A, const int64_t* lda, const void* W, int64_t ldw, const int32_t* K, int nseg,
+                                  const void* bias, void* out, int64_t ldo, int M, int N, void* stream) {
+  MERV_REQUIRE(A && lda && W && K && out, MERV_E_ARG, "merv_concat_linear: NULL pointer");
+  MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_concat_linear: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
+  MERV_REQUIRE(M >= 0 && N > 0, MERV_E_SHAPE, "merv_concat_linear: M=%d N=%d", M, N);
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  GemmSegment seg[MERV_MAX_SEGMENTS];
+  long long k0 = 0;
+  for (int s = 0; s < nseg; ++s) {
+    MERV_REQUIRE(K[s] > 0 && K[s] % 8 == 0, MERV_E_ALIGN, "merv_concat_linear: K[%d]=%d must be a positive multiple of 8", s, K[s]);
+    seg[s] = GemmSegment{A[s], lda[s], static_cast<const char*>(W) + k0 * 2, ldw, K[s]};  // column block k0 .. k0 + K_s of W
+    k0 += K[s];
+  }
+  MERV_REQUIRE(ldw >= k0, MERV_E_SHAPE, "merv_concat_linear: ldw=%lld < sum K = %lld", (long long)ldw, k0);
+  return launch_gemm_tcgen05(seg, nseg, nullptr, nullptr, M, bias, MERV_ACT_NONE, nullptr, nullptr, out, ldo, 0, M, N, 0,
+                             static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int merv_fused_forward(const merv_fused_desc* d, void* stream) {
   MERV_REQUIRE(d != nullptr, MERV_E_ARG, "merv_fused_forward: desc is NULL");
   const int E = d->num_encoders;

@@ -503,12 +503,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 // Which variant runs.  Measured on B200 (65536 x 4096, bf16): the CTA pair is 5 % faster for a plain K = 1024 GEMM
 // (1288 vs 1229 TFLOP/s: less L2->SM and shared-memory operand traffic) but 2 % slower for the fused 4-segment
 // K = 3584 GEMM (1393 vs 1421), which is power-bound, not operand-bound; for the fused K = 16384 GEMM it is 3 % faster
-// again.  So: pair for plain un-activated GEMMs and very deep fused ones, single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
+// again.  So: pair for plain GEMMs (activated or not) and very deep fused ones, single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
 static int gemm_cta_group(int nseg, int act, long long total_k) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
-  if (nseg == 1) return act == MERV_ACT_NONE ? 2 : 1;  // the GELU epilogue, not the operands, bounds the activated GEMM
+  if (nseg == 1) return 2;  // also with the GELU epilogue since it runs on the packed fp32 pipe (1262 vs 1228 TFLOP/s at K = 1024)
   return total_k >= 8192 ? 2 : 1;  // fused K = 4 x 4096 (second MLP layer): pair 6.30 ms vs 6.47; fused K = 3584: single wins
 }
 

@@ -39,7 +39,9 @@ from torch.nn.init import xavier_uniform_
 from torch.nn.parameter import Parameter
 
 from . import ops
-from ._lib import ACT_GELU_ERF, ACT_NONE
+from ._lib import ACT_GELU_ERF, ACT_NONE, MAX_SEGMENTS
+
+IGNORE_INDEX = -100  # merv.py:53
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -658,6 +660,37 @@ class ScalarAdapter(nn.Module):
         return out, weights[:1].to(dtype)
 
 
+class ConcatChannelFusion(LinearProjector):
+    """feature_fusion == "concat_channel" (merv.py:217-218): ``LinearProjector(E * llm_dim, llm_dim)`` applied to the
+    channel-wise concatenation of the projected tokens (merv.py:603-606).  Same parameters / state-dict keys as the
+    reference's LinearProjector (``feature_fusion.projector.{weight,bias}``).
+
+    ``forward(tensor)`` is the reference call (the glue concatenated already).  ``forward(list)`` takes the per-encoder
+    tokens and runs sum_e Y_e W[:, e-th block]^T + b as ONE K-segmented tcgen05 GEMM: the [B, T, E * llm_dim] tensor is
+    never built (saves writing and re-reading 2 x E x 8.4 MB per video at merv-full sizes)."""
+
+    def __init__(self, num_encoder: int, llm_dim: int) -> None:
+        super().__init__(num_encoder * llm_dim, llm_dim)
+        self.num_encoder = num_encoder
+
+    def forward(self, projected_patch_embeddings):
+        V = projected_patch_embeddings
+        if isinstance(V, torch.Tensor):
+            return super().forward(V)
+        V = [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
+        lin = self.projector
+        assert sum(v.shape[-1] for v in V) == lin.in_features, f"concat_channel expects {lin.in_features} channels in total"
+        dtype = _compute_dtype(V[0])
+        segmented = (dtype == torch.bfloat16 and len(V) <= MAX_SEGMENTS and all(v.shape[-1] % 8 == 0 for v in V)
+                     and not _needs_grad(self, *V))
+        if not segmented or V[0].numel() == 0:  # fp32 parity path / training / > 4 encoders: concatenate as the reference does
+            return super().forward(torch.concat(V, -1))
+        if not hasattr(self, "_cast_cache"):
+            self._cast_cache = _CastCache()
+        V = [v if v.dtype == dtype else v.to(dtype) for v in V]
+        return ops.concat_linear(V, self._cast_cache.get(lin.weight, dtype), self._cast_cache.get(lin.bias, dtype))
+
+
 # ------------------------------------------------------------------------------------------------------------
 # linking: the fused pipeline behind the unchanged MERV.forward glue
 # ------------------------------------------------------------------------------------------------------------
@@ -684,7 +717,7 @@ class MervFusion(nn.Module):
         super().__init__()
         self.projectors = nn.ModuleList(projectors)
         self.feature_fusion = feature_fusion
-        if fused:
+        if fused and not isinstance(feature_fusion, ConcatChannelFusion):  # concat_channel consumes the projected tokens themselves
             link_fused(self.projectors, self.feature_fusion)
 
     @classmethod
@@ -742,6 +775,9 @@ class MervFusion(nn.Module):
 
     def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
                 batch_index: Optional[torch.Tensor] = None, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if isinstance(self.feature_fusion, ConcatChannelFusion):  # merv.py:603-606: no mixing weights (mixer_value stays None)
+            assert out is None and batch_index is None and gather is None, "concat_channel supports the plain call only"
+            return self.feature_fusion([proj(x) for proj, x in zip(self.projectors, patch_features)]), None
         if gather is not None:  # fused all-gather of the prefixes over NVLink (parallel.SymmetricPrefixBuffer)
             projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
             return self.feature_fusion(projected, batch_index=batch_index, gather=gather)
@@ -771,6 +807,55 @@ class MervFusion(nn.Module):
                                   batch_index=None if idx is None else idx.to(torch.int32))
         return buf, weights
 
+    def forward_multimodal(self, patch_features: Sequence[torch.Tensor], input_embeddings: torch.Tensor,
+                           attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                           multimodal_indices: Optional[torch.Tensor] = None, bos_token_length: int = 1,
+                           unimodal_indices: Optional[torch.Tensor] = None):
+        """Everything MERV.forward does between the backbones and the LLM call (merv.py:572-720) for the accelerated
+        configurations: gather by ``multimodal_indices``, fuse, and assemble ``fused_embeddings`` / ``fused_attention_mask``
+        / ``fused_labels`` — multimodal examples first as ``[BOS | prefix | text]`` (mask True, labels IGNORE_INDEX over
+        the prefix, merv.py:622-664), then the text-only examples padded at the END with T zero embeddings (mask False,
+        labels IGNORE_INDEX, merv.py:668-720).  One buffer is allocated; the fused GEMM writes the prefix into it in place.
+
+        ``patch_features[e]`` is the backbone output for the WHOLE batch (it is gathered inside the pool kernel).
+        ``unimodal_indices`` may be passed to avoid the host sync the reference's Python loop (merv.py:668-672) implies.
+        Returns (fused_embeddings, fused_attention_mask | None, fused_labels | None, weights)."""
+        ff = self.feature_fusion
+        emb = input_embeddings
+        Bt, L, K = emb.shape
+        T = ff.token_length
+        dev = emb.device
+        idx = torch.arange(Bt, device=dev) if multimodal_indices is None else multimodal_indices.to(dev)
+        if unimodal_indices is None:
+            keep = torch.ones(Bt, dtype=torch.bool, device=dev)
+            keep[idx] = False
+            unimodal_indices = keep.nonzero().flatten()
+        uni = unimodal_indices.to(dev)
+        Bm, Bu = idx.numel(), uni.numel()
+        bos = bos_token_length
+        buf = torch.empty((Bm + Bu, L + T, K), dtype=torch.bfloat16, device=dev)
+        buf[:Bm, :bos].copy_(emb[idx, :bos])
+        buf[:Bm, bos + T:].copy_(emb[idx, bos:])
+        if Bu:
+            buf[Bm:, :L].copy_(emb[uni])
+            buf[Bm:, L:].zero_()
+        whole = multimodal_indices is None
+        _, weights = self.forward(patch_features, out=buf[:Bm, bos:bos + T], batch_index=None if whole else idx.to(torch.int32))
+
+        def splice(t, fill_mm, fill_uni):
+            if t is None:
+                return None
+            res = torch.empty((Bm + Bu, L + T), dtype=t.dtype, device=t.device)
+            res[:Bm, :bos] = t[idx, :bos]
+            res[:Bm, bos:bos + T] = fill_mm
+            res[:Bm, bos + T:] = t[idx, bos:]
+            if Bu:
+                res[Bm:, :L] = t[uni]
+                res[Bm:, L:] = fill_uni
+            return res
+
+        return buf, splice(attention_mask, True, False), splice(labels, IGNORE_INDEX, IGNORE_INDEX), weights
+
 
 def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
     """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
@@ -792,8 +877,15 @@ def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
     elif type(ff).__name__ == "ScalarAdapter":
         new_ff = ff if isinstance(ff, ScalarAdapter) else ScalarAdapter()
         new_ff.scalar = ff.scalar
+    elif type(ff).__name__ == "LinearProjector" and getattr(vidlm, "feature_fusion_type", "concat_channel") == "concat_channel":
+        # merv.py:217-218: the glue (merv.py:603-606) concatenates and then calls this module with a tensor -> plain tcgen05 GEMM
+        new_ff = ConcatChannelFusion.__new__(ConcatChannelFusion)
+        nn.Module.__init__(new_ff)
+        new_ff.projector, new_ff.layernorm = ff.projector, ff.layernorm
+        new_ff.num_encoder = len(new_projs)
+        fused = False
     else:
-        raise TypeError(f"patch_merv supports feature_fusion in {{'cross_attention_avg_lq', 'scalar'}}, found {type(ff).__name__}")
+        raise TypeError(f"patch_merv supports feature_fusion in {{'cross_attention_avg_lq', 'scalar', 'concat_channel'}}, found {type(ff).__name__}")
     vidlm.projectors = nn.ModuleList(new_projs)
     vidlm.feature_fusion = new_ff
     if fused:

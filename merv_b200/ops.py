@@ -340,6 +340,28 @@ def fused_linear_mix(
     return out
 
 
+def concat_linear(Ys: Sequence[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """concat(Ys, dim=-1) @ weight.T + bias without building the concatenation (one K-segmented tcgen05 GEMM, bf16).
+
+    feature_fusion == "concat_channel": merv.py:603-606 with the LinearProjector of merv.py:217-218."""
+    lib = _lib.load()
+    dev = _require_cuda(*Ys, weight, bias, out)
+    assert all(y.dtype == torch.bfloat16 for y in Ys) and weight.dtype == torch.bfloat16, "concat_linear is bf16 only"
+    lead = Ys[0].shape[:-1]
+    Ys = [y.reshape(-1, y.shape[-1]) for y in Ys]
+    Ys = [y if y.stride(1) == 1 else y.contiguous() for y in Ys]
+    weight = weight if weight.stride(1) == 1 else weight.contiguous()
+    M, N = Ys[0].shape[0], weight.shape[0]
+    assert all(y.shape[0] == M for y in Ys) and sum(y.shape[1] for y in Ys) == weight.shape[1], "concat_linear: shapes do not add up"
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        assert out.dtype == torch.bfloat16 and out.shape == (M, N) and out.stride(1) == 1
+        _call('merv_concat_linear', lib.merv_concat_linear, ptr_array([y.data_ptr() for y in Ys]), i64_array([y.stride(0) for y in Ys]),
+              weight.data_ptr(), weight.stride(0), i32_array([y.shape[1] for y in Ys]), len(Ys), _p(bias), out.data_ptr(), out.stride(0), M, N, _stream())
+    return out.view(*lead, N)
+
+
 class FusedLinearPlan:
     """Pre-built `merv_fused_desc` for the whole affine path (pool -> scores -> softmax -> fused GEMM) at fixed shapes:
     one FFI crossing per forward instead of ~20 Python-level operations.  Matters at small batch (generate runs the path

@@ -3,7 +3,9 @@
 This is the call a consumer without device-resident features makes, and what bench.py times as ``e2e``: every
 step includes the host->device copy of the inputs and the device->host copy of the result.  Videos are
 independent, so the batch is streamed in chunks: copy-in of chunk i+1, compute of chunk i and copy-out of chunk
-i-1 overlap on three CUDA streams with double-buffered device staging.
+i-1 overlap on three CUDA streams with double-buffered device staging.  The chunk sizes ramp up at the start and
+down at the end (2, 2, 4, 8, ..., 8, 4, 2, 2 for chunk_videos = 8): the bus sits idle only while the first chunk
+is in flight alone (fill) and after the last one landed (drain), so those are the small ones.
 """
 
 from __future__ import annotations
@@ -11,6 +13,26 @@ from __future__ import annotations
 from typing import List, Optional, Sequence, Tuple
 
 import torch
+
+
+def chunk_schedule(batch: int, chunk: int) -> List[Tuple[int, int]]:
+    """[lo, hi) video ranges covering `batch`: ramp-up, full-size chunks, ramp-down."""
+    ramp = [max(1, chunk // 4), max(1, chunk // 4), max(1, chunk // 2)]
+    sizes_head: List[int] = []
+    sizes_tail: List[int] = []
+    left = batch
+    for r in ramp:
+        if left >= 2 * chunk + 2 * r:  # keep at least two full chunks in the middle
+            sizes_head.append(r)
+            sizes_tail.append(r)
+            left -= 2 * r
+    middle = [chunk] * (left // chunk) + ([left % chunk] if left % chunk else [])
+    out, lo = [], 0
+    for n in sizes_head + middle + sizes_tail[::-1]:
+        out.append((lo, lo + n))
+        lo += n
+    assert lo == batch
+    return out
 
 
 class HostPipeline:
@@ -46,8 +68,7 @@ class HostPipeline:
         start.record(torch.cuda.current_stream(self.device))
         for s in (self.s_in, self.s_compute, self.s_out):
             s.wait_event(start)
-        for i, lo in enumerate(range(0, B, self.chunk)):
-            hi = min(B, lo + self.chunk)
+        for i, (lo, hi) in enumerate(chunk_schedule(B, self.chunk)):
             n, slot = hi - lo, i % 2
             with torch.cuda.stream(self.s_in):
                 if compute_done[slot] is not None:

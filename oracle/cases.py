@@ -33,7 +33,7 @@ class Case:
     offsets: Tuple[float, ...] = (0.0, 0.5, -0.5, 0.25)
     seed: int = 7
     resampler: str = "3davg"  # "3davg" (AveragePooling3DProjector) | "avg" (AveragePoolingProjector, 2-D per frame)
-    fusion: str = "cross_attention_avg_lq"  # | "scalar" (ScalarAdapter)
+    fusion: str = "cross_attention_avg_lq"  # | "scalar" (ScalarAdapter) | "concat_channel" (LinearProjector(E*K, K))
 
     @property
     def num_encoders(self) -> int:
@@ -91,6 +91,9 @@ CASES: Dict[str, Case] = {
             llm_dim=128, embed_dim=96, out_frames=(4, 4, 4, 4), out_size=4, mlp_type="linear", resampler="avg"),
         _mk("scalar_mixer", batch=2, frames=(4, 4, 4, 4), patches=(16, 16, 49, 49), dims=(64, 64, 48, 48),
             llm_dim=128, embed_dim=96, out_frames=(4, 4, 4, 4), out_size=4, mlp_type="linear", fusion="scalar"),
+        # feature_fusion == "concat_channel" (merv.py:217-218,603-606): channel concat + LinearProjector(E*llm_dim, llm_dim)
+        _mk("concat_channel", batch=2, frames=(8, 8, 8, 8), patches=(64, 64, 49, 49), dims=(256, 256, 192, 192),
+            llm_dim=512, embed_dim=384, out_frames=(8, 8, 8, 8), out_size=4, mlp_type="linear", fusion="concat_channel"),
         # full size, one video: stored as a digest (weights, sums, sampled elements), not in full
         _mk("merv_full_b1", batch=1, mlp_type="linear", q_scale=64.0, **MERV_FULL),
         _mk("merv_full_b1_gelu", batch=1, mlp_type="gelu-mlp", q_scale=64.0, **MERV_FULL),
@@ -146,6 +149,8 @@ def make_fusion_params(case: Case, seed: int = 2048) -> Dict[str, np.ndarray]:
     rng = np.random.default_rng(seed)
     if case.fusion == "scalar":
         return {"scalar": rng.standard_normal(4).astype(np.float32)}
+    if case.fusion == "concat_channel":
+        return _linear_params(rng, "projector", case.num_encoders * case.llm_dim, case.llm_dim)
     E, K = case.embed_dim, case.llm_dim
     xav = lambda fo, fi: math.sqrt(6.0 / (fi + fo))  # noqa: E731
     return {

@@ -164,6 +164,38 @@ def scalar_adapter_forward(V: Sequence[np.ndarray], params: Dict[str, np.ndarray
     return out.astype(V[0].dtype), w.astype(V[0].dtype)
 
 
+def concat_channel_forward(V: Sequence[np.ndarray], params: Dict[str, np.ndarray]) -> np.ndarray:
+    """feature_fusion == "concat_channel": ``torch.concat(projected, -1)`` then ``LinearProjector(E*llm_dim, llm_dim)``
+    (merv/models/vidlms/merv.py:217-218,603-606; LinearProjector is nn_utils.py:22-32, keys ``projector.{weight,bias}``)."""
+    return linear(np.concatenate(list(V), axis=-1), params["projector.weight"], params["projector.bias"])
+
+
+IGNORE_INDEX = -100  # merv/models/vidlms/merv.py:53
+
+
+def assemble_multimodal(prefix, input_embeddings, attention_mask, labels, multimodal_indices, bos_token_length=1):
+    """Restates merv/models/vidlms/merv.py:622-720: ``[BOS | prefix | text]`` rows for the multimodal examples (mask True
+    and labels IGNORE_INDEX over the prefix), then the text-only examples padded at the end with zero embeddings (mask
+    False, labels IGNORE_INDEX), stacked multimodal-first.  The MERV class itself cannot be imported here,
+    so this function is a restatement WITHOUT a reference-run pin; it is plain indexing / concatenation.
+    ``prefix`` [len(multimodal_indices), T, K]; returns (fused_embeddings, fused_attention_mask, fused_labels)."""
+    mm = np.asarray(multimodal_indices, dtype=np.int64)
+    Bt, L, K = input_embeddings.shape
+    T = prefix.shape[1]
+    bos = bos_token_length
+    emb = np.concatenate([input_embeddings[mm, :bos], prefix, input_embeddings[mm, bos:]], axis=1)  # merv.py:633-640
+    mask = np.concatenate([attention_mask[mm, :bos], np.ones((len(mm), T), attention_mask.dtype), attention_mask[mm, bos:]], axis=1)
+    lab = np.concatenate([labels[mm, :bos], np.full((len(mm), T), IGNORE_INDEX, labels.dtype), labels[mm, bos:]], axis=1)
+    uni = np.array([i for i in range(Bt) if i not in set(mm.tolist())], dtype=np.int64)  # merv.py:668-672
+    if len(uni) == 0:
+        return emb, mask, lab
+    padcount = (emb.shape[1] - L) // T  # merv.py:699-701 (== 1)
+    u_emb = np.concatenate([input_embeddings[uni]] + [np.zeros((len(uni), T, K), input_embeddings.dtype)] * padcount, axis=1)
+    u_mask = np.concatenate([attention_mask[uni]] + [np.zeros((len(uni), T), attention_mask.dtype)] * padcount, axis=1)
+    u_lab = np.concatenate([labels[uni]] + [np.full((len(uni), T), IGNORE_INDEX, labels.dtype)] * padcount, axis=1)
+    return np.vstack([emb, u_emb]), np.vstack([mask, u_mask]), np.vstack([lab, u_lab])
+
+
 # --------------------------------------------------------------------------------------------
 # whole path, as MERV.forward glues it
 # --------------------------------------------------------------------------------------------
@@ -185,6 +217,8 @@ def merv_fusion_forward(
         avgpool3d_projector_forward(x, p, t, out_size, mlp_type)
         for x, p, t in zip(features, projector_params, out_frames)
     ]
+    if "projector.weight" in fusion_params:  # feature_fusion == "concat_channel" (merv.py:217-218): no mixing weights
+        return concat_channel_forward(ys, fusion_params), np.zeros((features[0].shape[0], 0), features[0].dtype), ys
     if "scalar" in fusion_params:  # feature_fusion == "scalar" (merv.py:224-225)
         out, w = scalar_adapter_forward(ys, fusion_params)
     else:

@@ -40,6 +40,8 @@ def build_reference(ref, case: C.Case, dtype=torch.float32):
     )
     if case.fusion == "scalar":
         fusion = ref.ScalarAdapter(case.num_encoders)  # merv.py:224-225
+    elif case.fusion == "concat_channel":
+        fusion = ref.LinearProjector(case.num_encoders * case.llm_dim, case.llm_dim)  # merv.py:217-218
     else:
         fusion = ref.CrossAttentionAdapterLearnableQuery(
             embed_dim=case.embed_dim, llm_dim=case.llm_dim, token_length=case.token_length, averagetoken=True,
@@ -56,7 +58,10 @@ def build_reference(ref, case: C.Case, dtype=torch.float32):
 def run_reference(projs, fusion, feats, dtype=torch.float32):
     xs = [torch.from_numpy(f).to(dtype) for f in feats]
     ys = [p(x) for p, x in zip(projs, xs)]  # merv.py:587-589
-    out, w = fusion(ys)  # merv.py:607-609
+    if isinstance(fusion, type(projs[0].projector)) and not hasattr(fusion, "attention"):  # concat_channel: merv.py:603-606
+        out, w = fusion(torch.concat(ys, -1)), torch.zeros((xs[0].shape[0], 0), dtype=dtype)
+    else:
+        out, w = fusion(ys)  # merv.py:607-609
     pooled = []
     for p, x in zip(projs, xs):  # the intermediate of nn_utils.py:328-329, for the pool-kernel parity test
         import einops
@@ -74,7 +79,10 @@ def main() -> None:
     ref = load_reference_nn_utils()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    only = set(sys.argv[1:])  # `python -m oracle.make_golden concat_channel` regenerates just that fixture
     for name, case in C.CASES.items():
+        if only and name not in only:
+            continue
         feats = C.make_features(case)
         projs, fusion, pp, fp = build_reference(ref, case)
         out, w, ys, pooled = run_reference(projs, fusion, feats)
@@ -110,6 +118,8 @@ def main() -> None:
         print(f"{name:20s} w[0]={np.round(w.numpy()[0], 4)} sum={meta['out_sum']:.4f} "
               f"bf16-vs-fp32={meta['ref_bf16_vs_fp32']:.2e} -> {os.path.getsize(path) / 1e6:.2f} MB")
 
+    if only:
+        return
     # the reference's own seed-1024 construction order (merv.py:87,152-163,214-216) -> init digests
     torch.manual_seed(1024)
     full = C.CASES["merv_full_b1"]

@@ -122,6 +122,12 @@ try:
     t = timeit(lambda: ops.linear_bias_act(a, w, bias, 1, rowdot_vec=rv), n=5)
     report["gemm_65536x4096x1024_gelu_rowdot_ms"] = t
     print(f"tcgen05 GEMM 65536x4096x1024 act=1 + row-dot: {t:.3f} ms = {2 * B * 1024 * 4096 * 1024 / t / 1e9:.0f} TFLOP/s", flush=True)
+    for grp in ("1", "2"):  # which variant is faster for the activated GEMM (the default policy picks 1)
+        os.environ["MERV_GEMM_CTA_GROUP"] = grp
+        t = timeit(lambda: ops.linear_bias_act(a, w, bias, 1), n=5)
+        report[f"gemm_65536x4096x1024_gelu_cta_group{grp}_ms"] = t
+        print(f"  act=1 with cta_group {grp}: {t:.3f} ms = {2 * B * 1024 * 4096 * 1024 / t / 1e9:.0f} TFLOP/s", flush=True)
+    os.environ.pop("MERV_GEMM_CTA_GROUP", None)
     ref_t = timeit(lambda: torch.nn.functional.linear(a, w, bias), n=5)
     report["cublas_65536x4096x1024_TFLOPs"] = 2 * B * 1024 * 4096 * 1024 / ref_t / 1e9
     print(f"cuBLAS (torch F.linear) same shape: {ref_t:.3f} ms = {report['cublas_65536x4096x1024_TFLOPs']:.0f} TFLOP/s", flush=True)

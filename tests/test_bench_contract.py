@@ -35,3 +35,15 @@ def test_our_arm_refuses_to_run_without_a_gpu():
         return
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "no CPU path" in (r.stderr + r.stdout)
+
+
+def test_host_pipeline_chunk_schedule_covers_the_batch():
+    from merv_b200.pipeline import chunk_schedule
+
+    for chunk in (1, 4, 8):
+        for batch in list(range(0, 40)) + [64, 67, 128]:
+            sched = chunk_schedule(batch, chunk)
+            assert [lo for lo, _ in sched] == [0] + [hi for _, hi in sched[:-1]] if sched else batch == 0
+            assert (sched[-1][1] if sched else 0) == batch
+            assert all(0 < hi - lo <= chunk for lo, hi in sched)
+    assert [hi - lo for lo, hi in chunk_schedule(64, 8)] == [2, 2, 4, 8, 8, 8, 8, 8, 8, 4, 2, 2]

@@ -40,6 +40,8 @@ def build_module(case, pp, fp, dtype, fused):
         projs = [M.AveragePooling3DProjector(c, case.llm_dim, t, case.out_size, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
     if case.fusion == "scalar":
         fusion = M.ScalarAdapter(case.num_encoders)
+    elif case.fusion == "concat_channel":
+        fusion = M.ConcatChannelFusion(case.num_encoders, case.llm_dim)
     else:
         fusion = M.CrossAttentionAdapterLearnableQuery(case.embed_dim, case.llm_dim, case.token_length, averagetoken=True, num_encoder=case.num_encoders)
     m = M.MervFusion(projs, fusion, fused=fused)
@@ -194,12 +196,18 @@ def test_mix_kernels_match_oracle_incl_broadcast(dtype):
 # module paths vs the reference goldens
 # ---------------------------------------------------------------------------------------------------------
 SMALL = ["tiny_linear", "tiny_gelu", "tiny_fused_gelu", "frame_factor2", "ragged_windows", "single_encoder", "mid_linear", "mid_gelu",
-         "avg2d_linear", "scalar_mixer"]
+         "avg2d_linear", "scalar_mixer", "concat_channel"]
 
 
 def _check_against_golden(case, g, out, w, tol, wtol):
-    out_np, w_np = _np(out), _np(w)
     assert out.shape == (case.batch, case.token_length, case.llm_dim)
+    if case.fusion == "concat_channel":  # no mixing weights (merv.py:603-606: mixer_value stays None)
+        assert w is None
+        w = torch.zeros((case.batch, 0))
+        out_np = _np(out)
+        assert np.abs(out_np.reshape(-1)[g["sample_idx"]] - g["out_samples"]).max() / float(g["out_abs_max"]) < tol
+        return
+    out_np, w_np = _np(out), _np(w)
     assert w.shape == ((1 if case.fusion == "scalar" else case.batch), case.num_encoders)  # ScalarAdapter returns [1, E] (nn_utils.py:537)
     assert np.allclose(w_np.sum(-1), 1.0, atol=1e-2 if wtol > 1e-4 else 1e-5)
     scale = float(g["out_abs_max"])
@@ -576,3 +584,80 @@ def test_backbone_output_layouts_are_read_in_place():
         out_v, w_v = m([lb, vv])
         out_c, w_c = m([lb.contiguous(), vv.contiguous()])
     assert torch.equal(out_v, out_c) and torch.equal(w_v, w_c)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-buffer entry point (what bench.py times as e2e): chunked copy/compute/copy pipeline == one device call
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 5, 23])
+def test_host_pipeline_matches_device_call(batch):
+    from merv_b200.pipeline import HostPipeline
+
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=True)
+    reps = -(-batch // case.batch)
+    host = [torch.cat([torch.from_numpy(np.ascontiguousarray(f)).to(torch.bfloat16)] * reps)[:batch].contiguous().pin_memory() for f in feats]
+    with torch.inference_mode():
+        want, want_w = m([h.to(DEV) for h in host])
+    pipe = HostPipeline(m, chunk_videos=4)  # 23 videos -> ramp-up, full chunks, ragged chunk, ramp-down
+    got, got_w = pipe(host)
+    assert got.device.type == "cpu" and got.shape == (batch, case.token_length, case.llm_dim)
+    assert torch.equal(got, want.cpu()) and torch.equal(got_w, want_w.cpu())
+    got2, _ = pipe(host)  # staging buffers are reused across calls
+    assert torch.equal(got2, got)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# concat_channel as one K-segmented GEMM == the reference's concat + Linear
+# ---------------------------------------------------------------------------------------------------------
+def test_concat_channel_segmented_gemm_equals_concat_then_linear():
+    from merv_b200 import ops
+
+    torch.manual_seed(3)
+    M_, K_, N_ = 640, 256, 512
+    Ys = [torch.randn(M_, K_, device=DEV).to(torch.bfloat16) for _ in range(4)]
+    W = (torch.randn(N_, 4 * K_, device=DEV) / 32).to(torch.bfloat16)
+    b = torch.randn(N_, device=DEV).to(torch.bfloat16)
+    got = ops.concat_linear(Ys, W, b)
+    want, _ = ops.linear_bias_act(torch.cat(Ys, -1), W, b, 0)  # the plain GEMM on the materialised concatenation
+    ref = torch.cat(Ys, -1).float() @ W.float().T + b.float()
+    scale = float(ref.abs().max())
+    # per-segment TMEM accumulators summed in fp32 registers vs one accumulator: same values up to fp32 summation order
+    assert float((got.float() - want.float()).abs().max()) / scale < 1e-2 and float((got.float() - ref).abs().max()) / scale < 5e-3
+    mod = __import__("merv_b200").ConcatChannelFusion(4, N_).to(DEV, torch.bfloat16).eval().requires_grad_(False)
+    assert sorted(mod.state_dict()) == ["projector.bias", "projector.weight"]  # the reference LinearProjector's keys
+    V = [torch.randn(2, 128, N_, device=DEV).to(torch.bfloat16) for _ in range(4)]
+    with torch.inference_mode():
+        a_, b_ = mod(V), mod(torch.cat(V, -1))  # list call (segmented GEMM) vs the reference's tensor call (plain GEMM)
+    assert a_.shape == b_.shape == (2, 128, N_) and float((a_.float() - b_.float()).abs().max()) / float(b_.float().abs().max()) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the whole embedding / mask / label assembly of MERV.forward (merv.py:622-720), unimodal rows included
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mm", [[0, 1, 2, 3, 4], [3, 0], [4]])
+def test_forward_multimodal_assembly_matches_oracle(mm):
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    m = build_module(case, pp, fp, torch.bfloat16, fused=True)
+    T, K, Bt, L = case.token_length, case.llm_dim, 5, 7
+    rep = [torch.cat([_t(f, torch.bfloat16)] * 3)[:Bt].contiguous() for f in feats]  # backbone outputs for the whole batch of 5
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    emb = torch.randn(Bt, L, K, generator=gen).to(torch.bfloat16).to(DEV)
+    mask = (torch.rand(Bt, L, generator=gen) > 0.2).to(DEV)
+    labels = torch.randint(0, 32000, (Bt, L), generator=gen).to(DEV)
+    labels[:, 0] = -100
+    idx = torch.tensor(mm, device=DEV)
+    with torch.inference_mode():
+        prefix, w0 = m([f[idx] for f in rep])
+        whole = len(mm) == Bt
+        fe, fm, fl, w = m.forward_multimodal(rep, emb, mask, labels, multimodal_indices=None if whole else idx, bos_token_length=1)
+    want_e, want_m, want_l = O.assemble_multimodal(_np(prefix), _np(emb), mask.cpu().numpy(), labels.cpu().numpy(), mm, 1)
+    assert fe.shape == (Bt, L + T, K) and fm.dtype == mask.dtype and fl.dtype == labels.dtype
+    assert np.array_equal(_np(fe), want_e) and np.array_equal(fm.cpu().numpy(), want_m) and np.array_equal(fl.cpu().numpy(), want_l)
+    assert torch.equal(w, w0)
+    # no masks / labels given -> None, embeddings unchanged
+    with torch.inference_mode():
+        fe2, fm2, fl2, _ = m.forward_multimodal(rep, emb, multimodal_indices=None if whole else idx)
+    assert fm2 is None and fl2 is None and torch.equal(fe2, fe)

@@ -38,10 +38,13 @@ def test_oracle_matches_reference_golden(name):
     g, feats, pp, fp = regenerate(case)
     out, w, ys = O.merv_fusion_forward(feats, pp, fp, case.out_frames, case.out_size, case.mlp_type, case.token_length)
     assert out.shape == (case.batch, case.token_length, case.llm_dim)
-    assert w.shape == ((1 if case.fusion == "scalar" else case.batch), case.num_encoders)  # ScalarAdapter returns [1, E]
-    assert np.allclose(w.sum(-1), 1.0, atol=1e-5)
     scale = float(g["out_abs_max"])
-    assert np.abs(w - g["weights"]).max() < 2e-5
+    if case.fusion == "concat_channel":  # no mixing weights on this path (merv.py:603-606)
+        assert w.shape == (case.batch, 0) and g["weights"].shape == (case.batch, 0)
+    else:
+        assert w.shape == ((1 if case.fusion == "scalar" else case.batch), case.num_encoders)  # ScalarAdapter returns [1, E]
+        assert np.allclose(w.sum(-1), 1.0, atol=1e-5)
+        assert np.abs(w - g["weights"]).max() < 2e-5
     idx = g["sample_idx"]
     assert np.abs(out.reshape(-1)[idx] - g["out_samples"]).max() / scale < FP32_TOL
     assert abs(float(out.astype(np.float64).sum()) - float(g["out_sum"])) < 1e-4 * max(1.0, abs(float(g["out_abs_mean"])) * out.size) 
@@ -111,3 +114,21 @@ def test_torch_port_cpu_baseline_matches_golden(name):
     idx = g["sample_idx"]
     assert np.abs(out.numpy().reshape(-1)[idx] - g["out_samples"]).max() / float(g["out_abs_max"]) < FP32_TOL
     assert np.abs(w.numpy() - g["weights"]).max() < 2e-5
+
+
+def test_assemble_multimodal_layout():
+    # merv.py:622-720: [BOS | prefix | text] rows first, then text-only rows padded at the END; prefix positions IGNORE_INDEX / True
+    rng = np.random.default_rng(0)
+    Bt, L, T, K = 4, 5, 3, 2
+    emb = rng.standard_normal((Bt, L, K)).astype(np.float32)
+    mask = rng.random((Bt, L)) > 0.3
+    labels = rng.integers(0, 100, (Bt, L))
+    prefix = rng.standard_normal((2, T, K)).astype(np.float32)
+    fe, fm, fl = O.assemble_multimodal(prefix, emb, mask, labels, [2, 0], 1)
+    assert fe.shape == (Bt, L + T, K) and fm.shape == fl.shape == (Bt, L + T)
+    assert np.array_equal(fe[0, :1], emb[2, :1]) and np.array_equal(fe[0, 1:1 + T], prefix[0]) and np.array_equal(fe[0, 1 + T:], emb[2, 1:])
+    assert fm[:2, 1:1 + T].all() and (fl[:2, 1:1 + T] == O.IGNORE_INDEX).all()
+    assert np.array_equal(fe[2, :L], emb[1]) and not fe[2:, L:].any()          # unimodal rows 1 and 3, zero padded at the end
+    assert not fm[2:, L:].any() and (fl[2:, L:] == O.IGNORE_INDEX).all() and np.array_equal(fl[3, :L], labels[3])
+    fe2, fm2, fl2 = O.assemble_multimodal(np.concatenate([prefix, prefix]), emb, mask, labels, [0, 1, 2, 3], 1)
+    assert fe2.shape == (Bt, L + T, K)  # no unimodal rows: fused == multimodal
