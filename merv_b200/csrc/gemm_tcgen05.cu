@@ -546,8 +546,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
   const int ctas = gemm_cta_group(nseg, act, total_k);
-  // wide output boxes only pay when the boxes cross NVLink (MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests)
-  bool wide = num_extra > 0;
+  // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
+  // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
+  // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
+  bool wide = num_extra >= 2;
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
   MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
   if (act != MERV_ACT_NONE) {
