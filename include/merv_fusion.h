@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MERV_ABI_VERSION 1
+#define MERV_ABI_VERSION 2
 
 enum { MERV_F32 = 0, MERV_BF16 = 1 };
 enum { MERV_ACT_NONE = 0, MERV_ACT_GELU_ERF = 1 };
@@ -129,6 +129,19 @@ int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const f
                             float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
                             void* stream);
 size_t merv_scores_from_tokens_workspace(int B, int E, int T, int K);
+/* General form of merv_scores_from_tokens, covering the other two branches of CrossAttentionAdapterLearnableQuery.forward:
+ *   u_token_stride == K (averagetoken=False, merv/util/nn_utils.py:514-518): the key is the flattened [T*K] token block, so u
+ *       (merv_fusion_query_vec with llm_dim = T*K) has one row per token; s[b,e] = sum_t u[t,:] . V_e[b,t,:] with a single-token
+ *       encoder read T times (its repeat at nn_utils.py:502).  u_token_stride == 0 is the averagetoken=True form.
+ *   c (fp32 [E] or NULL): additive per-encoder constants, s[b,e] += c[e] — positional_embedding=True adds pe[e] to the mean
+ *       token (nn_utils.py:510-511), i.e. c[e] = u . pe[e] (merv_score_consts).
+ *   mean != 0 divides the sum by the number of tokens (the token mean of nn_utils.py:508). */
+int merv_scores_from_tokens_ex(const void* const* V, const int32_t* tokens, const float* u, int64_t u_token_stride,
+                               const float* c, int mean, float* scores, float* workspace, size_t workspace_floats, int B,
+                               int E, int T, int K, int dtype, void* stream);
+/* c_out[e] = u . pe[e,:] + (c_in && c_in[e] ? *c_in[e] : 0);  pe [E, K] (ldpe) in `dtype`, u fp32 [K], c_out fp32 [E]. */
+int merv_score_consts(const void* pe, int64_t ldpe, const float* u, const float* const* c_in, float* c_out, int E, int K,
+                      int dtype, void* stream);
 int merv_scores_from_partials(const float* const* partial, const int32_t* count,
                               const float* const* c /* per-encoder additive constants, entries or array may be NULL */,
                               float* scores, int B, int E, int T, void* stream);
@@ -239,6 +252,23 @@ int merv_mix_backward(const void* const* V, const void* dOut, const float* weigh
                       const float* u, const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias,
                       void* const* dV, void* dQ, void* dWq, void* dWk, void* dbias, float* workspace,
                       size_t workspace_floats, int B, int E, int T, int K, int embed, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm over the channel dimension of (possibly segmented) rows: Y[m, :] = LN(concat_s X_s[m, :]) * gamma + beta.
+ *   nseg == 1 : nn.LayerNorm(vision_dim) in front of a projector — `pre_proj_layernorm=True`
+ *               (merv/util/nn_utils.py:26-29,41-44,67-70,91-94; merv/models/vidlms/merv.py:165-171)
+ *   nseg == E : nn.LayerNorm(E * llm_dim) of feature_fusion == "concat_channel_ln" (merv.py:219-223) applied to the channel
+ *               concatenation of merv.py:603-605, which is never materialised un-normalised.
+ * X_s [M, K_s] (ldx[s]), gamma / beta [sum K_s] in `dtype` (either may be NULL), Y [M, sum K_s] (ldy).  Statistics in fp32,
+ * biased variance, two passes over register-resident values.  sum K_s <= 32768 (bf16) / 16384 (fp32).
+ * merv_layernorm_backward: dX = d/dX of the above (optional, [M, sum K_s]) and GX = dY * xhat (optional); the parameter
+ * gradients are the column sums dgamma = merv_colsum(GX), dbeta = merv_colsum(dY).
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_layernorm(const void* const* X, const int64_t* ldx, const int32_t* K, int nseg, const void* gamma, const void* beta,
+                   float eps, void* Y, int64_t ldy, int M, int dtype, void* stream);
+int merv_layernorm_backward(const void* const* X, const int64_t* ldx, const int32_t* K, int nseg, const void* dY, int64_t lddy,
+                            const void* gamma, float eps, void* dX, int64_t lddx, void* GX, int64_t ldgx, int M, int dtype,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,11 +17,13 @@ from .nn_utils import (  # noqa: E402
     AveragePooling3DProjector,
     AveragePoolingProjector,
     ConcatChannelFusion,
+    ConcatChannelLNFusion,
     CrossAttentionAdapterLearnableQuery,
     DeferredProjection,
     FusedMLPProjector,
     LinearProjector,
     MervFusion,
+    MLPDeepProjector,
     MLPProjector,
     ScalarAdapter,
     TokenResampler,
@@ -32,6 +34,6 @@ from .nn_utils import (  # noqa: E402
 )
 
 __all__ = [
-    "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
+    "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
     "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
 ]

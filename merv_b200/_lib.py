@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1
 MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 64
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}
 
@@ -65,6 +65,13 @@ _SIGNATURES = {
     "merv_affine_score_vec": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "merv_scores_from_tokens": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                                         c_int, c_void_p]),
+    "merv_scores_from_tokens_ex": (c_int, [_PP, POINTER(c_int32), c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                                           c_int, c_int, c_int, c_void_p]),
+    "merv_score_consts": (c_int, [c_void_p, c_int64, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_layernorm": (c_int, [_PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int, c_int,
+                               c_void_p]),
+    "merv_layernorm_backward": (c_int, [_PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_int64, c_void_p, c_float, c_void_p, c_int64,
+                                        c_void_p, c_int64, c_int, c_int, c_void_p]),
     "merv_scores_from_tokens_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "merv_scores_from_partials": (c_int, [_PP, POINTER(c_int32), _PP, c_void_p, c_int, c_int, c_int, c_void_p]),
     "merv_softmax_weights": (c_int, [c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -73,25 +73,31 @@ struct TokenScoreParams {
   int tokens[MERV_MAX_ENCODERS];
 };
 
-// partial[(b*E+e)*chunks + chunk] = sum_{t in chunk} sum_k u[k] * V_e[b,t,k]
+// partial[(b*E+e)*chunks + chunk] = sum_{t in chunk} sum_k u[t * u_stride + k] * V_e[b,t,k]
+//   u_stride == 0, full == 0 : the averagetoken=True branch (nn_utils.py:507-512) — one u for every token, T_e in {T, 1} tokens summed
+//   u_stride == K, full == 1 : the averagetoken=False branch (nn_utils.py:514-518) — key = the flattened [T*K] tokens, so u has one
+//                              row per token and a single-token encoder is read T times (its repeat at nn_utils.py:502)
 template <typename T>
 __global__ void __launch_bounds__(256) token_score_kernel(const __grid_constant__ TokenScoreParams p, const float* __restrict__ u,
-                                                          float* __restrict__ partial, int E, int K, int chunks) {
+                                                          float* __restrict__ partial, int E, int K, int chunks, int Ttok,
+                                                          long long u_stride, int full) {
   constexpr int VEC = Vec16<T>::kN;
   __shared__ float red[32];
   const int chunk = blockIdx.x, e = blockIdx.y, b = blockIdx.z;
   const int Te = p.tokens[e];
-  const int per = (Te + chunks - 1) / chunks;
-  const int t0 = chunk * per, t1 = min(Te, t0 + per);
+  const int Tl = full ? Ttok : Te;
+  const int per = (Tl + chunks - 1) / chunks;
+  const int t0 = chunk * per, t1 = min(Tl, t0 + per);
   const T* base = static_cast<const T*>(p.V[e]) + (long long)b * Te * K;
   const int nvec = K / VEC;
   float acc = 0.f;
   for (int t = t0; t < t1; ++t) {
-    const T* row = base + (long long)t * K;
+    const T* row = base + (long long)(Te == 1 ? 0 : t) * K;
+    const float* ut = u + (long long)t * u_stride;
     for (int v = threadIdx.x; v < nvec; v += 256) {
       float x[VEC];
       Vec16<T>::unpack(ldg_nc_v4(row + v * VEC), x);
-      const float4* uu = reinterpret_cast<const float4*>(u + v * VEC);
+      const float4* uu = reinterpret_cast<const float4*>(ut + v * VEC);
 #pragma unroll
       for (int c = 0; c < VEC; c += 4) {
         const float4 w = uu[c / 4];
@@ -103,17 +109,36 @@ __global__ void __launch_bounds__(256) token_score_kernel(const __grid_constant_
   if (threadIdx.x == 0) partial[((long long)b * E + e) * chunks + chunk] = acc;
 }
 
-// scores[b,e] = (sum of n contiguous partials) / T_e  — one warp per (b,e), fixed order
+// scores[b,e] = (sum of n contiguous partials) * inv[e] (+ c[e])  — one warp per (b,e), fixed order
 struct ScaleParams {
   float inv[MERV_MAX_ENCODERS];
 };
 __global__ void __launch_bounds__(32) reduce_scale_kernel(const float* __restrict__ partial, float* __restrict__ scores,
-                                                          const __grid_constant__ ScaleParams sp, int n, int E) {
+                                                          const __grid_constant__ ScaleParams sp, const float* __restrict__ c, int n, int E) {
   const long long id = blockIdx.x;
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += 32) acc += partial[id * n + i];
   acc = warp_sum(acc);
-  if (threadIdx.x == 0) scores[id] = acc * sp.inv[id % E];
+  if (threadIdx.x == 0) {
+    const float r = acc * sp.inv[id % E];
+    scores[id] = c != nullptr ? r + c[id % E] : r;
+  }
+}
+
+// c_out[e] = u . pe[e,:] (+ *c_in[e]) : the additive score constants of positional_embedding=True (nn_utils.py:510-511)
+struct ConstParams {
+  const float* c_in[MERV_MAX_ENCODERS];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) score_const_kernel(const T* __restrict__ pe, long long ldpe, const float* __restrict__ u,
+                                                          const __grid_constant__ ConstParams cp, float* __restrict__ c_out, int K) {
+  __shared__ float red[32];
+  const int e = blockIdx.x;
+  const T* row = pe + (long long)e * ldpe;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += 256) acc += u[k] * to_float(row[k]);
+  acc = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) c_out[e] = acc + (cp.c_in[e] != nullptr ? *cp.c_in[e] : 0.f);
 }
 
 // ---- scores from partial dot products (pool kernel's score_partial / GEMM epilogue's rowdot_out) ----------
@@ -356,19 +381,23 @@ extern "C" size_t merv_scores_from_tokens_workspace(int B, int E, int T, int K) 
   return (size_t)B * E * token_score_chunks(T);
 }
 
-extern "C" int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const float* u, float* scores,
-                                       float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
-                                       void* stream) {
+extern "C" int merv_scores_from_tokens_ex(const void* const* V, const int32_t* tokens, const float* u, int64_t u_token_stride,
+                                          const float* c, int mean, float* scores, float* workspace, size_t workspace_floats, int B,
+                                          int E, int T, int K, int dtype, void* stream) {
   MERV_DTYPE_OK("merv_scores_from_tokens");
   MERV_REQUIRE(V && tokens && u && scores && workspace, MERV_E_ARG, "merv_scores_from_tokens: NULL pointer");
   MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_from_tokens: E=%d", E);
   MERV_REQUIRE(B >= 0 && T > 0 && K > 0, MERV_E_SHAPE, "merv_scores_from_tokens: B=%d T=%d K=%d", B, T, K);
   const int vec = dtype == MERV_BF16 ? 8 : 4;
   MERV_REQUIRE(K % vec == 0, MERV_E_SHAPE, "merv_scores_from_tokens: K=%d must be a multiple of %d", K, vec);
+  MERV_REQUIRE(u_token_stride == 0 || u_token_stride >= K, MERV_E_SHAPE, "merv_scores_from_tokens: u_token_stride=%lld (0 or >= K)",
+               (long long)u_token_stride);
+  MERV_REQUIRE(aligned16(u) && u_token_stride % 4 == 0, MERV_E_ALIGN, "merv_scores_from_tokens: u rows must be 16-byte aligned");
   MERV_REQUIRE(workspace_floats >= merv_scores_from_tokens_workspace(B, E, T, K), MERV_E_ARG,
                "merv_scores_from_tokens: workspace too small");
   if (int rc = require_sm100()) return rc;
   if (B == 0) return MERV_OK;
+  const int full = u_token_stride != 0;  // one u row per token: every encoder contributes T terms (single-token ones repeated)
   TokenScoreParams p;
   ScaleParams sp;
   for (int e = 0; e < E; ++e) {
@@ -378,16 +407,40 @@ extern "C" int merv_scores_from_tokens(const void* const* V, const int32_t* toke
                  e, tokens[e], T);
     p.V[e] = V[e];
     p.tokens[e] = tokens[e];
-    sp.inv[e] = 1.0f / float(tokens[e]);
+    sp.inv[e] = mean ? 1.0f / float(full ? T : tokens[e]) : 1.0f;
   }
   const int chunks = token_score_chunks(T);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(chunks, E, B);
   if (dtype == MERV_BF16)
-    token_score_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks);
+    token_score_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks, T, u_token_stride, full);
   else
-    token_score_kernel<float><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks);
-  reduce_scale_kernel<<<B * E, 32, 0, s>>>(workspace, scores, sp, chunks, E);
+    token_score_kernel<float><<<grid, 256, 0, s>>>(p, u, workspace, E, K, chunks, T, u_token_stride, full);
+  reduce_scale_kernel<<<B * E, 32, 0, s>>>(workspace, scores, sp, c, chunks, E);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_scores_from_tokens(const void* const* V, const int32_t* tokens, const float* u, float* scores,
+                                       float* workspace, size_t workspace_floats, int B, int E, int T, int K, int dtype,
+                                       void* stream) {
+  return merv_scores_from_tokens_ex(V, tokens, u, 0, nullptr, 1, scores, workspace, workspace_floats, B, E, T, K, dtype, stream);
+}
+
+extern "C" int merv_score_consts(const void* pe, int64_t ldpe, const float* u, const float* const* c_in, float* c_out, int E, int K,
+                                 int dtype, void* stream) {
+  MERV_DTYPE_OK("merv_score_consts");
+  MERV_REQUIRE(pe && u && c_out, MERV_E_ARG, "merv_score_consts: NULL pointer");
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_score_consts: E=%d", E);
+  MERV_REQUIRE(K > 0 && ldpe >= K, MERV_E_SHAPE, "merv_score_consts: K=%d ldpe=%lld", K, (long long)ldpe);
+  if (int rc = require_sm100()) return rc;
+  ConstParams cp = {};
+  for (int e = 0; e < E; ++e) cp.c_in[e] = c_in ? c_in[e] : nullptr;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16)
+    score_const_kernel<__nv_bfloat16><<<E, 256, 0, s>>>((const __nv_bfloat16*)pe, ldpe, u, cp, c_out, K);
+  else
+    score_const_kernel<float><<<E, 256, 0, s>>>((const float*)pe, ldpe, u, cp, c_out, K);
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }

@@ -3,8 +3,9 @@
 Same class names, constructor signatures, parameter names/shapes (hence state-dict keys), properties and
 error behaviour as the reference (paths below are relative to the reference root):
 
-    LinearProjector                      merv/util/nn_utils.py:22-32
+    LinearProjector                      merv/util/nn_utils.py:22-32      (incl. pre_proj_layernorm)
     MLPProjector                         merv/util/nn_utils.py:35-59
+    MLPDeepProjector                     merv/util/nn_utils.py:62-83
     FusedMLPProjector                    merv/util/nn_utils.py:86-108
     get_mlp_projector                    merv/util/nn_utils.py:111-121
     TokenResampler                       merv/util/nn_utils.py:124-133
@@ -59,6 +60,16 @@ def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
+def _require_device(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("merv_b200 runs only on CUDA (sm_100a) tensors; there is deliberately no CPU fallback.")
+
+
+def _stream_key(dev: torch.device) -> Tuple[int, int]:
+    """(device index, current stream handle): cached plans own workspaces, so they are bound to one stream."""
+    return dev.index, torch.cuda.current_stream(dev).cuda_stream
+
+
 def _needs_grad(module: nn.Module, *tensors) -> bool:
     """True when the call must be recorded by autograd (training step: projectors and adapter are trainable in every
     stage, merv.py:318-320,342-343,363-365)."""
@@ -68,21 +79,30 @@ def _needs_grad(module: nn.Module, *tensors) -> bool:
 
 
 class _ProjectorFn(torch.autograd.Function):
-    """Linear / gelu-mlp / fused-gelu-mlp projector (nn_utils.py:22-59,86-108) with a hand-written backward.
+    """[LayerNorm ->] Linear / gelu-mlp / fused-gelu-mlp projector (nn_utils.py:22-108) with a hand-written backward.
 
-    forward : Z_i = X_i W_i^T + b_i on the sm_100a GEMM (pre-activations kept), X_{i+1} = gelu(Z_i)
+    forward : X_0 = LN(x) (pre_proj_layernorm) or x;  Z_i = X_i W_i^T + b_i on the sm_100a GEMM (pre-activations kept),
+              X_{i+1} = gelu(Z_i)
     backward: dZ_i = dX_{i+1} * gelu'(Z_i);  dW_i = dZ_i^T X_i and dX_i = dZ_i W_i (same GEMM on transposed copies — the
-              kernel is K-major);  db_i = colsum(dZ_i)
-    No gradient flows into the projector input: the backbones are frozen (merv.py:316,339,361) and pooling has no parameters.
+              kernel is K-major);  db_i = colsum(dZ_i);  LayerNorm: dgamma = colsum(dX_0 * xhat), dbeta = colsum(dX_0)
+    The gradient w.r.t. the input is produced only when the input requires it (projected tokens entering the
+    concat_channel fusion); the patch features never do: the backbones are frozen (merv.py:316,339,361).
     """
 
     @staticmethod
-    def forward(ctx, x, acts, dtype, cache, *params):
-        # params = (W_0, b_0, W_1, b_1, ...) — the nn.Parameters, so autograd routes the gradients; compute-dtype copies from `cache`
+    def forward(ctx, x, acts, dtype, cache, ln_eps, *params):
+        # params = ([gamma, beta,] W_0, b_0, W_1, b_1, ...) — the nn.Parameters, so autograd routes the gradients;
+        # compute-dtype copies come from `cache`
+        has_ln = ln_eps is not None
+        lin_params = params[2:] if has_ln else params
         n = len(acts)
+        x_in, gamma = x, None
+        if has_ln:
+            gamma = cache.get(params[0], dtype)
+            x = ops.layernorm([x], gamma, cache.get(params[1], dtype), ln_eps)
         xs, zs, ws = [x], [], []
         for i in range(n):
-            w_c, b_c = cache.get(params[2 * i], dtype), cache.get(params[2 * i + 1], dtype)
+            w_c, b_c = cache.get(lin_params[2 * i], dtype), cache.get(lin_params[2 * i + 1], dtype)
             z, _ = ops.linear_bias_act(xs[-1], w_c, b_c, ACT_NONE)
             ws.append(w_c)
             if acts[i] == ACT_GELU_ERF:
@@ -94,34 +114,45 @@ class _ProjectorFn(torch.autograd.Function):
         ctx.acts = acts
         ctx.param_dtypes = [p.dtype for p in params]
         ctx.nz = [z is not None for z in zs]
-        ctx.save_for_backward(*xs[:-1], *[z for z in zs if z is not None], *ws)
+        ctx.ln_eps = ln_eps
+        ctx.save_for_backward(*xs[:-1], *[z for z in zs if z is not None], *ws, *([x_in, gamma] if has_ln else []))
         return xs[-1]
 
     @staticmethod
     def backward(ctx, dy):
         n = len(ctx.acts)
+        has_ln = ctx.ln_eps is not None
         saved = list(ctx.saved_tensors)
         xs = saved[:n]
         nz = sum(ctx.nz)
         z_it = iter(saved[n:n + nz])
         zs = [next(z_it) if has else None for has in ctx.nz]
-        ws = saved[n + nz:]
+        ws = saved[n + nz:n + nz + n]
+        need_dx = ctx.needs_input_grad[0]
         g = dy.reshape(-1, dy.shape[-1])
         if g.dtype != xs[0].dtype:
             g = g.to(xs[0].dtype)
         if g.stride(1) != 1:
             g = g.contiguous()
-        grads = [None] * (2 * n)
+        off = 2 if has_ln else 0
+        grads = [None] * (2 * n + off)
         for i in reversed(range(n)):
             if zs[i] is not None:
                 g = ops.gelu(zs[i].reshape(g.shape), g)  # dZ_i
             x2 = xs[i].reshape(-1, xs[i].shape[-1])
             dW, _ = ops.linear_bias_act(ops.transpose(g), ops.transpose(x2), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
-            grads[2 * i] = dW.to(ctx.param_dtypes[2 * i])
-            grads[2 * i + 1] = ops.colsum(g).to(ctx.param_dtypes[2 * i + 1])
-            if i > 0:
+            grads[off + 2 * i] = dW.to(ctx.param_dtypes[off + 2 * i])
+            grads[off + 2 * i + 1] = ops.colsum(g).to(ctx.param_dtypes[off + 2 * i + 1])
+            if i > 0 or need_dx or has_ln:
                 g, _ = ops.linear_bias_act(g, ops.transpose(ws[i]), None, ACT_NONE)  # dX_i = dZ_i W_i: [M, N] x [K, N]^T -> [M, K]
-        return (None, None, None, None, *grads)
+        dx = g if need_dx else None
+        if has_ln:
+            x_in, gamma = saved[-2], saved[-1]
+            dx, dgamma, dbeta = ops.layernorm_backward([x_in], g, gamma, ctx.ln_eps, need_dx=need_dx)
+            grads[0], grads[1] = dgamma.to(ctx.param_dtypes[0]), dbeta.to(ctx.param_dtypes[1])
+        if dx is not None:
+            dx = dx.reshape(xs[0].shape)
+        return (dx, None, None, None, None, *grads)
 
 
 class _MixFn(torch.autograd.Function):
@@ -183,7 +214,7 @@ def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
     """[(linear, activation applied AFTER it)] for every reference projector type."""
     if isinstance(projector, LinearProjector):
         return [(projector.projector, ACT_NONE)]
-    if isinstance(projector, (MLPProjector, FusedMLPProjector)):
+    if isinstance(projector, (MLPProjector, MLPDeepProjector, FusedMLPProjector)):
         mods = list(projector.projector)
         layers = []
         for i, m in enumerate(mods):
@@ -196,13 +227,16 @@ def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
     raise TypeError(f"unsupported projector module {type(projector).__name__}")
 
 
-def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None, train: bool = False):
+def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, last_rowdot_vec=None, train: bool = False,
+                ln: Optional[nn.LayerNorm] = None):
     rd = None
     if train:
-        if any(lin.bias is None for lin, _ in layers):
-            raise NotImplementedError("bias-free projector layers are not covered by the backward")
-        params = [t for lin, _ in layers for t in (lin.weight, lin.bias)]
-        return _ProjectorFn.apply(x, tuple(act for _, act in layers), dtype, cache, *params), None
+        if any(lin.bias is None for lin, _ in layers) or (ln is not None and (ln.weight is None or ln.bias is None)):
+            raise NotImplementedError("bias-free projector layers / non-affine LayerNorm are not covered by the backward")
+        params = ([ln.weight, ln.bias] if ln is not None else []) + [t for lin, _ in layers for t in (lin.weight, lin.bias)]
+        return _ProjectorFn.apply(x, tuple(act for _, act in layers), dtype, cache, None if ln is None else ln.eps, *params), None
+    if ln is not None:
+        x = ops.layernorm([x], cache.get(ln.weight, dtype), cache.get(ln.bias, dtype), ln.eps)
     for i, (lin, act) in enumerate(layers):
         rv = last_rowdot_vec if i == len(layers) - 1 else None
         x, rd = ops.linear_bias_act(x, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), act, rv)
@@ -211,22 +245,27 @@ def _run_layers(x: torch.Tensor, layers, cache: _CastCache, dtype: torch.dtype, 
 
 # === Definitions for Various Projection Modules, with Signature :: [..., in_dim] --> [..., out_dim] ===
 class _ProjectorBase(nn.Module):
-    def _check_ln(self) -> None:
-        if not isinstance(self.layernorm, nn.Identity):
-            raise NotImplementedError(
-                "pre_proj_layernorm=True is outside the accelerated hot path (off in every shipped config, merv.py:67)"
-            )
+    def _pre_ln(self) -> Optional[nn.LayerNorm]:
+        """The nn.LayerNorm of `pre_proj_layernorm=True` (nn_utils.py:26-29), None for the nn.Identity default."""
+        ln = self.layernorm
+        if isinstance(ln, nn.Identity):
+            return None
+        if not isinstance(ln, nn.LayerNorm) or len(ln.normalized_shape) != 1:
+            raise TypeError(f"unsupported pre-projection normalisation {type(ln).__name__}")
+        return ln
 
     def forward(self, img_patches: torch.Tensor) -> torch.Tensor:
-        self._check_ln()
+        _require_device(img_patches)
+        ln = self._pre_ln()
         train = _needs_grad(self, img_patches)
-        if train and img_patches.requires_grad:
-            raise NotImplementedError("gradients w.r.t. the projector input are not implemented (frozen backbones, merv.py:316)")
         dtype = _compute_dtype(img_patches)
         if not hasattr(self, "_cast_cache"):
             self._cast_cache = _CastCache()
         x = img_patches if img_patches.dtype == dtype else img_patches.to(dtype)
-        y, _ = _run_layers(x, _projector_layers(self), self._cast_cache, dtype, train=train)
+        layers = _projector_layers(self)
+        if x.numel() == 0:
+            return torch.empty((*x.shape[:-1], layers[-1][0].out_features), dtype=dtype, device=x.device)
+        y, _ = _run_layers(x, layers, self._cast_cache, dtype, train=train, ln=ln)
         return y
 
 
@@ -261,6 +300,27 @@ class MLPProjector(_ProjectorBase):
     @property
     def output_token_length(self) -> int:
         return 1
+
+
+class MLPDeepProjector(_ProjectorBase):
+    def __init__(
+        self, vision_dim: int, llm_dim: int, mlp_type: str = "gelu-mlp", pre_proj_layernorm: bool = False
+    ) -> None:
+        super().__init__()
+        if pre_proj_layernorm:
+            self.layernorm = nn.LayerNorm(vision_dim)
+        else:
+            self.layernorm = nn.Identity()
+        if mlp_type == "gelu-mlp":
+            self.projector = nn.Sequential(
+                nn.Linear(vision_dim, llm_dim, bias=True),
+                nn.GELU(),
+                nn.Linear(llm_dim, llm_dim, bias=True),
+                nn.GELU(),
+                nn.Linear(llm_dim, llm_dim, bias=True),
+            )
+        else:
+            raise ValueError(f"Projector with `{mlp_type = }` is not supported!")
 
 
 class FusedMLPProjector(_ProjectorBase):
@@ -387,8 +447,7 @@ class AveragePooling3DProjector(TokenResampler):
 
     def forward(self, fused_img_patches: torch.Tensor) -> Union[torch.Tensor, DeferredProjection]:
         assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
-        if not fused_img_patches.is_cuda:
-            raise RuntimeError("merv_b200 runs only on CUDA (sm_100a) tensors; there is deliberately no CPU fallback.")
+        _require_device(fused_img_patches)
         fusion = self._linked_fusion() if self._linked_fusion is not None else None
         if fusion is not None and not torch.is_grad_enabled():
             return DeferredProjection(self, fused_img_patches)
@@ -502,20 +561,29 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             self._vc_cache[id(lin)] = hit
         return hit[1]
 
+    def _pe_consts(self, dtype: torch.dtype, c_in=None) -> Optional[torch.Tensor]:
+        """fp32 [E] with c[e] = u . pe[e] (+ c_in[e]): positional_embedding=True adds pe[e] to encoder e's mean token before
+        the attention (nn_utils.py:510-511), i.e. a constant to its score.  None when the module has no ``pe`` or runs with
+        averagetoken=False (the reference only uses ``pe`` inside the averagetoken branch)."""
+        if not (self.positional_embedding and self.averagetoken):
+            return None
+        u = self.query_vector(dtype)
+        tag = (self.pe.data_ptr(), _version(self.pe), id(u), None if c_in is None else tuple(id(c) for c in c_in))
+        hit = self._u_cache.get("pe")
+        if hit is None or hit[0] != tag:
+            hit = (tag, ops.score_consts(self._cast_cache.get(self.pe, dtype), u, c_in), c_in)  # c_in kept alive: ids are the key
+            self._u_cache["pe"] = hit
+        return hit[1]
+
     # ---- forward --------------------------------------------------------------------------------------------
     def forward(self, V, out: Optional[torch.Tensor] = None, batch_index: Optional[torch.Tensor] = None, gather=None):
         # V is a list of tensors with size (B, T, K). T should all be same, or 1.  (nn_utils.py:491-495)
         # `out` / `batch_index` are extensions of the linked (fused) path only, see _forward_fused.
         for emb in V:
             assert emb.shape[1] == self.token_length or emb.shape[1] == 1, (self.token_length, [e.shape for e in V])
-        if not self.averagetoken:
-            raise NotImplementedError(
-                "averagetoken=False (scores from the flattened T*K tokens) is not used by any shipped config "
-                "(merv.py:214-216 passes averagetoken=True) and is outside the accelerated hot path"
-            )
-        if self.positional_embedding:
-            raise NotImplementedError("positional_embedding=True is outside the accelerated hot path (default False)")
         assert 1 <= len(V) <= 8, f"1..8 encoders supported, got {len(V)}"
+        if self.positional_embedding and self.averagetoken:
+            assert len(V) == self.num_encoder, f"pe holds {self.num_encoder} rows, got {len(V)} encoders (nn_utils.py:511)"
         if V[0].shape[0] == 0:  # a rank that owns no videos (merv_b200/parallel.py): nothing to launch
             dt, dev = (V[0].dtype, V[0].device)
             return torch.empty((0, self.token_length, self.llm_dim), dtype=dt, device=dev), torch.empty((0, len(V)), dtype=dt, device=dev)
@@ -528,6 +596,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         if _needs_grad(self, *V):
             if any(v.shape[1] != self.token_length for v in V):
                 raise NotImplementedError("the backward does not cover single-token (broadcast) encoders")
+            if not self.averagetoken or self.positional_embedding:
+                raise NotImplementedError("the backward covers averagetoken=True without positional embedding only "
+                                          "(the configuration MERV constructs, merv.py:214-216)")
             att = self.attention
             return _MixFn.apply(self, _compute_dtype(V[0]), self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias, *V)
         return self._forward_tokens(V)
@@ -535,16 +606,17 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
     def _forward_tokens(self, V: Sequence[torch.Tensor], rowdots=None) -> Tuple[torch.Tensor, torch.Tensor]:
         dtype = _compute_dtype(V[0])
         V = [v if v.dtype == dtype else v.to(dtype) for v in V]
-        u = self.query_vector(dtype)
+        u = self.query_vector(dtype)  # [K] (averagetoken=True) or [T*K] (averagetoken=False: the key is the flattened token block)
         if rowdots is not None:
             scores = ops.scores_from_partials(rowdots, None, V[0].shape[0], self.token_length)
         else:
-            scores = ops.scores_from_tokens(V, u, self.token_length)
+            scores = ops.scores_from_tokens(V, u, self.token_length, per_token_u=not self.averagetoken,
+                                            consts=self._pe_consts(dtype), mean=self.averagetoken)
         out, weights = ops.softmax_mix(V, self.token_length, scores=scores)
         return out, weights.to(dtype)
 
     def _can_fuse(self, V: Sequence[DeferredProjection]) -> bool:
-        if len(V) > 4 or any(v.dtype != torch.bfloat16 for v in V):
+        if len(V) > 4 or any(v.dtype != torch.bfloat16 for v in V) or not self.averagetoken:
             return False
         if any(v.shape[1] != self.token_length for v in V):
             return False
@@ -580,6 +652,9 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         B, T, K = (xs[0].shape[0] if batch_index is None else batch_index.numel()), self.token_length, self.llm_dim
         lasts = [p.layers()[-1][0] for p in projs]
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
+        if self.positional_embedding:  # score_e += u . pe[e]: folded into the per-encoder score constants
+            cpe = self._pe_consts(dtype, [vc[1] for vc in vcs])
+            vcs = [(vc[0], cpe[e:e + 1]) for e, vc in enumerate(vcs)]
         biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
         Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
         if gather is not None:
@@ -611,8 +686,8 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
 
     def _fused_plan(self, projs, xs, vcs, Ws, biases, B) -> "ops.FusedLinearPlan":
         """One cached single-call plan per (shapes, strides, weight versions, stream)."""
-        key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), tuple(id(vc[0]) for vc in vcs),
-               tuple(w.data_ptr() for w in Ws), xs[0].device.index, torch.cuda.current_stream(xs[0].device).cuda_stream)
+        key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), tuple((id(vc[0]), vc[1].data_ptr()) for vc in vcs),
+               tuple(w.data_ptr() for w in Ws), *_stream_key(xs[0].device))
         plans = self.__dict__.setdefault("_plans", {})
         plan = plans.get(key)
         if plan is None:
@@ -691,6 +766,44 @@ class ConcatChannelFusion(LinearProjector):
         return ops.concat_linear(V, self._cast_cache.get(lin.weight, dtype), self._cast_cache.get(lin.bias, dtype))
 
 
+class ConcatChannelLNFusion(nn.Sequential):
+    """feature_fusion == "concat_channel_ln" (merv.py:219-223): ``Sequential(LayerNorm(E * llm_dim), LinearProjector(E * llm_dim,
+    llm_dim))`` applied to the channel-wise concatenation of the projected tokens (merv.py:603-606).  Same module tree as the
+    reference, hence the same state-dict keys (``feature_fusion.0.{weight,bias}``, ``feature_fusion.1.projector.{weight,bias}``).
+
+    ``forward(tensor)`` is the reference call.  ``forward(list)`` takes the per-encoder tokens: the LayerNorm kernel reads them as
+    row segments and writes the NORMALISED concatenation once (the un-normalised one is never built), then one plain tcgen05 GEMM."""
+
+    def __init__(self, num_encoder: int, llm_dim: int) -> None:
+        super().__init__(nn.LayerNorm(num_encoder * llm_dim), LinearProjector(num_encoder * llm_dim, llm_dim))
+        self.num_encoder = num_encoder
+
+    def forward(self, projected_patch_embeddings):
+        V = projected_patch_embeddings
+        ln, proj = self[0], self[1]
+        segs = [V] if isinstance(V, torch.Tensor) else [v.materialize() if isinstance(v, DeferredProjection) else v for v in V]
+        _require_device(segs[0])
+        lin = proj.projector
+        assert sum(v.shape[-1] for v in segs) == lin.in_features, f"concat_channel_ln expects {lin.in_features} channels in total"
+        dtype = _compute_dtype(segs[0])
+        if not hasattr(self, "_cast_cache"):
+            self._cast_cache = _CastCache()
+        cache = self._cast_cache
+        segs = [v if v.dtype == dtype else v.to(dtype) for v in segs]
+        if segs[0].numel() == 0:
+            return torch.empty((*segs[0].shape[:-1], lin.out_features), dtype=dtype, device=segs[0].device)
+        if _needs_grad(self, *segs):  # training: concatenate as the reference does, one autograd node with the hand-written backward
+            x = segs[0] if len(segs) == 1 else torch.concat(segs, -1)
+            y, _ = _run_layers(x, [(lin, ACT_NONE)], cache, dtype, train=True, ln=ln)
+            return y
+        vec = 8 if dtype == torch.bfloat16 else 4
+        if len(segs) > 8 or any(v.shape[-1] % vec for v in segs):
+            segs = [torch.concat(segs, -1)]
+        x = ops.layernorm(segs, cache.get(ln.weight, dtype), cache.get(ln.bias, dtype), ln.eps)
+        y, _ = ops.linear_bias_act(x, cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), ACT_NONE)
+        return y
+
+
 # ------------------------------------------------------------------------------------------------------------
 # linking: the fused pipeline behind the unchanged MERV.forward glue
 # ------------------------------------------------------------------------------------------------------------
@@ -712,13 +825,48 @@ class MervFusion(nn.Module):
     (``projectors``, ``feature_fusion``) so ``state_dict()`` keys match a MERV checkpoint's.
     """
 
-    def __init__(self, projectors: Sequence[AveragePooling3DProjector], feature_fusion: CrossAttentionAdapterLearnableQuery,
-                 fused: bool = True) -> None:
+    def __init__(self, projectors: Sequence[AveragePooling3DProjector], feature_fusion: Optional[nn.Module],
+                 fused: bool = True, fusion_type: Optional[str] = None) -> None:
         super().__init__()
         self.projectors = nn.ModuleList(projectors)
         self.feature_fusion = feature_fusion
-        if fused and not isinstance(feature_fusion, ConcatChannelFusion):  # concat_channel consumes the projected tokens themselves
+        # the parameter-free fusions of merv.py:598-601: "first" (encoder 0 only) and "concat" (token-wise concatenation)
+        self.fusion_type = fusion_type
+        if feature_fusion is None:
+            assert fusion_type in ("first", "concat"), "feature_fusion=None needs fusion_type 'first' or 'concat' (merv.py:598-601)"
+        # concat_channel(_ln) consume the projected tokens themselves
+        elif fused and not isinstance(feature_fusion, (ConcatChannelFusion, ConcatChannelLNFusion)):
             link_fused(self.projectors, self.feature_fusion)
+
+    def _forward_token_concat(self, patch_features: Sequence[torch.Tensor]) -> torch.Tensor:
+        """feature_fusion == "concat" (merv.py:600-601): ``torch.concat(projected, 1)`` -> [B, sum_e T_e, K].  For bf16 affine
+        projectors with tile-aligned token counts every projector's GEMM stores straight into its slice of the result through
+        the batch-strided TMA-store map (no concat copy); otherwise the projected tokens are copied into place."""
+        projs = list(self.projectors)
+        Ts = [p.output_frames * p.output_size**2 for p in projs]
+        x0 = patch_features[0]
+        dtype = _compute_dtype(x0)
+        B, K = x0.shape[0], projs[0].llm_dim
+        out = torch.empty((B, sum(Ts), K), dtype=dtype, device=x0.device)
+        t0 = 0
+        for p, x, T in zip(projs, patch_features, Ts):
+            dst = out[:, t0:t0 + T]
+            t0 += T
+            if B == 0:
+                continue
+            direct = (dtype == torch.bfloat16 and len(p.layers()) == 1 and T % 128 == 0 and not _needs_grad(p, x)
+                      and p.layers()[0][0].bias is not None)
+            if not direct:
+                dst.copy_(p._forward_unfused(x))
+                continue
+            xb = x.detach() if x.dtype == dtype else x.detach().to(dtype)
+            (pooled,), _ = ops.pool3d([xb], [p.output_frames], p.output_size)
+            lin = p.layers()[0][0]
+            # one encoder with scale softmax([0]) == 1 and bias rows 1 * bias: the batch-strided form of the fused GEMM
+            ones, bias_rows = ops.softmax_weights(torch.zeros((B, 1), dtype=torch.float32, device=x.device),
+                                                  [p._cast_cache.get(lin.bias, dtype)], K)
+            ops.fused_linear_mix([pooled], [p._cast_cache.get(lin.weight, dtype)], ones, bias_rows, T, out=dst)
+        return out
 
     @classmethod
     def build(cls, vision_dims: Sequence[int], llm_dim: int, output_frames: Sequence[int], projector_token_length: int = 64,
@@ -740,6 +888,8 @@ class MervFusion(nn.Module):
     def _param_tag(self):
         ff = self.feature_fusion
         ps = [ff.Q, ff.attention.q_proj_weight, ff.attention.k_proj_weight, ff.attention.in_proj_bias]
+        if ff.positional_embedding:
+            ps.append(ff.pe)
         for p in self.projectors:
             lin = p.projector.projector
             ps += [lin.weight, lin.bias]
@@ -756,8 +906,7 @@ class MervFusion(nn.Module):
         x0 = xs[0]
         if not x0.is_cuda or x0.shape[0] == 0 or any(x.dtype != torch.bfloat16 for x in xs) or (out is not None and out.dim() != 3):
             return None
-        key = (tuple((x.shape, x.stride()) for x in xs), None if batch_index is None else batch_index.numel(), x0.device.index,
-               torch.cuda.current_stream(x0.device).cuda_stream)
+        key = (tuple((x.shape, x.stride()) for x in xs), None if batch_index is None else batch_index.numel(), *_stream_key(x0.device))
         cache = self.__dict__.setdefault("_fast", {})
         hit = cache.get(key)
         if hit is not None and hit[0] == self._param_tag():
@@ -775,7 +924,12 @@ class MervFusion(nn.Module):
 
     def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
                 batch_index: Optional[torch.Tensor] = None, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        if isinstance(self.feature_fusion, ConcatChannelFusion):  # merv.py:603-606: no mixing weights (mixer_value stays None)
+        if self.feature_fusion is None:  # merv.py:598-601: "first" / "concat", no module and no mixing weights
+            assert out is None and batch_index is None and gather is None, "'first' / 'concat' support the plain call only"
+            if self.fusion_type == "first":
+                return self.projectors[0]._forward_unfused(patch_features[0]), None
+            return self._forward_token_concat(patch_features), None
+        if isinstance(self.feature_fusion, (ConcatChannelFusion, ConcatChannelLNFusion)):  # merv.py:603-606: no mixing weights
             assert out is None and batch_index is None and gather is None, "concat_channel supports the plain call only"
             return self.feature_fusion([proj(x) for proj, x in zip(self.projectors, patch_features)]), None
         if gather is not None:  # fused all-gather of the prefixes over NVLink (parallel.SymmetricPrefixBuffer)
@@ -857,35 +1011,72 @@ class MervFusion(nn.Module):
         return buf, splice(attention_mask, True, False), splice(labels, IGNORE_INDEX, IGNORE_INDEX), weights
 
 
+_PLAIN_PROJECTORS = {"LinearProjector": LinearProjector, "MLPProjector": MLPProjector, "MLPDeepProjector": MLPDeepProjector,
+                     "FusedMLPProjector": FusedMLPProjector}
+
+
+def _adopt_plain_projector(ref_module: nn.Module) -> nn.Module:
+    """B200 twin of a reference LinearProjector / MLPProjector / MLPDeepProjector / FusedMLPProjector sharing its submodules
+    (``projector`` and the ``layernorm`` of pre_proj_layernorm), so parameters and state-dict keys are untouched."""
+    cls = _PLAIN_PROJECTORS[type(ref_module).__name__]
+    if isinstance(ref_module, cls):
+        return ref_module
+    new = cls.__new__(cls)
+    nn.Module.__init__(new)
+    new.projector, new.layernorm = ref_module.projector, ref_module.layernorm
+    if hasattr(ref_module, "initial_projection_dim"):
+        new.initial_projection_dim = ref_module.initial_projection_dim
+    return new
+
+
 def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
     """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
 
     ``vidlm.projectors[i]`` (reference AveragePooling3DProjector) and ``vidlm.feature_fusion`` (reference
     CrossAttentionAdapterLearnableQuery) keep their names, so checkpoints, ``all_module_keys`` (merv.py:235) and the
     FSDP wrap policy (merv.py:473-497, extended via isinstance on these classes) keep working.
+
+    Covered: the "3davg" / "avg" resamplers and the un-resampled projectors (with or without ``pre_proj_layernorm``,
+    merv.py:165-171) in front of feature_fusion in {cross_attention_avg_lq, scalar, concat_channel, concat_channel_ln} or the
+    parameter-free "first" / "concat" (``feature_fusion is None``, merv.py:598-601).
     """
     proj_classes = {"AveragePooling3DProjector": AveragePooling3DProjector, "AveragePoolingProjector": AveragePoolingProjector}
     new_projs = []
     for p in vidlm.projectors:
-        cls = proj_classes.get(type(p).__name__)
+        name = type(p).__name__
+        if name in _PLAIN_PROJECTORS:  # tokens_resampled == False (merv.py:164-172): no pooling, nothing to link
+            new_projs.append(_adopt_plain_projector(p))
+            fused = False
+            continue
+        cls = proj_classes.get(name)
         if cls is None:
-            raise TypeError(f"patch_merv supports the 3davg / avg arch_specifiers only, found projector {type(p).__name__}")
+            raise TypeError(f"patch_merv supports the 3davg / avg arch_specifiers and the un-resampled projectors, found {name}")
         new_projs.append(p if isinstance(p, AveragePooling3DProjector) else cls.from_reference(p))
     ff = vidlm.feature_fusion
-    if type(ff).__name__ == "CrossAttentionAdapterLearnableQuery":
+    fusion_type = getattr(vidlm, "feature_fusion_type", None)
+    if ff is None:  # "first" / "concat": glue only (merv.py:598-601)
+        new_ff, fused = None, False
+    elif type(ff).__name__ == "CrossAttentionAdapterLearnableQuery":
         new_ff = ff if isinstance(ff, CrossAttentionAdapterLearnableQuery) else CrossAttentionAdapterLearnableQuery.from_reference(ff)
     elif type(ff).__name__ == "ScalarAdapter":
         new_ff = ff if isinstance(ff, ScalarAdapter) else ScalarAdapter()
         new_ff.scalar = ff.scalar
-    elif type(ff).__name__ == "LinearProjector" and getattr(vidlm, "feature_fusion_type", "concat_channel") == "concat_channel":
+    elif type(ff).__name__ == "LinearProjector" and (fusion_type or "concat_channel") == "concat_channel":
         # merv.py:217-218: the glue (merv.py:603-606) concatenates and then calls this module with a tensor -> plain tcgen05 GEMM
         new_ff = ConcatChannelFusion.__new__(ConcatChannelFusion)
         nn.Module.__init__(new_ff)
         new_ff.projector, new_ff.layernorm = ff.projector, ff.layernorm
         new_ff.num_encoder = len(new_projs)
         fused = False
+    elif isinstance(ff, nn.Sequential) and len(ff) == 2 and isinstance(ff[0], nn.LayerNorm) and type(ff[1]).__name__ == "LinearProjector":
+        # merv.py:219-223 "concat_channel_ln": same two submodules (shared), B200 forward
+        new_ff = ConcatChannelLNFusion.__new__(ConcatChannelLNFusion)
+        nn.Sequential.__init__(new_ff, ff[0], _adopt_plain_projector(ff[1]))
+        new_ff.num_encoder = len(new_projs)
+        fused = False
     else:
-        raise TypeError(f"patch_merv supports feature_fusion in {{'cross_attention_avg_lq', 'scalar', 'concat_channel'}}, found {type(ff).__name__}")
+        raise TypeError("patch_merv supports feature_fusion in {'cross_attention_avg_lq', 'scalar', 'concat_channel', "
+                        f"'concat_channel_ln', 'first', 'concat'}}, found {type(ff).__name__}")
     vidlm.projectors = nn.ModuleList(new_projs)
     vidlm.feature_fusion = new_ff
     if fused:

@@ -56,6 +56,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
+    "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
 
@@ -224,20 +225,101 @@ def affine_score_vec(W: torch.Tensor, bias: Optional[torch.Tensor], u: torch.Ten
     return v, c
 
 
-def scores_from_tokens(Vs: Sequence[torch.Tensor], u: torch.Tensor, token_length: int) -> torch.Tensor:
-    """scores[b, e] = mean_t(u . V_e[b, t, :]) read from the tokens (general path)."""
+def scores_from_tokens(Vs: Sequence[torch.Tensor], u: torch.Tensor, token_length: int, per_token_u: bool = False,
+                       consts: Optional[torch.Tensor] = None, mean: bool = True) -> torch.Tensor:
+    """scores[b, e] = mean_t(u . V_e[b, t, :]) (+ consts[e]) read from the tokens (general path).
+
+    ``per_token_u``: u is [T*K] with one row per token and nothing is averaged unless ``mean`` — the averagetoken=False
+    branch (nn_utils.py:514-518).  ``consts`` (fp32 [E]): additive constants, u . pe[e] for positional_embedding=True
+    (nn_utils.py:510-511)."""
     lib = _lib.load()
-    dev = _require_cuda(*Vs, u)
+    dev = _require_cuda(*Vs, u, consts)
     B, _, K = Vs[0].shape
     E = len(Vs)
     Vs = [v.contiguous() for v in Vs]
+    assert u.dtype == torch.float32 and u.is_contiguous() and u.numel() == (token_length * K if per_token_u else K)
+    assert consts is None or (consts.dtype == torch.float32 and consts.is_contiguous() and consts.numel() == E)
     with torch.cuda.device(dev):
         scores = torch.empty((B, E), dtype=torch.float32, device=dev)
         n = lib.merv_scores_from_tokens_workspace(B, E, token_length, K)
         ws = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
-        _call('merv_scores_from_tokens', lib.merv_scores_from_tokens, ptr_array([v.data_ptr() for v in Vs]), i32_array([v.shape[1] for v in Vs]), u.data_ptr(),
-                                          scores.data_ptr(), ws.data_ptr(), n, B, E, token_length, K, dtype_code(Vs[0].dtype), _stream())
+        if not per_token_u and consts is None and mean:
+            _call('merv_scores_from_tokens', lib.merv_scores_from_tokens, ptr_array([v.data_ptr() for v in Vs]), i32_array([v.shape[1] for v in Vs]),
+                  u.data_ptr(), scores.data_ptr(), ws.data_ptr(), n, B, E, token_length, K, dtype_code(Vs[0].dtype), _stream())
+        else:
+            _call('merv_scores_from_tokens_ex', lib.merv_scores_from_tokens_ex, ptr_array([v.data_ptr() for v in Vs]),
+                  i32_array([v.shape[1] for v in Vs]), u.data_ptr(), K if per_token_u else 0, _p(consts), int(mean), scores.data_ptr(),
+                  ws.data_ptr(), n, B, E, token_length, K, dtype_code(Vs[0].dtype), _stream())
     return scores
+
+
+def score_consts(pe: torch.Tensor, u: torch.Tensor, c_in: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """c[e] = u . pe[e] (+ c_in[e]) — what positional_embedding=True adds to encoder e's score (nn_utils.py:510-511)."""
+    lib = _lib.load()
+    dev = _require_cuda(pe, u, *(c_in or []))
+    E, K = pe.shape
+    if pe.stride(1) != 1:
+        pe = pe.contiguous()
+    assert u.dtype == torch.float32 and u.numel() == K and u.is_contiguous()
+    with torch.cuda.device(dev):
+        c = torch.empty(E, dtype=torch.float32, device=dev)
+        cptr = ptr_array([_p(t) for t in c_in]) if c_in is not None else None
+        _call('merv_score_consts', lib.merv_score_consts, pe.data_ptr(), pe.stride(0), u.data_ptr(), cptr, c.data_ptr(), E, K, dtype_code(pe.dtype),
+              _stream())
+    return c
+
+
+def _segments(xs: Sequence[torch.Tensor]):
+    lead = xs[0].shape[:-1]
+    xs = [x.reshape(-1, x.shape[-1]) for x in xs]
+    vec = 8 if xs[0].dtype == torch.bfloat16 else 4
+    xs = [x if x.stride(1) == 1 and x.stride(0) % vec == 0 and x.data_ptr() % 16 == 0 else x.contiguous() for x in xs]
+    M = xs[0].shape[0]
+    assert all(x.shape[0] == M and x.dtype == xs[0].dtype for x in xs), "segments must share rows and dtype"
+    return lead, xs, M
+
+
+def layernorm(xs: Sequence[torch.Tensor], weight: Optional[torch.Tensor], bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last dimension of concat(xs, -1) without building the concatenation: [..., sum K_s].
+
+    nn.LayerNorm in front of a projector (pre_proj_layernorm, nn_utils.py:26-29) with one segment; the LayerNorm(E * llm_dim)
+    of feature_fusion == "concat_channel_ln" (merv.py:219-223,603-606) with E segments."""
+    lib = _lib.load()
+    dev = _require_cuda(*xs, weight, bias)
+    lead, xs, M = _segments(xs)
+    total = sum(x.shape[1] for x in xs)
+    dt = xs[0].dtype
+    assert weight is None or (weight.dtype == dt and weight.numel() == total and weight.is_contiguous())
+    assert bias is None or (bias.dtype == dt and bias.numel() == total and bias.is_contiguous())
+    with torch.cuda.device(dev):
+        y = torch.empty((M, total), dtype=dt, device=dev)
+        _call('merv_layernorm', lib.merv_layernorm, ptr_array([x.data_ptr() for x in xs]), i64_array([x.stride(0) for x in xs]),
+              i32_array([x.shape[1] for x in xs]), len(xs), _p(weight), _p(bias), float(eps), y.data_ptr(), y.stride(0), M, dtype_code(dt), _stream())
+    return y.view(*lead, total)
+
+
+def layernorm_backward(xs: Sequence[torch.Tensor], dy: torch.Tensor, weight: Optional[torch.Tensor], eps: float = 1e-5,
+                       need_dx: bool = True, need_params: bool = True):
+    """Backward of `layernorm`: returns (dx [M, sum K_s] | None, dweight | None, dbias | None) in the compute dtype."""
+    lib = _lib.load()
+    dev = _require_cuda(*xs, dy, weight)
+    _, xs, M = _segments(xs)
+    total = sum(x.shape[1] for x in xs)
+    dt = xs[0].dtype
+    dy = dy.reshape(M, total)
+    if dy.dtype != dt:
+        dy = dy.to(dt)
+    if dy.stride(1) != 1 or dy.stride(0) % (8 if dt == torch.bfloat16 else 4) or dy.data_ptr() % 16:
+        dy = dy.contiguous()
+    with torch.cuda.device(dev):
+        dx = torch.empty((M, total), dtype=dt, device=dev) if need_dx else None
+        gx = torch.empty((M, total), dtype=dt, device=dev) if need_params else None
+        _call('merv_layernorm_backward', lib.merv_layernorm_backward, ptr_array([x.data_ptr() for x in xs]), i64_array([x.stride(0) for x in xs]),
+              i32_array([x.shape[1] for x in xs]), len(xs), dy.data_ptr(), dy.stride(0), _p(weight), float(eps), _p(dx),
+              dx.stride(0) if need_dx else 0, _p(gx), gx.stride(0) if need_params else 0, M, dtype_code(dt), _stream())
+    if not need_params:
+        return dx, None, None
+    return dx, colsum(gx), colsum(dy)
 
 
 def scores_from_partials(partials: Sequence[torch.Tensor], consts: Optional[Sequence[Optional[torch.Tensor]]], B: int, T: int) -> torch.Tensor:

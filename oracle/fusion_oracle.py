@@ -74,12 +74,28 @@ def linear(x: np.ndarray, weight: np.ndarray, bias: np.ndarray) -> np.ndarray:
     return x @ weight.T + bias
 
 
+def layer_norm(x: np.ndarray, weight: np.ndarray, bias: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """``nn.LayerNorm(C)`` over the last dimension (merv/util/nn_utils.py:27,41,68,92; merv/models/vidlms/merv.py:221):
+    (x - mean) / sqrt(biased_var + eps) * weight + bias, statistics in at least fp32 (ATen accumulates in fp32)."""
+    acc = np.float64 if x.dtype == np.float64 else np.float32
+    xf = x.astype(acc)
+    mean = xf.mean(axis=-1, keepdims=True)
+    var = ((xf - mean) ** 2).mean(axis=-1, keepdims=True)
+    return ((xf - mean) / np.sqrt(var + acc(eps)) * weight + bias).astype(x.dtype)
+
+
 def projector_forward(x: np.ndarray, params: Dict[str, np.ndarray], mlp_type: str) -> np.ndarray:
-    """``get_mlp_projector`` variants (merv/util/nn_utils.py:22-59,86-121).
+    """``get_mlp_projector`` variants (merv/util/nn_utils.py:22-59,86-121) and ``MLPDeepProjector`` (:62-83, "deep-gelu-mlp").
 
     ``params`` uses the reference state-dict keys relative to ``AveragePooling3DProjector.projector``:
-    linear -> projector.{weight,bias}; gelu-mlp -> projector.{0,2}.*; fused-gelu-mlp -> projector.{0,2,4}.*.
+    linear -> projector.{weight,bias}; gelu-mlp -> projector.{0,2}.*; fused-gelu-mlp / deep-gelu-mlp -> projector.{0,2,4}.*.
+    ``layernorm.{weight,bias}`` present <=> the module was built with ``pre_proj_layernorm=True`` (nn_utils.py:26-32): the
+    input is layer-normalised first.
     """
+    if "layernorm.weight" in params:
+        x = layer_norm(x, params["layernorm.weight"], params["layernorm.bias"])
+    if mlp_type == "deep-gelu-mlp":
+        mlp_type = "fused-gelu-mlp"  # same Sequential(Linear, GELU, Linear, GELU, Linear) structure, different widths
     if mlp_type == "linear":
         return linear(x, params["projector.weight"], params["projector.bias"])
     if mlp_type == "gelu-mlp":
@@ -138,20 +154,27 @@ def fusion_query_vector(params: Dict[str, np.ndarray]) -> np.ndarray:
 
 
 def cross_attention_fusion_forward(
-    V: Sequence[np.ndarray], params: Dict[str, np.ndarray], token_length: int
+    V: Sequence[np.ndarray], params: Dict[str, np.ndarray], token_length: int, averagetoken: bool = True
 ) -> Tuple[np.ndarray, np.ndarray]:
-    """``CrossAttentionAdapterLearnableQuery.forward`` with averagetoken=True, no positional embedding.
+    """``CrossAttentionAdapterLearnableQuery.forward`` (merv/util/nn_utils.py:487-521).
 
-    merv/util/nn_utils.py:487-521: assert T in {token_length, 1}; broadcast T==1 encoders; stack to
-    [B, E, T, K]; Vbar = mean over tokens; weights from the MHA; out = sum_e w[b,e] * V[b,e].
-    Returns (out [B, T, K], weights [B, E]).
+    assert T in {token_length, 1}; broadcast T==1 encoders (:502); stack to [B, E, T, K] (:503).
+    averagetoken=True  (:507-512): key = mean over tokens (+ ``pe`` when the module has positional_embedding=True, :510-511)
+    averagetoken=False (:514-518): key = the flattened [T*K] token block (``k_proj_weight`` is [embed, T*K]; ``pe`` unused)
+    weights from the MHA; out = sum_e w[b,e] * V[b,e] (:521).  Returns (out [B, T, K], weights [B, E]).
     """
     for emb in V:
         assert emb.shape[1] == token_length or emb.shape[1] == 1, (token_length, [e.shape for e in V])
     Vs = [np.repeat(e, token_length, axis=1) if e.shape[1] == 1 else e for e in V]
     stacked = np.stack(Vs, axis=1)  # [B, E, T, K]
-    vbar = stacked.mean(axis=2)
-    w = fusion_weights_mha(vbar, params)
+    B, E, T, K = stacked.shape
+    if averagetoken:
+        key = stacked.mean(axis=2)
+        if "pe" in params:
+            key = key + params["pe"][None, :, :]
+    else:
+        key = stacked.reshape(B, E, T * K)
+    w = fusion_weights_mha(key, params)
     out = np.einsum("be,betk->btk", w, stacked)
     return out.astype(stacked.dtype), w.astype(stacked.dtype)
 
@@ -168,6 +191,19 @@ def concat_channel_forward(V: Sequence[np.ndarray], params: Dict[str, np.ndarray
     """feature_fusion == "concat_channel": ``torch.concat(projected, -1)`` then ``LinearProjector(E*llm_dim, llm_dim)``
     (merv/models/vidlms/merv.py:217-218,603-606; LinearProjector is nn_utils.py:22-32, keys ``projector.{weight,bias}``)."""
     return linear(np.concatenate(list(V), axis=-1), params["projector.weight"], params["projector.bias"])
+
+
+def concat_channel_ln_forward(V: Sequence[np.ndarray], params: Dict[str, np.ndarray]) -> np.ndarray:
+    """feature_fusion == "concat_channel_ln": ``torch.concat(projected, -1)`` (merv.py:603-605), then
+    ``Sequential(LayerNorm(E*llm_dim), LinearProjector(E*llm_dim, llm_dim))`` (merv.py:219-223; keys ``0.{weight,bias}``,
+    ``1.projector.{weight,bias}``)."""
+    x = layer_norm(np.concatenate(list(V), axis=-1), params["0.weight"], params["0.bias"])
+    return linear(x, params["1.projector.weight"], params["1.projector.bias"])
+
+
+def token_concat_forward(V: Sequence[np.ndarray]) -> np.ndarray:
+    """feature_fusion == "concat" (merv.py:600-601): ``torch.concat(projected, 1)``; "first" (:598-599) is ``V[0]``."""
+    return np.concatenate(list(V), axis=1)
 
 
 IGNORE_INDEX = -100  # merv/models/vidlms/merv.py:53

@@ -75,11 +75,66 @@ def run_reference(projs, fusion, feats, dtype=torch.float32):
     return out, w, ys, pooled
 
 
+def build_variant(ref, name: str, dtype=torch.float32):
+    """The reference module of one oracle/variants.py entry, weights loaded through its own state-dict keys."""
+    from oracle import variants as V
+
+    v = V.VARIANTS[name]
+    inputs, params = V.make_variant(name)
+    if v["kind"] == "projector":
+        cls = getattr(ref, v["cls"])
+        mod = cls(v["vision_dim"], v["llm_dim"], pre_proj_layernorm=True)  # as merv.py:165-171 does
+    elif v["kind"] == "concat_channel_ln":  # merv.py:219-223
+        mod = torch.nn.Sequential(torch.nn.LayerNorm(v["E"] * v["K"]), ref.LinearProjector(v["E"] * v["K"], v["K"]))
+    else:
+        mod = ref.CrossAttentionAdapterLearnableQuery(embed_dim=v["embed"], llm_dim=v["K"], token_length=v["T"],
+                                                      averagetoken=v["averagetoken"], num_encoder=v["E"], positional_embedding=v["pe"])
+    mod.load_state_dict({k: torch.from_numpy(a) for k, a in params.items()})
+    return mod.to(dtype).eval(), inputs, v
+
+
+@torch.no_grad()
+def run_variant(mod, inputs, v, dtype=torch.float32):
+    xs = [torch.from_numpy(a).to(dtype) for a in inputs]
+    if v["kind"] == "projector":
+        return mod(xs[0]), None
+    if v["kind"] == "concat_channel_ln":
+        return mod(torch.concat(xs, -1)), None  # merv.py:603-606
+    return mod(xs)
+
+
+def make_variants(ref) -> None:
+    from oracle import variants as V
+
+    store = {}
+    for name in V.VARIANTS:
+        mod, inputs, v = build_variant(ref, name)
+        out, w = run_variant(mod, inputs, v)
+        mod16, _, _ = build_variant(ref, name, torch.bfloat16)
+        out16, w16 = run_variant(mod16, inputs, v, torch.bfloat16)
+        store[f"{name}.out"] = out.numpy()
+        store[f"{name}.out_bf16"] = out16.float().numpy()
+        if w is not None:
+            store[f"{name}.weights"] = w.numpy()
+            store[f"{name}.weights_bf16"] = w16.float().numpy()
+        _, params = V.make_variant(name)
+        store[f"{name}.checksum"] = np.float64(sum(float(np.abs(a.astype(np.float64)).sum()) for a in inputs)
+                                               + sum(float(np.abs(a.astype(np.float64)).sum()) for a in params.values()))
+        dev = float(np.abs(store[f"{name}.out_bf16"] - store[f"{name}.out"]).max() / np.abs(store[f"{name}.out"]).max())
+        print(f"{name:24s} out {tuple(out.shape)} bf16-vs-fp32={dev:.2e}" + ("" if w is None else f" w[0]={np.round(w.numpy()[0], 4)}"))
+    path = os.path.join(GOLDEN_DIR, "variants.npz")
+    np.savez_compressed(path, **store)
+    print(f"wrote variants.npz ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def main() -> None:
     ref = load_reference_nn_utils()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     only = set(sys.argv[1:])  # `python -m oracle.make_golden concat_channel` regenerates just that fixture
+    if only == {"variants"}:  # `python -m oracle.make_golden variants`: only tests/golden/variants.npz
+        make_variants(ref)
+        return
     for name, case in C.CASES.items():
         if only and name not in only:
             continue
@@ -120,6 +175,7 @@ def main() -> None:
 
     if only:
         return
+    make_variants(ref)
     # the reference's own seed-1024 construction order (merv.py:87,152-163,214-216) -> init digests
     torch.manual_seed(1024)
     full = C.CASES["merv_full_b1"]

@@ -661,3 +661,172 @@ def test_forward_multimodal_assembly_matches_oracle(mm):
     with torch.inference_mode():
         fe2, fm2, fl2, _ = m.forward_multimodal(rep, emb, multimodal_indices=None if whole else idx)
     assert fm2 is None and fl2 is None and torch.equal(fe2, fe)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configuration variants: pre_proj_layernorm, concat_channel_ln, averagetoken=False, positional embedding,
+# "first" / "concat" — goldens recorded from the unmodified reference modules (tests/golden/variants.npz)
+# ---------------------------------------------------------------------------------------------------------
+def _variant_names():
+    from oracle import variants as V
+
+    return list(V.VARIANTS)
+
+
+@pytest.mark.parametrize("name", _variant_names())
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_variants_match_reference(name, dtype):
+    from tests.variant_util import build_variant_module, run_variant
+
+    mod, v, inputs, gold = build_variant_module(name, dtype, DEV)
+    with torch.inference_mode():
+        out, w = run_variant(mod, v, inputs, dtype, DEV)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == gold["out"].shape and out.dtype == dtype and out.is_contiguous()
+    if dtype == torch.float32:
+        assert O.rel_err(_np(out), gold["out"]) < FP32_TOL
+        if w is not None:
+            assert np.abs(_np(w) - gold["weights"]).max() < 2e-5
+    else:
+        assert O.rel_err(_np(out), gold["out"]) < BF16_TOL
+        assert O.rel_err(_np(out), gold["out_bf16"]) < BF16_TOL  # the reference's own bf16 run
+        if w is not None:
+            assert np.abs(_np(w) - gold["weights"]).max() < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("widths", [[64], [128, 64, 192], [1024, 1024, 768, 768], [4096] * 4])
+def test_layernorm_kernel_matches_oracle_incl_segments(widths, dtype):
+    # warp-per-row (<= 256 vectors) and CTA-per-row layouts, one and several row segments, strided segment rows
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(len(widths) * 1000 + widths[0])
+    M_ = 37
+    total = sum(widths)
+    segs = [rng.standard_normal((M_, k), dtype=np.float32) * (1.0 + 0.5 * i) + 0.3 * i for i, k in enumerate(widths)]
+    gamma = (1.0 + 0.3 * rng.standard_normal(total)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(total)).astype(np.float32)
+    xs = [_t(s, dtype) for s in segs]
+    if len(xs) > 1:  # segment 1 as a column slice of a wider buffer: row stride > width
+        wide = torch.zeros((M_, widths[1] + 16), dtype=dtype, device=DEV)
+        wide[:, :widths[1]] = xs[1]
+        xs[1] = wide[:, :widths[1]]
+    y = ops.layernorm(xs, _t(gamma, dtype), _t(beta, dtype), 1e-5)
+    torch.cuda.synchronize()
+    want = O.layer_norm(np.concatenate([_np(_t(s, dtype)).astype(np.float64) for s in segs], -1), _np(_t(gamma, dtype)).astype(np.float64),
+                        _np(_t(beta, dtype)).astype(np.float64))
+    assert y.shape == (M_, total) and y.dtype == dtype
+    assert O.rel_err(_np(y), want) < (FP32_TOL if dtype == torch.float32 else 6e-3)
+    y0 = ops.layernorm(xs, None, None, 1e-5)  # elementwise_affine=False form
+    want0 = O.layer_norm(np.concatenate([_np(_t(s, dtype)).astype(np.float64) for s in segs], -1), np.ones(total), np.zeros(total))
+    assert O.rel_err(_np(y0), want0) < (FP32_TOL if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("widths", [[96], [1024, 512], [4096] * 4])
+def test_layernorm_backward_kernel_matches_autograd(widths, dtype, tol):
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(17 + len(widths))
+    M_, total = 29, sum(widths)
+    segs = [_t(rng.standard_normal((M_, k), dtype=np.float32) + 0.2 * i, dtype) for i, k in enumerate(widths)]
+    gamma = _t((1.0 + 0.3 * rng.standard_normal(total)).astype(np.float32), dtype)
+    dy = _t(rng.standard_normal((M_, total), dtype=np.float32), dtype)
+    dx, dg, db = ops.layernorm_backward(segs, dy, gamma, 1e-5)
+    torch.cuda.synchronize()
+    x64 = torch.cat([s.double() for s in segs], -1).cpu().requires_grad_(True)
+    g64 = gamma.double().cpu().requires_grad_(True)
+    b64 = torch.zeros(total, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.layer_norm(x64, (total,), g64, b64, 1e-5).backward(dy.double().cpu())
+    assert O.rel_err(_np(dx), x64.grad.numpy()) < tol
+    assert O.rel_err(_np(dg), g64.grad.numpy()) < tol
+    assert O.rel_err(_np(db), b64.grad.numpy()) < tol
+
+
+@pytest.mark.parametrize("name", ["pre_ln_linear", "pre_ln_gelu", "pre_ln_fused_gelu", "pre_ln_linear_wide"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_pre_layernorm_projector_backward(name, dtype, tol):
+    from tests.variant_util import build_variant_module
+
+    mod, v, inputs, _ = build_variant_module(name, dtype, DEV)
+    if dtype == torch.bfloat16 and v["vision_dim"] % 8:
+        pytest.skip("bf16 path needs C % 8 == 0")
+    mod.requires_grad_(True).train()
+    x = _t(inputs[0], dtype)
+    rng = np.random.default_rng(3)
+    y = mod(x)
+    dy = _t(rng.standard_normal(tuple(y.shape), dtype=np.float32), dtype)
+    y.backward(dy)
+    got = {k: _np(p.grad) for k, p in mod.named_parameters()}
+    # fp64 autograd through the same op sequence at the same (rounded) operating point
+    ln = torch.nn.LayerNorm(v["vision_dim"]).double()
+    ln.load_state_dict({k: t.double().cpu() for k, t in mod.layernorm.state_dict().items()})
+    import copy
+
+    seq = copy.deepcopy(mod.projector).cpu().double()
+    for p in list(ln.parameters()) + list(seq.parameters()):
+        p.grad = None
+    seq(ln(x.double().cpu())).backward(dy.double().cpu())
+    want = {**{"layernorm." + k: p.grad.numpy() for k, p in ln.named_parameters()}, **{"projector." + k: p.grad.numpy() for k, p in seq.named_parameters()}}
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert O.rel_err(got[k], want[k]) < tol, k
+
+
+def test_first_and_token_concat_fusions_on_gpu():
+    import merv_b200 as M
+
+    case = C.CASES["mid_linear"]  # 256 tokens per encoder: the direct (batch-strided TMA store) form of "concat"
+    g, feats, pp, fp = regenerate(case)
+    projs = [M.AveragePooling3DProjector(c, case.llm_dim, t, case.out_size, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
+    for proj, p in zip(projs, pp):
+        proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    want = [O.avgpool3d_projector_forward(_bf16_round(f).astype(np.float64), {k: _bf16_round(a).astype(np.float64) for k, a in p.items()}, t,
+                                          case.out_size, case.mlp_type) for f, p, t in zip(feats, pp, case.out_frames)]
+    for dtype, tol in ((torch.bfloat16, 8e-3), (torch.float32, 8e-3)):
+        xs = [_t(f, dtype) for f in feats]
+        first = M.MervFusion(projs, None, fusion_type="first").to(device=DEV, dtype=dtype).eval().requires_grad_(False)
+        cat = M.MervFusion(projs, None, fusion_type="concat").to(device=DEV, dtype=dtype).eval().requires_grad_(False)
+        with torch.inference_mode():
+            o1, w1 = first(xs)
+            o2, w2 = cat(xs)
+        assert w1 is None and w2 is None and o2.shape == (case.batch, case.token_length * case.num_encoders, case.llm_dim)
+        assert O.rel_err(_np(o1), want[0]) < tol
+        assert O.rel_err(_np(o2), O.token_concat_forward(want)) < tol
+        if dtype == torch.bfloat16:  # direct stores must equal "project, then copy into place" bit for bit
+            ys = [p._forward_unfused(x) for p, x in zip(first.projectors, xs)]
+            assert torch.equal(o2, torch.cat(ys, 1))
+
+
+def test_positional_embedding_linked_equals_unlinked_on_gpu():
+    import merv_b200 as M
+
+    case = C.CASES["mid_linear"]
+    g, feats, pp, fp = regenerate(case)
+    res = []
+    for fused in (False, True):
+        projs = [M.AveragePooling3DProjector(c, case.llm_dim, t, case.out_size, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
+        ff = M.CrossAttentionAdapterLearnableQuery(case.embed_dim, case.llm_dim, case.token_length, averagetoken=True,
+                                                   num_encoder=case.num_encoders, positional_embedding=True)
+        m = M.MervFusion(projs, ff, fused=fused)
+        for proj, p in zip(m.projectors, pp):
+            proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+        ff.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()}, strict=False)
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(9)
+            ff.pe.copy_(torch.randn(ff.pe.shape, generator=gen) * 0.5)
+        m = m.to(device=DEV, dtype=torch.bfloat16).eval().requires_grad_(False)
+        with torch.inference_mode():
+            res.append(m([_t(f, torch.bfloat16) for f in feats]))
+        pe = _np(ff.pe)
+    (o0, w0), (o1, w1) = res
+    assert np.abs(_np(w0) - _np(w1)).max() < 1e-2 and O.rel_err(_np(o1), _np(o0)) < 8e-3
+    # and against the oracle with the positional embedding (fp64 on the rounded operating point)
+    fpr = {k: _bf16_round(v).astype(np.float64) for k, v in fp.items()}
+    fpr["pe"] = pe.astype(np.float64)
+    ys = [O.avgpool3d_projector_forward(_bf16_round(f).astype(np.float64), {k: _bf16_round(a).astype(np.float64) for k, a in p.items()}, t,
+                                        case.out_size, case.mlp_type) for f, p, t in zip(feats, pp, case.out_frames)]
+    want, want_w = O.cross_attention_fusion_forward(ys, fpr, case.token_length)
+    assert np.abs(_np(w1) - want_w).max() < 1e-2 and O.rel_err(_np(o1), want) < 8e-3
+    no_pe = {k: a for k, a in fpr.items() if k != "pe"}
+    assert np.abs(O.cross_attention_fusion_forward(ys, no_pe, case.token_length)[1] - want_w).max() > 0.02, "pe must matter in this fixture"

@@ -132,3 +132,51 @@ def test_assemble_multimodal_layout():
     assert not fm[2:, L:].any() and (fl[2:, L:] == O.IGNORE_INDEX).all() and np.array_equal(fl[3, :L], labels[3])
     fe2, fm2, fl2 = O.assemble_multimodal(np.concatenate([prefix, prefix]), emb, mask, labels, [0, 1, 2, 3], 1)
     assert fe2.shape == (Bt, L + T, K)  # no unimodal rows: fused == multimodal
+
+
+# ---- configuration variants: pre_proj_layernorm, concat_channel_ln, averagetoken=False, positional embedding ----
+def oracle_variant(v, inputs, params):
+    if v["kind"] == "projector":
+        return O.projector_forward(inputs[0], params, v["mlp_type"]), None
+    if v["kind"] == "concat_channel_ln":
+        return O.concat_channel_ln_forward(inputs, params), None
+    return O.cross_attention_fusion_forward(inputs, params, v["T"], averagetoken=v["averagetoken"])
+
+
+def _variant_names():
+    from oracle import variants as V
+
+    return list(V.VARIANTS)
+
+
+@pytest.mark.parametrize("name", _variant_names())
+def test_oracle_variants_match_reference_golden(name):
+    from tests.golden_util import load_variant
+
+    v, inputs, params, gold = load_variant(name)
+    out, w = oracle_variant(v, inputs, params)
+    assert out.shape == gold["out"].shape
+    assert O.rel_err(out, gold["out"]) < FP32_TOL
+    if w is not None:
+        assert np.abs(w - gold["weights"]).max() < 2e-5 and np.allclose(w.sum(-1), 1.0, atol=1e-5)
+        assert np.abs(w - 1.0 / w.shape[1]).max() > 0.03, "degenerate (flat) softmax: the fixture would not catch a broken score path"
+
+
+def test_variant_fixtures_are_sensitive_to_the_variant():
+    # the positional embedding / the flattened key / the LayerNorm must move the reference's output well beyond the parity tolerance
+    from tests.golden_util import load_variant
+
+    v, inputs, params, gold = load_variant("xattn_pe")
+    no_pe = {k: a for k, a in params.items() if k != "pe"}
+    _, w = O.cross_attention_fusion_forward(inputs, no_pe, v["T"])
+    assert np.abs(w - gold["weights"]).max() > 0.02
+    v, inputs, params, gold = load_variant("pre_ln_linear")
+    no_ln = {k: a for k, a in params.items() if not k.startswith("layernorm")}
+    assert O.rel_err(O.projector_forward(inputs[0], no_ln, "linear"), gold["out"]) > 0.1
+
+
+def test_token_concat_and_first():
+    rng = np.random.default_rng(0)
+    V = [rng.standard_normal((2, 3, 4)).astype(np.float32) for _ in range(3)]
+    out = O.token_concat_forward(V)
+    assert out.shape == (2, 9, 4) and np.array_equal(out[:, 3:6], V[1])
