@@ -140,7 +140,7 @@ class _ProjectorFn(torch.autograd.Function):
             if zs[i] is not None:
                 g = ops.gelu(zs[i].reshape(g.shape), g)  # dZ_i
             x2 = xs[i].reshape(-1, xs[i].shape[-1])
-            dW, _ = ops.linear_bias_act(ops.transpose(g), ops.transpose(x2), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
+            dW, _ = ops.linear_bias_act(ops.transpose(g, pad=True), ops.transpose(x2, pad=True), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
             grads[off + 2 * i] = dW.to(ctx.param_dtypes[off + 2 * i])
             grads[off + 2 * i + 1] = ops.colsum(g).to(ctx.param_dtypes[off + 2 * i + 1])
             if i > 0 or need_dx or has_ln:

@@ -505,14 +505,18 @@ class FusedLinearPlan:
 
 
 # ---- backward building blocks (SURVEY.md §8 f-1) ------------------------------------------------------------------
-def transpose(x: torch.Tensor) -> torch.Tensor:
-    """[R, C] -> contiguous [C, R]."""
+def transpose(x: torch.Tensor, pad: bool = False) -> torch.Tensor:
+    """[R, C] -> contiguous [C, R].  ``pad``: the result is [C, R'] with R' = R rounded up to one 16-byte vector and zeros in the
+    extra columns — as the K-major operand of a GEMM whose contraction runs over R (dW = dY^T X over the token rows) it then meets
+    the GEMM's K % 8 (bf16) / K % 4 (fp32) requirement whatever the number of tokens."""
     lib = _lib.load()
     dev = _require_cuda(x)
     assert x.dim() == 2 and x.stride(1) == 1
     R, Cc = x.shape
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    Rp = -(-R // vec) * vec if pad else R
     with torch.cuda.device(dev):
-        y = torch.empty((Cc, R), dtype=x.dtype, device=dev)
+        y = torch.empty((Cc, R), dtype=x.dtype, device=dev) if Rp == R else torch.zeros((Cc, Rp), dtype=x.dtype, device=dev)
         _call('merv_transpose', lib.merv_transpose, x.data_ptr(), y.data_ptr(), R, Cc, x.stride(0), y.stride(0), dtype_code(x.dtype), _stream())
     return y
 

@@ -1,0 +1,87 @@
+"""Throughput of the variant kernels at production shapes (bf16, B200): LayerNorm over row segments (concat_channel_ln),
+pre-projection LayerNorm, per-token-u scores (averagetoken=False).  Algorithmic bytes = distinct inputs + outputs.
+
+    python scripts/gpu_variants_diag.py        # prints a summary, writes gpurun_out/variants_diag.json
+"""
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import torch
+
+from merv_b200 import ops
+
+dev = "cuda:0"
+PEAK = 6553.6
+try:
+    PEAK = float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))).get("hbm_gbs", PEAK))
+except Exception:
+    pass
+
+
+def timed(fns, iters=24, warm=4):
+    """Steady-state ms per call over ROTATING argument sets (each larger than L2 together with its output), one CUDA-event pair
+    around the whole loop: no dirty-line flush that the timed kernel would have to write back."""
+    for i in range(warm):
+        fns[i % len(fns)]()
+    torch.cuda.synchronize()
+    # the loop is replayed from a CUDA graph: a 60 us kernel would otherwise be timed at the rate Python can issue it
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(iters):
+            fns[i % len(fns)]()
+    graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+rep = {"device": torch.cuda.get_device_name(0), "hbm_peak_GBps": PEAK}
+g = torch.Generator(device=dev).manual_seed(1)
+
+# concat_channel_ln at merv-full width: 16 videos x 1024 tokens, 4 encoders x 4096 channels
+M, K, E = 16 * 1024, 4096, 4
+SETS = 3
+segsets = [[torch.randn(M, K, generator=g, device=dev).to(torch.bfloat16) for _ in range(E)] for _ in range(SETS)]
+segs = segsets[0]
+gamma = torch.ones(E * K, device=dev, dtype=torch.bfloat16)
+beta = torch.zeros(E * K, device=dev, dtype=torch.bfloat16)
+ms = timed([lambda ss=ss: ops.layernorm(ss, gamma, beta) for ss in segsets])
+b = 2 * M * E * K * 2
+rep["layernorm_segments_4x4096"] = {"rows": M, "ms": ms, "GBps": b / ms / 1e6, "frac": b / ms / 1e6 / PEAK}
+
+# pre-projection LayerNorm on pooled LanguageBind tokens: 64 videos x 1024 tokens x 1024 channels (warp per row)
+M2, K2 = 64 * 1024, 1024
+xs = [torch.randn(M2, K2, generator=g, device=dev).to(torch.bfloat16) for _ in range(SETS)]
+x = xs[0]
+g2, b2 = torch.ones(K2, device=dev, dtype=torch.bfloat16), torch.zeros(K2, device=dev, dtype=torch.bfloat16)
+ms = timed([lambda xx=xx: ops.layernorm([xx], g2, b2) for xx in xs])
+b = 2 * M2 * K2 * 2
+rep["layernorm_1024"] = {"rows": M2, "ms": ms, "GBps": b / ms / 1e6, "frac": b / ms / 1e6 / PEAK}
+
+# LayerNorm backward (dX + dY*xhat) on the same tensor: reads x, dy; writes dx, gx
+dy = torch.randn(M2, K2, generator=g, device=dev).to(torch.bfloat16)
+ms = timed([lambda xx=xx: ops.layernorm_backward([xx], dy, g2) for xx in xs])
+b = 4 * M2 * K2 * 2
+rep["layernorm_backward_1024_incl_colsums"] = {"rows": M2, "ms": ms, "GBps_of_main_kernel_bytes": b / ms / 1e6}
+
+# scores with one u row per token (averagetoken=False), 16 videos, 4 encoders, T = 1024, K = 4096
+B, T = 16, 1024
+V = [s.view(B, T, K) for s in segs]
+u = torch.randn(T * K, generator=g, device=dev)
+Vs = [[t.view(B, T, K) for t in ss] for ss in segsets]
+ms = timed([lambda vv=vv: ops.scores_from_tokens(vv, u, T, per_token_u=True, mean=False) for vv in Vs])
+b = E * B * T * K * 2 + T * K * 4
+rep["scores_per_token_u"] = {"ms": ms, "GBps": b / ms / 1e6, "frac": b / ms / 1e6 / PEAK}
+
+os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+json.dump(rep, open(os.path.join(REPO, "gpurun_out", "variants_diag.json"), "w"), indent=1)
+for k, v in rep.items():
+    print(k, v)

@@ -157,8 +157,11 @@ def layernorm_backward(xs, dy, weight, eps=1e-5, need_dx=True, need_params=True)
     return (dx.to(dt) if need_dx else None), (dw.to(dt) if need_params else None), (db.to(dt) if need_params else None)
 
 
-def transpose(x):
-    return x.T.contiguous()
+def transpose(x, pad=False):
+    y = x.T.contiguous()
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    extra = (-y.shape[1]) % vec if pad else 0
+    return F.pad(y, (0, extra)) if extra else y
 
 
 def gelu(z, dy=None):
