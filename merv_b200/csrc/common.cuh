@@ -152,6 +152,37 @@ __device__ __forceinline__ unsigned long long f32x2_mul(unsigned long long a, un
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
+// 16-byte vector <-> packed fp32 pairs.  The streaming kernels (LayerNorm, pooling) turned out instruction-ISSUE bound before they
+// were HBM-bound, so their arithmetic runs on Blackwell's packed fp32 pipe (fma.rn.f32x2: one instruction per two elements).
+template <typename T> struct Pairs;
+template <> struct Pairs<__nv_bfloat16> {
+  static constexpr int kP = 4;
+  __device__ static __forceinline__ void unpack(const uint4& r, unsigned long long (&x)[4]) {
+    x[0] = f32x2_pack(bf16_lo(r.x), bf16_hi(r.x));
+    x[1] = f32x2_pack(bf16_lo(r.y), bf16_hi(r.y));
+    x[2] = f32x2_pack(bf16_lo(r.z), bf16_hi(r.z));
+    x[3] = f32x2_pack(bf16_lo(r.w), bf16_hi(r.w));
+  }
+  __device__ static __forceinline__ uint4 pack(const unsigned long long (&x)[4]) {
+    float a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f32x2_unpack(x[q], a[q], b[q]);
+    return make_uint4(pack_bf16x2(a[0], b[0]), pack_bf16x2(a[1], b[1]), pack_bf16x2(a[2], b[2]), pack_bf16x2(a[3], b[3]));
+  }
+};
+template <> struct Pairs<float> {
+  static constexpr int kP = 2;
+  __device__ static __forceinline__ void unpack(const uint4& r, unsigned long long (&x)[2]) {
+    x[0] = f32x2_pack(__uint_as_float(r.x), __uint_as_float(r.y));
+    x[1] = f32x2_pack(__uint_as_float(r.z), __uint_as_float(r.w));
+  }
+  __device__ static __forceinline__ uint4 pack(const unsigned long long (&x)[2]) {
+    float a[2], b[2];
+    f32x2_unpack(x[0], a[0], b[0]);
+    f32x2_unpack(x[1], a[1], b[1]);
+    return make_uint4(__float_as_uint(a[0]), __float_as_uint(b[0]), __float_as_uint(a[1]), __float_as_uint(b[1]));
+  }
+};
 __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
 #define MERV_C2(v) f32x2_pack(v, v)
   const unsigned long long x = f32x2_pack(x0, x1);

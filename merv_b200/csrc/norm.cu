@@ -70,37 +70,6 @@ __device__ __forceinline__ void seg_col(const LnSegments& p, int i, const T*& co
   ld = (int)l;
 }
 
-// 16-byte vector <-> packed fp32 pairs: the forward kernel is issue-bound before it is HBM-bound (three passes over every
-// element), so its arithmetic runs on Blackwell's packed fp32 pipe (fma.rn.f32x2: one instruction per two elements)
-template <typename T> struct Pairs;
-template <> struct Pairs<__nv_bfloat16> {
-  static constexpr int kP = 4;
-  __device__ static __forceinline__ void unpack(const uint4& r, unsigned long long (&x)[4]) {
-    x[0] = f32x2_pack(bf16_lo(r.x), bf16_hi(r.x));
-    x[1] = f32x2_pack(bf16_lo(r.y), bf16_hi(r.y));
-    x[2] = f32x2_pack(bf16_lo(r.z), bf16_hi(r.z));
-    x[3] = f32x2_pack(bf16_lo(r.w), bf16_hi(r.w));
-  }
-  __device__ static __forceinline__ uint4 pack(const unsigned long long (&x)[4]) {
-    float a[4], b[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) f32x2_unpack(x[q], a[q], b[q]);
-    return make_uint4(pack_bf16x2(a[0], b[0]), pack_bf16x2(a[1], b[1]), pack_bf16x2(a[2], b[2]), pack_bf16x2(a[3], b[3]));
-  }
-};
-template <> struct Pairs<float> {
-  static constexpr int kP = 2;
-  __device__ static __forceinline__ void unpack(const uint4& r, unsigned long long (&x)[2]) {
-    x[0] = f32x2_pack(__uint_as_float(r.x), __uint_as_float(r.y));
-    x[1] = f32x2_pack(__uint_as_float(r.z), __uint_as_float(r.w));
-  }
-  __device__ static __forceinline__ uint4 pack(const unsigned long long (&x)[2]) {
-    float a[2], b[2];
-    f32x2_unpack(x[0], a[0], b[0]);
-    f32x2_unpack(x[1], a[1], b[1]);
-    return make_uint4(__float_as_uint(a[0]), __float_as_uint(b[0]), __float_as_uint(a[1]), __float_as_uint(b[1]));
-  }
-};
 template <typename T> __device__ __forceinline__ uint4 vec_of_ones();
 template <> __device__ __forceinline__ uint4 vec_of_ones<__nv_bfloat16>() { return make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u); }
 template <> __device__ __forceinline__ uint4 vec_of_ones<float>() { return make_uint4(0x3F800000u, 0x3F800000u, 0x3F800000u, 0x3F800000u); }

@@ -89,6 +89,29 @@ def test_pool3d_matches_oracle(name, dtype, impl, monkeypatch):
         assert np.abs(got - want_dot).max() < 2e-4 * max(1.0, np.abs(want_dot).max())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,F,T,C", [(16, 4, 4, 192), (14, 4, 4, 192), (16, 8, 4, 64), (14, 6, 4, 200), (14, 5, 3, 72)])
+def test_pool3d_square_grid_consumer_matches_oracle(H, F, T, C, dtype):
+    # the separable compile-time-window consumer of the TMA kernel (16 x 16 and 14 x 14 patches -> 8 x 8, 128-byte channel slabs):
+    # temporal windows of 1, 2 and ragged 1-2 frames, a channel tail that hangs over the last slab, strided frames, score partials
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(H * 100 + F * 10 + T)
+    B = 3
+    full = _t(rng.standard_normal((B, F, H * H + 1, C), dtype=np.float32) + 0.25, dtype)
+    x = full[:, :, 1:, :]  # CLS-dropping slice: frame stride (N + 1) * C
+    sv = rng.standard_normal(C).astype(np.float32)
+    (y,), (pt,) = ops.pool3d([x], [T], 8, score_vecs=[_t(sv)])
+    (yd,), _ = ops.pool3d([x.contiguous()], [T], 8)
+    torch.cuda.synchronize()
+    want = O.avg_pool3d_tokens(_np(x), T, 8)
+    assert y.shape == want.shape == (B, T * 64, C) and y.dtype == dtype
+    assert O.rel_err(_np(y), want) < (1e-6 if dtype == torch.float32 else 4e-3)
+    assert torch.equal(y, yd)
+    want_dot = (_np(y).astype(np.float64).sum(1) * sv).sum(-1)
+    assert np.abs(_np(pt).astype(np.float64).sum(1) - want_dot).max() < 2e-4 * max(1.0, np.abs(want_dot).max())
+
+
 def test_pool3d_strided_input_drops_cls_token():
     # backbones hand over slices that drop a CLS token (languagebind/__init__.py:94): token stride stays C,
     # frame stride is (N+1)*C — the kernel must honour strides instead of forcing a copy
