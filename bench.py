@@ -340,7 +340,7 @@ def main():
         gbs = (BYTES_IN + BYTES_POOLED) * B / (pool_ms * 1e-3) / 1e9
         kernels["merv_pool3d"] = {"bound": "hbm", "ms": pool_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                                   "algorithmic_bytes": (BYTES_IN + BYTES_POOLED) * B,
-                                  "traffic": ncu_traffic_bytes("r1f_prof_pool3d_tma.txt") if B == 64 else None}
+                                  "traffic": ncu_traffic_bytes("r1g_prof_pool3d_tma.txt") if B == 64 else None}
     flops = FLOPS_LINEAR if args.projector == "linear" else FLOPS_GELU
     if args.mode == "fused":
         gemm_name = "merv_fused_linear_mix"
@@ -356,7 +356,7 @@ def main():
                     "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"], "frac_of_burst_peak": tf / peaks["tf_burst"], "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                     "ms_per_launch": g_ms,
                     # ncu capture of this kernel at this exact configuration (B=64, linear, fused), committed under profiles/
-                    "traffic": ncu_traffic_bytes("r1f_prof_gemm_bf16_tcgen05.txt") if (args.projector == "linear" and B == 64) else None,
+                    "traffic": ncu_traffic_bytes("r1g_prof_gemm_bf16_tcgen05.txt") if (args.projector == "linear" and B == 64) else None,
                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                     "algorithmic_bytes": (BYTES_POOLED + BYTES_OUT) * B + sum(LLM_DIM * c * 2 for c in DIMS)}
         kernels[gemm_name] = roofline

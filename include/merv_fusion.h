@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MERV_ABI_VERSION 2
+#define MERV_ABI_VERSION 3
 
 enum { MERV_F32 = 0, MERV_BF16 = 1 };
 enum { MERV_ACT_NONE = 0, MERV_ACT_GELU_ERF = 1 };
@@ -252,6 +252,51 @@ int merv_mix_backward(const void* const* V, const void* dOut, const float* weigh
                       const float* u, const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias,
                       void* const* dV, void* dQ, void* dWq, void* dWk, void* dbias, float* workspace,
                       size_t workspace_floats, int B, int E, int T, int K, int embed, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward of the FUSED path (linear projectors linked to the adapter, forward = merv_fused_linear_mix): the training step of
+ * the shipped configs (merv/models/vidlms/merv.py:587-589,608 under base_strategy.py:210-241) without ever materialising the
+ * per-encoder projections Y_e or their gradients dV_e.  With P_e the pooled tokens (kept from the forward), Z_e = dOut W_e:
+ *     dw_e = <Z_e, P_e> + b_e . colsum_t(dOut)        ds = softmax backward of (dw + dweights_out)
+ *     dW_e = dOut^T (w_e (.) P_e) + u (x) g_e          g_e = sum_b ds_e[b] mean_t P_e[b]
+ *     db_e = sum_b w_e[b] colsum_t(dOut[b]) + u sum_b ds_e[b]          du = sum_e (W_e g_e + b_e sum_b ds_e[b])  ->  dQ, dWq, dWk, db_q
+ * The two GEMMs per encoder (Z_e and dOut^T (w_e (.) P_e)) are merv_linear_bias_act calls; the entry points below are the rest:
+ *   merv_video_colsum       out[b, k] = scale * sum_t x[b, t, k]  (fp32 [B, K]); x rows `ld` apart, videos `batch_stride` apart
+ *   merv_pair_dot           partial[b, c] = chunk c of sum_i x[b, i] y[b, i], c < merv_pair_dot_chunks(); x, y [B, n] contiguous
+ *   merv_transpose_rowscale y[c, r] = scale[(r / rows_per_scale) * scale_stride] * x[r, c] (scale NULL: 1); columns R..R_pad-1 of y are
+ *                           zero-filled (K-major GEMM operands need R_pad % 8 == 0 in bf16)
+ *   merv_fused_backward     everything after the GEMMs: ds, g_e, db_e, the rank-1 update of dW_e (in place), du and the adapter's
+ *                           parameter gradients.  workspace: merv_fused_backward_workspace(desc) floats.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, E, K, embed;                 /* videos, encoders, llm_dim, text embedding dim */
+  int32_t C[MERV_MAX_ENCODERS];           /* channels per encoder */
+  const float* weights;                   /* [B, E] mixing weights of the forward (fp32) */
+  const float* dweights_out;              /* [B, E] gradient w.r.t. the returned weights, or NULL */
+  const float* u;                         /* [K] merv_fusion_query_vec */
+  const float* gsum;                      /* [B, K] merv_video_colsum(dOut) */
+  const float* dw_partial[MERV_MAX_ENCODERS]; /* [B, merv_pair_dot_chunks()] merv_pair_dot(Z_e, P_e) */
+  const float* pbar[MERV_MAX_ENCODERS];   /* [B, C_e] merv_video_colsum(P_e, scale = 1 / T) */
+  const void* W[MERV_MAX_ENCODERS];       /* [K, C_e] projector weights (`dtype`), row stride ldw */
+  int64_t ldw[MERV_MAX_ENCODERS];
+  const void* bias[MERV_MAX_ENCODERS];    /* [K] or NULL */
+  const void *Q, *Wq, *Wk, *in_proj_bias; /* adapter parameters (`dtype`); in_proj_bias may be NULL */
+  float* ds;                              /* out [B, E] */
+  void* dW[MERV_MAX_ENCODERS];            /* in/out [K, C_e]: dOut^T (w_e (.) P_e) on entry, + u (x) g_e on exit */
+  int64_t lddw[MERV_MAX_ENCODERS];
+  void* db[MERV_MAX_ENCODERS];            /* out [K] or NULL */
+  void *dQ, *dWq, *dWk, *dbias;           /* out [embed], [embed, embed], [embed, K], [3 * embed] */
+  float* workspace;
+  size_t workspace_floats;
+} merv_fused_bwd_desc;
+int merv_video_colsum(const void* x, float* out, int B, int T, int K, int64_t ld, int64_t batch_stride, float scale, int dtype,
+                      void* stream);
+int merv_pair_dot_chunks(void);
+int merv_pair_dot(const void* x, const void* y, float* partial, int B, int64_t n, int dtype, void* stream);
+int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,
+                            int64_t scale_stride, int rows_per_scale, int dtype, void* stream);
+size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* desc);
+int merv_fused_backward(const merv_fused_bwd_desc* desc, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * LayerNorm over the channel dimension of (possibly segmented) rows: Y[m, :] = LN(concat_s X_s[m, :]) * gamma + beta.

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1
 MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 64
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}
 
@@ -47,6 +47,20 @@ class FusedDesc(C.Structure):
         ("W", c_void_p * 4), ("ldw", c_int64 * 4), ("bias", c_void_p * 4), ("c", c_void_p * 4),
         ("scores", c_void_p), ("weights", c_void_p), ("bias_mix", c_void_p), ("weights_bf16", c_void_p),
         ("out", c_void_p), ("ldo", c_int64), ("out_batch_stride", c_int64),
+    ]
+
+
+class FusedBwdDesc(C.Structure):
+    """merv_fused_bwd_desc"""
+
+    _fields_ = [
+        ("B", c_int32), ("E", c_int32), ("K", c_int32), ("embed", c_int32), ("C", c_int32 * 8),
+        ("weights", c_void_p), ("dweights_out", c_void_p), ("u", c_void_p), ("gsum", c_void_p),
+        ("dw_partial", c_void_p * 8), ("pbar", c_void_p * 8), ("W", c_void_p * 8), ("ldw", c_int64 * 8), ("bias", c_void_p * 8),
+        ("Q", c_void_p), ("Wq", c_void_p), ("Wk", c_void_p), ("in_proj_bias", c_void_p),
+        ("ds", c_void_p), ("dW", c_void_p * 8), ("lddw", c_int64 * 8), ("db", c_void_p * 8),
+        ("dQ", c_void_p), ("dWq", c_void_p), ("dWk", c_void_p), ("dbias", c_void_p),
+        ("workspace", c_void_p), ("workspace_floats", c_size_t),
     ]
 
 
@@ -84,6 +98,12 @@ _SIGNATURES = {
     "merv_scores_softmax_weights": (c_int, [_PP, POINTER(c_int32), _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p]),
     "merv_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "merv_video_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p]),
+    "merv_pair_dot_chunks": (c_int, []),
+    "merv_pair_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "merv_transpose_rowscale": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "merv_fused_backward_workspace": (c_size_t, [POINTER(FusedBwdDesc)]),
+    "merv_fused_backward": (c_int, [POINTER(FusedBwdDesc), c_int, c_void_p]),
     "merv_gelu": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "merv_colsum_workspace": (c_size_t, [c_int, c_int]),
     "merv_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_void_p]),

@@ -249,9 +249,276 @@ static int launch_mix_dv(const BwdPtrs& p, const void* dOut, const float* weight
   return MERV_OK;
 }
 
+
+// ============================================================================================================
+// Backward of the FUSED path (linear projectors linked to the adapter; merv_fused_linear_mix forward).
+//   forward :  s_e = u . mean_t(P_e W_e^T + b_e),  w = softmax_e(s),  out = sum_e w_e (P_e W_e^T + b_e)      (P_e = pooled tokens)
+//   backward:  neither the per-encoder projections Y_e nor their gradients dV_e are ever materialised (2 x 33.5 MB per video):
+//        dw_e = <dOut, Y_e> = <dOut W_e, P_e> + b_e . colsum_t(dOut)         Z_e = dOut W_e: dgrad-shaped tcgen05 GEMM, [M, C_e] only
+//        ds   = softmax backward of (dw + dweights_out)
+//        dW_e = dV_e^T P_e = dOut^T (w_e (.) P_e) + u (x) g_e,   g_e = sum_b ds_e[b] mean_t P_e[b]      (w_e scales the rows of P_e per video)
+//        db_e = sum_b w_e[b] colsum_t(dOut[b]) + u sum_b ds_e[b]
+//        du   = sum_e (W_e g_e + b_e sum_b ds_e[b])        then dq, dWk, dWq, db_q, dQ as in merv_mix_backward
+// The kernels below are the HBM-bound / tiny pieces; the two GEMMs per encoder run on the tcgen05 kernel.
+// ============================================================================================================
+
+// ---- out[b, k] = scale * sum_t x[b, t, k] (fp32): CTA = (256-byte column block, video), 8 row groups, fixed-order reduction ----
+template <typename T>
+__global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int Ttok, int K, long long ld,
+                                                           long long batch_stride, float scale) {
+  constexpr int VEC = Vec16<T>::kN;
+  __shared__ float part[8][32 * VEC + 1];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int k0 = (blockIdx.x * 32 + lane) * VEC;
+  const int b = blockIdx.y;
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  if (k0 < K) {
+    const T* base = x + (long long)b * batch_stride + k0;
+    int t = rg;
+    for (; t + 24 < Ttok; t += 32) {  // four independent 16-byte loads in flight per thread
+      uint4 r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r[i] = ldg_nc_v4(base + (long long)(t + 8 * i) * ld);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float f[VEC];
+        Vec16<T>::unpack(r[i], f);
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] += f[c];
+      }
+    }
+    for (; t < Ttok; t += 8) {
+      float f[VEC];
+      Vec16<T>::unpack(ldg_nc_v4(base + (long long)t * ld), f);
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] += f[c];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) part[rg][lane * VEC + c] = acc[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VEC; i += 256) {
+    const int k = blockIdx.x * 32 * VEC + i;
+    if (k < K) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += part[g][i];
+      out[(long long)b * K + k] = sum * scale;
+    }
+  }
+}
+
+// ---- partial[b, chunk] = sum over the chunk of x[b, i] * y[b, i]  (both [B, n] contiguous) --------------------------------
+constexpr int kPairDotChunks = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) pair_dot_kernel(const T* __restrict__ x, const T* __restrict__ y, float* __restrict__ partial, long long nvec) {
+  constexpr int VEC = Vec16<T>::kN;
+  __shared__ float red[32];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const long long per = (nvec + kPairDotChunks - 1) / kPairDotChunks;
+  const long long v0 = chunk * per, v1 = v0 + per < nvec ? v0 + per : nvec;
+  const T* xb = x + (long long)b * nvec * VEC;
+  const T* yb = y + (long long)b * nvec * VEC;
+  float acc = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += 512) {
+    const long long v2 = v + 256;
+    const bool has2 = v2 < v1;
+    const uint4 a1 = ldg_nc_v4(xb + v * VEC), b1 = ldg_nc_v4(yb + v * VEC);
+    uint4 a2 = make_uint4(0u, 0u, 0u, 0u), b2 = a2;
+    if (has2) {
+      a2 = ldg_nc_v4(xb + v2 * VEC);
+      b2 = ldg_nc_v4(yb + v2 * VEC);
+    }
+    float fa[VEC], fb[VEC];
+    Vec16<T>::unpack(a1, fa);
+    Vec16<T>::unpack(b1, fb);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc = fmaf(fa[c], fb[c], acc);
+    Vec16<T>::unpack(a2, fa);
+    Vec16<T>::unpack(b2, fb);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc = fmaf(fa[c], fb[c], acc);
+  }
+  acc = bwd_block_sum<256>(acc, red);
+  if (threadIdx.x == 0) partial[(long long)b * kPairDotChunks + chunk] = acc;
+}
+
+// ---- y[c, r] = scale(r) * x[r, c] for r < R, 0 for R <= r < R_pad : 64 x 64 tiles, 4-byte accesses both ways (bf16) --------------
+// scale(r) = scale[(r / rows_per_scale) * scale_stride] (fp32) or 1: the per-video mixing weight applied to the pooled tokens.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_rowscale_kernel(const T* __restrict__ x, T* __restrict__ y, int R, int R_pad, int C, long long ldx,
+                                                                 long long ldy, const float* __restrict__ scale, long long scale_stride,
+                                                                 int rows_per_scale) {
+  __shared__ float tile[64][65];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = to_float(x[(long long)r * ldx + c]);
+      if (scale != nullptr) v *= scale[(long long)(r / rows_per_scale) * scale_stride];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R_pad && c < C) y[(long long)c * ldy + r] = from_float<T>(tile[tx][i]);
+  }
+}
+
+// ---- the same for bf16 with 16-byte global accesses both ways (C % 8 == 0, R_pad % 8 == 0, 16-byte aligned rows) ----------------
+// 64 x 64 tile as 32-bit words (bf16 pairs) with a 33-word pitch.  Load: one 16-byte vector = 4 words per thread and row, written
+// conflict-free (bank = row + 4 * vec + k).  Store: a thread owns a column PAIR and 8 consecutive rows: 8 word reads give it two
+// 16-byte output vectors (rows c and c + 1 of y); the 8 lanes of a column pair write 128 contiguous bytes.
+__global__ void __launch_bounds__(256) transpose_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int R, int R_pad, int C,
+                                                                 long long ldx, long long ldy, const float* __restrict__ scale, long long scale_stride,
+                                                                 int rows_per_scale) {
+  __shared__ uint32_t tile[64][33];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int id = threadIdx.x + it * 256;
+    const int row = id >> 3, v = id & 7;
+    const int r = r0 + row, c = c0 + v * 8;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (r < R && c < C) {
+      q = ldg_nc_v4(x + (long long)r * ldx + c);
+      if (scale != nullptr) {
+        const float sc = scale[(long long)(r / rows_per_scale) * scale_stride];
+        float f[8];
+        Vec16<__nv_bfloat16>::unpack(q, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= sc;
+        q = Vec16<__nv_bfloat16>::pack(f);
+      }
+    }
+    tile[row][v * 4 + 0] = q.x;
+    tile[row][v * 4 + 1] = q.y;
+    tile[row][v * 4 + 2] = q.z;
+    tile[row][v * 4 + 3] = q.w;
+  }
+  __syncthreads();
+  const int rb = threadIdx.x & 7, cp = threadIdx.x >> 3;  // 8 row blocks x 32 column pairs
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = tile[rb * 8 + i][cp];
+  const int r = r0 + rb * 8, c = c0 + cp * 2;
+  if (r < R_pad && c < C) {
+    // low halves -> row c of y, high halves -> row c + 1 (C is even)
+    const uint4 lo = make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410), __byte_perm(w[4], w[5], 0x5410),
+                                __byte_perm(w[6], w[7], 0x5410));
+    const uint4 hi = make_uint4(__byte_perm(w[0], w[1], 0x7632), __byte_perm(w[2], w[3], 0x7632), __byte_perm(w[4], w[5], 0x7632),
+                                __byte_perm(w[6], w[7], 0x7632));
+    *reinterpret_cast<uint4*>(y + (long long)c * ldy + r) = lo;
+    *reinterpret_cast<uint4*>(y + (long long)(c + 1) * ldy + r) = hi;
+  }
+}
+
+// ---- tiny kernels of the fused backward ------------------------------------------------------------------------------------------
+struct FusedBwdPtrs {
+  const float* dw_partial[MERV_MAX_ENCODERS];  // [B, kPairDotChunks]
+  const float* pbar[MERV_MAX_ENCODERS];        // [B, C_e] per-video column means of the pooled tokens
+  const void* W[MERV_MAX_ENCODERS];            // [K, C_e]
+  const void* bias[MERV_MAX_ENCODERS];         // [K] or NULL
+  void* dW[MERV_MAX_ENCODERS];                 // [K, C_e] in/out
+  void* db[MERV_MAX_ENCODERS];                 // [K] or NULL
+  long long ldw[MERV_MAX_ENCODERS], lddw[MERV_MAX_ENCODERS];
+  int C[MERV_MAX_ENCODERS];
+  int goff[MERV_MAX_ENCODERS];                 // offset of g_e in the workspace
+};
+
+// one warp per video: dw_e = sum of the pair-dot partials + b_e . gsum[b] (+ dweights_out), ds = softmax backward
+template <typename T>
+__global__ void __launch_bounds__(32) fused_bwd_scores_kernel(const __grid_constant__ FusedBwdPtrs p, const float* __restrict__ gsum,
+                                                              const float* __restrict__ weights, const float* __restrict__ dweights_out,
+                                                              float* __restrict__ ds, int E, int K) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  float mine = 0.f;
+  for (int e = 0; e < E; ++e) {
+    float acc = 0.f;
+    if (lane < kPairDotChunks) acc = p.dw_partial[e][(long long)b * kPairDotChunks + lane];
+    if (p.bias[e] != nullptr) {
+      const T* be = static_cast<const T*>(p.bias[e]);
+      for (int k = lane; k < K; k += 32) acc = fmaf(to_float(be[k]), gsum[(long long)b * K + k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == e) mine = acc;
+  }
+  float w = 0.f;
+  if (lane < E) {
+    if (dweights_out != nullptr) mine += dweights_out[(long long)b * E + lane];
+    w = weights[(long long)b * E + lane];
+  }
+  const float inner = warp_sum(lane < E ? w * mine : 0.f);
+  if (lane < E) ds[(long long)b * E + lane] = w * (mine - inner);
+}
+
+// g_e[c] = sum_b ds[b, e] * pbar_e[b, c]   grid (ceil(C_max / 256), E)
+__global__ void __launch_bounds__(256) fused_bwd_g_kernel(const __grid_constant__ FusedBwdPtrs p, const float* __restrict__ ds, float* __restrict__ g,
+                                                          int B, int E) {
+  const int e = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= p.C[e]) return;
+  float acc = 0.f;
+  for (int b = 0; b < B; ++b) acc = fmaf(ds[(long long)b * E + e], p.pbar[e][(long long)b * p.C[e] + c], acc);
+  g[p.goff[e] + c] = acc;
+}
+
+// db_e[n] = sum_b w[b, e] gsum[b, n] + u[n] sum_b ds[b, e]   grid (ceil(K / 256), E)
+template <typename T>
+__global__ void __launch_bounds__(256) fused_bwd_db_kernel(const __grid_constant__ FusedBwdPtrs p, const float* __restrict__ gsum,
+                                                           const float* __restrict__ weights, const float* __restrict__ ds, const float* __restrict__ u,
+                                                           int B, int E, int K) {
+  const int e = blockIdx.y, n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= K || p.db[e] == nullptr) return;
+  float acc = 0.f, sig = 0.f;
+  for (int b = 0; b < B; ++b) {
+    acc = fmaf(weights[(long long)b * E + e], gsum[(long long)b * K + n], acc);
+    sig += ds[(long long)b * E + e];
+  }
+  static_cast<T*>(p.db[e])[n] = from_float<T>(fmaf(u[n], sig, acc));
+}
+
+// dW_e[n, c] += u[n] * g_e[c]
+template <typename T>
+__global__ void __launch_bounds__(256) fused_bwd_rank1_kernel(T* __restrict__ dW, long long ld, const float* __restrict__ u, const float* __restrict__ g,
+                                                              int K, int C) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= (long long)K * C) return;
+  const int n = int(idx / C), c = int(idx % C);
+  T* d = dW + (long long)n * ld + c;
+  *d = from_float<T>(fmaf(u[n], g[c], to_float(*d)));
+}
+
+// du[n] (+)= sum_c W_e[n, c] g_e[c] + sig_e b_e[n] : one warp per row, encoders accumulated by successive launches (fixed order)
+template <typename T>
+__global__ void __launch_bounds__(256) fused_bwd_du_kernel(const T* __restrict__ W, long long ldw, const T* __restrict__ bias, const float* __restrict__ g,
+                                                           const float* __restrict__ ds, float* __restrict__ du, int K, int C, int B, int E, int e,
+                                                           int accumulate) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= K) return;
+  const int lane = threadIdx.x & 31;
+  const T* w = W + (long long)row * ldw;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc = fmaf(to_float(w[c]), g[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float sig = 0.f;
+    for (int b = 0; b < B; ++b) sig += ds[(long long)b * E + e];
+    const float v = acc + (bias != nullptr ? sig * to_float(bias[row]) : 0.f);
+    du[row] = accumulate ? du[row] + v : v;
+  }
+}
+
 }  // namespace merv
 
 using namespace merv;
+
+extern "C" int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,
+                                       int64_t scale_stride, int rows_per_scale, int dtype, void* stream);
 
 extern "C" int merv_transpose(const void* x, void* y, int R, int C, int64_t ldx, int64_t ldy, int dtype, void* stream) {
   MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_transpose: unknown dtype %d", dtype);
@@ -259,6 +526,8 @@ extern "C" int merv_transpose(const void* x, void* y, int R, int C, int64_t ldx,
   MERV_REQUIRE(R >= 0 && C >= 0 && ldx >= C && ldy >= R, MERV_E_SHAPE, "merv_transpose: R=%d C=%d ldx=%lld ldy=%lld", R, C, (long long)ldx, (long long)ldy);
   if (int rc = require_sm100()) return rc;
   if (R == 0 || C == 0) return MERV_OK;
+  if (dtype == MERV_BF16 && C % 8 == 0 && R % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y))
+    return merv_transpose_rowscale(x, y, R, R, C, ldx, ldy, nullptr, 0, 1, dtype, stream);
   dim3 grid((C + 31) / 32, (R + 31) / 32);
   MERV_REQUIRE(grid.y <= 65535, MERV_E_SHAPE, "merv_transpose: R=%d too large", R);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -380,6 +649,139 @@ extern "C" int merv_gelu(const void* z, const void* dy, void* out, int64_t n, in
     if (dy) gelu_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>((const float*)z, (const float*)dy, (float*)out, nvec);
     else gelu_kernel<float, false><<<(unsigned)blocks, 256, 0, s>>>((const float*)z, nullptr, (float*)out, nvec);
   }
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+// ---- fused-path backward entry points (see the block comment above the kernels) ---------------------------------------------------
+extern "C" int merv_video_colsum(const void* x, float* out, int B, int T, int K, int64_t ld, int64_t batch_stride, float scale, int dtype,
+                                 void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_video_colsum: unknown dtype %d", dtype);
+  MERV_REQUIRE(x && out, MERV_E_ARG, "merv_video_colsum: NULL pointer");
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(B >= 0 && T > 0 && K > 0 && K % vec == 0 && ld >= K && ld % vec == 0 && batch_stride % vec == 0, MERV_E_SHAPE,
+               "merv_video_colsum: B=%d T=%d K=%d ld=%lld batch_stride=%lld", B, T, K, (long long)ld, (long long)batch_stride);
+  MERV_REQUIRE(aligned16(x), MERV_E_ALIGN, "merv_video_colsum: x must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid((K / vec + 31) / 32, B);
+  if (dtype == MERV_BF16)
+    video_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, out, T, K, ld, batch_stride, scale);
+  else
+    video_colsum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, out, T, K, ld, batch_stride, scale);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_pair_dot_chunks(void) { return kPairDotChunks; }
+
+extern "C" int merv_pair_dot(const void* x, const void* y, float* partial, int B, int64_t n, int dtype, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_pair_dot: unknown dtype %d", dtype);
+  MERV_REQUIRE(x && y && partial, MERV_E_ARG, "merv_pair_dot: NULL pointer");
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(B >= 0 && n > 0 && n % vec == 0, MERV_E_SHAPE, "merv_pair_dot: B=%d n=%lld", B, (long long)n);
+  MERV_REQUIRE(aligned16(x) && aligned16(y), MERV_E_ALIGN, "merv_pair_dot: operands must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  if (B == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid(kPairDotChunks, B);
+  if (dtype == MERV_BF16)
+    pair_dot_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, partial, n / vec);
+  else
+    pair_dot_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)y, partial, n / vec);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,
+                                       int64_t scale_stride, int rows_per_scale, int dtype, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_transpose_rowscale: unknown dtype %d", dtype);
+  MERV_REQUIRE(x && y, MERV_E_ARG, "merv_transpose_rowscale: NULL pointer");
+  MERV_REQUIRE(R >= 0 && C >= 0 && R_pad >= R && ldx >= C && ldy >= R_pad && (scale == nullptr || rows_per_scale > 0), MERV_E_SHAPE,
+               "merv_transpose_rowscale: R=%d R_pad=%d C=%d ldx=%lld ldy=%lld rows_per_scale=%d", R, R_pad, C, (long long)ldx, (long long)ldy,
+               rows_per_scale);
+  if (int rc = require_sm100()) return rc;
+  if (R_pad == 0 || C == 0) return MERV_OK;
+  dim3 grid((C + 63) / 64, (R_pad + 63) / 64);
+  MERV_REQUIRE(grid.y <= 65535, MERV_E_SHAPE, "merv_transpose_rowscale: R=%d too large", R);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool vec_ok = dtype == MERV_BF16 && C % 8 == 0 && R_pad % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && aligned16(x) && aligned16(y);
+  if (vec_ok)
+    transpose_bf16_vec_kernel<<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, R, R_pad, C, ldx, ldy, scale, scale_stride, rows_per_scale);
+  else if (dtype == MERV_BF16)
+    transpose_rowscale_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, R, R_pad, C, ldx, ldy, scale, scale_stride,
+                                                                 rows_per_scale);
+  else
+    transpose_rowscale_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, R, R_pad, C, ldx, ldy, scale, scale_stride, rows_per_scale);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+extern "C" size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* d) {
+  if (d == nullptr || d->E <= 0) return 0;
+  size_t g = 0;
+  for (int e = 0; e < d->E && e < MERV_MAX_ENCODERS; ++e) g += (size_t)d->C[e];
+  return g + (size_t)d->K + 2 * (size_t)d->embed;
+}
+
+extern "C" int merv_fused_backward(const merv_fused_bwd_desc* d, int dtype, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_fused_backward: unknown dtype %d", dtype);
+  MERV_REQUIRE(d != nullptr, MERV_E_ARG, "merv_fused_backward: NULL descriptor");
+  const int B = d->B, E = d->E, K = d->K, embed = d->embed;
+  MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_fused_backward: E=%d", E);
+  MERV_REQUIRE(B > 0 && K > 0 && embed > 0, MERV_E_SHAPE, "merv_fused_backward: B=%d K=%d embed=%d", B, K, embed);
+  MERV_REQUIRE(d->weights && d->u && d->gsum && d->ds && d->Q && d->Wq && d->Wk && d->dQ && d->dWq && d->dWk && d->dbias && d->workspace, MERV_E_ARG,
+               "merv_fused_backward: NULL pointer");
+  MERV_REQUIRE(d->workspace_floats >= merv_fused_backward_workspace(d), MERV_E_ARG, "merv_fused_backward: workspace too small");
+  if (int rc = require_sm100()) return rc;
+  FusedBwdPtrs p = {};
+  int goff = 0, cmax = 0;
+  for (int e = 0; e < E; ++e) {
+    MERV_REQUIRE(d->dw_partial[e] && d->pbar[e] && d->W[e] && d->dW[e] && d->C[e] > 0 && d->ldw[e] >= d->C[e] && d->lddw[e] >= d->C[e], MERV_E_ARG,
+                 "merv_fused_backward: encoder %d: NULL pointer or bad leading dimension", e);
+    p.dw_partial[e] = d->dw_partial[e];
+    p.pbar[e] = d->pbar[e];
+    p.W[e] = d->W[e];
+    p.bias[e] = d->bias[e];
+    p.dW[e] = d->dW[e];
+    p.db[e] = d->db[e];
+    p.ldw[e] = d->ldw[e];
+    p.lddw[e] = d->lddw[e];
+    p.C[e] = d->C[e];
+    p.goff[e] = goff;
+    goff += d->C[e];
+    cmax = d->C[e] > cmax ? d->C[e] : cmax;
+  }
+  float* g = d->workspace;
+  float* du = g + goff;
+  float* q = du + K;
+  float* dq = q + embed;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float rs = 1.0f / sqrtf(float(embed));
+  const long long nWk = (long long)embed * K, nWq = (long long)embed * embed;
+#define MERV_FUSED_BWD_BODY(T_)                                                                                                                   \
+  fused_bwd_scores_kernel<T_><<<B, 32, 0, s>>>(p, d->gsum, d->weights, d->dweights_out, d->ds, E, K);                                             \
+  fused_bwd_g_kernel<<<dim3((cmax + 255) / 256, E), 256, 0, s>>>(p, d->ds, g, B, E);                                                              \
+  fused_bwd_db_kernel<T_><<<dim3((K + 255) / 256, E), 256, 0, s>>>(p, d->gsum, d->weights, d->ds, d->u, B, E, K);                                 \
+  for (int e = 0; e < E; ++e) {                                                                                                                   \
+    const long long n = (long long)K * p.C[e];                                                                                                    \
+    fused_bwd_rank1_kernel<T_><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((T_*)p.dW[e], p.lddw[e], d->u, g + p.goff[e], K, p.C[e]);               \
+    fused_bwd_du_kernel<T_><<<(K + 7) / 8, 256, 0, s>>>((const T_*)p.W[e], p.ldw[e], (const T_*)p.bias[e], g + p.goff[e], d->ds, du, K, p.C[e], B, \
+                                                        E, e, e > 0);                                                                             \
+  }                                                                                                                                               \
+  gemv_n_kernel<T_, T_><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)d->Wq, (const T_*)d->Q, (const T_*)d->in_proj_bias, q, embed, embed, 1.0f);    \
+  gemv_n_kernel<T_, float><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)d->Wk, du, nullptr, dq, embed, K, rs);                                      \
+  outer_kernel<T_, float><<<(unsigned)((nWk + 255) / 256), 256, 0, s>>>(q, du, (T_*)d->dWk, embed, K, rs);                                        \
+  outer_kernel<T_, T_><<<(unsigned)((nWq + 255) / 256), 256, 0, s>>>(dq, (const T_*)d->Q, (T_*)d->dWq, embed, embed, 1.0f);                       \
+  gemv_tf_kernel<T_><<<(embed + 31) / 32, 256, 0, s>>>((const T_*)d->Wq, dq, (T_*)d->dQ, embed, embed);                                           \
+  bias_grad_kernel<T_><<<(3 * embed + 255) / 256, 256, 0, s>>>(dq, (T_*)d->dbias, embed);
+  if (dtype == MERV_BF16) {
+    MERV_FUSED_BWD_BODY(__nv_bfloat16)
+  } else {
+    MERV_FUSED_BWD_BODY(float)
+  }
+#undef MERV_FUSED_BWD_BODY
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }

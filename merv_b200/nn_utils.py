@@ -210,6 +210,71 @@ class _CastCache:
         return hit[1]
 
 
+class _FusedLinearFn(torch.autograd.Function):
+    """Training step of the shipped configuration (3d-avg pool + linear projectors + learnable-query mixer, merv.py:587-589,608)
+    through the FUSED forward, with a backward that never materialises the per-encoder projections Y_e or their gradients.
+
+    forward : merv_pool3d (+ score partials) -> scores -> softmax -> merv_fused_linear_mix; keeps the pooled tokens P_e and the weights
+    backward: Z_e = dOut W_e (tcgen05, [M, C_e]);  dw_e = <Z_e, P_e> + b_e . colsum_t(dOut);  ds = softmax'(dw + dweights);
+              dW_e = dOut^T (w_e (.) P_e) (tcgen05) + u (x) g_e;  db_e, du -> dQ, dWq, dWk, db_q  (include/merv_fusion.h: merv_fused_backward)
+    Per video this moves ~100 MB less through HBM in the forward and ~130 MB less in the backward than the module-by-module
+    path and keeps 7 MB instead of 41 MB of activations.  No gradient flows into the patch features (frozen backbones).
+    """
+
+    @staticmethod
+    def forward(ctx, fusion, projs, xs, Q, Wq, Wk, in_proj_bias, *proj_params):
+        dtype = torch.bfloat16
+        E = len(projs)
+        T, K = fusion.token_length, fusion.llm_dim
+        B = xs[0].shape[0]
+        lasts = [p.layers()[-1][0] for p in projs]
+        vcs = [fusion._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
+        Ws = [p._cast_cache.get(lin.weight, dtype) for lin, p in zip(lasts, projs)]
+        biases = [p._cast_cache.get(lin.bias, dtype) for lin, p in zip(lasts, projs)]
+        pooled, partials = fusion._fused_stage1(projs, xs, vcs, dtype)
+        scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
+        weights, bias_mix = ops.softmax_weights(scores, biases, K)
+        out = ops.fused_linear_mix(pooled, Ws, weights, bias_mix, T)
+        c = fusion._cast_cache
+        ctx.fusion_dims = (B, E, T, K)
+        ctx.param_dtypes = [t.dtype for t in (Q, Wq, Wk, in_proj_bias, *proj_params)]
+        ctx.save_for_backward(weights, fusion.query_vector(dtype), c.get(Q, dtype), c.get(Wq, dtype), c.get(Wk, dtype), c.get(in_proj_bias, dtype),
+                              *pooled, *Ws, *biases)
+        w_out = weights.to(dtype)
+        return out.view(B, T, K), w_out
+
+    @staticmethod
+    def backward(ctx, dout, dweights):
+        B, E, T, K = ctx.fusion_dims
+        saved = list(ctx.saved_tensors)
+        weights, u, Qc, Wqc, Wkc, bc = saved[:6]
+        pooled, Ws, biases = saved[6:6 + E], saved[6 + E:6 + 2 * E], saved[6 + 2 * E:6 + 3 * E]
+        dt = Ws[0].dtype
+        g = dout.reshape(B * T, K)
+        if g.dtype != dt:
+            g = g.to(dt)
+        if g.stride(1) != 1 or g.stride(0) != K:
+            g = g.contiguous()
+        dwo = None if dweights is None else dweights.float().contiguous()
+        gsum = ops.video_colsum(g.view(B, T, K))
+        gT = ops.transpose(g, pad=True)  # [K, M'] : A operand of every dW_e GEMM
+        dw_partials, pbars, dWs = [], [], []
+        for e in range(E):
+            P = pooled[e].reshape(B * T, -1)
+            Z, _ = ops.linear_bias_act(g, ops.transpose(Ws[e]), None, ACT_NONE)  # dOut W_e : [M, K] x [C_e, K]^T -> [M, C_e]
+            dw_partials.append(ops.pair_dot(Z.reshape(B, -1), P.reshape(B, -1)))
+            pbars.append(ops.video_colsum(P.reshape(B, T, -1), 1.0 / T))
+            PsT = ops.transpose(P, pad=True, row_scale=weights[:, e], rows_per_scale=T)  # (w_e (.) P_e)^T : [C_e, M']
+            dW, _ = ops.linear_bias_act(gT, PsT, None, ACT_NONE)  # [K, M'] x [C_e, M']^T -> [K, C_e]
+            dWs.append(dW)
+        _, dbs, dQ, dWq, dWk, dbias = ops.fused_backward(weights, dwo, u, gsum, dw_partials, pbars, Ws, biases, Qc, Wqc, Wkc, bc, dWs)
+        grads = [dQ.reshape(1, -1), dWq, dWk, dbias]
+        for e in range(E):
+            grads += [dWs[e], dbs[e]]
+        grads = [gr.to(pd) if gr is not None else None for gr, pd in zip(grads, ctx.param_dtypes)]
+        return (None, None, None, *grads)
+
+
 def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
     """[(linear, activation applied AFTER it)] for every reference projector type."""
     if isinstance(projector, LinearProjector):
@@ -449,7 +514,7 @@ class AveragePooling3DProjector(TokenResampler):
         assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
         _require_device(fused_img_patches)
         fusion = self._linked_fusion() if self._linked_fusion is not None else None
-        if fusion is not None and not torch.is_grad_enabled():
+        if fusion is not None and (not torch.is_grad_enabled() or getattr(fusion, "fused_training", False)):
             return DeferredProjection(self, fused_img_patches)
         return self._forward_unfused(fused_img_patches)
 
@@ -519,6 +584,10 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         self._cast_cache = _CastCache()
         self._u_cache = {}
         self._vc_cache = {}
+        # opt-in (MervFusion(fused_training=True) / patch_merv(fused_training=True)): linked projectors defer in grad mode too and the
+        # training step runs _FusedLinearFn.  Off by default because it needs every projector's parameters at the adapter's forward,
+        # which per-projector FSDP units (merv.py:473-485) do not provide; wrap MervFusion as one unit to use it.
+        self.fused_training = False
 
     def _reset_parameters(self):
         xavier_uniform_(self.Q)
@@ -588,7 +657,11 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             dt, dev = (V[0].dtype, V[0].device)
             return torch.empty((0, self.token_length, self.llm_dim), dtype=dt, device=dev), torch.empty((0, len(V)), dtype=dt, device=dev)
 
-        if all(isinstance(v, DeferredProjection) for v in V) and self._can_fuse(V):
+        deferred = all(isinstance(v, DeferredProjection) for v in V)
+        if deferred and torch.is_grad_enabled() and _needs_grad(self, *[t for v in V for t in v.projector.parameters()]):
+            if out is None and batch_index is None and gather is None and self._can_fuse_training(V):
+                return self._forward_fused_train(V)
+        elif deferred and self._can_fuse(V):
             return self._forward_fused(V, out=out, batch_index=batch_index, gather=gather)
         if out is not None or batch_index is not None or gather is not None:
             raise NotImplementedError("out= / batch_index= / gather= are supported on the linked bf16 path only")
@@ -621,6 +694,27 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         if any(v.shape[1] != self.token_length for v in V):
             return False
         return all(len(v.projector.layers()) >= 1 for v in V)
+
+    def _can_fuse_training(self, V: Sequence[DeferredProjection]) -> bool:
+        """The fused backward (_FusedLinearFn) covers what MERV constructs (merv.py:152-163,214-216): single-Linear projectors with
+        bias in front of the averagetoken mixer without positional embedding, bf16 compute, frozen features."""
+        if not self._can_fuse(V) or self.positional_embedding or type(self) is not CrossAttentionAdapterLearnableQuery:
+            return False
+        for v in V:
+            layers = v.projector.layers()
+            if len(layers) != 1 or layers[0][0].bias is None or v.features.requires_grad:
+                return False
+        return self.attention.in_proj_bias is not None
+
+    def _forward_fused_train(self, V: Sequence[DeferredProjection]) -> Tuple[torch.Tensor, torch.Tensor]:
+        dtype = torch.bfloat16
+        projs = [v.projector for v in V]
+        xs = [v.features.detach() for v in V]
+        xs = [x if x.dtype == dtype else x.to(dtype) for x in xs]
+        xs = [x if x.stride(3) == 1 and not any(st % 8 for st in x.stride()[:3]) else x.contiguous() for x in xs]
+        att = self.attention
+        params = [t for p in projs for t in (p.layers()[0][0].weight, p.layers()[0][0].bias)]
+        return _FusedLinearFn.apply(self, projs, xs, self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias, *params)
 
     # ---- fused pipeline ------------------------------------------------------------------------------------
     def _fused_stage1(self, projs, xs, vcs, dtype, max_ctas: int = 0, batch_index=None):
@@ -826,10 +920,13 @@ class MervFusion(nn.Module):
     """
 
     def __init__(self, projectors: Sequence[AveragePooling3DProjector], feature_fusion: Optional[nn.Module],
-                 fused: bool = True, fusion_type: Optional[str] = None) -> None:
+                 fused: bool = True, fusion_type: Optional[str] = None, fused_training: bool = False) -> None:
         super().__init__()
         self.projectors = nn.ModuleList(projectors)
         self.feature_fusion = feature_fusion
+        if fused_training:  # the training step through the fused forward + _FusedLinearFn backward (needs `fused`)
+            assert fused and isinstance(feature_fusion, CrossAttentionAdapterLearnableQuery), "fused_training needs the linked learnable-query mixer"
+            feature_fusion.fused_training = True
         # the parameter-free fusions of merv.py:598-601: "first" (encoder 0 only) and "concat" (token-wise concatenation)
         self.fusion_type = fusion_type
         if feature_fusion is None:
@@ -1029,7 +1126,7 @@ def _adopt_plain_projector(ref_module: nn.Module) -> nn.Module:
     return new
 
 
-def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
+def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: bool = False) -> nn.Module:
     """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
 
     ``vidlm.projectors[i]`` (reference AveragePooling3DProjector) and ``vidlm.feature_fusion`` (reference
@@ -1081,4 +1178,6 @@ def patch_merv(vidlm: nn.Module, fused: bool = True) -> nn.Module:
     vidlm.feature_fusion = new_ff
     if fused:
         link_fused(new_projs, new_ff)
+        if fused_training and isinstance(new_ff, CrossAttentionAdapterLearnableQuery):
+            new_ff.fused_training = True  # the training step runs the fused forward + _FusedLinearFn (see its docstring for the FSDP caveat)
     return vidlm

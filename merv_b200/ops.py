@@ -6,6 +6,7 @@ happens in the hand-written sm_100a kernels.  CPU tensors are rejected: there is
 
 from __future__ import annotations
 
+import ctypes as C
 import math
 from typing import List, Optional, Sequence, Tuple
 
@@ -56,6 +57,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
+    "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 17,
     "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
@@ -505,20 +507,100 @@ class FusedLinearPlan:
 
 
 # ---- backward building blocks (SURVEY.md §8 f-1) ------------------------------------------------------------------
-def transpose(x: torch.Tensor, pad: bool = False) -> torch.Tensor:
+def transpose(x: torch.Tensor, pad: bool = False, row_scale: Optional[torch.Tensor] = None, rows_per_scale: int = 1) -> torch.Tensor:
     """[R, C] -> contiguous [C, R].  ``pad``: the result is [C, R'] with R' = R rounded up to one 16-byte vector and zeros in the
     extra columns — as the K-major operand of a GEMM whose contraction runs over R (dW = dY^T X over the token rows) it then meets
-    the GEMM's K % 8 (bf16) / K % 4 (fp32) requirement whatever the number of tokens."""
+    the GEMM's K % 8 (bf16) / K % 4 (fp32) requirement whatever the number of tokens.  ``row_scale`` (fp32, one entry per
+    ``rows_per_scale`` rows, any stride): y[c, r] = row_scale[r // rows_per_scale] * x[r, c] — the per-video mixing weight applied
+    to the pooled tokens in the fused backward."""
     lib = _lib.load()
-    dev = _require_cuda(x)
+    dev = _require_cuda(x, row_scale)
     assert x.dim() == 2 and x.stride(1) == 1
     R, Cc = x.shape
     vec = 8 if x.dtype == torch.bfloat16 else 4
     Rp = -(-R // vec) * vec if pad else R
     with torch.cuda.device(dev):
-        y = torch.empty((Cc, R), dtype=x.dtype, device=dev) if Rp == R else torch.zeros((Cc, Rp), dtype=x.dtype, device=dev)
-        _call('merv_transpose', lib.merv_transpose, x.data_ptr(), y.data_ptr(), R, Cc, x.stride(0), y.stride(0), dtype_code(x.dtype), _stream())
+        y = torch.empty((Cc, Rp), dtype=x.dtype, device=dev)
+        if Rp == R and row_scale is None:
+            _call('merv_transpose', lib.merv_transpose, x.data_ptr(), y.data_ptr(), R, Cc, x.stride(0), y.stride(0), dtype_code(x.dtype), _stream())
+        else:
+            if row_scale is not None:
+                assert row_scale.dtype == torch.float32 and row_scale.dim() == 1 and row_scale.numel() * rows_per_scale >= R
+            _call('merv_transpose_rowscale', lib.merv_transpose_rowscale, x.data_ptr(), y.data_ptr(), R, Rp, Cc, x.stride(0), y.stride(0),
+                  _p(row_scale), row_scale.stride(0) if row_scale is not None else 0, rows_per_scale, dtype_code(x.dtype), _stream())
     return y
+
+
+def video_colsum(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """out[b, k] = scale * sum_t x[b, t, k] (fp32 [B, K]) for x [B, T, K]."""
+    lib = _lib.load()
+    dev = _require_cuda(x)
+    assert x.dim() == 3
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    if x.stride(2) != 1 or x.stride(1) % vec or x.stride(0) % vec or x.data_ptr() % 16:
+        x = x.contiguous()
+    B, T, K = x.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((B, K), dtype=torch.float32, device=dev)
+        _call('merv_video_colsum', lib.merv_video_colsum, x.data_ptr(), out.data_ptr(), B, T, K, x.stride(1), x.stride(0), float(scale),
+              dtype_code(x.dtype), _stream())
+    return out
+
+
+def pair_dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Fixed-order partial sums [B, chunks] of sum_i x[b, i] * y[b, i] for x, y [B, ...] of equal shape."""
+    lib = _lib.load()
+    dev = _require_cuda(x, y)
+    assert x.shape == y.shape and x.dtype == y.dtype
+    B = x.shape[0]
+    x, y = x.reshape(B, -1).contiguous(), y.reshape(B, -1).contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty((B, lib.merv_pair_dot_chunks()), dtype=torch.float32, device=dev)
+        _call('merv_pair_dot', lib.merv_pair_dot, x.data_ptr(), y.data_ptr(), out.data_ptr(), B, x.shape[1], dtype_code(x.dtype), _stream())
+    return out
+
+
+def fused_backward(weights: torch.Tensor, dweights_out: Optional[torch.Tensor], u: torch.Tensor, gsum: torch.Tensor,
+                   dw_partials: Sequence[torch.Tensor], pbars: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor],
+                   biases: Sequence[Optional[torch.Tensor]], Q: torch.Tensor, Wq: torch.Tensor, Wk: torch.Tensor,
+                   in_proj_bias: Optional[torch.Tensor], dWs: Sequence[torch.Tensor]):
+    """Everything of the fused path's backward after its GEMMs (include/merv_fusion.h: merv_fused_backward).
+
+    dWs[e] holds dOut^T (w_e (.) P_e) on entry and receives the rank-1 term u (x) g_e in place.
+    Returns (ds [B, E] fp32, [db_e], dQ [1, embed], dWq, dWk, dbias [3 * embed]) in the compute dtype."""
+    lib = _lib.load()
+    dev = _require_cuda(weights, dweights_out, u, gsum, *dw_partials, *pbars, *Ws, *biases, Q, Wq, Wk, in_proj_bias, *dWs)
+    B, E = weights.shape
+    K = u.numel()
+    embed = Wk.shape[0]
+    dt = Ws[0].dtype
+    assert weights.dtype == torch.float32 and weights.is_contiguous() and u.dtype == torch.float32 and gsum.shape == (B, K)
+    assert dweights_out is None or (dweights_out.dtype == torch.float32 and dweights_out.is_contiguous() and dweights_out.shape == (B, E))
+    assert all(w.stride(1) == 1 and w.dtype == dt for w in Ws) and all(d.stride(1) == 1 and d.dtype == dt for d in dWs)
+    assert all(t.is_contiguous() for t in (Q, Wq, Wk)) and (in_proj_bias is None or in_proj_bias.is_contiguous())
+    d = _lib.FusedBwdDesc()
+    d.B, d.E, d.K, d.embed = B, E, K, embed
+    with torch.cuda.device(dev):
+        ds = torch.empty((B, E), dtype=torch.float32, device=dev)
+        dbs = [torch.empty(K, dtype=dt, device=dev) if b is not None else None for b in biases]
+        dQ = torch.empty((1, embed), dtype=dt, device=dev)
+        dWq = torch.empty((embed, embed), dtype=dt, device=dev)
+        dWk = torch.empty((embed, K), dtype=dt, device=dev)
+        dbias = torch.empty(3 * embed, dtype=dt, device=dev)
+        for e in range(E):
+            d.C[e] = Ws[e].shape[1]
+            assert dw_partials[e].is_contiguous() and pbars[e].is_contiguous() and pbars[e].shape == (B, Ws[e].shape[1]) and dWs[e].shape == Ws[e].shape
+            d.dw_partial[e], d.pbar[e] = dw_partials[e].data_ptr(), pbars[e].data_ptr()
+            d.W[e], d.ldw[e], d.bias[e] = Ws[e].data_ptr(), Ws[e].stride(0), _p(biases[e])
+            d.dW[e], d.lddw[e], d.db[e] = dWs[e].data_ptr(), dWs[e].stride(0), _p(dbs[e])
+        d.weights, d.dweights_out, d.u, d.gsum = weights.data_ptr(), _p(dweights_out), u.data_ptr(), gsum.data_ptr()
+        d.Q, d.Wq, d.Wk, d.in_proj_bias = Q.data_ptr(), Wq.data_ptr(), Wk.data_ptr(), _p(in_proj_bias)
+        d.ds, d.dQ, d.dWq, d.dWk, d.dbias = ds.data_ptr(), dQ.data_ptr(), dWq.data_ptr(), dWk.data_ptr(), dbias.data_ptr()
+        n = lib.merv_fused_backward_workspace(C.byref(d))
+        ws = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+        d.workspace, d.workspace_floats = ws.data_ptr(), n
+        _call('merv_fused_backward', lib.merv_fused_backward, C.byref(d), dtype_code(dt), _stream())
+    return ds, dbs, dQ, dWq, dWk, dbias
 
 
 def gelu(z: torch.Tensor, dy: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -118,6 +118,46 @@ def avgpool3d_projector_forward(
 
 
 # --------------------------------------------------------------------------------------------
+# attentive pooler ("attntv" resampler)
+# --------------------------------------------------------------------------------------------
+def cross_attention_block_forward(q: np.ndarray, x: np.ndarray, params: Dict[str, np.ndarray], num_heads: int, prefix: str = "cross_attn.") -> np.ndarray:
+    """``CrossAttentionBlock.forward`` (merv/util/nn_utils.py:447-451) with ``CrossAttention.forward`` (:393-412) and ``MLP.forward``
+    (:425-431, dropout 0):  y = xattn(q, norm1(x));  q = q + y;  q = q + mlp(norm2(q)).
+
+    q [B', n, C] queries, x [B', N, C] keys/values.  Heads split the channel dimension contiguously (``reshape(B, n, heads, C // heads)``,
+    :395; ``kv(x).reshape(B, N, 2, heads, C // heads)``, :398: the first C output channels of ``kv`` are K, the last C are V);
+    scores are scaled by ``head_dim ** -0.5`` (SDPA default == ``self.scale``, :388,403-407)."""
+    g = lambda k: params[prefix + k]  # noqa: E731
+    Bq, n, C = q.shape
+    N = x.shape[1]
+    hd = C // num_heads
+    xn = layer_norm(x, g("norm1.weight"), g("norm1.bias"))
+    qp = linear(q, g("xattn.q.weight"), g("xattn.q.bias")).reshape(Bq, n, num_heads, hd).transpose(0, 2, 1, 3)
+    kv = linear(xn, g("xattn.kv.weight"), g("xattn.kv.bias")).reshape(Bq, N, 2, num_heads, hd).transpose(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]  # [B', heads, N, hd]
+    att = _softmax_last((qp @ k.transpose(0, 1, 3, 2)) * (hd ** -0.5))
+    y = (att @ v).transpose(0, 2, 1, 3).reshape(Bq, n, C)
+    y = linear(y, g("xattn.proj.weight"), g("xattn.proj.bias"))
+    q = q + y
+    h = layer_norm(q, g("norm2.weight"), g("norm2.bias"))
+    h = gelu_erf(linear(h, g("mlp.fc1.weight"), g("mlp.fc1.bias")))
+    return q + linear(h, g("mlp.fc2.weight"), g("mlp.fc2.bias"))
+
+
+def attentive_pooler_forward(x: np.ndarray, params: Dict[str, np.ndarray], num_heads: int, mlp_type: str) -> np.ndarray:
+    """``AttentivePooler.forward`` (merv/util/nn_utils.py:229-238): every frame's N patch tokens are resampled to
+    ``num_query_tokens`` tokens by one cross-attention block with learned queries, then projected.
+    x [B, F, N, C] -> [B, F * num_query_tokens, llm_dim]; token index = f * num_query_tokens + query (:237)."""
+    B, F, N, C = x.shape
+    xf = x.reshape(B * F, N, C)
+    q = np.broadcast_to(params["query_tokens"], (B * F,) + params["query_tokens"].shape[1:])
+    q = cross_attention_block_forward(q, xf, params, num_heads)
+    proj = {k[len("projector."):]: a for k, a in params.items() if k.startswith("projector.")}  # keys of the get_mlp_projector module (:206)
+    y = projector_forward(q, proj, mlp_type)
+    return y.reshape(B, F * y.shape[1], y.shape[2])
+
+
+# --------------------------------------------------------------------------------------------
 # learnable-query cross-attention mixer
 # --------------------------------------------------------------------------------------------
 def _softmax_last(x: np.ndarray) -> np.ndarray:

@@ -8,6 +8,7 @@ Each variant exercises ONE reference module directly on seeded numpy inputs (PCG
     concat_channel_ln   Sequential(LayerNorm(E*K), LinearProjector(E*K, K))       (merv.py:219-223,603-606)
     xattn_flat          CrossAttentionAdapterLearnableQuery(averagetoken=False)    (nn_utils.py:514-518), one T==1 encoder
     xattn_pe            CrossAttentionAdapterLearnableQuery(averagetoken=True, positional_embedding=True)  (nn_utils.py:510-511)
+    attntv_*            AttentivePooler (cross-attention resampler with learned queries)                    (nn_utils.py:177-246,380-452)
     *_wide              the same at tcgen05 tile sizes / CTA-per-row LayerNorm widths (E*K = 4 * 1024 channels)
 
 ``oracle/make_golden.py`` runs the unmodified reference modules on them and stores the outputs in
@@ -36,6 +37,13 @@ VARIANTS: Dict[str, dict] = {
     "xattn_flat": dict(kind="xattn", E=4, T=16, K=128, B=3, embed=96, averagetoken=False, pe=False, single=(2,)),
     "xattn_pe": dict(kind="xattn", E=4, T=64, K=128, B=3, embed=96, averagetoken=True, pe=True, single=()),
     "xattn_pe_single": dict(kind="xattn", E=3, T=32, K=256, B=2, embed=64, averagetoken=True, pe=True, single=(0,)),
+    # AttentivePooler ("attntv" resampler, merv/util/nn_utils.py:177-246; constructed at merv.py:124-130 with num_heads=8)
+    "attntv_tiny": dict(kind="attntv", C=32, llm_dim=48, queries=4, heads=4, F=3, N=9, B=2, mlp_type="gelu-mlp"),
+    "attntv_linear": dict(kind="attntv", C=64, llm_dim=128, queries=16, heads=8, F=2, N=49, B=2, mlp_type="linear"),
+    # tcgen05-sized GEMMs, head_dim 32, 196 keys (a 14 x 14 frame)
+    "attntv_wide": dict(kind="attntv", C=256, llm_dim=512, queries=64, heads=8, F=2, N=196, B=1, mlp_type="linear"),
+    # the SigLIP / ViViT width: head_dim 96, 64 queries, one 14 x 14 frame
+    "attntv_hd96": dict(kind="attntv", C=768, llm_dim=256, queries=64, heads=8, F=1, N=196, B=1, mlp_type="linear"),
 }
 
 
@@ -59,6 +67,25 @@ def make_variant(name: str) -> Tuple[List[np.ndarray], Dict[str, np.ndarray]]:
         else:
             p.update({**_linear_params(rng, "projector.0", C, 4 * C), **_linear_params(rng, "projector.2", 4 * C, K),
                       **_linear_params(rng, "projector.4", K, K)})
+        return [x], p
+    if v["kind"] == "attntv":
+        C, K, n = v["C"], v["llm_dim"], v["queries"]
+        x = rng.standard_normal((v["B"], v["F"], v["N"], C), dtype=np.float32) * np.float32(1.3) + np.float32(0.2)
+        p = {"query_tokens": rng.standard_normal((1, n, C), dtype=np.float32) * np.float32(0.7),
+             "cross_attn.norm1.weight": (1.0 + 0.3 * rng.standard_normal(C)).astype(np.float32),
+             "cross_attn.norm1.bias": (0.2 * rng.standard_normal(C)).astype(np.float32),
+             "cross_attn.norm2.weight": (1.0 + 0.3 * rng.standard_normal(C)).astype(np.float32),
+             "cross_attn.norm2.bias": (0.2 * rng.standard_normal(C)).astype(np.float32)}
+        # 4x the nn.Linear default bound on q / kv so that the attention is far from uniform (a broken score path must show)
+        p.update({k: a * np.float32(4.0) for k, a in _linear_params(rng, "cross_attn.xattn.q", C, C).items()})
+        p.update({k: a * np.float32(4.0) for k, a in _linear_params(rng, "cross_attn.xattn.kv", C, 2 * C).items()})
+        p.update(_linear_params(rng, "cross_attn.xattn.proj", C, C))
+        p.update(_linear_params(rng, "cross_attn.mlp.fc1", C, 4 * C))
+        p.update(_linear_params(rng, "cross_attn.mlp.fc2", 4 * C, C))
+        if v["mlp_type"] == "linear":
+            p.update(_linear_params(rng, "projector.projector", C, K))
+        else:
+            p.update({**_linear_params(rng, "projector.projector.0", C, K), **_linear_params(rng, "projector.projector.2", K, K)})
         return [x], p
     E, T, K, B = v["E"], v["T"], v["K"], v["B"]
     offsets = (0.0, 0.5, -0.5, 0.25)

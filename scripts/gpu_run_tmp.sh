@@ -1,4 +1,3 @@
-TAG=r1g BENCH_ARGS="--no-torch-eager" bash scripts/gpu_profile.sh 2>&1 | grep -v "^-\|^total" | tail -12
-echo "=== full capture: layernorm ==="
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:layernorm_kernel -s 8 -c 2 -f -o gpurun_out/r1g_prof_layernorm python scripts/gpu_variants_diag.py > gpurun_out/r1g_prof_layernorm.log 2>&1
-echo "rc=$?"; ls -la gpurun_out/*.ncu-rep
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests -m gpu -q -x -k "backward or fused_training or helper_kernels" > gpurun_out/pytest_bwd.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest_bwd.log | cut -c1-300
+timeout 300 python scripts/gpu_train_step.py 16 64 > gpurun_out/train_step.log 2>&1; echo "train rc=$?"; tail -4 gpurun_out/train_step.log | cut -c1-1500

@@ -157,11 +157,54 @@ def layernorm_backward(xs, dy, weight, eps=1e-5, need_dx=True, need_params=True)
     return (dx.to(dt) if need_dx else None), (dw.to(dt) if need_params else None), (db.to(dt) if need_params else None)
 
 
-def transpose(x, pad=False):
-    y = x.T.contiguous()
+def transpose(x, pad=False, row_scale=None, rows_per_scale=1):
+    xf = x.float()
+    if row_scale is not None:
+        xf = xf * row_scale.float().repeat_interleave(rows_per_scale)[:x.shape[0], None]
+    y = xf.T.contiguous().to(x.dtype)
     vec = 8 if x.dtype == torch.bfloat16 else 4
     extra = (-y.shape[1]) % vec if pad else 0
     return F.pad(y, (0, extra)) if extra else y
+
+
+def video_colsum(x, scale=1.0):
+    return x.float().sum(1) * scale
+
+
+def pair_dot(x, y):
+    B = x.shape[0]
+    full = (x.float().reshape(B, -1) * y.float().reshape(B, -1)).sum(1, keepdim=True)
+    return torch.cat([full, torch.zeros(B, 15)], 1)  # the real kernel emits 16 partials; only their sum is contractual
+
+
+def fused_backward(weights, dweights_out, u, gsum, dw_partials, pbars, Ws, biases, Q, Wq, Wk, in_proj_bias, dWs):
+    """The contract of merv_fused_backward (include/merv_fusion.h), restated with torch ops."""
+    B, E = weights.shape
+    dt = Ws[0].dtype
+    embed = Wk.shape[0]
+    dw = torch.stack([p.sum(1) for p in dw_partials], 1)
+    for e, b in enumerate(biases):
+        if b is not None:
+            dw[:, e] += gsum @ b.float()
+    if dweights_out is not None:
+        dw = dw + dweights_out
+    ds = weights * (dw - (weights * dw).sum(1, keepdim=True))
+    du = torch.zeros_like(u)
+    dbs = []
+    for e in range(E):
+        g = ds[:, e] @ pbars[e]  # [C_e]
+        sig = ds[:, e].sum()
+        dWs[e].copy_((dWs[e].float() + torch.outer(u, g)).to(dt))
+        dbs.append(None if biases[e] is None else (weights[:, e] @ gsum + u * sig).to(dt))
+        du = du + Ws[e].float() @ g + (sig * biases[e].float() if biases[e] is not None else 0.0)
+    rs = 1.0 / math.sqrt(embed)
+    q = Wq.float() @ Q.float().reshape(-1) + (in_proj_bias.float()[:embed] if in_proj_bias is not None else 0.0)
+    dq = (Wk.float() @ du) * rs
+    dWk = torch.outer(q, du) * rs
+    dWq = torch.outer(dq, Q.float().reshape(-1))
+    dQ = (Wq.float().T @ dq).reshape(1, embed)
+    dbias = torch.cat([dq, torch.zeros(2 * embed)])
+    return ds, dbs, dQ.to(dt), dWq.to(dt), dWk.to(dt), dbias.to(dt)
 
 
 def gelu(z, dy=None):
@@ -212,7 +255,7 @@ class FusedLinearPlan:
 
 _NAMES = ["pool3d", "linear_bias_act", "fusion_query_vec", "affine_score_vec", "scores_from_tokens", "score_consts", "scores_from_partials",
           "softmax_weights", "softmax_mix", "fused_linear_mix", "concat_linear", "layernorm", "layernorm_backward", "transpose", "gelu",
-          "colsum", "mix_backward", "FusedLinearPlan"]
+          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "fused_backward"]
 
 
 def emulate(monkeypatch) -> None:

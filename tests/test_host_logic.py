@@ -87,7 +87,8 @@ def test_fused_wiring_bf16(name):
 def _variants():
     from oracle import variants as V
 
-    return [n for n in V.VARIANTS if not n.endswith("_wide")]
+    # the attentive pooler ("attntv") has an oracle and goldens (tests/test_oracle.py) but no CUDA module yet
+    return [n for n, v in V.VARIANTS.items() if not n.endswith("_wide") and v["kind"] != "attntv"]
 
 
 @pytest.mark.parametrize("name", _variants())
@@ -251,3 +252,46 @@ def test_patch_merv_shares_parameters_and_reproduces_the_reference(fusion_type):
     with torch.inference_mode():
         got = glue(vid)
     assert O.rel_err(_np(got), _np(want)) < 2e-5
+
+
+# ---- fused training step (the fused forward + _FusedLinearFn backward) vs autograd through the reference's op sequence ----
+def test_fused_training_gradients_match_reference_autograd():
+    from oracle import torch_port
+
+    case = C.CASES["tiny_linear"]
+    g, feats, pp, fp = regenerate(case)
+    rnd = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()  # noqa: E731  (the operating point the bf16 modules see)
+    feats_r, pp_r, fp_r = [rnd(f) for f in feats], [{k: rnd(v) for k, v in p.items()} for p in pp], {k: rnd(v) for k, v in fp.items()}
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((case.batch, case.token_length, case.llm_dim)).astype(np.float32)
+    H = rng.standard_normal((case.batch, case.num_encoders)).astype(np.float32)
+    tt = lambda d: {k: torch.from_numpy(v).double().requires_grad_(True) for k, v in d.items()}  # noqa: E731
+    ppt, fpt = [tt(p) for p in pp_r], tt(fp_r)
+    out, w = torch_port.fusion_forward_autograd([torch.from_numpy(f).double() for f in feats_r], ppt, fpt, case.out_frames, case.out_size,
+                                                case.mlp_type, case.token_length)
+    ((out * torch.from_numpy(G).double()).sum() + (w * torch.from_numpy(H).double()).sum()).backward()
+
+    import merv_b200 as M
+
+    projs = [M.AveragePooling3DProjector(c, case.llm_dim, t, case.out_size, case.mlp_type) for c, t in zip(case.dims, case.out_frames)]
+    fusion = M.CrossAttentionAdapterLearnableQuery(case.embed_dim, case.llm_dim, case.token_length, averagetoken=True, num_encoder=case.num_encoders)
+    m = M.MervFusion(projs, fusion, fused=True, fused_training=True)
+    for proj, p in zip(m.projectors, pp_r):
+        proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    m.feature_fusion.load_state_dict({k: torch.from_numpy(v) for k, v in fp_r.items()})
+    m = m.to(torch.bfloat16).train()
+    got_out, got_w = m([torch.from_numpy(f).to(torch.bfloat16) for f in feats_r])
+    assert got_out.requires_grad and got_w.requires_grad and type(got_out.grad_fn).__name__.startswith("_FusedLinearFn")
+    assert O.rel_err(_np(got_out), out.detach().numpy()) < 2e-2
+    ((got_out.float() * torch.from_numpy(G)).sum() + (got_w.float() * torch.from_numpy(H)).sum()).backward()
+    tol = 3e-2
+    for i, proj in enumerate(m.projectors):
+        for k, p in proj.projector.named_parameters():
+            assert p.grad is not None and O.rel_err(_np(p.grad), ppt[i][k].grad.numpy()) < tol, (i, k)
+    ff = m.feature_fusion
+    E = case.embed_dim
+    assert O.rel_err(_np(ff.Q.grad), fpt["Q"].grad.numpy()) < tol
+    assert O.rel_err(_np(ff.attention.q_proj_weight.grad), fpt["attention.q_proj_weight"].grad.numpy()) < tol
+    assert O.rel_err(_np(ff.attention.k_proj_weight.grad), fpt["attention.k_proj_weight"].grad.numpy()) < tol
+    assert O.rel_err(_np(ff.attention.in_proj_bias.grad)[:E], fpt["attention.in_proj_bias"].grad.numpy()[:E]) < tol
+    assert ff.attention.v_proj_weight.grad is None and ff.attention.out_proj.weight.grad is None
