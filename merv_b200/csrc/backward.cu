@@ -176,6 +176,50 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(const T* __restrict__ W, co
   acc = warp_sum(acc);
   if (lane == 0) out[row] = acc * scale + (bias ? to_float(bias[row]) : 0.f);
 }
+// the same with 16-byte loads of W (K % VEC == 0, rows 16-byte aligned)
+template <typename T> __device__ __forceinline__ void load_vec_as_float(const T* p, float (&f)[Vec16<T>::kN]) { Vec16<T>::unpack(ldg_v4(p), f); }
+template <typename T>
+__device__ __forceinline__ void load_x_vec(const float* x, float (&f)[Vec16<T>::kN]) {
+#pragma unroll
+  for (int c = 0; c < Vec16<T>::kN; c += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + c));
+    f[c] = v.x; f[c + 1] = v.y; f[c + 2] = v.z; f[c + 3] = v.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void load_x_vec(const __nv_bfloat16* x, float (&f)[Vec16<T>::kN]) {
+  static_assert(Vec16<T>::kN == 8, "bf16 x goes with bf16 W");
+  Vec16<__nv_bfloat16>::unpack(ldg_v4(x), f);
+}
+template <typename T, typename X>
+__global__ void __launch_bounds__(256) gemv_n_vec_kernel(const T* __restrict__ W, const X* __restrict__ x, const T* __restrict__ bias, float* __restrict__ out,
+                                                         int D, int K, float scale) {
+  constexpr int VEC = Vec16<T>::kN;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= D) return;
+  const int lane = threadIdx.x & 31;
+  const T* w = W + (long long)row * K;
+  float acc = 0.f;
+  for (int k = lane * VEC; k < K; k += 32 * VEC) {
+    float a[VEC], b[VEC];
+    Vec16<T>::unpack(ldg_nc_v4(w + k), a);
+    load_x_vec<T>(x + k, b);
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc = fmaf(a[c], b[c], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = acc * scale + (bias ? to_float(bias[row]) : 0.f);
+}
+template <typename T, typename X>
+static void launch_gemv_n(const T* W, const X* x, const T* bias, float* out, int D, int K, float scale, cudaStream_t s) {
+  constexpr int VEC = Vec16<T>::kN;
+  const bool vec_ok = K % VEC == 0 && aligned16(W) && aligned16(x) && (sizeof(X) == 4 || sizeof(T) == 2);
+  if (vec_ok)
+    gemv_n_vec_kernel<T, X><<<(D + 7) / 8, 256, 0, s>>>(W, x, bias, out, D, K, scale);
+  else
+    gemv_n_kernel<T, X><<<(D + 7) / 8, 256, 0, s>>>(W, x, bias, out, D, K, scale);
+}
+
 // out[j] = sum_d W[d,j] x[d]  (W [D, J] row-major), fp32 x
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_tf_kernel(const T* __restrict__ W, const float* __restrict__ x, T* __restrict__ out, int D, int J) {
@@ -262,14 +306,15 @@ static int launch_mix_dv(const BwdPtrs& p, const void* dOut, const float* weight
 // The kernels below are the HBM-bound / tiny pieces; the two GEMMs per encoder run on the tcgen05 kernel.
 // ============================================================================================================
 
-// ---- out[b, k] = scale * sum_t x[b, t, k] (fp32): CTA = (256-byte column block, video), 8 row groups, fixed-order reduction ----
+// ---- out[b, k] = scale * sum_t x[b, t, k] (fp32): CTA = (8 vectors = 128-byte column block, video), 32 row groups, fixed-order
+//      reduction; narrow column blocks keep enough CTAs in flight at the small per-device batches of the training step ----
 template <typename T>
 __global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int Ttok, int K, long long ld,
                                                            long long batch_stride, float scale) {
   constexpr int VEC = Vec16<T>::kN;
-  __shared__ float part[8][32 * VEC + 1];
-  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int k0 = (blockIdx.x * 32 + lane) * VEC;
+  __shared__ float part[32][8 * VEC + 1];
+  const int cv = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const int k0 = (blockIdx.x * 8 + cv) * VEC;
   const int b = blockIdx.y;
   float acc[VEC];
 #pragma unroll
@@ -277,10 +322,10 @@ __global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__
   if (k0 < K) {
     const T* base = x + (long long)b * batch_stride + k0;
     int t = rg;
-    for (; t + 24 < Ttok; t += 32) {  // four independent 16-byte loads in flight per thread
+    for (; t + 96 < Ttok; t += 128) {  // four independent 16-byte loads in flight per thread
       uint4 r[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) r[i] = ldg_nc_v4(base + (long long)(t + 8 * i) * ld);
+      for (int i = 0; i < 4; ++i) r[i] = ldg_nc_v4(base + (long long)(t + 32 * i) * ld);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float f[VEC];
@@ -289,7 +334,7 @@ __global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__
         for (int c = 0; c < VEC; ++c) acc[c] += f[c];
       }
     }
-    for (; t < Ttok; t += 8) {
+    for (; t < Ttok; t += 32) {
       float f[VEC];
       Vec16<T>::unpack(ldg_nc_v4(base + (long long)t * ld), f);
 #pragma unroll
@@ -297,21 +342,21 @@ __global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__
     }
   }
 #pragma unroll
-  for (int c = 0; c < VEC; ++c) part[rg][lane * VEC + c] = acc[c];
+  for (int c = 0; c < VEC; ++c) part[rg][cv * VEC + c] = acc[c];
   __syncthreads();
-  for (int i = threadIdx.x; i < 32 * VEC; i += 256) {
-    const int k = blockIdx.x * 32 * VEC + i;
+  if (threadIdx.x < 8 * VEC) {
+    const int k = blockIdx.x * 8 * VEC + threadIdx.x;
     if (k < K) {
       float sum = 0.f;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) sum += part[g][i];
+      for (int g = 0; g < 32; ++g) sum += part[g][threadIdx.x];
       out[(long long)b * K + k] = sum * scale;
     }
   }
 }
 
 // ---- partial[b, chunk] = sum over the chunk of x[b, i] * y[b, i]  (both [B, n] contiguous) --------------------------------
-constexpr int kPairDotChunks = 16;
+constexpr int kPairDotChunks = 32;
 template <typename T>
 __global__ void __launch_bounds__(256) pair_dot_kernel(const T* __restrict__ x, const T* __restrict__ y, float* __restrict__ partial, long long nvec) {
   constexpr int VEC = Vec16<T>::kN;
@@ -482,35 +527,122 @@ __global__ void __launch_bounds__(256) fused_bwd_db_kernel(const __grid_constant
   static_cast<T*>(p.db[e])[n] = from_float<T>(fmaf(u[n], sig, acc));
 }
 
-// dW_e[n, c] += u[n] * g_e[c]
-template <typename T>
-__global__ void __launch_bounds__(256) fused_bwd_rank1_kernel(T* __restrict__ dW, long long ld, const float* __restrict__ u, const float* __restrict__ g,
-                                                              int K, int C) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= (long long)K * C) return;
-  const int n = int(idx / C), c = int(idx % C);
-  T* d = dW + (long long)n * ld + c;
-  *d = from_float<T>(fmaf(u[n], g[c], to_float(*d)));
+// dW_e[n, c] += u[n] * g_e[c]   grid (blocks, E): block-stride loop over the K x C_e elements of encoder blockIdx.y, 16 bytes per
+// thread when the rows allow it (kVecOK: C_e % VEC == 0, 16-byte aligned rows — always true for buffers the GEMM wrote)
+template <typename T, bool kVecOK>
+__global__ void __launch_bounds__(256) fused_bwd_rank1_kernel(const __grid_constant__ FusedBwdPtrs p, const float* __restrict__ u, const float* __restrict__ g,
+                                                              int K) {
+  constexpr int VEC = kVecOK ? Vec16<T>::kN : 1;
+  const int e = blockIdx.y, C = p.C[e], cv = C / VEC;
+  T* dW = static_cast<T*>(p.dW[e]);
+  const long long ld = p.lddw[e];
+  const float* ge = g + p.goff[e];
+  const long long total = (long long)K * cv;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int n = int(idx / cv), c = int(idx - (long long)n * cv) * VEC;
+    T* d = dW + (long long)n * ld + c;
+    const float un = u[n];
+    if constexpr (kVecOK) {
+      float f[Vec16<T>::kN], gg[Vec16<T>::kN];
+      Vec16<T>::unpack(*reinterpret_cast<const uint4*>(d), f);
+      load_x_vec<T>(ge + c, gg);
+#pragma unroll
+      for (int i = 0; i < Vec16<T>::kN; ++i) f[i] = fmaf(un, gg[i], f[i]);
+      *reinterpret_cast<uint4*>(d) = Vec16<T>::pack(f);
+    } else {
+      *d = from_float<T>(fmaf(un, ge[c], to_float(*d)));
+    }
+  }
 }
 
-// du[n] (+)= sum_c W_e[n, c] g_e[c] + sig_e b_e[n] : one warp per row, encoders accumulated by successive launches (fixed order)
-template <typename T>
-__global__ void __launch_bounds__(256) fused_bwd_du_kernel(const T* __restrict__ W, long long ldw, const T* __restrict__ bias, const float* __restrict__ g,
-                                                           const float* __restrict__ ds, float* __restrict__ du, int K, int C, int B, int E, int e,
-                                                           int accumulate) {
+// du[n] = sum_e (sum_c W_e[n, c] g_e[c] + sig_e b_e[n]) : one warp per row, encoders in order (fixed summation order)
+template <typename T, bool kVecOK>
+__global__ void __launch_bounds__(256) fused_bwd_du_kernel(const __grid_constant__ FusedBwdPtrs p, const float* __restrict__ g, const float* __restrict__ ds,
+                                                           float* __restrict__ du, int K, int B, int E) {
+  constexpr int VEC = kVecOK ? Vec16<T>::kN : 1;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= K) return;
   const int lane = threadIdx.x & 31;
-  const T* w = W + (long long)row * ldw;
-  float acc = 0.f;
-  for (int c = lane; c < C; c += 32) acc = fmaf(to_float(w[c]), g[c], acc);
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    float sig = 0.f;
-    for (int b = 0; b < B; ++b) sig += ds[(long long)b * E + e];
-    const float v = acc + (bias != nullptr ? sig * to_float(bias[row]) : 0.f);
-    du[row] = accumulate ? du[row] + v : v;
+  float total = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const T* w = static_cast<const T*>(p.W[e]) + (long long)row * p.ldw[e];
+    const float* ge = g + p.goff[e];
+    float acc = 0.f;
+    for (int c = lane * VEC; c < p.C[e]; c += 32 * VEC) {
+      if constexpr (kVecOK) {
+        float a[Vec16<T>::kN], b[Vec16<T>::kN];
+        Vec16<T>::unpack(ldg_nc_v4(w + c), a);
+        load_x_vec<T>(ge + c, b);
+#pragma unroll
+        for (int i = 0; i < Vec16<T>::kN; ++i) acc = fmaf(a[i], b[i], acc);
+      } else {
+        acc = fmaf(to_float(w[c]), ge[c], acc);
+      }
+    }
+    if (p.bias[e] != nullptr) {  // sig_e = sum_b ds[b, e], spread over the lanes
+      float sig = 0.f;
+      for (int b = lane; b < B; b += 32) sig += ds[(long long)b * E + e];
+      acc = fmaf(sig, to_float(static_cast<const T*>(p.bias[e])[row]), acc);
+    }
+    total += warp_sum(acc);
   }
+  if (lane == 0) du[row] = total;
+}
+
+// two outer products in one launch: blockIdx.y == 0: dWk[i, j] = rs * q[i] * du[j];  == 1: dWq[i, j] = dq[i] * Q[j]
+template <typename T, bool kVecOK>
+__global__ void __launch_bounds__(256) fused_bwd_outer_kernel(const float* __restrict__ q, const float* __restrict__ du, const float* __restrict__ dq,
+                                                              const T* __restrict__ Q, T* __restrict__ dWk, T* __restrict__ dWq, int embed, int K, float rs) {
+  constexpr int VEC = kVecOK ? Vec16<T>::kN : 1;
+  const bool first = blockIdx.y == 0;
+  const int J = first ? K : embed, jv = J / VEC;
+  const long long total = (long long)embed * jv;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int i = int(idx / jv), j = int(idx - (long long)i * jv) * VEC;
+    const float a = first ? rs * q[i] : dq[i];
+    T* dst = (first ? dWk : dWq) + (long long)i * J + j;
+    if constexpr (kVecOK) {
+      float b[Vec16<T>::kN];
+      if (first) load_x_vec<T>(du + j, b);
+      else Vec16<T>::unpack(ldg_v4(Q + j), b);
+#pragma unroll
+      for (int c = 0; c < Vec16<T>::kN; ++c) b[c] *= a;
+      stg_na_v4(dst, Vec16<T>::pack(b));
+    } else {
+      *dst = from_float<T>(a * (first ? du[j] : to_float(Q[j])));
+    }
+  }
+}
+
+// dQ[j] = sum_d Wq[d, j] dq[d], stage 1: partial[s, j] over the rows d = s, s + S, ... (grid (ceil(J / 32), S), 8 row groups per CTA)
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_tf_partial_kernel(const T* __restrict__ W, const float* __restrict__ x, float* __restrict__ partial, int D, int J) {
+  __shared__ float part[8][33];
+  const int jx = threadIdx.x & 31, dy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + jx;
+  float acc = 0.f;
+  if (j < J)
+    for (int d = blockIdx.y * 8 + dy; d < D; d += 8 * gridDim.y) acc += to_float(W[(long long)d * J + j]) * x[d];
+  part[dy][jx] = acc;
+  __syncthreads();
+  if (dy == 0 && j < J) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += part[i][jx];
+    partial[(long long)blockIdx.y * J + j] = sum;
+  }
+}
+// stage 2 merged with the in_proj_bias gradient: dQ[j] = sum_s partial[s, j];  dbias = [dq, 0, 0]
+template <typename T>
+__global__ void __launch_bounds__(256) fused_bwd_final_kernel(const float* __restrict__ partial, int S, const float* __restrict__ dq, T* __restrict__ dQ,
+                                                              T* __restrict__ dbias, int embed) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < embed) {
+    float sum = 0.f;
+    for (int k = 0; k < S; ++k) sum += partial[(long long)k * embed + i];
+    dQ[i] = from_float<T>(sum);
+  }
+  if (i < 3 * embed) dbias[i] = from_float<T>(i < embed ? dq[i] : 0.f);  // b_k cancels in the softmax, b_v is dead
 }
 
 }  // namespace merv
@@ -604,8 +736,8 @@ extern "C" int merv_mix_backward(const void* const* V, const void* dOut, const f
     mix_bwd_scores_kernel<<<B, 32, 0, s>>>(dw_partial, weights, dweights_out, ds, E, kblocks);
     if (int rc = launch_mix_dv<T_>(p, dOut, weights, ds, u, B, E, T, K, s)) return rc;
     du_kernel<<<(K + 255) / 256, 256, 0, s>>>(ds, vbar, du, B * E, K);
-    gemv_n_kernel<T_, T_><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)Wq, (const T_*)Q, (const T_*)in_proj_bias, q, embed, embed, 1.0f);
-    gemv_n_kernel<T_, float><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)Wk, du, nullptr, dq, embed, K, rs);
+    launch_gemv_n<T_, T_>((const T_*)Wq, (const T_*)Q, (const T_*)in_proj_bias, q, embed, embed, 1.0f, s);
+    launch_gemv_n<T_, float>((const T_*)Wk, du, nullptr, dq, embed, K, rs, s);
     outer_kernel<T_, float><<<(unsigned)((nWk + 255) / 256), 256, 0, s>>>(q, du, (T_*)dWk, embed, K, rs);
     outer_kernel<T_, T_><<<(unsigned)((nWq + 255) / 256), 256, 0, s>>>(dq, (const T_*)Q, (T_*)dWq, embed, embed, 1.0f);
     gemv_tf_kernel<T_><<<(embed + 31) / 32, 256, 0, s>>>((const T_*)Wq, dq, (T_*)dQ, embed, embed);
@@ -616,8 +748,8 @@ extern "C" int merv_mix_backward(const void* const* V, const void* dOut, const f
     mix_bwd_scores_kernel<<<B, 32, 0, s>>>(dw_partial, weights, dweights_out, ds, E, kblocks);
     if (int rc = launch_mix_dv<T_>(p, dOut, weights, ds, u, B, E, T, K, s)) return rc;
     du_kernel<<<(K + 255) / 256, 256, 0, s>>>(ds, vbar, du, B * E, K);
-    gemv_n_kernel<T_, T_><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)Wq, (const T_*)Q, (const T_*)in_proj_bias, q, embed, embed, 1.0f);
-    gemv_n_kernel<T_, float><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)Wk, du, nullptr, dq, embed, K, rs);
+    launch_gemv_n<T_, T_>((const T_*)Wq, (const T_*)Q, (const T_*)in_proj_bias, q, embed, embed, 1.0f, s);
+    launch_gemv_n<T_, float>((const T_*)Wk, du, nullptr, dq, embed, K, rs, s);
     outer_kernel<T_, float><<<(unsigned)((nWk + 255) / 256), 256, 0, s>>>(q, du, (T_*)dWk, embed, K, rs);
     outer_kernel<T_, T_><<<(unsigned)((nWq + 255) / 256), 256, 0, s>>>(dq, (const T_*)Q, (T_*)dWq, embed, embed, 1.0f);
     gemv_tf_kernel<T_><<<(embed + 31) / 32, 256, 0, s>>>((const T_*)Wq, dq, (T_*)dQ, embed, embed);
@@ -665,7 +797,7 @@ extern "C" int merv_video_colsum(const void* x, float* out, int B, int T, int K,
   if (int rc = require_sm100()) return rc;
   if (B == 0) return MERV_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid((K / vec + 31) / 32, B);
+  dim3 grid((K / vec + 7) / 8, B);
   if (dtype == MERV_BF16)
     video_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, out, T, K, ld, batch_stride, scale);
   else
@@ -718,11 +850,12 @@ extern "C" int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad,
   return MERV_OK;
 }
 
+constexpr int kDqSplits = 8;
 extern "C" size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* d) {
   if (d == nullptr || d->E <= 0) return 0;
   size_t g = 0;
   for (int e = 0; e < d->E && e < MERV_MAX_ENCODERS; ++e) g += (size_t)d->C[e];
-  return g + (size_t)d->K + 2 * (size_t)d->embed;
+  return g + (size_t)d->K + (2 + kDqSplits) * (size_t)d->embed;
 }
 
 extern "C" int merv_fused_backward(const merv_fused_bwd_desc* d, int dtype, void* stream) {
@@ -757,25 +890,33 @@ extern "C" int merv_fused_backward(const merv_fused_bwd_desc* d, int dtype, void
   float* du = g + goff;
   float* q = du + K;
   float* dq = q + embed;
+  float* dqp = dq + embed;
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  bool vec_rows = goff % 4 == 0;  // g_e offsets stay 16-byte aligned
+  for (int e = 0; e < E; ++e)
+    vec_rows = vec_rows && p.C[e] % vec == 0 && p.ldw[e] % vec == 0 && p.lddw[e] % vec == 0 && aligned16(p.W[e]) && aligned16(p.dW[e]) && p.goff[e] % 4 == 0;
+  const bool vec_outer = K % vec == 0 && embed % vec == 0 && goff % 4 == 0 && aligned16(d->workspace) && aligned16(d->Q) && aligned16(d->dWk) && aligned16(d->dWq);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float rs = 1.0f / sqrtf(float(embed));
-  const long long nWk = (long long)embed * K, nWq = (long long)embed * embed;
 #define MERV_FUSED_BWD_BODY(T_)                                                                                                                   \
   fused_bwd_scores_kernel<T_><<<B, 32, 0, s>>>(p, d->gsum, d->weights, d->dweights_out, d->ds, E, K);                                             \
   fused_bwd_g_kernel<<<dim3((cmax + 255) / 256, E), 256, 0, s>>>(p, d->ds, g, B, E);                                                              \
   fused_bwd_db_kernel<T_><<<dim3((K + 255) / 256, E), 256, 0, s>>>(p, d->gsum, d->weights, d->ds, d->u, B, E, K);                                 \
-  for (int e = 0; e < E; ++e) {                                                                                                                   \
-    const long long n = (long long)K * p.C[e];                                                                                                    \
-    fused_bwd_rank1_kernel<T_><<<(unsigned)((n + 255) / 256), 256, 0, s>>>((T_*)p.dW[e], p.lddw[e], d->u, g + p.goff[e], K, p.C[e]);               \
-    fused_bwd_du_kernel<T_><<<(K + 7) / 8, 256, 0, s>>>((const T_*)p.W[e], p.ldw[e], (const T_*)p.bias[e], g + p.goff[e], d->ds, du, K, p.C[e], B, \
-                                                        E, e, e > 0);                                                                             \
+  if (vec_rows) {                                                                                                                                 \
+    fused_bwd_rank1_kernel<T_, true><<<dim3(sm_count() * 4, E), 256, 0, s>>>(p, d->u, g, K);                                                      \
+    fused_bwd_du_kernel<T_, true><<<(K + 7) / 8, 256, 0, s>>>(p, g, d->ds, du, K, B, E);                                                          \
+  } else {                                                                                                                                        \
+    fused_bwd_rank1_kernel<T_, false><<<dim3(sm_count() * 4, E), 256, 0, s>>>(p, d->u, g, K);                                                     \
+    fused_bwd_du_kernel<T_, false><<<(K + 7) / 8, 256, 0, s>>>(p, g, d->ds, du, K, B, E);                                                         \
   }                                                                                                                                               \
-  gemv_n_kernel<T_, T_><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)d->Wq, (const T_*)d->Q, (const T_*)d->in_proj_bias, q, embed, embed, 1.0f);    \
-  gemv_n_kernel<T_, float><<<(embed + 7) / 8, 256, 0, s>>>((const T_*)d->Wk, du, nullptr, dq, embed, K, rs);                                      \
-  outer_kernel<T_, float><<<(unsigned)((nWk + 255) / 256), 256, 0, s>>>(q, du, (T_*)d->dWk, embed, K, rs);                                        \
-  outer_kernel<T_, T_><<<(unsigned)((nWq + 255) / 256), 256, 0, s>>>(dq, (const T_*)d->Q, (T_*)d->dWq, embed, embed, 1.0f);                       \
-  gemv_tf_kernel<T_><<<(embed + 31) / 32, 256, 0, s>>>((const T_*)d->Wq, dq, (T_*)d->dQ, embed, embed);                                           \
-  bias_grad_kernel<T_><<<(3 * embed + 255) / 256, 256, 0, s>>>(dq, (T_*)d->dbias, embed);
+  launch_gemv_n<T_, T_>((const T_*)d->Wq, (const T_*)d->Q, (const T_*)d->in_proj_bias, q, embed, embed, 1.0f, s);                                \
+  launch_gemv_n<T_, float>((const T_*)d->Wk, du, nullptr, dq, embed, K, rs, s);                                                                  \
+  if (vec_outer)                                                                                                                                  \
+    fused_bwd_outer_kernel<T_, true><<<dim3(sm_count() * 4, 2), 256, 0, s>>>(q, du, dq, (const T_*)d->Q, (T_*)d->dWk, (T_*)d->dWq, embed, K, rs); \
+  else                                                                                                                                            \
+    fused_bwd_outer_kernel<T_, false><<<dim3(sm_count() * 4, 2), 256, 0, s>>>(q, du, dq, (const T_*)d->Q, (T_*)d->dWk, (T_*)d->dWq, embed, K, rs);\
+  gemv_tf_partial_kernel<T_><<<dim3((embed + 31) / 32, kDqSplits), 256, 0, s>>>((const T_*)d->Wq, dq, dqp, embed, embed);                         \
+  fused_bwd_final_kernel<T_><<<(3 * embed + 255) / 256, 256, 0, s>>>(dqp, kDqSplits, dq, (T_*)d->dQ, (T_*)d->dbias, embed);
   if (dtype == MERV_BF16) {
     MERV_FUSED_BWD_BODY(__nv_bfloat16)
   } else {
