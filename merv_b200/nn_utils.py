@@ -250,6 +250,8 @@ class _FusedLinearFn(torch.autograd.Function):
         weights, u, Qc, Wqc, Wkc, bc = saved[:6]
         pooled, Ws, biases = saved[6:6 + E], saved[6 + E:6 + 2 * E], saved[6 + 2 * E:6 + 3 * E]
         dt = Ws[0].dtype
+        if dout is None:  # only the mixing weights were used downstream
+            dout = torch.zeros((B, T, K), dtype=dt, device=weights.device)
         g = dout.reshape(B * T, K)
         if g.dtype != dt:
             g = g.to(dt)
