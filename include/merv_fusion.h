@@ -106,15 +106,19 @@ int merv_linear_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw,
  *   u = Wk^T (Wq Q^T + b_q) / sqrt(embed).
  * Replaces the q/k projections inside nn.MultiheadAttention as called at merv/util/nn_utils.py:499-512.
  *   Q [1, embed], Wq [embed, embed], Wk [embed, llm_dim], in_proj_bias [3*embed] (dtype); u [llm_dim] fp32;
- *   workspace: embed floats.
+ *   workspace: at least embed floats; with round_up(embed, 4) + merv_gemv_t_workspace(embed, llm_dim) floats the transposed
+ *   GEMV Wk^T q runs in its two-stage form (row blocks in parallel; matters when llm_dim / 32 CTAs cannot fill the GPU).
+ *   Both run once per weight version in inference but once per optimizer step in training.
  * ------------------------------------------------------------------------------------------------------- */
+size_t merv_gemv_t_workspace(int D, int K); /* floats; 0 = the single-stage kernel is used for a [D, K] matrix */
 int merv_fusion_query_vec(const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias, float* u,
-                          float* workspace, int embed, int llm_dim, int dtype, void* stream);
+                          float* workspace, size_t workspace_floats, int embed, int llm_dim, int dtype, void* stream);
 
 /* For an affine last projector layer y = W x + b:  u . y = (W^T u) . x + u . b.
- *   W [N, K] (ldw), bias [N] or NULL, u [N] fp32  ->  v [K] fp32, c [1] fp32. */
-int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, int N,
-                          int K, int dtype, void* stream);
+ *   W [N, K] (ldw), bias [N] or NULL, u [N] fp32  ->  v [K] fp32, c [1] fp32.
+ *   workspace (optional, merv_gemv_t_workspace(N, K) floats): two-stage W^T u. */
+int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, float* workspace,
+                          size_t workspace_floats, int N, int K, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Scores -> softmax over encoders -> mixing weights.  Two sources for the raw scores [B, E] (fp32):

@@ -75,8 +75,9 @@ _SIGNATURES = {
     "merv_pool3d": (c_int, [POINTER(PoolDesc), c_int, c_int, c_int, c_int, c_void_p]),
     "merv_linear_bias_act": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "merv_fusion_query_vec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "merv_affine_score_vec": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "merv_gemv_t_workspace": (c_size_t, [c_int, c_int]),
+    "merv_fusion_query_vec": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "merv_affine_score_vec": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "merv_scores_from_tokens": (c_int, [_PP, POINTER(c_int32), c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                                         c_int, c_void_p]),
     "merv_scores_from_tokens_ex": (c_int, [_PP, POINTER(c_int32), c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int,

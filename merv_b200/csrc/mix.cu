@@ -56,6 +56,71 @@ __global__ void __launch_bounds__(256) gemv_t_kernel(const T* __restrict__ W, lo
   }
 }
 
+// Two-stage form for narrow outputs (K / 32 CTAs of the kernel above cannot fill the GPU: W_e^T u has K = C_e = 768..1024):
+// stage 1: CTA = (256-byte column block, block of rows), 16-byte loads, 8 row lanes reduced in fixed order -> partial[row block, k]
+// stage 2: out[k] = scale * sum over the row blocks (fixed order).  Deterministic like the single-stage kernel.
+constexpr int kGemvTRows = 64;  // rows per CTA
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_t_partial_kernel(const T* __restrict__ W, long long ldw, const float* __restrict__ x,
+                                                             float* __restrict__ partial, int D, int K) {
+  constexpr int VEC = Vec16<T>::kN;
+  __shared__ float part[8][32 * VEC + 1];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int k0 = (blockIdx.x * 32 + cv) * VEC;
+  const int d0 = blockIdx.y * kGemvTRows, d1 = min(D, d0 + kGemvTRows);
+  float acc[VEC];
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
+  if (k0 < K) {
+    for (int d = d0 + rl; d < d1; d += 8) {
+      float w[VEC];
+      Vec16<T>::unpack(ldg_nc_v4(W + (long long)d * ldw + k0), w);
+      const float xd = x[d];
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w[c], xd, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; ++c) part[rl][cv * VEC + c] = acc[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VEC; i += 256) {
+    const int k = blockIdx.x * 32 * VEC + i;
+    if (k < K) {
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) sum += part[g][i];
+      partial[(long long)blockIdx.y * K + k] = sum;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) gemv_t_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int K, int nblocks, float scale) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= K) return;
+  float sum = 0.f;
+  for (int b = 0; b < nblocks; ++b) sum += partial[(long long)b * K + k];
+  out[k] = sum * scale;
+}
+
+// floats of workspace the two-stage form needs for a [D, K] matrix; 0 = the single-stage kernel already fills the GPU (wide K)
+static size_t gemv_t_workspace(int D, int K) {
+  if (D <= 0 || K <= 0 || (K + 31) / 32 >= 4 * sm_count()) return 0;
+  return (size_t)((D + kGemvTRows - 1) / kGemvTRows) * (size_t)K;
+}
+
+template <typename T>
+static void launch_gemv_t(const T* W, long long ldw, const float* x, float* out, int D, int K, float scale, float* workspace, size_t workspace_floats,
+                          cudaStream_t s) {
+  constexpr int VEC = Vec16<T>::kN;
+  const size_t need = gemv_t_workspace(D, K);
+  if (need > 0 && workspace != nullptr && workspace_floats >= need && K % VEC == 0 && ldw % VEC == 0 && aligned16(W)) {
+    const int nblocks = (D + kGemvTRows - 1) / kGemvTRows;
+    gemv_t_partial_kernel<T><<<dim3((K / VEC + 31) / 32, nblocks), 256, 0, s>>>(W, ldw, x, workspace, D, K);
+    gemv_t_final_kernel<<<(K + 255) / 256, 256, 0, s>>>(workspace, out, K, nblocks, scale);
+  } else {
+    gemv_t_kernel<T><<<(K + 31) / 32, 256, 0, s>>>(W, ldw, x, out, D, K, scale);
+  }
+}
+
 // c = sum_n u[n] * bias[n]
 template <typename T>
 __global__ void __launch_bounds__(256) dot_kernel(const T* __restrict__ bias, const float* __restrict__ u, float* __restrict__ c, int N) {
@@ -332,29 +397,36 @@ using namespace merv;
 
 #define MERV_DTYPE_OK(fn) MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, fn ": unknown dtype %d", dtype)
 
+extern "C" size_t merv_gemv_t_workspace(int D, int K) { return gemv_t_workspace(D, K); }
+
 extern "C" int merv_fusion_query_vec(const void* Q, const void* Wq, const void* Wk, const void* in_proj_bias, float* u,
-                                     float* workspace, int embed, int llm_dim, int dtype, void* stream) {
+                                     float* workspace, size_t workspace_floats, int embed, int llm_dim, int dtype, void* stream) {
   MERV_DTYPE_OK("merv_fusion_query_vec");
   MERV_REQUIRE(Q && Wq && Wk && u && workspace, MERV_E_ARG, "merv_fusion_query_vec: NULL pointer");
   MERV_REQUIRE(embed > 0 && llm_dim > 0, MERV_E_SHAPE, "merv_fusion_query_vec: embed=%d llm_dim=%d", embed, llm_dim);
+  MERV_REQUIRE(workspace_floats >= (size_t)embed, MERV_E_ARG, "merv_fusion_query_vec: workspace holds %zu floats, need >= %d", workspace_floats, embed);
   if (int rc = require_sm100()) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float scale = 1.0f / sqrtf(float(embed));
+  // q in the first `embed` floats (rounded up to a 16-byte boundary), the rest is the two-stage workspace of Wk^T q
+  const size_t qpad = ((size_t)embed + 3) & ~(size_t)3;
+  float* rest = workspace_floats > qpad ? workspace + qpad : nullptr;
+  const size_t rest_floats = workspace_floats > qpad ? workspace_floats - qpad : 0;
   if (dtype == MERV_BF16) {
     using T = __nv_bfloat16;
     qproj_kernel<T><<<(embed + 7) / 8, 256, 0, s>>>((const T*)Wq, (const T*)Q, (const T*)in_proj_bias, workspace, embed);
-    gemv_t_kernel<T><<<(llm_dim + 31) / 32, 256, 0, s>>>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale);
+    launch_gemv_t<T>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale, rest, rest_floats, s);
   } else {
     using T = float;
     qproj_kernel<T><<<(embed + 7) / 8, 256, 0, s>>>((const T*)Wq, (const T*)Q, (const T*)in_proj_bias, workspace, embed);
-    gemv_t_kernel<T><<<(llm_dim + 31) / 32, 256, 0, s>>>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale);
+    launch_gemv_t<T>((const T*)Wk, llm_dim, workspace, u, embed, llm_dim, scale, rest, rest_floats, s);
   }
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }
 
-extern "C" int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, int N,
-                                     int K, int dtype, void* stream) {
+extern "C" int merv_affine_score_vec(const void* W, int64_t ldw, const void* bias, const float* u, float* v, float* c, float* workspace,
+                                     size_t workspace_floats, int N, int K, int dtype, void* stream) {
   MERV_DTYPE_OK("merv_affine_score_vec");
   MERV_REQUIRE(W && u && v && c, MERV_E_ARG, "merv_affine_score_vec: NULL pointer");
   MERV_REQUIRE(N > 0 && K > 0 && ldw >= K, MERV_E_SHAPE, "merv_affine_score_vec: N=%d K=%d ldw=%lld", N, K, (long long)ldw);
@@ -362,11 +434,11 @@ extern "C" int merv_affine_score_vec(const void* W, int64_t ldw, const void* bia
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (dtype == MERV_BF16) {
     using T = __nv_bfloat16;
-    gemv_t_kernel<T><<<(K + 31) / 32, 256, 0, s>>>((const T*)W, ldw, u, v, N, K, 1.0f);
+    launch_gemv_t<T>((const T*)W, ldw, u, v, N, K, 1.0f, workspace, workspace_floats, s);
     dot_kernel<T><<<1, 256, 0, s>>>((const T*)bias, u, c, N);
   } else {
     using T = float;
-    gemv_t_kernel<T><<<(K + 31) / 32, 256, 0, s>>>((const T*)W, ldw, u, v, N, K, 1.0f);
+    launch_gemv_t<T>((const T*)W, ldw, u, v, N, K, 1.0f, workspace, workspace_floats, s);
     dot_kernel<T><<<1, 256, 0, s>>>((const T*)bias, u, c, N);
   }
   MERV_CUDA_OK(cudaGetLastError());

@@ -53,7 +53,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 # ---- launch accounting ----------------------------------------------------------------------------------------
 # kernels launched by one call of each entry point (used for bench.py's `gpu_launches` and per-kernel timing)
 KERNELS_PER_CALL = {
-    "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 2, "merv_affine_score_vec": 2,
+    "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 3, "merv_affine_score_vec": 3,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
@@ -206,9 +206,10 @@ def fusion_query_vec(Q: torch.Tensor, Wq: torch.Tensor, Wk: torch.Tensor, in_pro
     Q, Wq, Wk = Q.contiguous(), Wq.contiguous(), Wk.contiguous()
     with torch.cuda.device(dev):
         u = torch.empty(llm_dim, dtype=torch.float32, device=dev)
-        ws = torch.empty(embed, dtype=torch.float32, device=dev)
+        n = -(-embed // 4) * 4 + lib.merv_gemv_t_workspace(embed, llm_dim)
+        ws = torch.empty(n, dtype=torch.float32, device=dev)
         _call('merv_fusion_query_vec', lib.merv_fusion_query_vec, Q.data_ptr(), Wq.data_ptr(), Wk.data_ptr(), _p(in_proj_bias), u.data_ptr(), ws.data_ptr(),
-                                        embed, llm_dim, code, _stream())
+                                        n, embed, llm_dim, code, _stream())
     return u
 
 
@@ -222,8 +223,10 @@ def affine_score_vec(W: torch.Tensor, bias: Optional[torch.Tensor], u: torch.Ten
     with torch.cuda.device(dev):
         v = torch.empty(K, dtype=torch.float32, device=dev)
         c = torch.empty(1, dtype=torch.float32, device=dev)
-        _call('merv_affine_score_vec', lib.merv_affine_score_vec, W.data_ptr(), W.stride(0), _p(bias), u.data_ptr(), v.data_ptr(), c.data_ptr(), N, K,
-                                        dtype_code(W.dtype), _stream())
+        n = lib.merv_gemv_t_workspace(N, K)
+        ws = torch.empty(n, dtype=torch.float32, device=dev) if n else None
+        _call('merv_affine_score_vec', lib.merv_affine_score_vec, W.data_ptr(), W.stride(0), _p(bias), u.data_ptr(), v.data_ptr(), c.data_ptr(), _p(ws), n,
+                                        N, K, dtype_code(W.dtype), _stream())
     return v, c
 
 

@@ -925,3 +925,21 @@ def test_fused_training_matches_module_by_module_training():
     assert O.rel_err(o1, o0) < 8e-3 and np.abs(w1 - w0).max() < 1e-2
     for k in g0:
         assert O.rel_err(g1[k], g0[k]) < 3e-2, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,K", [(4096, 1024), (512, 768), (384, 4096), (100, 72)])
+def test_affine_score_vec_two_stage_gemv(N, K, dtype):
+    # v = W^T u, c = u . b: the narrow shapes take the two-stage transposed GEMV, (100, 72) the single-stage kernel's tail handling
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(N + K)
+    W = _t(rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(N), dtype)
+    b = _t(rng.standard_normal(N, dtype=np.float32), dtype)
+    u = _t(rng.standard_normal(N, dtype=np.float32))
+    v, c = ops.affine_score_vec(W, b, u)
+    want_v = _np(W).astype(np.float64).T @ _np(u).astype(np.float64)
+    assert O.rel_err(_np(v), want_v) < 1e-5
+    assert abs(float(c) - float(_np(b).astype(np.float64) @ _np(u).astype(np.float64))) < 1e-4 * max(1.0, abs(float(c)))
+    v2, _ = ops.affine_score_vec(W, b, u)
+    assert torch.equal(v, v2)  # fixed summation order
