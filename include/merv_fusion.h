@@ -303,6 +303,22 @@ size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* desc);
 int merv_fused_backward(const merv_fused_bwd_desc* desc, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Attentive pooler ("attntv" resampler: AttentivePooler.forward, merv/util/nn_utils.py:229-238; constructed at
+ * merv/models/vidlms/merv.py:124-130).  Its LayerNorms, Linears and GELU are merv_layernorm / merv_linear_bias_act; these are the rest:
+ *   merv_cross_attention  CrossAttention.forward (nn_utils.py:393-412) after the q / kv Linears:
+ *         out[b, i, h*hd + d] = sum_k softmax_k(scale * q[b, i, h, :] . K[b, k, h, :]) V[b, k, h, d]
+ *         q [n_q, heads * hd] rows `ldq` apart, batch entries `q_batch_stride` apart (0: the same learned queries for every entry);
+ *         kv [batches * n_kv, 2 * heads * hd] rows `ldkv` apart: K in the first heads * hd columns, V in the last (nn_utils.py:398-399);
+ *         out [batches * n_q, heads * hd] rows `ldo` apart.  fp32 softmax; head_dim <= 128, a multiple of 8 (bf16) / 4 (fp32).
+ *   merv_add_rows         out[m, :] = a[m, :] + b[m % period, :]  — the residual adds of CrossAttentionBlock.forward (nn_utils.py:449-450);
+ *         period = n_q adds the learned query tokens to every frame's attention output.
+ * ------------------------------------------------------------------------------------------------------- */
+int merv_cross_attention(const void* q, int64_t ldq, int64_t q_batch_stride, const void* kv, int64_t ldkv, void* out, int64_t ldo,
+                         int batches, int n_q, int n_kv, int heads, int head_dim, float scale, int dtype, void* stream);
+int merv_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int C, int period, int dtype,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * LayerNorm over the channel dimension of (possibly segmented) rows: Y[m, :] = LN(concat_s X_s[m, :]) * gamma + beta.
  *   nseg == 1 : nn.LayerNorm(vision_dim) in front of a projector — `pre_proj_layernorm=True`
  *               (merv/util/nn_utils.py:26-29,41-44,67-70,91-94; merv/models/vidlms/merv.py:165-171)

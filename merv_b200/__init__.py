@@ -14,6 +14,7 @@ from . import _lib
 _lib.load()  # fail loudly at import time if the CUDA library has not been built
 
 from .nn_utils import (  # noqa: E402
+    AttentivePooler,
     AveragePooling3DProjector,
     AveragePoolingProjector,
     ConcatChannelFusion,
@@ -34,6 +35,6 @@ from .nn_utils import (  # noqa: E402
 )
 
 __all__ = [
-    "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
+    "AttentivePooler", "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
     "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
 ]

@@ -99,6 +99,9 @@ _SIGNATURES = {
     "merv_scores_softmax_weights": (c_int, [_PP, POINTER(c_int32), _PP, _PP, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p]),
     "merv_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "merv_cross_attention": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, c_int,
+                                     c_void_p]),
+    "merv_add_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "merv_video_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p]),
     "merv_pair_dot_chunks": (c_int, []),
     "merv_pair_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),

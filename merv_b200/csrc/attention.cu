@@ -1,0 +1,264 @@
+// Cross attention of the attentive pooler ("attntv" resampler): a few learned queries attend to the patch tokens of one frame.
+//   CrossAttention.forward, merv/util/nn_utils.py:393-412 (called from CrossAttentionBlock.forward :447-451 inside
+//   AttentivePooler.forward :229-238):  out[b, q, h*hd:(h+1)*hd] = softmax_k(scale * Q[q, h] . K[b, k, h]) V[b, k, h]
+// with K, V the two halves of the `kv` Linear's output row ([K(C) | V(C)], heads contiguous inside each half, :398-399) and the
+// same projected queries for every batch entry (the query tokens are parameters, :196,232).
+//
+// First version: fp32 SIMT flash-style kernel for both storage dtypes (exact softmax in fp32: it is also what the fp32 parity path
+// needs).  CTA = (head, batch entry), 8 warps; a warp owns 4 queries at a time, keys are staged in shared memory 64 (bf16) / 32
+// (fp32) at a time, online softmax across the chunks, probabilities go through a per-warp shared tile to the P.V phase.  K/V are
+// read from HBM/L2 once per 32 queries.  The two contractions are 2 * n_q * n_kv * C FLOP per frame on the CUDA cores; a tcgen05
+// version is the round-2 item.
+#include "common.cuh"
+
+namespace merv {
+
+constexpr int kAttWarps = 8;
+constexpr int kAttQB = 4;  // queries per warp and pass
+
+template <typename T> struct AttChunk;
+template <> struct AttChunk<__nv_bfloat16> { static constexpr int kKeys = 64; };
+template <> struct AttChunk<float> { static constexpr int kKeys = 32; };
+
+template <typename T>
+__host__ __device__ constexpr size_t att_smem_bytes(int hd) {
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int KC = AttChunk<T>::kKeys;
+  return (size_t)KC * (hd + VEC) * sizeof(T) + (size_t)KC * hd * sizeof(T) + (size_t)kAttWarps * kAttQB * hd * sizeof(T) +
+         (size_t)kAttWarps * kAttQB * KC * sizeof(float);
+}
+
+template <typename T, int DPL>
+__global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T* __restrict__ q, long long ldq, long long q_batch_stride,
+                                                                        const T* __restrict__ kv, long long ldkv, T* __restrict__ out, long long ldo,
+                                                                        int n_q, int n_kv, int hd, int C, float scale) {
+  constexpr int VEC = Vec16<T>::kN;
+  constexpr int KC = AttChunk<T>::kKeys;
+  constexpr int KPL = KC / 32;  // keys per lane in the score phase
+  extern __shared__ uint4 att_smem[];
+  const int kpitch = hd + VEC;  // padded K rows: lanes read different rows with 16-byte loads, conflict-free
+  T* Ks = reinterpret_cast<T*>(att_smem);
+  T* Vs = Ks + KC * kpitch;
+  T* Qs = Vs + KC * hd;
+  float* Ps = reinterpret_cast<float*>(Qs + kAttWarps * kAttQB * hd);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* kb = kv + (long long)b * n_kv * ldkv + (long long)h * hd;  // K head slice of row 0; V is C columns further
+  const T* qb = q + (long long)b * q_batch_stride + (long long)h * hd;
+  T* Qw = Qs + warp * kAttQB * hd;
+  float* Pw = Ps + warp * kAttQB * KC;
+  const int hv = hd / VEC;
+
+  for (int q0 = 0; q0 < n_q; q0 += kAttWarps * kAttQB) {
+    const int qbase = q0 + warp * kAttQB;
+    // this warp's queries -> shared (zeros past n_q)
+    for (int i = lane; i < kAttQB * hv; i += 32) {
+      const int j = i / hv, v = i - j * hv;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (qbase + j < n_q) r = ldg_v4(qb + (long long)(qbase + j) * ldq + v * VEC);
+      *reinterpret_cast<uint4*>(Qw + j * hd + v * VEC) = r;
+    }
+    float m[kAttQB], l[kAttQB], o[kAttQB][DPL];
+#pragma unroll
+    for (int j = 0; j < kAttQB; ++j) {
+      m[j] = -INFINITY;
+      l[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[j][i] = 0.f;
+    }
+    for (int c0 = 0; c0 < n_kv; c0 += KC) {
+      __syncthreads();  // everyone is done with the previous chunk (and the Q tile is written)
+      for (int i = threadIdx.x; i < KC * hv; i += kAttWarps * 32) {
+        const int r = i / hv, v = i - r * hv;
+        uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+        if (c0 + r < n_kv) {
+          const T* row = kb + (long long)(c0 + r) * ldkv + v * VEC;
+          kk = ldg_nc_v4(row);
+          vv = ldg_nc_v4(row + C);
+        }
+        *reinterpret_cast<uint4*>(Ks + r * kpitch + v * VEC) = kk;
+        *reinterpret_cast<uint4*>(Vs + r * hd + v * VEC) = vv;
+      }
+      __syncthreads();
+      // ---- scores of this warp's 4 queries against the chunk: lane owns keys lane (+ 32) ----
+      float s[kAttQB][KPL];
+#pragma unroll
+      for (int j = 0; j < kAttQB; ++j)
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) s[j][t] = 0.f;
+      for (int v = 0; v < hv; ++v) {
+        float kf[KPL][VEC];
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) Vec16<T>::unpack(*reinterpret_cast<const uint4*>(Ks + (t * 32 + lane) * kpitch + v * VEC), kf[t]);
+#pragma unroll
+        for (int j = 0; j < kAttQB; ++j) {
+          float qf[VEC];
+          Vec16<T>::unpack(*reinterpret_cast<const uint4*>(Qw + j * hd + v * VEC), qf);  // broadcast
+#pragma unroll
+          for (int t = 0; t < KPL; ++t)
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) s[j][t] = fmaf(qf[c], kf[t][c], s[j][t]);
+        }
+      }
+      // ---- online softmax update, probabilities to the warp's shared tile ----
+#pragma unroll
+      for (int j = 0; j < kAttQB; ++j) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) {
+          s[j][t] = (c0 + t * 32 + lane < n_kv) ? s[j][t] * scale : -INFINITY;
+          mx = fmaxf(mx, s[j][t]);
+        }
+        mx = warp_max(mx);
+        const float m_new = fmaxf(m[j], mx);  // finite: every chunk holds at least one key
+        const float alpha = expf(m[j] - m_new);
+        float rs = 0.f;
+#pragma unroll
+        for (int t = 0; t < KPL; ++t) {
+          const float p = expf(s[j][t] - m_new);
+          Pw[j * KC + t * 32 + lane] = p;
+          rs += p;
+        }
+        rs = warp_sum(rs);
+        l[j] = l[j] * alpha + rs;
+        m[j] = m_new;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) o[j][i] *= alpha;
+      }
+      __syncwarp();
+      // ---- o += P V: lane owns head dims lane, lane + 32, ... ----
+      for (int k4 = 0; k4 < KC; k4 += 4) {
+        float4 p[kAttQB];
+#pragma unroll
+        for (int j = 0; j < kAttQB; ++j) p[j] = *reinterpret_cast<const float4*>(Pw + j * KC + k4);  // broadcast
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int i = 0; i < DPL; ++i) {
+            const int d = i * 32 + lane;
+            const float vv = d < hd ? to_float(Vs[(k4 + t) * hd + d]) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kAttQB; ++j) {
+              const float pj = t == 0 ? p[j].x : t == 1 ? p[j].y : t == 2 ? p[j].z : p[j].w;
+              o[j][i] = fmaf(pj, vv, o[j][i]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- normalise and store (heads concatenated along the channel dimension, nn_utils.py:409) ----
+#pragma unroll
+    for (int j = 0; j < kAttQB; ++j) {
+      if (qbase + j < n_q) {
+        const float inv = 1.0f / l[j];
+        T* dst = out + ((long long)b * n_q + qbase + j) * ldo + (long long)h * hd;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) {
+          const int d = i * 32 + lane;
+          if (d < hd) {
+            if constexpr (sizeof(T) == 2) dst[d] = __float2bfloat16_rn(o[j][i] * inv);
+            else dst[d] = o[j][i] * inv;
+          }
+        }
+      }
+    }
+  }
+}
+
+// out[m, :] = a[m, :] + b[m % period, :]   (the two residual adds of CrossAttentionBlock.forward, nn_utils.py:449-450; period = number
+// of query tokens when b holds the learned queries that every frame starts from, period = M for a plain tensor sum)
+template <typename T>
+__global__ void __launch_bounds__(256) add_rows_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb, T* __restrict__ out,
+                                                       long long ldo, long long M, int cv, int period) {
+  constexpr int VEC = Vec16<T>::kN;
+  const long long total = M * cv;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long m = i / cv;
+    const int c = int(i - m * cv) * VEC;
+    float x[VEC], y[VEC];
+    Vec16<T>::unpack(ldg_nc_v4(a + m * lda + c), x);
+    Vec16<T>::unpack(ldg_v4(b + (m % period) * ldb + c), y);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) x[k] += y[k];
+    stg_na_v4(out + m * ldo + c, Vec16<T>::pack(x));
+  }
+}
+
+template <typename T>
+static int launch_attention(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, void* out, long long ldo,
+                            int batches, int n_q, int n_kv, int heads, int hd, float scale, cudaStream_t s) {
+  const int C = heads * hd;
+  const size_t smem = att_smem_bytes<T>(hd);
+  MERV_REQUIRE(smem <= 160 * 1024, MERV_E_SHAPE, "merv_cross_attention: head_dim %d needs %zu bytes of shared memory", hd, smem);
+  const int dpl = (hd + 31) / 32;
+  dim3 grid(heads, batches);
+#define MERV_ATT_CASE(n)                                                                                                              \
+  case n: {                                                                                                                           \
+    static bool opted[64] = {};                                                                                                       \
+    int dev = 0;                                                                                                                      \
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;                                                          \
+    if (!opted[dev]) {                                                                                                                \
+      cudaFuncSetAttribute(cross_attention_kernel<T, n>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);                    \
+      opted[dev] = true;                                                                                                              \
+    }                                                                                                                                 \
+    cross_attention_kernel<T, n><<<grid, kAttWarps * 32, smem, s>>>((const T*)q, ldq, q_batch_stride, (const T*)kv, ldkv, (T*)out, ldo, n_q, n_kv, \
+                                                                   hd, C, scale);                                                     \
+  } break;
+  switch (dpl) {
+    MERV_ATT_CASE(1) MERV_ATT_CASE(2) MERV_ATT_CASE(3) MERV_ATT_CASE(4)
+    default: return fail(MERV_E_SHAPE, "merv_cross_attention: head_dim %d > 128", hd);
+  }
+#undef MERV_ATT_CASE
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
+}  // namespace merv
+
+using namespace merv;
+
+extern "C" int merv_cross_attention(const void* q, int64_t ldq, int64_t q_batch_stride, const void* kv, int64_t ldkv, void* out, int64_t ldo,
+                                    int batches, int n_q, int n_kv, int heads, int head_dim, float scale, int dtype, void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_cross_attention: unknown dtype %d", dtype);
+  MERV_REQUIRE(q && kv && out, MERV_E_ARG, "merv_cross_attention: NULL pointer");
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  const long long C = (long long)heads * head_dim;
+  MERV_REQUIRE(batches >= 0 && n_q > 0 && n_kv > 0 && heads > 0 && heads <= 65535 && head_dim > 0 && head_dim % vec == 0, MERV_E_SHAPE,
+               "merv_cross_attention: batches=%d n_q=%d n_kv=%d heads=%d head_dim=%d (head_dim must be a multiple of %d)", batches, n_q, n_kv, heads,
+               head_dim, vec);
+  MERV_REQUIRE(batches <= 65535, MERV_E_SHAPE, "merv_cross_attention: %d batch entries exceed the grid limit; split the call", batches);
+  MERV_REQUIRE(ldq >= C && ldkv >= 2 * C && ldo >= C && ldq % vec == 0 && ldkv % vec == 0 && q_batch_stride % vec == 0 && aligned16(q) && aligned16(kv),
+               MERV_E_ALIGN, "merv_cross_attention: rows must be 16-byte aligned with ldq >= C, ldkv >= 2C, ldo >= C");
+  if (int rc = require_sm100()) return rc;
+  if (batches == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == MERV_BF16)
+    return launch_attention<__nv_bfloat16>(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);
+  return launch_attention<float>(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);
+}
+
+extern "C" int merv_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int C, int period, int dtype,
+                             void* stream) {
+  MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_add_rows: unknown dtype %d", dtype);
+  MERV_REQUIRE(a && b && out, MERV_E_ARG, "merv_add_rows: NULL pointer");
+  const int vec = dtype == MERV_BF16 ? 8 : 4;
+  MERV_REQUIRE(M >= 0 && C > 0 && C % vec == 0 && period > 0 && lda >= C && ldb >= C && ldo >= C && lda % vec == 0 && ldb % vec == 0 && ldo % vec == 0,
+               MERV_E_SHAPE, "merv_add_rows: M=%lld C=%d period=%d lda=%lld ldb=%lld ldo=%lld", (long long)M, C, period, (long long)lda, (long long)ldb,
+               (long long)ldo);
+  MERV_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), MERV_E_ALIGN, "merv_add_rows: operands must be 16-byte aligned");
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int cv = C / vec;
+  long long blocks = (M * cv + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == MERV_BF16)
+    add_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, s>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, (__nv_bfloat16*)out, ldo, M, cv,
+                                                                   period);
+  else
+    add_rows_kernel<float><<<(unsigned)blocks, 256, 0, s>>>((const float*)a, lda, (const float*)b, ldb, (float*)out, ldo, M, cv, period);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}

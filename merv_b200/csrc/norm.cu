@@ -303,10 +303,12 @@ static void launch_ln(cudaStream_t s, const LnSegments& p, const void* gamma, co
   constexpr int kThreads = kTPR > 256 ? kTPR : 256;
   constexpr int kRows = kThreads / kTPR;
   const size_t smem = (size_t)2 * nvec * sizeof(uint4);  // gamma + beta, <= 128 KB
-  static bool opted_in = false;  // per instantiation
-  if (!opted_in) {
+  static bool opted_in[64] = {};  // per instantiation and device (function attributes are per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (!opted_in[dev]) {
     cudaFuncSetAttribute(layernorm_kernel<T, kTPR, kMaxVec>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * (int)sizeof(uint4));
-    opted_in = true;
+    opted_in[dev] = true;
   }
   int resident = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, layernorm_kernel<T, kTPR, kMaxVec>, kThreads, smem) != cudaSuccess || resident < 1)

@@ -559,6 +559,139 @@ class AveragePoolingProjector(AveragePooling3DProjector):
         return super().forward(fused_img_patches)
 
 
+class CrossAttention(nn.Module):
+    """Parameter container with the reference's attribute names (merv/util/nn_utils.py:380-391); the arithmetic of its forward
+    (:393-412) runs in AttentivePooler.forward below."""
+
+    def __init__(self, dim, num_heads=12, qkv_bias=False, use_sdpa=True):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim**-0.5
+        self.q = nn.Linear(dim, dim, bias=qkv_bias)
+        self.kv = nn.Linear(dim, int(dim * 2), bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_sdpa = use_sdpa
+
+
+class MLP(nn.Module):
+    """merv/util/nn_utils.py:415-423 (parameter container)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+
+class CrossAttentionBlock(nn.Module):
+    """merv/util/nn_utils.py:434-445 (parameter container)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, out_dim=None, act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.xattn = CrossAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias)
+        self.norm2 = norm_layer(dim)
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.mlp = MLP(in_features=dim, hidden_features=mlp_hidden_dim, out_features=out_dim, act_layer=act_layer)
+
+
+class AttentivePooler(TokenResampler):
+    """Attentive pooler from JEPA, the "attntv" resampler (merv/util/nn_utils.py:177-246; merv.py:124-130): every frame's N patch tokens
+    are resampled to ``num_query_tokens`` tokens by one cross-attention block with learned queries, then projected.
+
+    Same constructor signature, module tree (hence state-dict keys: ``query_tokens``, ``cross_attn.{norm1,xattn.{q,kv,proj},norm2,
+    mlp.{fc1,fc2}}``, ``projector.*``) and initialisation sequence as the reference.  forward: LayerNorm (merv_layernorm), the kv / proj /
+    MLP / projector Linears on the tcgen05 GEMM (GELU in the epilogue), merv_cross_attention, merv_add_rows for the two residuals.
+    Inference only: the backward of this ablation resampler is not built (raises)."""
+
+    def __init__(self, fused_vision_dim: int, llm_dim: int, num_query_tokens: int, num_heads: int = 8, output_frames: int = 8,
+                 mlp_type: str = "gelu-mlp") -> None:
+        super().__init__()
+        self.num_query_tokens = num_query_tokens
+        self.output_frames = output_frames
+        assert fused_vision_dim % num_heads == 0, "fused_vision_dim must be divisible by num_heads"
+
+        self.query_tokens = nn.Parameter(torch.zeros(1, num_query_tokens, fused_vision_dim))
+        self.cross_attn = CrossAttentionBlock(dim=fused_vision_dim, num_heads=num_heads, qkv_bias=True)
+        self.projector = get_mlp_projector(fused_vision_dim, llm_dim, mlp_type)
+
+        nn.init.trunc_normal_(self.query_tokens, std=0.02)
+        self.apply(self._init_weights)
+        self._rescale_blocks()
+        self._cast_cache = _CastCache()
+
+    def _rescale_blocks(self):
+        def rescale(param, layer_id):
+            param.div_(math.sqrt(2.0 * layer_id))
+
+        rescale(self.cross_attn.xattn.proj.weight.data, 1)
+        rescale(self.cross_attn.mlp.fc2.weight.data, 1)
+
+    def _init_weights(self, m):
+        init_std = 0.02
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=init_std)
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @classmethod
+    def from_reference(cls, ref_module: nn.Module) -> "AttentivePooler":
+        """Adopt a reference ``AttentivePooler``: its ``query_tokens``, ``cross_attn`` and projector sub-modules are shared, not copied."""
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.num_query_tokens, new.output_frames = ref_module.num_query_tokens, ref_module.output_frames
+        new.query_tokens, new.cross_attn = ref_module.query_tokens, ref_module.cross_attn
+        new.projector = _adopt_plain_projector(ref_module.projector)
+        new._cast_cache = _CastCache()
+        return new
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        # x: [B, F, N, C]
+        assert x.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
+        num_frames = x.shape[1]
+        assert num_frames == self.output_frames  # nn_utils.py:232
+        _require_device(x)
+        if _needs_grad(self, x):
+            raise NotImplementedError("the backward of the attentive pooler is not built (ablation resampler; inference only)")
+        dtype = _compute_dtype(x)
+        c = self._cast_cache
+        blk, att = self.cross_attn, self.cross_attn.xattn
+        B, F, N, C_ = x.shape
+        n = self.num_query_tokens
+        layers = _projector_layers(self.projector)
+        if B == 0:
+            return torch.empty((0, F * n, layers[-1][0].out_features), dtype=dtype, device=x.device)
+        xf = (x if x.dtype == dtype else x.to(dtype)).reshape(B * F * N, C_)
+        xn = ops.layernorm([xf], c.get(blk.norm1.weight, dtype), c.get(blk.norm1.bias, dtype), blk.norm1.eps)
+        kv, _ = ops.linear_bias_act(xn, c.get(att.kv.weight, dtype), c.get(att.kv.bias, dtype), ACT_NONE)  # [B F N, 2C] = [K | V]
+        qt = c.get(self.query_tokens, dtype)[0]  # the same learned queries for every frame (nn_utils.py:234)
+        qp, _ = ops.linear_bias_act(qt, c.get(att.q.weight, dtype), c.get(att.q.bias, dtype), ACT_NONE)
+        a = ops.cross_attention(qp, kv, B * F, att.num_heads, att.scale)  # [B F, n, C]
+        y, _ = ops.linear_bias_act(a.view(B * F * n, C_), c.get(att.proj.weight, dtype), c.get(att.proj.bias, dtype), ACT_NONE)
+        q1 = ops.add_rows(y, qt)  # q + xattn(q, norm1(x)), q = the query tokens of every frame
+        h = ops.layernorm([q1], c.get(blk.norm2.weight, dtype), c.get(blk.norm2.bias, dtype), blk.norm2.eps)
+        h, _ = ops.linear_bias_act(h, c.get(blk.mlp.fc1.weight, dtype), c.get(blk.mlp.fc1.bias, dtype), ACT_GELU_ERF)
+        h, _ = ops.linear_bias_act(h, c.get(blk.mlp.fc2.weight, dtype), c.get(blk.mlp.fc2.bias, dtype), ACT_NONE)
+        q2 = ops.add_rows(q1, h)  # q + mlp(norm2(q))
+        out, _ = _run_layers(q2, layers, c, dtype)
+        return out.view(B, F * n, out.shape[-1])  # "(B F) N C -> B (F N) C"
+
+    @property
+    def output_token_length(self) -> int:
+        return self.num_query_tokens
+
+    @property
+    def output_frame_length(self) -> int:
+        return self.output_frames
+
+
 # Adapters here
 class CrossAttentionAdapterLearnableQuery(nn.Module):
     def __init__(
@@ -1147,9 +1280,13 @@ def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: bool = Fals
             new_projs.append(_adopt_plain_projector(p))
             fused = False
             continue
+        if name == "AttentivePooler":  # "attntv" (merv.py:124-130): its own tokens, nothing to link
+            new_projs.append(p if isinstance(p, AttentivePooler) else AttentivePooler.from_reference(p))
+            fused = False
+            continue
         cls = proj_classes.get(name)
         if cls is None:
-            raise TypeError(f"patch_merv supports the 3davg / avg arch_specifiers and the un-resampled projectors, found {name}")
+            raise TypeError(f"patch_merv supports the 3davg / avg / attntv arch_specifiers and the un-resampled projectors, found {name}")
         new_projs.append(p if isinstance(p, AveragePooling3DProjector) else cls.from_reference(p))
     ff = vidlm.feature_fusion
     fusion_type = getattr(vidlm, "feature_fusion_type", None)

@@ -57,7 +57,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
-    "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10,
+    "merv_cross_attention": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10,
     "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
@@ -532,6 +532,38 @@ def transpose(x: torch.Tensor, pad: bool = False, row_scale: Optional[torch.Tens
             _call('merv_transpose_rowscale', lib.merv_transpose_rowscale, x.data_ptr(), y.data_ptr(), R, Rp, Cc, x.stride(0), y.stride(0),
                   _p(row_scale), row_scale.stride(0) if row_scale is not None else 0, rows_per_scale, dtype_code(x.dtype), _stream())
     return y
+
+
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, batches: int, heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """Multi-head cross attention of `q` [n_q, C] (the same learned queries for every batch entry) or [batches, n_q, C] against
+    kv [batches * n_kv, 2C] = [K | V] rows (CrossAttention.forward, nn_utils.py:393-412) -> [batches, n_q, C]."""
+    lib = _lib.load()
+    dev = _require_cuda(q, kv)
+    C_ = q.shape[-1]
+    assert kv.dim() == 2 and kv.shape[1] == 2 * C_ and kv.shape[0] % max(batches, 1) == 0 and C_ % heads == 0 and q.dtype == kv.dtype
+    n_q, n_kv, hd = q.shape[-2], kv.shape[0] // max(batches, 1), C_ // heads
+    q = q if q.stride(-1) == 1 else q.contiguous()
+    kv = kv if kv.stride(1) == 1 else kv.contiguous()
+    qbs = 0 if q.dim() == 2 else q.stride(0)
+    with torch.cuda.device(dev):
+        out = torch.empty((batches, n_q, C_), dtype=q.dtype, device=dev)
+        _call('merv_cross_attention', lib.merv_cross_attention, q.data_ptr(), q.stride(-2), qbs, kv.data_ptr(), kv.stride(0), out.data_ptr(), C_,
+              batches, n_q, n_kv, heads, hd, float(hd ** -0.5 if scale is None else scale), dtype_code(q.dtype), _stream())
+    return out
+
+
+def add_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [M, C] + b [period, C] broadcast over row blocks (row m gets b[m % period]); period == M is a plain sum."""
+    lib = _lib.load()
+    dev = _require_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype and a.shape[0] % b.shape[0] == 0
+    a = a if a.stride(1) == 1 else a.contiguous()
+    b = b if b.stride(1) == 1 else b.contiguous()
+    with torch.cuda.device(dev):
+        out = torch.empty(a.shape, dtype=a.dtype, device=dev)
+        _call('merv_add_rows', lib.merv_add_rows, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0), a.shape[0],
+              a.shape[1], b.shape[0], dtype_code(a.dtype), _stream())
+    return out
 
 
 def video_colsum(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:

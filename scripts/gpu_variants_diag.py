@@ -85,3 +85,26 @@ os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
 json.dump(rep, open(os.path.join(REPO, "gpurun_out", "variants_diag.json"), "w"), indent=1)
 for k, v in rep.items():
     print(k, v)
+
+# attentive pooler at the LanguageBind shape (16 frames x 256 patches x 1024 channels -> 64 queries per frame, 8 heads), 16 videos
+try:
+    import merv_b200 as M
+
+    Ba = 16
+    pool = M.AttentivePooler(1024, 4096, num_query_tokens=64, num_heads=8, output_frames=16, mlp_type="linear").to(device=dev, dtype=torch.bfloat16)
+    pool = pool.eval().requires_grad_(False)
+    xa = [torch.randn(Ba, 16, 256, 1024, generator=g, device=dev).to(torch.bfloat16) for _ in range(2)]
+    with torch.inference_mode():
+        ms_all = timed([lambda xx=xx: pool(xx) for xx in xa], iters=8, warm=2)
+        with ops.KernelTimer(timing=True) as kt:
+            pool(xa[0])
+        per = {k: round(sum(v), 4) for k, v in kt.durations_ms().items()}
+    att_flop = 2 * 2 * 64 * 256 * 1024 * 16 * Ba  # QK^T and PV
+    rep["attentive_pooler_languagebind_16_videos"] = {
+        "ms": ms_all, "device_ms_by_entry_point": dict(sorted(per.items(), key=lambda kv: -kv[1])),
+        "attention_TFLOPs_fp32_simt": att_flop / per.get("merv_cross_attention", float("nan")) / 1e9,
+    }
+    print("attentive_pooler", rep["attentive_pooler_languagebind_16_videos"])
+    json.dump(rep, open(os.path.join(REPO, "gpurun_out", "variants_diag.json"), "w"), indent=1)
+except Exception as e:  # noqa: BLE001
+    print("attentive pooler diag failed:", repr(e))

@@ -167,6 +167,23 @@ def transpose(x, pad=False, row_scale=None, rows_per_scale=1):
     return F.pad(y, (0, extra)) if extra else y
 
 
+def cross_attention(q, kv, batches, heads, scale=None):
+    Cc = q.shape[-1]
+    hd = Cc // heads
+    n_kv = kv.shape[0] // batches
+    scale = hd ** -0.5 if scale is None else scale
+    qf = q.float().expand(batches, -1, -1) if q.dim() == 2 else q.float()
+    k = kv.float()[:, :Cc].reshape(batches, n_kv, heads, hd).permute(0, 2, 1, 3)
+    v = kv.float()[:, Cc:].reshape(batches, n_kv, heads, hd).permute(0, 2, 1, 3)
+    qh = qf.reshape(batches, -1, heads, hd).permute(0, 2, 1, 3)
+    att = torch.softmax((qh @ k.transpose(-1, -2)) * scale, -1)
+    return (att @ v).permute(0, 2, 1, 3).reshape(batches, -1, Cc).to(q.dtype)
+
+
+def add_rows(a, b):
+    return (a.float().reshape(-1, b.shape[0], a.shape[1]) + b.float()).reshape(a.shape).to(a.dtype)
+
+
 def video_colsum(x, scale=1.0):
     return x.float().sum(1) * scale
 
@@ -255,7 +272,7 @@ class FusedLinearPlan:
 
 _NAMES = ["pool3d", "linear_bias_act", "fusion_query_vec", "affine_score_vec", "scores_from_tokens", "score_consts", "scores_from_partials",
           "softmax_weights", "softmax_mix", "fused_linear_mix", "concat_linear", "layernorm", "layernorm_backward", "transpose", "gelu",
-          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "fused_backward"]
+          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "fused_backward", "cross_attention", "add_rows"]
 
 
 def emulate(monkeypatch) -> None:

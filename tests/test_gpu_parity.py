@@ -701,7 +701,7 @@ def test_forward_multimodal_assembly_matches_oracle(mm):
 def _variant_names():
     from oracle import variants as V
 
-    return [n for n, v in V.VARIANTS.items() if v["kind"] != "attntv"]  # attntv: oracle + goldens only so far
+    return list(V.VARIANTS)
 
 
 @pytest.mark.parametrize("name", _variant_names())
@@ -720,7 +720,9 @@ def test_variants_match_reference(name, dtype):
             assert np.abs(_np(w) - gold["weights"]).max() < 2e-5
     else:
         assert O.rel_err(_np(out), gold["out"]) < BF16_TOL
-        assert O.rel_err(_np(out), gold["out_bf16"]) < BF16_TOL  # the reference's own bf16 run
+        # the reference's own bf16 run; for the attentive pooler that run alone is 1.0-1.2e-2 away from its fp32 result (bf16 scores
+        # and probabilities inside SDPA), so two independent bf16 evaluations get 1.5x the bound between them
+        assert O.rel_err(_np(out), gold["out_bf16"]) < (1.5 * BF16_TOL if v["kind"] == "attntv" else BF16_TOL)
         if w is not None:
             assert np.abs(_np(w) - gold["weights"]).max() < 2e-2
 
@@ -943,3 +945,32 @@ def test_affine_score_vec_two_stage_gemv(N, K, dtype):
     assert abs(float(c) - float(_np(b).astype(np.float64) @ _np(u).astype(np.float64))) < 1e-4 * max(1.0, abs(float(c)))
     v2, _ = ops.affine_score_vec(W, b, u)
     assert torch.equal(v, v2)  # fixed summation order
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("heads,hd,n_q,n_kv,batches,shared_q", [(8, 128, 64, 256, 3, True), (8, 96, 64, 196, 2, True), (4, 8, 5, 9, 2, False),
+                                                                  (2, 32, 37, 70, 1, True)])
+def test_cross_attention_kernel_matches_oracle(heads, hd, n_q, n_kv, batches, shared_q, dtype):
+    # head dims 128 / 96 / 32 / 8, ragged query and key counts (tails of the 32-query pass and of the key chunks), shared and per-entry queries
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(heads * 1000 + hd)
+    C_ = heads * hd
+    q = _t(rng.standard_normal((n_q, C_) if shared_q else (batches, n_q, C_), dtype=np.float32), dtype)
+    kv = _t(rng.standard_normal((batches * n_kv, 2 * C_), dtype=np.float32), dtype)
+    out = ops.cross_attention(q, kv, batches, heads)
+    torch.cuda.synchronize()
+    qf = _np(q).astype(np.float64)
+    qf = np.broadcast_to(qf, (batches, n_q, C_)) if shared_q else qf
+    kvf = _np(kv).astype(np.float64).reshape(batches, n_kv, 2, heads, hd)
+    k, v = kvf[:, :, 0].transpose(0, 2, 1, 3), kvf[:, :, 1].transpose(0, 2, 1, 3)
+    qh = qf.reshape(batches, n_q, heads, hd).transpose(0, 2, 1, 3)
+    att = O._softmax_last((qh @ k.transpose(0, 1, 3, 2)) * hd ** -0.5)
+    want = (att @ v).transpose(0, 2, 1, 3).reshape(batches, n_q, C_)
+    assert out.shape == want.shape and out.dtype == dtype
+    assert O.rel_err(_np(out), want) < (FP32_TOL if dtype == torch.float32 else 6e-3)
+    a = _t(rng.standard_normal((batches * n_q, C_), dtype=np.float32), dtype)
+    b = _t(rng.standard_normal((n_q, C_), dtype=np.float32), dtype)
+    got = ops.add_rows(a, b)
+    want_add = (_np(a).reshape(batches, n_q, C_) + _np(b)).reshape(batches * n_q, C_)
+    assert O.rel_err(_np(got), want_add) < (1e-6 if dtype == torch.float32 else 4e-3)

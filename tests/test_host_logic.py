@@ -87,8 +87,7 @@ def test_fused_wiring_bf16(name):
 def _variants():
     from oracle import variants as V
 
-    # the attentive pooler ("attntv") has an oracle and goldens (tests/test_oracle.py) but no CUDA module yet
-    return [n for n, v in V.VARIANTS.items() if not n.endswith("_wide") and v["kind"] != "attntv"]
+    return [n for n in V.VARIANTS if not n.endswith("_wide") and n != "attntv_hd96"]  # the big ones run on the GPU only
 
 
 @pytest.mark.parametrize("name", _variants())
@@ -295,3 +294,30 @@ def test_fused_training_gradients_match_reference_autograd():
     assert O.rel_err(_np(ff.attention.k_proj_weight.grad), fpt["attention.k_proj_weight"].grad.numpy()) < tol
     assert O.rel_err(_np(ff.attention.in_proj_bias.grad)[:E], fpt["attention.in_proj_bias"].grad.numpy()[:E]) < tol
     assert ff.attention.v_proj_weight.grad is None and ff.attention.out_proj.weight.grad is None
+
+
+@pytest.mark.skipif(not REF_PRESENT, reason="reference tree not present on this box")
+def test_attentive_pooler_init_sequence_and_adoption_match_the_reference():
+    # same seed -> same initial parameters (module tree and init order mirror nn_utils.py:182-227); patch_merv adopts the reference module
+    import merv_b200 as M
+    from oracle.ref_loader import load_reference_nn_utils
+
+    ref = load_reference_nn_utils()
+    torch.manual_seed(77)
+    r = ref.AttentivePooler(32, 48, num_query_tokens=4, num_heads=4, output_frames=3, mlp_type="gelu-mlp")
+    torch.manual_seed(77)
+    m = M.AttentivePooler(32, 48, num_query_tokens=4, num_heads=4, output_frames=3, mlp_type="gelu-mlp")
+    rs, ms = r.state_dict(), m.state_dict()
+    assert list(rs) == list(ms)
+    assert all(torch.equal(rs[k], ms[k]) for k in rs)
+    x = torch.randn(2, 3, 9, 32)
+    with torch.no_grad():
+        want = r.eval()(x)
+    vid = _FakeMerv([r], None, "first").eval().requires_grad_(False)
+    ptrs = {k: t.data_ptr() for k, t in vid.state_dict().items()}
+    M.patch_merv(vid)
+    assert isinstance(vid.projectors[0], M.AttentivePooler) and {k: t.data_ptr() for k, t in vid.state_dict().items()} == ptrs
+    with torch.inference_mode():
+        got = vid.projectors[0](x)
+    assert O.rel_err(_np(got), _np(want)) < 2e-5
+    assert vid.projectors[0].output_token_length == 4 and vid.projectors[0].output_frame_length == 3

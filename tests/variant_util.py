@@ -12,6 +12,9 @@ def build_variant_module(name, dtype=torch.float32, device="cpu"):
     v, inputs, params, gold = load_variant(name)
     if v["kind"] == "projector":  # merv.py:165-171 constructs these with pre_proj_layernorm=True
         mod = getattr(M, v["cls"])(v["vision_dim"], v["llm_dim"], pre_proj_layernorm=True)
+    elif v["kind"] == "attntv":  # merv.py:124-130
+        mod = M.AttentivePooler(v["C"], v["llm_dim"], num_query_tokens=v["queries"], num_heads=v["heads"], output_frames=v["F"],
+                                mlp_type=v["mlp_type"])
     elif v["kind"] == "concat_channel_ln":  # merv.py:219-223
         mod = M.ConcatChannelLNFusion(v["E"], v["K"])
     else:
@@ -25,7 +28,7 @@ def build_variant_module(name, dtype=torch.float32, device="cpu"):
 def run_variant(mod, v, inputs, dtype=torch.float32, device="cpu", as_list=True):
     """Call the module the way MERV.forward does; returns (out, weights | None)."""
     xs = [torch.from_numpy(a).to(device).to(dtype) for a in inputs]
-    if v["kind"] == "projector":
+    if v["kind"] in ("projector", "attntv"):
         return mod(xs[0]), None
     if v["kind"] == "concat_channel_ln":
         return mod(xs if as_list else torch.concat(xs, -1)), None  # merv.py:603-606 passes the concatenation
