@@ -5,8 +5,8 @@
 // same projected queries for every batch entry (the query tokens are parameters, :196,232).
 //
 // First version: fp32 SIMT flash-style kernel for both storage dtypes (exact softmax in fp32: it is also what the fp32 parity path
-// needs).  CTA = (head, batch entry), 8 warps; a warp owns 4 queries at a time, keys are staged in shared memory 64 (bf16) / 32
-// (fp32) at a time, online softmax across the chunks, probabilities go through a per-warp shared tile to the P.V phase.  K/V are
+// needs).  CTA = (head, batch entry), 8 warps; a warp owns 4 queries at a time, keys are staged in shared memory 64 at a time (as
+// fp32, converted while staging), online softmax across the chunks, probabilities go through a per-warp shared tile to the P.V phase.  K/V are
 // read from HBM/L2 once per 32 queries.  The two contractions are 2 * n_q * n_kv * C FLOP per frame on the CUDA cores; a tcgen05
 // version is the round-2 item.
 #include "common.cuh"
@@ -16,16 +16,21 @@ namespace merv {
 constexpr int kAttWarps = 8;
 constexpr int kAttQB = 4;  // queries per warp and pass
 
-template <typename T> struct AttChunk;
-template <> struct AttChunk<__nv_bfloat16> { static constexpr int kKeys = 64; };
-template <> struct AttChunk<float> { static constexpr int kKeys = 32; };
+constexpr int kAttKeys = 64;  // keys staged per chunk
+
+// Q, K and V live in shared memory as fp32 (converted once while staging): the two hot loops then hold no conversion instructions,
+// only 16-byte shared loads and FMAs.
+__host__ __device__ constexpr size_t att_smem_bytes(int hd) {
+  return ((size_t)kAttKeys * (hd + 4) + (size_t)kAttKeys * hd + (size_t)kAttWarps * kAttQB * hd + (size_t)kAttWarps * kAttQB * kAttKeys) * sizeof(float);
+}
 
 template <typename T>
-__host__ __device__ constexpr size_t att_smem_bytes(int hd) {
-  constexpr int VEC = 16 / (int)sizeof(T);
-  constexpr int KC = AttChunk<T>::kKeys;
-  return (size_t)KC * (hd + VEC) * sizeof(T) + (size_t)KC * hd * sizeof(T) + (size_t)kAttWarps * kAttQB * hd * sizeof(T) +
-         (size_t)kAttWarps * kAttQB * KC * sizeof(float);
+__device__ __forceinline__ void att_stage(float* dst, const uint4& r) {
+  constexpr int VEC = Vec16<T>::kN;
+  float f[VEC];
+  Vec16<T>::unpack(r, f);
+#pragma unroll
+  for (int c = 0; c < VEC; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(f[c], f[c + 1], f[c + 2], f[c + 3]);
 }
 
 template <typename T, int DPL>
@@ -33,21 +38,21 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
                                                                         const T* __restrict__ kv, long long ldkv, T* __restrict__ out, long long ldo,
                                                                         int n_q, int n_kv, int hd, int C, float scale) {
   constexpr int VEC = Vec16<T>::kN;
-  constexpr int KC = AttChunk<T>::kKeys;
+  constexpr int KC = kAttKeys;
   constexpr int KPL = KC / 32;  // keys per lane in the score phase
   extern __shared__ uint4 att_smem[];
-  const int kpitch = hd + VEC;  // padded K rows: lanes read different rows with 16-byte loads, conflict-free
-  T* Ks = reinterpret_cast<T*>(att_smem);
-  T* Vs = Ks + KC * kpitch;
-  T* Qs = Vs + KC * hd;
-  float* Ps = reinterpret_cast<float*>(Qs + kAttWarps * kAttQB * hd);
+  const int kpitch = hd + 4;  // padded K rows: lanes read different rows with 16-byte loads, conflict-free
+  float* Ks = reinterpret_cast<float*>(att_smem);
+  float* Vs = Ks + KC * kpitch;
+  float* Qs = Vs + KC * hd;
+  float* Ps = Qs + kAttWarps * kAttQB * hd;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* kb = kv + (long long)b * n_kv * ldkv + (long long)h * hd;  // K head slice of row 0; V is C columns further
   const T* qb = q + (long long)b * q_batch_stride + (long long)h * hd;
-  T* Qw = Qs + warp * kAttQB * hd;
+  float* Qw = Qs + warp * kAttQB * hd;
   float* Pw = Ps + warp * kAttQB * KC;
-  const int hv = hd / VEC;
+  const int hv = hd / VEC, h4 = hd / 4;
 
   for (int q0 = 0; q0 < n_q; q0 += kAttWarps * kAttQB) {
     const int qbase = q0 + warp * kAttQB;
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
       const int j = i / hv, v = i - j * hv;
       uint4 r = make_uint4(0u, 0u, 0u, 0u);
       if (qbase + j < n_q) r = ldg_v4(qb + (long long)(qbase + j) * ldq + v * VEC);
-      *reinterpret_cast<uint4*>(Qw + j * hd + v * VEC) = r;
+      att_stage<T>(Qw + j * hd + v * VEC, r);
     }
     float m[kAttQB], l[kAttQB], o[kAttQB][DPL];
 #pragma unroll
@@ -76,28 +81,31 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
           kk = ldg_nc_v4(row);
           vv = ldg_nc_v4(row + C);
         }
-        *reinterpret_cast<uint4*>(Ks + r * kpitch + v * VEC) = kk;
-        *reinterpret_cast<uint4*>(Vs + r * hd + v * VEC) = vv;
+        att_stage<T>(Ks + r * kpitch + v * VEC, kk);
+        att_stage<T>(Vs + r * hd + v * VEC, vv);
       }
       __syncthreads();
-      // ---- scores of this warp's 4 queries against the chunk: lane owns keys lane (+ 32) ----
+      // ---- scores of this warp's 4 queries against the chunk: lane owns keys lane and lane + 32 ----
       float s[kAttQB][KPL];
 #pragma unroll
       for (int j = 0; j < kAttQB; ++j)
 #pragma unroll
         for (int t = 0; t < KPL; ++t) s[j][t] = 0.f;
-      for (int v = 0; v < hv; ++v) {
-        float kf[KPL][VEC];
+#pragma unroll 2
+      for (int v = 0; v < h4; ++v) {
+        float4 kf[KPL];
 #pragma unroll
-        for (int t = 0; t < KPL; ++t) Vec16<T>::unpack(*reinterpret_cast<const uint4*>(Ks + (t * 32 + lane) * kpitch + v * VEC), kf[t]);
+        for (int t = 0; t < KPL; ++t) kf[t] = *reinterpret_cast<const float4*>(Ks + (t * 32 + lane) * kpitch + v * 4);
 #pragma unroll
         for (int j = 0; j < kAttQB; ++j) {
-          float qf[VEC];
-          Vec16<T>::unpack(*reinterpret_cast<const uint4*>(Qw + j * hd + v * VEC), qf);  // broadcast
+          const float4 qf = *reinterpret_cast<const float4*>(Qw + j * hd + v * 4);  // broadcast
 #pragma unroll
-          for (int t = 0; t < KPL; ++t)
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) s[j][t] = fmaf(qf[c], kf[t][c], s[j][t]);
+          for (int t = 0; t < KPL; ++t) {
+            s[j][t] = fmaf(qf.x, kf[t].x, s[j][t]);
+            s[j][t] = fmaf(qf.y, kf[t].y, s[j][t]);
+            s[j][t] = fmaf(qf.z, kf[t].z, s[j][t]);
+            s[j][t] = fmaf(qf.w, kf[t].w, s[j][t]);
+          }
         }
       }
       // ---- online softmax update, probabilities to the warp's shared tile ----
@@ -127,6 +135,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
       }
       __syncwarp();
       // ---- o += P V: lane owns head dims lane, lane + 32, ... ----
+#pragma unroll 2
       for (int k4 = 0; k4 < KC; k4 += 4) {
         float4 p[kAttQB];
 #pragma unroll
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
 #pragma unroll
           for (int i = 0; i < DPL; ++i) {
             const int d = i * 32 + lane;
-            const float vv = d < hd ? to_float(Vs[(k4 + t) * hd + d]) : 0.f;
+            const float vv = d < hd ? Vs[(k4 + t) * hd + d] : 0.f;
 #pragma unroll
             for (int j = 0; j < kAttQB; ++j) {
               const float pj = t == 0 ? p[j].x : t == 1 ? p[j].y : t == 2 ? p[j].z : p[j].w;
@@ -189,7 +198,7 @@ template <typename T>
 static int launch_attention(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, void* out, long long ldo,
                             int batches, int n_q, int n_kv, int heads, int hd, float scale, cudaStream_t s) {
   const int C = heads * hd;
-  const size_t smem = att_smem_bytes<T>(hd);
+  const size_t smem = att_smem_bytes(hd);
   MERV_REQUIRE(smem <= 160 * 1024, MERV_E_SHAPE, "merv_cross_attention: head_dim %d needs %zu bytes of shared memory", hd, smem);
   const int dpl = (hd + 31) / 32;
   dim3 grid(heads, batches);
