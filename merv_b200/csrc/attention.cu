@@ -5,23 +5,27 @@
 // same projected queries for every batch entry (the query tokens are parameters, :196,232).
 //
 // First version: fp32 SIMT flash-style kernel for both storage dtypes (exact softmax in fp32: it is also what the fp32 parity path
-// needs).  CTA = (head, batch entry), 8 warps; a warp owns 4 queries at a time, keys are staged in shared memory 64 at a time (as
-// fp32, converted while staging), online softmax across the chunks, probabilities go through a per-warp shared tile to the P.V phase.  K/V are
-// read from HBM/L2 once per 32 queries.  The two contractions are 2 * n_q * n_kv * C FLOP per frame on the CUDA cores; a tcgen05
+// needs).  CTA = (head, batch entry), 8 warps; a warp owns 8 queries at a time, keys are staged in shared memory 64 at a time, online
+// softmax across the chunks, probabilities go through a per-warp shared tile to the P.V phase.  K/V are read from HBM/L2 once per 64
+// queries.  The two contractions are 2 * n_q * n_kv * C FLOP per frame on the CUDA cores; a tcgen05
 // version is the round-2 item.
 #include "common.cuh"
 
 namespace merv {
 
 constexpr int kAttWarps = 8;
-constexpr int kAttQB = 4;  // queries per warp and pass
-
+constexpr int kAttQB = 8;     // queries per warp and pass: 64 queries per CTA pass
 constexpr int kAttKeys = 64;  // keys staged per chunk
 
-// Q, K and V live in shared memory as fp32 (converted once while staging): the two hot loops then hold no conversion instructions,
-// only 16-byte shared loads and FMAs.
+// Shared memory per CTA: K chunk in the storage dtype (padded rows), V chunk and the queries as fp32, one probability tile per warp.
+// The kernel is issue- and shared-memory-bound, not FMA-bound (profiles/r1g_prof_cross_attention.txt), hence: 8 queries x 2 keys of
+// register blocking per lane (one K load feeds 8 queries, one Q load 2 keys), K read 8 dims per 16-byte load when it is bf16, and both
+// contractions on the packed fp32 pipe (fma.rn.f32x2): pairs of head dims in Q K^T, pairs of queries in P V.
+template <typename T>
 __host__ __device__ constexpr size_t att_smem_bytes(int hd) {
-  return ((size_t)kAttKeys * (hd + 4) + (size_t)kAttKeys * hd + (size_t)kAttWarps * kAttQB * hd + (size_t)kAttWarps * kAttQB * kAttKeys) * sizeof(float);
+  constexpr int VEC = 16 / (int)sizeof(T);
+  return (size_t)kAttKeys * (hd + VEC) * sizeof(T) +
+         ((size_t)kAttKeys * hd + (size_t)kAttWarps * kAttQB * hd + (size_t)kAttWarps * kAttQB * kAttKeys) * sizeof(float);
 }
 
 template <typename T>
@@ -38,39 +42,45 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
                                                                         const T* __restrict__ kv, long long ldkv, T* __restrict__ out, long long ldo,
                                                                         int n_q, int n_kv, int hd, int C, float scale) {
   constexpr int VEC = Vec16<T>::kN;
+  constexpr int P = Pairs<T>::kP;  // fp32 pairs per 16-byte vector of T
   constexpr int KC = kAttKeys;
   constexpr int KPL = KC / 32;  // keys per lane in the score phase
+  constexpr int QB = kAttQB;
+  typedef unsigned long long u64;
   extern __shared__ uint4 att_smem[];
-  const int kpitch = hd + 4;  // padded K rows: lanes read different rows with 16-byte loads, conflict-free
-  float* Ks = reinterpret_cast<float*>(att_smem);
-  float* Vs = Ks + KC * kpitch;
+  const int kpitch = hd + VEC;  // padded K rows: lanes read different rows with 16-byte loads, conflict-free
+  T* Ks = reinterpret_cast<T*>(att_smem);
+  float* Vs = reinterpret_cast<float*>(Ks + KC * kpitch);
   float* Qs = Vs + KC * hd;
-  float* Ps = Qs + kAttWarps * kAttQB * hd;
+  float* Ps = Qs + kAttWarps * QB * hd;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* kb = kv + (long long)b * n_kv * ldkv + (long long)h * hd;  // K head slice of row 0; V is C columns further
   const T* qb = q + (long long)b * q_batch_stride + (long long)h * hd;
-  float* Qw = Qs + warp * kAttQB * hd;
-  float* Pw = Ps + warp * kAttQB * KC;
-  const int hv = hd / VEC, h4 = hd / 4;
+  float* Qw = Qs + warp * QB * hd;
+  float* Pw = Ps + warp * QB * KC;  // [key][query]: the 8 queries of one key are adjacent (pairs of queries in the P V phase)
+  const int hv = hd / VEC;
 
-  for (int q0 = 0; q0 < n_q; q0 += kAttWarps * kAttQB) {
-    const int qbase = q0 + warp * kAttQB;
-    // this warp's queries -> shared (zeros past n_q)
-    for (int i = lane; i < kAttQB * hv; i += 32) {
+  for (int q0 = 0; q0 < n_q; q0 += kAttWarps * QB) {
+    const int qbase = q0 + warp * QB;
+    // this warp's queries -> shared as fp32 (zeros past n_q)
+    for (int i = lane; i < QB * hv; i += 32) {
       const int j = i / hv, v = i - j * hv;
       uint4 r = make_uint4(0u, 0u, 0u, 0u);
       if (qbase + j < n_q) r = ldg_v4(qb + (long long)(qbase + j) * ldq + v * VEC);
       att_stage<T>(Qw + j * hd + v * VEC, r);
     }
-    float m[kAttQB], l[kAttQB], o[kAttQB][DPL];
+    float m[QB], l[QB];
+    u64 o2[QB / 2][DPL];  // (query 2 jp, query 2 jp + 1) x head dim i * 32 + lane
 #pragma unroll
-    for (int j = 0; j < kAttQB; ++j) {
+    for (int j = 0; j < QB; ++j) {
       m[j] = -INFINITY;
       l[j] = 0.f;
-#pragma unroll
-      for (int i = 0; i < DPL; ++i) o[j][i] = 0.f;
     }
+#pragma unroll
+    for (int jp = 0; jp < QB / 2; ++jp)
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o2[jp][i] = f32x2_pack(0.f, 0.f);
     for (int c0 = 0; c0 < n_kv; c0 += KC) {
       __syncthreads();  // everyone is done with the previous chunk (and the Q tile is written)
       for (int i = threadIdx.x; i < KC * hv; i += kAttWarps * 32) {
@@ -81,41 +91,44 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
           kk = ldg_nc_v4(row);
           vv = ldg_nc_v4(row + C);
         }
-        att_stage<T>(Ks + r * kpitch + v * VEC, kk);
+        *reinterpret_cast<uint4*>(Ks + r * kpitch + v * VEC) = kk;
         att_stage<T>(Vs + r * hd + v * VEC, vv);
       }
       __syncthreads();
-      // ---- scores of this warp's 4 queries against the chunk: lane owns keys lane and lane + 32 ----
-      float s[kAttQB][KPL];
+      // ---- scores of this warp's 8 queries against the chunk: lane owns keys lane and lane + 32; pairs of head dims ----
+      u64 s2[QB][KPL];
 #pragma unroll
-      for (int j = 0; j < kAttQB; ++j)
+      for (int j = 0; j < QB; ++j)
 #pragma unroll
-        for (int t = 0; t < KPL; ++t) s[j][t] = 0.f;
-#pragma unroll 2
-      for (int v = 0; v < h4; ++v) {
-        float4 kf[KPL];
+        for (int t = 0; t < KPL; ++t) s2[j][t] = f32x2_pack(0.f, 0.f);
+      for (int v = 0; v < hv; ++v) {
+        u64 kf[KPL][P];
 #pragma unroll
-        for (int t = 0; t < KPL; ++t) kf[t] = *reinterpret_cast<const float4*>(Ks + (t * 32 + lane) * kpitch + v * 4);
+        for (int t = 0; t < KPL; ++t) Pairs<T>::unpack(*reinterpret_cast<const uint4*>(Ks + (t * 32 + lane) * kpitch + v * VEC), kf[t]);
 #pragma unroll
-        for (int j = 0; j < kAttQB; ++j) {
-          const float4 qf = *reinterpret_cast<const float4*>(Qw + j * hd + v * 4);  // broadcast
+        for (int j = 0; j < QB; ++j) {
 #pragma unroll
-          for (int t = 0; t < KPL; ++t) {
-            s[j][t] = fmaf(qf.x, kf[t].x, s[j][t]);
-            s[j][t] = fmaf(qf.y, kf[t].y, s[j][t]);
-            s[j][t] = fmaf(qf.z, kf[t].z, s[j][t]);
-            s[j][t] = fmaf(qf.w, kf[t].w, s[j][t]);
+          for (int h2 = 0; h2 < P / 2; ++h2) {
+            const ulonglong2 qq = *reinterpret_cast<const ulonglong2*>(Qw + j * hd + v * VEC + h2 * 4);  // broadcast: two pairs
+#pragma unroll
+            for (int t = 0; t < KPL; ++t) {
+              s2[j][t] = f32x2_fma(qq.x, kf[t][2 * h2], s2[j][t]);
+              s2[j][t] = f32x2_fma(qq.y, kf[t][2 * h2 + 1], s2[j][t]);
+            }
           }
         }
       }
       // ---- online softmax update, probabilities to the warp's shared tile ----
 #pragma unroll
-      for (int j = 0; j < kAttQB; ++j) {
+      for (int j = 0; j < QB; ++j) {
+        float sv[KPL];
         float mx = -INFINITY;
 #pragma unroll
         for (int t = 0; t < KPL; ++t) {
-          s[j][t] = (c0 + t * 32 + lane < n_kv) ? s[j][t] * scale : -INFINITY;
-          mx = fmaxf(mx, s[j][t]);
+          float a0, a1;
+          f32x2_unpack(s2[j][t], a0, a1);
+          sv[t] = (c0 + t * 32 + lane < n_kv) ? (a0 + a1) * scale : -INFINITY;
+          mx = fmaxf(mx, sv[t]);
         }
         mx = warp_max(mx);
         const float m_new = fmaxf(m[j], mx);  // finite: every chunk holds at least one key
@@ -123,51 +136,53 @@ __global__ void __launch_bounds__(kAttWarps * 32) cross_attention_kernel(const T
         float rs = 0.f;
 #pragma unroll
         for (int t = 0; t < KPL; ++t) {
-          const float p = expf(s[j][t] - m_new);
-          Pw[j * KC + t * 32 + lane] = p;
+          const float p = expf(sv[t] - m_new);
+          Pw[(t * 32 + lane) * QB + j] = p;
           rs += p;
         }
         rs = warp_sum(rs);
         l[j] = l[j] * alpha + rs;
         m[j] = m_new;
+        // rescale this query's half of its accumulator pairs
+        const u64 a2 = (j & 1) ? f32x2_pack(1.0f, alpha) : f32x2_pack(alpha, 1.0f);
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) o[j][i] *= alpha;
+        for (int i = 0; i < DPL; ++i) o2[j / 2][i] = f32x2_mul(o2[j / 2][i], a2);
       }
       __syncwarp();
-      // ---- o += P V: lane owns head dims lane, lane + 32, ... ----
+      // ---- o += P V: lane owns head dims lane, lane + 32, ...; pairs of queries ----
 #pragma unroll 2
-      for (int k4 = 0; k4 < KC; k4 += 4) {
-        float4 p[kAttQB];
+      for (int k = 0; k < KC; ++k) {
+        const ulonglong2 pa = *reinterpret_cast<const ulonglong2*>(Pw + k * QB);      // broadcast: queries 0..3 of key k
+        const ulonglong2 pb = *reinterpret_cast<const ulonglong2*>(Pw + k * QB + 4);  // queries 4..7
 #pragma unroll
-        for (int j = 0; j < kAttQB; ++j) p[j] = *reinterpret_cast<const float4*>(Pw + j * KC + k4);  // broadcast
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-#pragma unroll
-          for (int i = 0; i < DPL; ++i) {
-            const int d = i * 32 + lane;
-            const float vv = d < hd ? Vs[(k4 + t) * hd + d] : 0.f;
-#pragma unroll
-            for (int j = 0; j < kAttQB; ++j) {
-              const float pj = t == 0 ? p[j].x : t == 1 ? p[j].y : t == 2 ? p[j].z : p[j].w;
-              o[j][i] = fmaf(pj, vv, o[j][i]);
-            }
-          }
+        for (int i = 0; i < DPL; ++i) {
+          const int d = i * 32 + lane;
+          const float vv = d < hd ? Vs[k * hd + d] : 0.f;
+          const u64 v2 = f32x2_pack(vv, vv);
+          o2[0][i] = f32x2_fma(pa.x, v2, o2[0][i]);
+          o2[1][i] = f32x2_fma(pa.y, v2, o2[1][i]);
+          o2[2][i] = f32x2_fma(pb.x, v2, o2[2][i]);
+          o2[3][i] = f32x2_fma(pb.y, v2, o2[3][i]);
         }
       }
       __syncwarp();
     }
     // ---- normalise and store (heads concatenated along the channel dimension, nn_utils.py:409) ----
 #pragma unroll
-    for (int j = 0; j < kAttQB; ++j) {
-      if (qbase + j < n_q) {
-        const float inv = 1.0f / l[j];
-        T* dst = out + ((long long)b * n_q + qbase + j) * ldo + (long long)h * hd;
+    for (int jp = 0; jp < QB / 2; ++jp) {
 #pragma unroll
-        for (int i = 0; i < DPL; ++i) {
-          const int d = i * 32 + lane;
-          if (d < hd) {
-            if constexpr (sizeof(T) == 2) dst[d] = __float2bfloat16_rn(o[j][i] * inv);
-            else dst[d] = o[j][i] * inv;
+      for (int i = 0; i < DPL; ++i) {
+        const int d = i * 32 + lane;
+        float oa, ob;
+        f32x2_unpack(o2[jp][i], oa, ob);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = 2 * jp + half;
+          if (qbase + j < n_q && d < hd) {
+            const float val = (half ? ob : oa) / l[j];
+            T* dst = out + ((long long)b * n_q + qbase + j) * ldo + (long long)h * hd + d;
+            if constexpr (sizeof(T) == 2) *dst = __float2bfloat16_rn(val);
+            else *dst = val;
           }
         }
       }
@@ -198,7 +213,7 @@ template <typename T>
 static int launch_attention(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, void* out, long long ldo,
                             int batches, int n_q, int n_kv, int heads, int hd, float scale, cudaStream_t s) {
   const int C = heads * hd;
-  const size_t smem = att_smem_bytes(hd);
+  const size_t smem = att_smem_bytes<T>(hd);
   MERV_REQUIRE(smem <= 160 * 1024, MERV_E_SHAPE, "merv_cross_attention: head_dim %d needs %zu bytes of shared memory", hd, smem);
   const int dpl = (hd + 31) / 32;
   dim3 grid(heads, batches);
