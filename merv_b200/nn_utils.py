@@ -70,6 +70,12 @@ def _stream_key(dev: torch.device) -> Tuple[int, int]:
     return dev.index, torch.cuda.current_stream(dev).cuda_stream
 
 
+def _is_sharded_param(p: torch.Tensor) -> bool:
+    """Parameter managed by FSDP (flattened original parameter of FSDP1, DTensor of FSDP2): its full value only exists inside its own
+    unit's forward / backward."""
+    return bool(getattr(p, "_fsdp_flattened", False)) or hasattr(p, "_local_tensor") or type(p).__name__ == "FlatParameter"
+
+
 def _needs_grad(module: nn.Module, *tensors) -> bool:
     """True when the call must be recorded by autograd (training step: projectors and adapter are trainable in every
     stage, merv.py:318-320,342-343,363-365)."""
@@ -516,7 +522,7 @@ class AveragePooling3DProjector(TokenResampler):
         assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
         _require_device(fused_img_patches)
         fusion = self._linked_fusion() if self._linked_fusion is not None else None
-        if fusion is not None and (not torch.is_grad_enabled() or getattr(fusion, "fused_training", False)):
+        if fusion is not None and (not torch.is_grad_enabled() or (hasattr(fusion, "_defer_in_grad_mode") and fusion._defer_in_grad_mode(self))):
             return DeferredProjection(self, fused_img_patches)
         return self._forward_unfused(fused_img_patches)
 
@@ -719,10 +725,11 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         self._cast_cache = _CastCache()
         self._u_cache = {}
         self._vc_cache = {}
-        # opt-in (MervFusion(fused_training=True) / patch_merv(fused_training=True)): linked projectors defer in grad mode too and the
-        # training step runs _FusedLinearFn.  Off by default because it needs every projector's parameters at the adapter's forward,
-        # which per-projector FSDP units (merv.py:473-485) do not provide; wrap MervFusion as one unit to use it.
-        self.fused_training = False
+        # True / False force the training step onto / off the fused path (_FusedLinearFn); None (default) decides per call: fused unless
+        # a parameter involved is managed by FSDP.  The fused path reads every projector's parameters inside THIS module's forward, and
+        # per-projector FSDP units (merv.py:473-485) have resharded them by then; wrap MervFusion as one unit and
+        # set True to use it under FSDP.
+        self.fused_training: Optional[bool] = None
 
     def _reset_parameters(self):
         xavier_uniform_(self.Q)
@@ -829,6 +836,12 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         if any(v.shape[1] != self.token_length for v in V):
             return False
         return all(len(v.projector.layers()) >= 1 for v in V)
+
+    def _defer_in_grad_mode(self, projector: nn.Module) -> bool:
+        """Whether a linked projector should hand its input over (DeferredProjection) although autograd is recording."""
+        if self.fused_training is not None:
+            return bool(self.fused_training)
+        return not any(_is_sharded_param(p) for m in (self, projector) for p in m.parameters())
 
     def _can_fuse_training(self, V: Sequence[DeferredProjection]) -> bool:
         """The fused backward (_FusedLinearFn) covers what MERV constructs (merv.py:152-163,214-216): single-Linear projectors with
@@ -1055,13 +1068,15 @@ class MervFusion(nn.Module):
     """
 
     def __init__(self, projectors: Sequence[AveragePooling3DProjector], feature_fusion: Optional[nn.Module],
-                 fused: bool = True, fusion_type: Optional[str] = None, fused_training: bool = False) -> None:
+                 fused: bool = True, fusion_type: Optional[str] = None, fused_training: Optional[bool] = None) -> None:
         super().__init__()
         self.projectors = nn.ModuleList(projectors)
         self.feature_fusion = feature_fusion
-        if fused_training:  # the training step through the fused forward + _FusedLinearFn backward (needs `fused`)
-            assert fused and isinstance(feature_fusion, CrossAttentionAdapterLearnableQuery), "fused_training needs the linked learnable-query mixer"
-            feature_fusion.fused_training = True
+        if fused_training is not None:  # force the training step onto / off the fused forward + _FusedLinearFn backward (None: automatic)
+            assert not fused_training or (fused and isinstance(feature_fusion, CrossAttentionAdapterLearnableQuery)), \
+                "fused_training needs the linked learnable-query mixer"
+            if isinstance(feature_fusion, CrossAttentionAdapterLearnableQuery):
+                feature_fusion.fused_training = fused_training
         # the parameter-free fusions of merv.py:598-601: "first" (encoder 0 only) and "concat" (token-wise concatenation)
         self.fusion_type = fusion_type
         if feature_fusion is None:
@@ -1261,7 +1276,7 @@ def _adopt_plain_projector(ref_module: nn.Module) -> nn.Module:
     return new
 
 
-def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: bool = False) -> nn.Module:
+def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: Optional[bool] = None) -> nn.Module:
     """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
 
     ``vidlm.projectors[i]`` (reference AveragePooling3DProjector) and ``vidlm.feature_fusion`` (reference
@@ -1317,6 +1332,6 @@ def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: bool = Fals
     vidlm.feature_fusion = new_ff
     if fused:
         link_fused(new_projs, new_ff)
-        if fused_training and isinstance(new_ff, CrossAttentionAdapterLearnableQuery):
-            new_ff.fused_training = True  # the training step runs the fused forward + _FusedLinearFn (see its docstring for the FSDP caveat)
+        if fused_training is not None and isinstance(new_ff, CrossAttentionAdapterLearnableQuery):
+            new_ff.fused_training = fused_training  # None: per call, fused unless FSDP manages a parameter involved
     return vidlm

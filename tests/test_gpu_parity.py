@@ -482,8 +482,7 @@ def test_backward_matches_reference_autograd(name, dtype, tol, fused_training):
     import merv_b200 as M
 
     m = M.MervFusion.build(case.dims, case.llm_dim, case.out_frames, case.out_size**2, case.mlp_type, text_embedding_dim=case.embed_dim, fused=True)
-    if fused_training:
-        m.feature_fusion.fused_training = True
+    m.feature_fusion.fused_training = fused_training  # forced on / off (the default, None, picks the fused path whenever it applies)
     for proj, p in zip(m.projectors, pp):
         proj.projector.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
     m.feature_fusion.load_state_dict({k: torch.from_numpy(v) for k, v in fp.items()})

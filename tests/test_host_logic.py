@@ -321,3 +321,28 @@ def test_attentive_pooler_init_sequence_and_adoption_match_the_reference():
         got = vid.projectors[0](x)
     assert O.rel_err(_np(got), _np(want)) < 2e-5
     assert vid.projectors[0].output_token_length == 4 and vid.projectors[0].output_frame_length == 3
+
+
+def test_fused_training_is_automatic_unless_fsdp_manages_a_parameter():
+    import merv_b200 as M
+
+    def grad_fn_name(mark_sharded):
+        torch.manual_seed(0)
+        m = M.MervFusion.build([16, 24], 32, [2, 2], 4, "linear", text_embedding_dim=24).to(torch.bfloat16).train()
+        assert m.feature_fusion.fused_training is None  # automatic
+        if mark_sharded:  # what FSDP1 does to the original parameters it flattens
+            m.projectors[1].projector.projector.weight._fsdp_flattened = True
+        g = torch.Generator().manual_seed(1)
+        out, w = m([torch.randn(2, 2, 16, c, generator=g).to(torch.bfloat16) for c in (16, 24)])
+        out.float().sum().backward()
+        assert all(p.grad is not None for p in m.projectors.parameters())
+        return type(out.grad_fn).__name__
+
+    assert grad_fn_name(False).startswith("_FusedLinearFn")
+    assert not grad_fn_name(True).startswith("_FusedLinearFn")  # module-by-module autograd path
+    # MLP projectors are outside the fused backward: automatic mode falls back to the module-by-module path
+    torch.manual_seed(0)
+    m = M.MervFusion.build([16, 24], 32, [2, 2], 4, "gelu-mlp", text_embedding_dim=24).to(torch.bfloat16).train()
+    g = torch.Generator().manual_seed(1)
+    out, w = m([torch.randn(2, 2, 16, c, generator=g).to(torch.bfloat16) for c in (16, 24)])
+    assert out.requires_grad and not type(out.grad_fn).__name__.startswith("_FusedLinearFn")
