@@ -9,8 +9,12 @@ error behaviour as the reference (paths below are relative to the reference root
     FusedMLPProjector                    merv/util/nn_utils.py:86-108
     get_mlp_projector                    merv/util/nn_utils.py:111-121
     TokenResampler                       merv/util/nn_utils.py:124-133
+    AveragePoolingProjector              merv/util/nn_utils.py:136-174    (2-D "avg")
+    AttentivePooler (+ CrossAttention, MLP, CrossAttentionBlock containers)   merv/util/nn_utils.py:177-246,380-452  ("attntv", inference)
     AveragePooling3DProjector            merv/util/nn_utils.py:306-338
-    CrossAttentionAdapterLearnableQuery  merv/util/nn_utils.py:455-521
+    CrossAttentionAdapterLearnableQuery  merv/util/nn_utils.py:455-521    (averagetoken either way, positional embedding)
+    ScalarAdapter                        merv/util/nn_utils.py:524-537
+    ConcatChannelFusion / ConcatChannelLNFusion                               merv/models/vidlms/merv.py:217-223,603-606
 
 ``forward`` runs hand-written sm_100a kernels through the C ABI (``merv_b200.ops``); nothing here calls a
 torch compute op on the data path, and CPU tensors raise.  ``nn.Linear`` / ``nn.MultiheadAttention`` are used
@@ -24,7 +28,9 @@ Two execution modes:
 * linked (``link_fused`` / ``MervFusion`` / ``patch_merv``): projectors return a ``DeferredProjection`` and the
   adapter runs the whole path as pool -> [hidden layers] -> scores -> ONE tcgen05 GEMM whose epilogue applies the
   mixing weights, so the per-encoder projections never touch HBM.  Valid whenever the LAST projector layer is
-  affine (true for every projector type of the reference), inference only.
+  affine (true for every projector type of the reference).  In grad mode the linear projectors take the same fused
+  forward with a backward that keeps only the pooled tokens (``_FusedLinearFn``) unless FSDP manages a parameter involved;
+  everything else trains through the module-by-module autograd Functions.
 """
 
 from __future__ import annotations
@@ -495,10 +501,7 @@ class AveragePooling3DProjector(TokenResampler):
         n = len(lins)
         mlp_type = {1: "linear", 2: "gelu-mlp", 3: "fused-gelu-mlp"}[n]
         new = cls(lins[0].in_features, lins[-1].out_features, ref_module.output_frames, ref_module.output_size, mlp_type)
-        if n == 1:
-            new.projector.projector = inner.projector
-        else:
-            new.projector.projector = inner.projector
+        new.projector.projector = inner.projector  # nn.Linear ("linear") or the nn.Sequential of the MLP types: shared, not copied
         return new
 
     def layers(self) -> List[Tuple[nn.Linear, int]]:
