@@ -28,6 +28,7 @@ from .nn_utils import (  # noqa: E402
     MLPProjector,
     ScalarAdapter,
     TokenResampler,
+    fsdp_wrap_policy,
     get_mlp_projector,
     link_fused,
     patch_merv,
@@ -36,5 +37,5 @@ from .nn_utils import (  # noqa: E402
 
 __all__ = [
     "AttentivePooler", "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
-    "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
+    "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "fsdp_wrap_policy", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
 ]

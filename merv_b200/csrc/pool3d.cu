@@ -457,6 +457,7 @@ struct PoolEnc {
   float* score_partial;
   const int* batch_index;
   int F, H, W, C, T, S;
+  int src_batch;              // videos in x (bound of the batch_index gather)
   int rows_per_item, groups;  // output rows handled by one CTA; groups = ceil(S / rows_per_item)
   int items;                  // B * T * groups
   long long xbs, xfs, xts, ybs, yrs;
@@ -480,7 +481,10 @@ __global__ void __launch_bounds__(256) pool3d_direct_kernel(const __grid_constan
   const int i_begin = g * e.rows_per_item;
   const int i_end = min(e.S, i_begin + e.rows_per_item);
   const int nvec = e.C / VEC;
-  const T* __restrict__ xb = static_cast<const T*>(e.x) + (long long)(e.batch_index ? e.batch_index[b] : b) * e.xbs;
+  // an out-of-range gather index must never read outside x: clamp it (the TMA kernel's loads are bounds-checked by the tensor map)
+  int src = e.batch_index ? e.batch_index[b] : b;
+  src = src < 0 ? 0 : (src >= e.src_batch ? e.src_batch - 1 : src);
+  const T* __restrict__ xb = static_cast<const T*>(e.x) + (long long)src * e.xbs;
   T* __restrict__ yb = static_cast<T*>(e.y) + (long long)b * e.ybs;
   float dot = 0.f;
 
@@ -656,6 +660,7 @@ static int launch_direct(const merv_pool_desc* enc, int n, int B, int dtype, cud
     PoolEnc& e = p.enc[i];
     e.x = d.x; e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial; e.batch_index = d.batch_index;
     e.F = d.F; e.H = d.H; e.W = d.W; e.C = d.C; e.T = d.T; e.S = d.S;
+    e.src_batch = d.batch_index && d.src_batch > 0 ? d.src_batch : B;
     e.rows_per_item = direct_rows_per_item(d.S);
     e.groups = (d.S + e.rows_per_item - 1) / e.rows_per_item;
     e.items = B * d.T * e.groups;

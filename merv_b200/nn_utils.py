@@ -71,6 +71,22 @@ def _require_device(t: torch.Tensor) -> None:
         raise RuntimeError("merv_b200 runs only on CUDA (sm_100a) tensors; there is deliberately no CPU fallback.")
 
 
+def _tma_readable(x: torch.Tensor) -> bool:
+    """Feature tensor the pool kernel reads in place: channels contiguous, every other stride a multiple of one 16-byte vector
+    (bf16), 16-byte aligned base — e.g. a CLS-dropping slice of a backbone output.  Anything else is copied first."""
+    return x.stride(3) == 1 and not any(st % 8 for st in x.stride()[:3]) and x.data_ptr() % 16 == 0
+
+
+def _as_batch_index(batch_index: Optional[torch.Tensor], like: torch.Tensor) -> Optional[torch.Tensor]:
+    """`multimodal_indices` (merv.py:572; int64 in the reference) as the contiguous int32 device vector the kernels gather by."""
+    if batch_index is None:
+        return None
+    assert batch_index.dim() == 1 and not batch_index.is_floating_point(), "batch_index must be a 1-D integer tensor"
+    if batch_index.device != like.device or batch_index.dtype != torch.int32 or not batch_index.is_contiguous():
+        batch_index = batch_index.to(device=like.device, dtype=torch.int32).contiguous()
+    return batch_index
+
+
 def _stream_key(dev: torch.device) -> Tuple[int, int]:
     """(device index, current stream handle): cached plans own workspaces, so they are bound to one stream."""
     return dev.index, torch.cuda.current_stream(dev).cuda_stream
@@ -200,6 +216,14 @@ def _version(p: torch.Tensor) -> int:
         return 0
 
 
+def _is_volatile(p: Optional[torch.Tensor]) -> bool:
+    """A "parameter" that is not an ``nn.Parameter``: inside an FSDP1 unit's forward (``use_orig_params=True``, fsdp.py:240) the
+    module attributes are fresh VIEWS into the unit's unsharded flat buffer.  That buffer keeps its address from step to step
+    while the optimizer rewrites its contents through the sharded master copy, and a fresh view always reports ``_version`` 0 —
+    so nothing derived from such a tensor may be cached on (data_ptr, version)."""
+    return p is not None and not isinstance(p, nn.Parameter)
+
+
 class _CastCache:
     """Weights cast to the compute dtype, keyed on (storage, version) so in-place optimiser updates invalidate them."""
 
@@ -211,6 +235,8 @@ class _CastCache:
             return None
         if p.dtype == dtype and p.data_ptr() % 16 == 0 and p.is_contiguous():
             return p.detach()
+        if _is_volatile(p):  # FSDP view: a new object with unknowable contents every forward — convert, never remember
+            return p.detach().to(dtype).contiguous().clone() if p.dtype == dtype else p.detach().to(dtype).contiguous()
         # (a same-dtype parameter that is a misaligned / strided view — e.g. FSDP's use_orig_params views into a flat
         #  buffer, fsdp.py:240 — is copied once per version: TMA and the 128-bit loads need 16-byte aligned rows)
         key = (id(p), dtype)
@@ -289,8 +315,15 @@ class _FusedLinearFn(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+def _unwrap(module: nn.Module) -> nn.Module:
+    """The module behind an FSDP1 wrapper (FSDP(LinearProjector) is what the reference's wrap policy, merv.py:473-485, turns the
+    inner ``projector`` of every resampler into); anything else is returned unchanged."""
+    return getattr(module, "_fsdp_wrapped_module", module)
+
+
 def _projector_layers(projector: nn.Module) -> List[Tuple[nn.Linear, int]]:
     """[(linear, activation applied AFTER it)] for every reference projector type."""
+    projector = _unwrap(projector)
     if isinstance(projector, LinearProjector):
         return [(projector.projector, ACT_NONE)]
     if isinstance(projector, (MLPProjector, MLPDeepProjector, FusedMLPProjector)):
@@ -507,26 +540,30 @@ class AveragePooling3DProjector(TokenResampler):
     def layers(self) -> List[Tuple[nn.Linear, int]]:
         return _projector_layers(self.projector)
 
-    def _forward_unfused(self, fused_img_patches: torch.Tensor, rowdot_vec: Optional[torch.Tensor] = None):
+    def _forward_unfused(self, fused_img_patches: torch.Tensor):
+        """pool -> ``self.projector(pooled)``.  The inner projector is CALLED as a module, exactly as the reference does
+        (nn_utils.py:330): under the reference's FSDP policy it is its own unit (merv.py:473-485) and its parameters only exist
+        unsharded inside its own forward."""
         dtype = _compute_dtype(fused_img_patches)
-        train = _needs_grad(self, fused_img_patches)
-        if train and fused_img_patches.requires_grad:
+        if torch.is_grad_enabled() and fused_img_patches.requires_grad:
             raise NotImplementedError("gradients w.r.t. the patch features are not implemented (frozen backbones, merv.py:316)")
         x = fused_img_patches.detach()
         x = x if x.dtype == dtype else x.to(dtype)
         if x.shape[0] == 0:
-            y = torch.empty((0, self.output_frames * self.output_size**2, self.llm_dim), dtype=dtype, device=x.device)
-            return (y, None) if rowdot_vec is not None else y
+            return torch.empty((0, self.output_frames * self.output_size**2, self.llm_dim), dtype=dtype, device=x.device)
         (pooled,), _ = ops.pool3d([x], [self.output_frames], self.output_size)
-        y, rd = _run_layers(pooled, self.layers(), self._cast_cache, dtype, rowdot_vec, train=train)
-        return (y, rd) if rowdot_vec is not None else y
+        return self.projector(pooled)
 
     def forward(self, fused_img_patches: torch.Tensor) -> Union[torch.Tensor, DeferredProjection]:
         assert fused_img_patches.dim() == 4, "expected [B, F, N, C] patch features (merv.py:576-585)"
         _require_device(fused_img_patches)
         fusion = self._linked_fusion() if self._linked_fusion is not None else None
-        if fusion is not None and (not torch.is_grad_enabled() or (hasattr(fusion, "_defer_in_grad_mode") and fusion._defer_in_grad_mode(self))):
-            return DeferredProjection(self, fused_img_patches)
+        if fusion is not None:
+            # Deferring moves the read of THIS module's weights into the adapter's forward.  Under FSDP with per-projector units
+            # (merv.py:473-485) they are resharded again by then — in eval / no_grad passes just as in training.
+            defer = fusion._may_defer(self) if hasattr(fusion, "_may_defer") else not torch.is_grad_enabled()
+            if defer:
+                return DeferredProjection(self, fused_img_patches)
         return self._forward_unfused(fused_img_patches)
 
     @property
@@ -689,7 +726,7 @@ class AttentivePooler(TokenResampler):
         h, _ = ops.linear_bias_act(h, c.get(blk.mlp.fc1.weight, dtype), c.get(blk.mlp.fc1.bias, dtype), ACT_GELU_ERF)
         h, _ = ops.linear_bias_act(h, c.get(blk.mlp.fc2.weight, dtype), c.get(blk.mlp.fc2.bias, dtype), ACT_NONE)
         q2 = ops.add_rows(q1, h)  # q + mlp(norm2(q))
-        out, _ = _run_layers(q2, layers, c, dtype)
+        out = self.projector(q2)  # called as a module: its own FSDP unit under the reference's policy (merv.py:473-485)
         return out.view(B, F * n, out.shape[-1])  # "(B F) N C -> B (F N) C"
 
     @property
@@ -756,7 +793,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         params = (self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias)
         tag = tuple((p.data_ptr(), _version(p)) for p in params if p is not None) + (dtype, self.Q.device)
         hit = self._u_cache.get("u")
-        if hit is None or hit[0] != tag:
+        if hit is None or hit[0] != tag or any(_is_volatile(p) for p in params):
             c = self._cast_cache
             u = ops.fusion_query_vec(c.get(self.Q, dtype), c.get(att.q_proj_weight, dtype), c.get(att.k_proj_weight, dtype),
                                      c.get(att.in_proj_bias, dtype))
@@ -770,7 +807,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         u = self.query_vector(dtype)
         tag = (lin.weight.data_ptr(), _version(lin.weight), None if lin.bias is None else _version(lin.bias), dtype, id(u))
         hit = self._vc_cache.get(id(lin))
-        if hit is None or hit[0] != tag:
+        if hit is None or hit[0] != tag or _is_volatile(lin.weight) or _is_volatile(lin.bias):
             hit = (tag, ops.affine_score_vec(cache.get(lin.weight, dtype), cache.get(lin.bias, dtype), u))
             self._vc_cache[id(lin)] = hit
         return hit[1]
@@ -784,7 +821,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         u = self.query_vector(dtype)
         tag = (self.pe.data_ptr(), _version(self.pe), id(u), None if c_in is None else tuple(id(c) for c in c_in))
         hit = self._u_cache.get("pe")
-        if hit is None or hit[0] != tag:
+        if hit is None or hit[0] != tag or _is_volatile(self.pe):
             hit = (tag, ops.score_consts(self._cast_cache.get(self.pe, dtype), u, c_in), c_in)  # c_in kept alive: ids are the key
             self._u_cache["pe"] = hit
         return hit[1]
@@ -838,12 +875,27 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             return False
         if any(v.shape[1] != self.token_length for v in V):
             return False
+        # one pool launch / one GEMM row space for all encoders: the same S x S grid everywhere (equal T*S*S alone would also admit
+        # e.g. 16 x 8 x 8 next to 4 x 16 x 16, which the module-by-module path handles)
+        if len({v.projector.output_size for v in V}) != 1:
+            return False
         return all(len(v.projector.layers()) >= 1 for v in V)
 
     def _defer_in_grad_mode(self, projector: nn.Module) -> bool:
         """Whether a linked projector should hand its input over (DeferredProjection) although autograd is recording."""
         if self.fused_training is not None:
             return bool(self.fused_training)
+        return not any(_is_sharded_param(p) for m in (self, projector) for p in m.parameters())
+
+    def _may_defer(self, projector: nn.Module) -> bool:
+        """Whether a linked projector hands its input over to this adapter instead of projecting it itself.  The fused pipeline
+        reads the projector's weights inside THIS module's forward, so parameters managed by a different FSDP unit (already
+        resharded by then) rule it out — with or without autograd — unless ``fused_training=True`` states that projectors and
+        adapter share one unit."""
+        if torch.is_grad_enabled():
+            return hasattr(self, "_defer_in_grad_mode") and self._defer_in_grad_mode(projector)
+        if self.fused_training:
+            return True
         return not any(_is_sharded_param(p) for m in (self, projector) for p in m.parameters())
 
     def _can_fuse_training(self, V: Sequence[DeferredProjection]) -> bool:
@@ -862,7 +914,7 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         projs = [v.projector for v in V]
         xs = [v.features.detach() for v in V]
         xs = [x if x.dtype == dtype else x.to(dtype) for x in xs]
-        xs = [x if x.stride(3) == 1 and not any(st % 8 for st in x.stride()[:3]) else x.contiguous() for x in xs]
+        xs = [x if _tma_readable(x) else x.contiguous() for x in xs]
         att = self.attention
         params = [t for p in projs for t in (p.layers()[0][0].weight, p.layers()[0][0].bias)]
         return _FusedLinearFn.apply(self, projs, xs, self.Q, att.q_proj_weight, att.k_proj_weight, att.in_proj_bias, *params)
@@ -893,8 +945,12 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
         dtype = torch.bfloat16
         projs = [v.projector for v in V]
         xs = [v.features if v.features.dtype == dtype else v.features.to(dtype) for v in V]
-        xs = [x if x.stride(3) == 1 and not any(st % 8 for st in x.stride()[:3]) else x.contiguous() for x in xs]
+        xs = [x if _tma_readable(x) else x.contiguous() for x in xs]
+        batch_index = _as_batch_index(batch_index, xs[0])
         B, T, K = (xs[0].shape[0] if batch_index is None else batch_index.numel()), self.token_length, self.llm_dim
+        if out is not None:
+            assert out.shape == (B, T, K) and out.dtype == dtype and out.stride(2) == 1 and out.device == xs[0].device, \
+                f"out must be a bf16 [B, T, K] = {(B, T, K)} view with contiguous rows on {xs[0].device}, got {out.dtype} {tuple(out.shape)}"
         lasts = [p.layers()[-1][0] for p in projs]
         vcs = [self._affine_vec(lin, p._cast_cache, dtype) for lin, p in zip(lasts, projs)]
         if self.positional_embedding:  # score_e += u . pe[e]: folded into the per-encoder score constants
@@ -930,18 +986,33 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
 
 
     def _fused_plan(self, projs, xs, vcs, Ws, biases, B) -> "ops.FusedLinearPlan":
-        """One cached single-call plan per (shapes, strides, weight versions, stream)."""
-        key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), tuple((id(vc[0]), vc[1].data_ptr()) for vc in vcs),
-               tuple(w.data_ptr() for w in Ws), *_stream_key(xs[0].device))
+        """One cached single-call plan per (shapes, strides, stream).  A plan owns ~B x 7.3 MB of workspaces, so a new parameter
+        version (an optimizer step between two eval passes) re-binds the existing plan's pointers instead of building another."""
+        key = (B, tuple((tuple(x.shape), x.stride()) for x in xs), *_stream_key(xs[0].device))
+        ptag = (tuple((id(vc[0]), vc[1].data_ptr()) for vc in vcs), tuple(w.data_ptr() for w in Ws),
+                tuple(None if b is None else b.data_ptr() for b in biases))
         plans = self.__dict__.setdefault("_plans", {})
-        plan = plans.get(key)
-        if plan is None:
-            if len(plans) >= 8:  # shapes rarely change; keep the cache (and its workspaces) small
+        hit = plans.get(key)
+        if hit is None:
+            if len(plans) >= 4:  # shapes rarely change; keep the cache (and its workspaces) small
                 plans.clear()
             plan = ops.FusedLinearPlan(xs, [p.output_frames for p in projs], projs[0].output_size, [vc[0] for vc in vcs],
                                        [vc[1] for vc in vcs], Ws, biases, B, xs[0].shape[0])
-            plans[key] = plan
-        return plan
+            plans[key] = (ptag, plan)
+            return plan
+        if hit[0] != ptag:
+            hit[1].rebind([vc[0] for vc in vcs], [vc[1] for vc in vcs], Ws, biases)
+            plans[key] = (ptag, hit[1])
+        return hit[1]
+
+    def invalidate_caches(self) -> None:
+        """Drop every cached derived quantity (u, v_e, cast weights, plans).  Staleness is detected through ``Tensor._version``,
+        which an update through ``.data`` (``p.data.mul_()``) or a raw-pointer write does not bump: call this after such an update."""
+        self._u_cache.clear()
+        self._vc_cache.clear()
+        self._cast_cache = _CastCache()
+        self.__dict__.pop("_plans", None)
+        self.__dict__.pop("_last_plan", None)
 
 
 class ScalarAdapter(nn.Module):
@@ -962,7 +1033,8 @@ class ScalarAdapter(nn.Module):
         first = V[0].features if linked else V[0]
         B = first.shape[0]
         scores = self.scalar.detach().float().reshape(1, E).expand(B, E).contiguous()  # softmax happens in the kernels
-        if linked and all(v.dtype == torch.bfloat16 and len(v.projector.layers()) == 1 for v in V):
+        if linked and all(v.dtype == torch.bfloat16 and len(v.projector.layers()) == 1 for v in V) and \
+                len({(v.projector.output_size, v.shape[1]) for v in V}) == 1:
             # affine projectors: out = sum_e w_e (P_e W_e^T + b_e) in one tcgen05 GEMM, Y_e never written
             dtype = torch.bfloat16
             projs = [v.projector for v in V]
@@ -1134,6 +1206,105 @@ class MervFusion(nn.Module):
                                                      averagetoken=True, num_encoder=len(projs))
         return cls(projs, fusion, fused=fused)
 
+    @classmethod
+    def from_config(cls, vision_dims: Sequence[int], llm_dim: int, temporal_resolutions: Sequence[int], arch_specifier: str = "gelu-mlp",
+                    feature_fusion: Optional[str] = None, projector_token_length: int = 64, visual_feature_length: int = 512,
+                    pre_proj_layernorm: bool = False, text_embedding_dim: int = 3072, num_patches: Optional[Sequence[int]] = None,
+                    seed: Optional[int] = -1, fused: bool = True, fused_training: Optional[bool] = None) -> "MervFusion":
+        """Build the projectors and the feature-fusion module from the reference's OWN config strings, as ``MERV.__init__`` does
+        (merv.py:87-227; config surface ``conf/models.py:28-43``): same parsing of ``arch_specifier`` (suffix = projector type,
+        ``+``-separated resampler, optional ``frameN`` temporal factor) and ``feature_fusion``, same construction order — hence the
+        same RNG consumption under the projector-consistency seed ``torch.manual_seed(video_backbones[0].embed_dim)`` (merv.py:87;
+        ``seed=-1`` reproduces it, ``None`` leaves the RNG alone) — same consistency asserts and the same exceptions.
+
+        ``vision_dims[i]`` / ``temporal_resolutions[i]`` / ``num_patches[i]`` stand for ``video_backbones[i].embed_dim`` /
+        ``.temporal_resolution`` / ``.num_patches``.  The ``conv`` / ``3dconv`` resamplers and the ``query_mlp`` mixer are ablations
+        outside the accelerated path (DESIGN.md "Out of scope"): they raise NotImplementedError instead of falling back."""
+        import re
+        from functools import partial
+
+        if seed is not None:
+            torch.manual_seed(vision_dims[0] if seed == -1 else seed)  # merv.py:87
+        # merv.py:89-105
+        if arch_specifier.endswith("linear"):
+            mlp_type, Projector = "linear", LinearProjector
+        elif arch_specifier.endswith("fused-gelu-mlp"):
+            mlp_type, Projector = "fused-gelu-mlp", FusedMLPProjector
+        elif arch_specifier.endswith("gelu-mlp"):
+            mlp_type, Projector = "gelu-mlp", MLPProjector
+        elif arch_specifier.endswith("none"):
+            mlp_type, Projector = "none", None  # "will get overriden later" (merv.py:100-103): only valid with a resampler
+        else:
+            raise ValueError(f"MERV with `{arch_specifier = }` is not supported!")
+        # merv.py:107-150
+        tokens_resampled, factor = False, 1
+        size = int(projector_token_length**0.5)
+        assert projector_token_length == size**2, "projector_token_length should be square number"
+        parts = arch_specifier.split("+")
+
+        def frame_factor() -> int:
+            return int(re.search(r"frame(\d+)", arch_specifier).group(1)) if "frame" in arch_specifier else 1
+
+        if "avg" in parts:
+            tokens_resampled, Projector = True, partial(AveragePoolingProjector, output_size=size)
+        elif "attntv" in parts:
+            tokens_resampled, Projector = True, partial(AttentivePooler, num_query_tokens=projector_token_length, num_heads=8)
+        elif "conv" in parts:
+            raise NotImplementedError("the `conv` resampler (ConvolutionalProjector, nn_utils.py:249-303) is not part of the accelerated path")
+        elif "3davg" in parts:
+            factor = frame_factor()
+            tokens_resampled, Projector = True, partial(AveragePooling3DProjector, output_size=size)
+        elif "3dconv" in parts:
+            raise NotImplementedError("the `3dconv` resampler (Convolutional3DProjector, nn_utils.py:341-377) is not part of the accelerated path")
+        # merv.py:152-172
+        if tokens_resampled:
+            projs = [Projector(c, llm_dim, output_frames=t // factor, mlp_type=mlp_type) for c, t in zip(vision_dims, temporal_resolutions)]
+        else:
+            if Projector is None:
+                raise ValueError(f"MERV with `{arch_specifier = }` is not supported!")  # an nn.Identity() instance is not constructible
+            projs = [Projector(c, llm_dim, pre_proj_layernorm=pre_proj_layernorm) for c in vision_dims]
+        # merv.py:174-208
+        if len(vision_dims) > 1:
+            if tokens_resampled:
+                assert all(p.output_token_length * p.output_frame_length in [1, visual_feature_length] for p in projs), (
+                    "Output token length is not consistent across all projectors!"
+                    f" visual_feature_length={visual_feature_length}."
+                    f" {[(p.__class__.__name__, p.output_token_length, 'X', p.output_frame_length) for p in projs]}")
+            else:
+                assert all(getattr(p, "output_token_length", 1) * t in [1, visual_feature_length] for p, t in zip(projs, temporal_resolutions)), (
+                    "Output token length is not consistent across all projectors!" f" visual_feature_length={visual_feature_length}.")
+        else:
+            if tokens_resampled:
+                correct_length = projs[0].output_token_length * projs[0].output_frame_length
+            else:
+                assert num_patches is not None, "a single un-resampled encoder needs num_patches (video_backbones[0].num_patches, merv.py:200)"
+                correct_length = num_patches[0]
+            visual_feature_length = correct_length
+        # merv.py:211-227
+        E = len(vision_dims)
+        if feature_fusion == "query_mlp":
+            raise NotImplementedError("the `query_mlp` mixer (merv.py:211-212) has no forward branch in the reference either (merv.py:598-612)")
+        elif feature_fusion == "cross_attention_avg_lq":
+            ff = CrossAttentionAdapterLearnableQuery(embed_dim=3072, llm_dim=llm_dim, token_length=visual_feature_length, averagetoken=True)
+        elif feature_fusion == "concat_channel":
+            ff = ConcatChannelFusion(E, llm_dim)
+        elif feature_fusion == "concat_channel_ln":
+            ff = ConcatChannelLNFusion(E, llm_dim)
+        elif feature_fusion == "scalar":
+            ff = ScalarAdapter(E)
+        else:
+            ff = None
+            if feature_fusion not in ("first", "concat"):  # merv.py:610-612
+                print(f'feature_fusion "{feature_fusion}" doesn\'t exist')
+                raise NotImplementedError
+        linkable = fused and tokens_resampled and all(isinstance(p, AveragePooling3DProjector) for p in projs) and \
+            isinstance(ff, (CrossAttentionAdapterLearnableQuery, ScalarAdapter))
+        m = cls(projs, ff, fused=linkable, fusion_type=feature_fusion if ff is None else None,
+                fused_training=fused_training if linkable and isinstance(ff, CrossAttentionAdapterLearnableQuery) else None)
+        m.arch_specifier, m.feature_fusion_type, m.tokens_resampled = arch_specifier, feature_fusion, tokens_resampled
+        m.visual_feature_length, m.text_embedding_dim = visual_feature_length, text_embedding_dim
+        return m
+
     # ---- small-batch fast path: skip the per-module Python glue when nothing changed since the last call -------------
     def _param_tag(self):
         ff = self.feature_fusion
@@ -1143,6 +1314,8 @@ class MervFusion(nn.Module):
         for p in self.projectors:
             lin = p.projector.projector
             ps += [lin.weight, lin.bias]
+        if any(_is_volatile(t) for t in ps):  # FSDP views: contents change behind a constant (data_ptr, version)
+            return None
         return tuple((t.data_ptr(), _version(t)) for t in ps)
 
     def _fast_forward(self, xs, out, batch_index):
@@ -1156,10 +1329,18 @@ class MervFusion(nn.Module):
         x0 = xs[0]
         if not x0.is_cuda or x0.shape[0] == 0 or any(x.dtype != torch.bfloat16 for x in xs) or (out is not None and out.dim() != 3):
             return None
+        # the plan's descriptor records the strides it was built with: only inputs the kernels read IN PLACE may re-run it
+        # (anything else is copied to contiguous memory by the general path, whose plan then describes the copy)
+        if not all(_tma_readable(x) for x in xs):
+            return None
+        batch_index = _as_batch_index(batch_index, x0)
         key = (tuple((x.shape, x.stride()) for x in xs), None if batch_index is None else batch_index.numel(), *_stream_key(x0.device))
         cache = self.__dict__.setdefault("_fast", {})
         hit = cache.get(key)
-        if hit is not None and hit[0] == self._param_tag():
+        tag = self._param_tag()
+        if tag is None:
+            return None
+        if hit is not None and hit[0] == tag:
             return hit[1].run(xs, out, batch_index)
         # general path once; remember the plan it used (if it took the single-call route)
         ff.__dict__["_last_plan"] = None
@@ -1167,17 +1348,35 @@ class MervFusion(nn.Module):
         res = ff(projected, out=out, batch_index=batch_index) if (out is not None or batch_index is not None) else ff(projected)
         plan = ff.__dict__.get("_last_plan")
         if plan is not None and all(isinstance(p.projector, LinearProjector) for p in self.projectors):
-            if len(cache) >= 8:
+            if len(cache) >= 4:
                 cache.clear()
-            cache[key] = (self._param_tag(), plan)
+            cache[key] = (tag, plan)
         return res
+
+    def invalidate_caches(self) -> None:
+        """See CrossAttentionAdapterLearnableQuery.invalidate_caches (needed after parameter updates that bypass ``_version``)."""
+        self.__dict__.pop("_fast", None)
+        for p in self.projectors:
+            if hasattr(p, "_cast_cache"):
+                p._cast_cache = _CastCache()
+        if hasattr(self.feature_fusion, "invalidate_caches"):
+            self.feature_fusion.invalidate_caches()
 
     def forward(self, patch_features: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None,
                 batch_index: Optional[torch.Tensor] = None, gather=None) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.feature_fusion is None:  # merv.py:598-601: "first" / "concat", no module and no mixing weights
             assert out is None and batch_index is None and gather is None, "'first' / 'concat' support the plain call only"
             if self.fusion_type == "first":
-                return self.projectors[0]._forward_unfused(patch_features[0]), None
+                p0 = self.projectors[0]
+                return (p0._forward_unfused(patch_features[0]) if hasattr(p0, "_forward_unfused") else p0(patch_features[0])), None
+            if not all(isinstance(p, AveragePooling3DProjector) for p in self.projectors):  # un-resampled / attntv projectors
+                ys = [p(x) for p, x in zip(self.projectors, patch_features)]
+                out_cat = torch.empty((ys[0].shape[0], sum(y.shape[1] for y in ys), ys[0].shape[2]), dtype=ys[0].dtype, device=ys[0].device)
+                t0 = 0
+                for y in ys:  # merv.py:600-601 (token-wise concatenation: a copy, no arithmetic)
+                    out_cat[:, t0:t0 + y.shape[1]].copy_(y)
+                    t0 += y.shape[1]
+                return out_cat, None
             return self._forward_token_concat(patch_features), None
         if isinstance(self.feature_fusion, (ConcatChannelFusion, ConcatChannelLNFusion)):  # merv.py:603-606: no mixing weights
             assert out is None and batch_index is None and gather is None, "concat_channel supports the plain call only"
@@ -1185,7 +1384,7 @@ class MervFusion(nn.Module):
         if gather is not None:  # fused all-gather of the prefixes over NVLink (parallel.SymmetricPrefixBuffer)
             projected = [proj(x) for proj, x in zip(self.projectors, patch_features)]
             return self.feature_fusion(projected, batch_index=batch_index, gather=gather)
-        if not torch.is_grad_enabled() and len(self.projectors) and self.projectors[0]._linked_fusion is not None:
+        if not torch.is_grad_enabled() and len(self.projectors) and getattr(self.projectors[0], "_linked_fusion", None) is not None:
             res = self._fast_forward(patch_features, out, batch_index)
             if res is not None:
                 return res
@@ -1279,12 +1478,49 @@ def _adopt_plain_projector(ref_module: nn.Module) -> nn.Module:
     return new
 
 
+def fsdp_wrap_policy(fused_training: Optional[bool] = None):
+    """The VidLM part of the reference's FSDP auto-wrap policy (merv.py:473-485) over the B200 classes: every projector class is its
+    own FSDP unit, ``feature_fusion`` folds into the root unit.  ``fused_training=True`` returns a policy that wraps NONE of them:
+    projectors and adapter then share the root unit, whose parameters stay unsharded for the whole forward / backward, which is
+    what the fused training step (``_FusedLinearFn``: it reads every projector's weights inside the adapter's forward) needs.
+    Combine with the backbones' policies through ``_or_policy`` exactly as merv.py:487-497 does; ``patch_merv`` does that for a
+    live ``MERV`` by extending its ``get_fsdp_wrapping_policy``."""
+    from functools import partial
+
+    from torch.distributed.fsdp.wrap import _module_wrap_policy
+
+    classes = set() if fused_training else {LinearProjector, MLPProjector, FusedMLPProjector, AveragePoolingProjector, MLPDeepProjector,
+                                            AveragePooling3DProjector}
+    return partial(_module_wrap_policy, module_classes=classes)
+
+
+def _extend_fsdp_policy(vidlm: nn.Module, fused_training: Optional[bool]) -> None:
+    """Make ``vidlm.get_fsdp_wrapping_policy()`` (merv.py:465-497, called by fsdp.py:208) cover the swapped-in classes."""
+    orig = getattr(vidlm, "get_fsdp_wrapping_policy", None)
+    if orig is None or getattr(orig, "_merv_b200_extended", False):
+        return
+    from functools import partial
+
+    from torch.distributed.fsdp.wrap import _or_policy
+
+    def get_fsdp_wrapping_policy():
+        # the reference's own union stays (backbones, LLM; its projector-class entry matches nothing any more: no reference
+        # projector instance is left in the module tree) and the B200 classes are added to it
+        return partial(_or_policy, policies=[orig(), fsdp_wrap_policy(fused_training)])
+
+    get_fsdp_wrapping_policy._merv_b200_extended = True
+    vidlm.get_fsdp_wrapping_policy = get_fsdp_wrapping_policy
+
+
 def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: Optional[bool] = None) -> nn.Module:
     """Swap a live reference ``MERV``'s hot-path modules for the B200 ones in place (parameters are shared, not copied).
 
     ``vidlm.projectors[i]`` (reference AveragePooling3DProjector) and ``vidlm.feature_fusion`` (reference
-    CrossAttentionAdapterLearnableQuery) keep their names, so checkpoints, ``all_module_keys`` (merv.py:235) and the
-    FSDP wrap policy (merv.py:473-497, extended via isinstance on these classes) keep working.
+    CrossAttentionAdapterLearnableQuery) keep their names, so checkpoints and ``all_module_keys`` (merv.py:235) keep working, and
+    ``vidlm.get_fsdp_wrapping_policy()`` (merv.py:465-497, consumed at fsdp.py:208) is extended to the B200 classes: call
+    ``patch_merv`` BEFORE the FSDP wrap.  Under that policy every projector is its own FSDP unit, the linked (deferred) path
+    switches itself off per call and the modules run one by one, each inside its unit; ``fused_training=True`` instead keeps the
+    projectors in the root unit next to ``feature_fusion`` so the fused forward / backward can read all weights at once.
 
     Covered: the "3davg" / "avg" resamplers and the un-resampled projectors (with or without ``pre_proj_layernorm``,
     merv.py:165-171) in front of feature_fusion in {cross_attention_avg_lq, scalar, concat_channel, concat_channel_ln} or the
@@ -1333,6 +1569,7 @@ def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: Optional[bo
                         f"'concat_channel_ln', 'first', 'concat'}}, found {type(ff).__name__}")
     vidlm.projectors = nn.ModuleList(new_projs)
     vidlm.feature_fusion = new_ff
+    _extend_fsdp_policy(vidlm, fused_training if fused else None)
     if fused:
         link_fused(new_projs, new_ff)
         if fused_training is not None and isinstance(new_ff, CrossAttentionAdapterLearnableQuery):

@@ -408,6 +408,8 @@ def fused_linear_mix(
     As = [a if a.stride(1) == 1 else a.contiguous() for a in As]
     Ws = [w if w.stride(1) == 1 else w.contiguous() for w in Ws]
     M, N = As[0].shape[0], Ws[0].shape[0]
+    assert all(a.shape[0] == M for a in As), f"every segment must have the same {M} rows, got {[a.shape[0] for a in As]}"
+    assert all(w.shape[0] == N and w.shape[1] == a.shape[1] for a, w in zip(As, Ws)), "weights must be [N, K_s] for A_s [M, K_s]"
     assert scale.dtype == torch.float32 and scale.is_contiguous() and scale.shape == (M // rows_per_video, len(As))
     with torch.cuda.device(dev):
         if out is None:
@@ -493,10 +495,40 @@ class FusedLinearPlan:
             self.bias_mix = torch.empty((B, N), dtype=torch.float32, device=dev)
             d.scores, d.weights, d.bias_mix = self.scores.data_ptr(), self.weights.data_ptr(), self.bias_mix.data_ptr()
         self.N, self.T_tok = N, T_tok
+        self.x_meta = [(tuple(x.shape), tuple(x.stride())) for x in xs]
         self.fn = lib.merv_fused_forward
+
+    def rebind(self, vs: Sequence[torch.Tensor], cs: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor],
+               biases: Sequence[Optional[torch.Tensor]]) -> None:
+        """Point the plan at a new version of the parameters (same shapes): workspaces are kept, no new plan is built."""
+        d = self.desc
+        assert len(Ws) == self.E and all(w.shape[0] == self.N and w.shape[1] == d.pool[e].C and w.dtype == torch.bfloat16 for e, w in enumerate(Ws))
+        _require_cuda(*vs, *cs, *Ws, *biases)
+        self.keep = [vs, cs, Ws, biases]
+        for e in range(self.E):
+            d.pool[e].score_vec = vs[e].data_ptr()
+            d.W[e], d.ldw[e], d.bias[e], d.c[e] = Ws[e].data_ptr(), Ws[e].stride(0), _p(biases[e]), cs[e].data_ptr()
 
     def run(self, xs: Sequence[torch.Tensor], out: Optional[torch.Tensor], batch_index: Optional[torch.Tensor]):
         d = self.desc
+        # the descriptor was built for these shapes / strides and this device: anything else would read or write out of bounds
+        if len(xs) != self.E:
+            raise ValueError(f"plan was built for {self.E} encoders, got {len(xs)}")
+        for x, (shape, stride) in zip(xs, self.x_meta):
+            if tuple(x.shape) != shape or tuple(x.stride()) != stride or x.dtype != torch.bfloat16 or x.device != self.dev:
+                raise ValueError(f"plan was built for bf16 features {shape} with strides {stride} on {self.dev}, "
+                                 f"got {x.dtype} {tuple(x.shape)} with strides {tuple(x.stride())} on {x.device}")
+        if batch_index is not None:
+            if (batch_index.dtype != torch.int32 or batch_index.dim() != 1 or not batch_index.is_contiguous() or batch_index.device != self.dev
+                    or batch_index.numel() != self.B):
+                raise ValueError(f"batch_index must be a contiguous int32 [{self.B}] tensor on {self.dev}, got {batch_index.dtype} "
+                                 f"{tuple(batch_index.shape)} on {batch_index.device}")
+        elif self.B != self.src_B:
+            raise ValueError(f"plan gathers {self.B} of {self.src_B} videos: batch_index is required")
+        if out is not None and (out.shape != (self.B, self.T_tok, self.N) or out.dtype != torch.bfloat16 or out.stride(2) != 1
+                                or out.stride(1) % 8 or out.stride(0) % 8 or out.device != self.dev):
+            raise ValueError(f"out must be a bf16 [{self.B}, {self.T_tok}, {self.N}] view with contiguous, 16-byte aligned rows on {self.dev}, "
+                             f"got {out.dtype} {tuple(out.shape)} strides {tuple(out.stride())} on {out.device}")
         with torch.cuda.device(self.dev):
             if out is None:
                 out = torch.empty((self.B, self.T_tok, self.N), dtype=torch.bfloat16, device=self.dev)

@@ -9,12 +9,14 @@ if REPO not in sys.path:
 
 
 def _ensure_library_built():
-    """The CUDA library is a build artefact (git-ignored): build it with nvcc if this checkout has none yet.
-    This is the same step as __graft_entry__.build(); there is still no fallback if nvcc is missing."""
-    lib = os.path.join(REPO, "merv_b200", "libmerv_fusion.so")
-    if os.path.isfile(lib):
-        return
+    """The CUDA library is a build artefact (git-ignored): (re)build it with nvcc when this checkout has none or its sources
+    changed (digest check, a no-op otherwise).  Same step as __graft_entry__.build(); still no fallback if nvcc is missing."""
     import importlib.util
+    import shutil
+
+    lib = os.path.join(REPO, "merv_b200", "libmerv_fusion.so")
+    if os.path.isfile(lib) and shutil.which("nvcc") is None and not os.path.isfile("/usr/local/cuda/bin/nvcc"):
+        return  # a box without the toolchain uses the library that travelled with the snapshot
 
     spec = importlib.util.spec_from_file_location("merv_b200_build", os.path.join(REPO, "merv_b200", "build.py"))
     mod = importlib.util.module_from_spec(spec)

@@ -257,8 +257,13 @@ class FusedLinearPlan:
     def __init__(self, xs, out_frames, out_size, vs, cs, Ws, biases, B, src_B):
         self.a = (list(out_frames), out_size, list(vs), list(cs), list(Ws), list(biases))
         self.B = B
+        self.x_meta = [(tuple(x.shape), tuple(x.stride())) for x in xs]
+
+    def rebind(self, vs, cs, Ws, biases):
+        self.a = (*self.a[:2], list(vs), list(cs), list(Ws), list(biases))
 
     def run(self, xs, out, batch_index):
+        assert [(tuple(x.shape), tuple(x.stride())) for x in xs] == self.x_meta, "plan re-run with different shapes / strides"
         out_frames, out_size, vs, cs, Ws, biases = self.a
         pooled, partials = pool3d(xs, out_frames, out_size, score_vecs=vs, batch_index=batch_index)
         T = out_frames[0] * out_size**2

@@ -156,3 +156,105 @@ def test_product_never_touches_the_oracle_or_a_cpu_path():
     for needle in ("torch.matmul", "torch.mm", "torch.bmm", "F.linear", "torch.nn.functional.linear", "F.adaptive_avg_pool3d",
                    "torch.softmax", "F.softmax", "F.gelu", "torch.einsum", "torch.stack"):
         assert needle not in called, f"ops.py calls a torch compute op: {needle}"
+
+
+def test_integration_md_struct_sketch_matches_the_abi():
+    # the ctypes sketch a maintainer would paste from INTEGRATION.md §2 must list merv_pool_desc's fields in ABI order
+    from merv_b200 import _lib
+
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    block = text[text.index("class merv_pool_desc(ctypes.Structure)"):text.index("class AveragePooling3DProjector(TokenResampler)")]
+    documented = re.findall(r'\("([A-Za-z_]+)",\s*ctypes\.(c_[a-z0-9_]+)\)', block)
+    actual = [(name, ctype.__name__) for name, ctype in _lib.PoolDesc._fields_]
+    norm = lambda t: {"c_int": "c_int32", "c_long": "c_int64", "c_longlong": "c_int64"}.get(t, t)  # noqa: E731  (ctypes aliases the fixed-width names)
+    assert [(n, norm(t)) for n, t in documented] == [(n, norm(t)) for n, t in actual]
+    # ... and the header declares the same order
+    hdr = open(os.path.join(REPO, "include", "merv_fusion.h")).read()
+    struct = hdr[hdr.index("typedef struct {"):hdr.index("} merv_pool_desc;")]
+    struct = re.sub(r"/\*.*?\*/", "", struct, flags=re.S)
+    names = [n for decl in struct.split(";") for n in re.findall(r"[\*\s]([A-Za-z_]+)\s*(?:,|$)", decl.strip().replace("typedef struct {", ""))]
+    assert names == [n for n, _ in actual], names
+
+
+_CONFIGS = [
+    # (arch_specifier, feature_fusion, kwargs) as in merv/conf/models.py:28-43,100-157 and the ablations it lists
+    ("no-align+3davg+linear", "cross_attention_avg_lq", {}),
+    ("3davg+gelu-mlp", "cross_attention_avg_lq", {}),
+    ("3davg+fused-gelu-mlp", "concat_channel", {}),
+    ("3davg+frame2+linear", "concat_channel_ln", {"visual_feature_length": 32}),
+    ("avg+linear", "scalar", {}),
+    ("attntv+gelu-mlp", "concat", {}),
+    ("linear", "first", {"pre_proj_layernorm": True, "visual_feature_length": 4}),
+    ("gelu-mlp", "concat_channel", {"visual_feature_length": 4}),
+]
+
+
+@pytest.mark.parametrize("arch,fusion,kw", _CONFIGS)
+def test_from_config_builds_what_merv_init_builds(arch, fusion, kw):
+    """MervFusion.from_config parses the reference's config strings (merv.py:87-227) into the same module tree with the same
+    seeded initial parameters as the reference classes constructed in MERV.__init__'s order."""
+    import functools
+
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    if not reference_available():
+        pytest.skip("needs the reference's nn_utils.py")
+    import merv_b200 as M
+
+    ref = load_reference_nn_utils()
+    dims, llm, temporal, ptl = [32, 24], 48, [4, 4], 16
+    vfl = kw.get("visual_feature_length", 64)
+    m = M.MervFusion.from_config(dims, llm, temporal, arch_specifier=arch, feature_fusion=fusion, projector_token_length=ptl,
+                                 visual_feature_length=vfl, pre_proj_layernorm=kw.get("pre_proj_layernorm", False))
+    # the reference, constructed as merv.py:87-227 does
+    torch.manual_seed(dims[0])
+    mlp_type = "linear" if arch.endswith("linear") else "fused-gelu-mlp" if arch.endswith("fused-gelu-mlp") else "gelu-mlp"
+    parts, factor = arch.split("+"), (int(re.search(r"frame(\d+)", arch).group(1)) if "frame" in arch else 1)
+    if "avg" in parts:
+        P = functools.partial(ref.AveragePoolingProjector, output_size=4)
+    elif "attntv" in parts:
+        P = functools.partial(ref.AttentivePooler, num_query_tokens=ptl, num_heads=8)
+    elif "3davg" in parts:
+        P = functools.partial(ref.AveragePooling3DProjector, output_size=4)
+    else:
+        P = None
+    if P is not None:
+        projs = [P(c, llm, output_frames=t // factor, mlp_type=mlp_type) for c, t in zip(dims, temporal)]
+    else:
+        cls = {"linear": ref.LinearProjector, "gelu-mlp": ref.MLPProjector, "fused-gelu-mlp": ref.FusedMLPProjector}[mlp_type]
+        projs = [cls(c, llm, pre_proj_layernorm=kw.get("pre_proj_layernorm", False)) for c in dims]
+    if fusion == "cross_attention_avg_lq":
+        ff = ref.CrossAttentionAdapterLearnableQuery(embed_dim=3072, llm_dim=llm, token_length=vfl, averagetoken=True)
+    elif fusion == "concat_channel":
+        ff = ref.LinearProjector(len(dims) * llm, llm)
+    elif fusion == "concat_channel_ln":
+        ff = torch.nn.Sequential(torch.nn.LayerNorm(len(dims) * llm), ref.LinearProjector(len(dims) * llm, llm))
+    elif fusion == "scalar":
+        ff = ref.ScalarAdapter(len(dims))
+    else:
+        ff = None
+    want = {f"projectors.{k}": v for k, v in torch.nn.ModuleList(projs).state_dict().items()}
+    if ff is not None:
+        want.update({f"feature_fusion.{k}": v for k, v in ff.state_dict().items()})
+    got = m.state_dict()
+    assert list(got) == list(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    assert m.arch_specifier == arch and m.feature_fusion_type == fusion
+
+
+def test_from_config_rejects_what_merv_rejects():
+    import merv_b200 as M
+
+    with pytest.raises(ValueError, match="is not supported"):  # merv.py:105
+        M.MervFusion.from_config([8], 8, [2], arch_specifier="3davg+relu", feature_fusion="first")
+    with pytest.raises(AssertionError, match="square number"):  # merv.py:112
+        M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier="3davg+linear", feature_fusion="first", projector_token_length=12)
+    with pytest.raises(AssertionError, match="not consistent"):  # merv.py:177-183
+        M.MervFusion.from_config([8, 8], 8, [2, 4], arch_specifier="3davg+linear", feature_fusion="cross_attention_avg_lq",
+                                 projector_token_length=4, visual_feature_length=8)
+    with pytest.raises(NotImplementedError):  # merv.py:610-612
+        M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier="3davg+linear", feature_fusion="bogus", projector_token_length=4, visual_feature_length=8)
+    for arch in ("conv+linear", "3dconv+linear"):  # ablation resamplers outside the accelerated path: loud, never a fallback
+        with pytest.raises(NotImplementedError, match="not part of the accelerated path"):
+            M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier=arch, feature_fusion="first")
