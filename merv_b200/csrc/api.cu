@@ -1,4 +1,5 @@
 // extern "C" surface shared by all kernels: error state, device checks, GEMM entry points.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -35,6 +36,11 @@ int require_sm100() {
   }
   if (g_dev_ok[dev] < 0) return fail(MERV_E_ARCH, "device %d is not compute capability 10.x; libmerv_fusion is built for sm_100a only", dev);
   return MERV_OK;
+}
+
+bool pdl_enabled() {
+  const char* e = getenv("MERV_PDL");
+  return !(e != nullptr && e[0] == '0');
 }
 
 int sm_count() {
@@ -207,10 +213,17 @@ extern "C" int merv_fused_forward(const merv_fused_desc* d, void* stream) {
     MERV_REQUIRE(p.score_vec && p.score_partial && d->parts[e] > 0, MERV_E_ARG, "merv_fused_forward: encoder %d needs score_vec / score_partial / parts", e);
     A[e] = p.y; lda[e] = p.y_row_stride; K[e] = p.C; partial[e] = p.score_partial;
   }
+  // Three launches chained by programmatic dependent launch: the pool kernel releases its dependents at once, so the tiny
+  // scores kernel is resident (blocked in griddepcontrol.wait) when the pool's last CTA retires, and the GEMM's CTAs run their
+  // prologue (barriers, TMEM allocation, tensor-map prefetch) on every SM the pool has left — no launch gap between the stages.
+  const bool pdl = pdl_enabled();
   if (int rc = merv_pool3d(d->pool, E, d->B, MERV_BF16, 0, stream)) return rc;
-  if (int rc = merv_scores_softmax_weights(partial, d->parts, d->c, d->bias, d->scores, d->weights, d->weights_bf16, d->bias_mix, d->B, E,
-                                           d->rows_per_video, d->N, stream))
+  if (int rc = launch_scores_softmax_weights(partial, d->parts, d->c, d->bias, d->scores, d->weights, d->weights_bf16, d->bias_mix, d->B, E,
+                                             d->rows_per_video, d->N, static_cast<cudaStream_t>(stream), pdl))
     return rc;
-  return merv_fused_linear_mix(A, lda, d->W, d->ldw, K, E, d->weights, d->bias_mix, d->out, d->ldo, d->out_batch_stride,
-                               d->B * d->rows_per_video, d->N, d->rows_per_video, 0, stream);
+  MERV_REQUIRE(d->B * (long long)d->rows_per_video <= 0x7fffffffLL, MERV_E_SHAPE, "merv_fused_forward: B * rows_per_video overflows");
+  GemmSegment seg[MERV_MAX_SEGMENTS];
+  for (int e = 0; e < E; ++e) seg[e] = GemmSegment{A[e], lda[e], d->W[e], d->ldw[e], K[e]};
+  return launch_gemm_tcgen05(seg, E, d->weights, d->bias_mix, d->rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, d->out, d->ldo,
+                             d->out_batch_stride, d->B * d->rows_per_video, d->N, 0, static_cast<cudaStream_t>(stream), nullptr, 0, pdl);
 }

@@ -38,13 +38,27 @@ struct GemmSegment {
   long long ldw;
   int K;
 };
+// pdl: launch with programmatic stream serialization — the kernel's prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) may overlap the tail of the preceding kernel in the stream; it executes griddepcontrol.wait before touching global memory.
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out = nullptr, int num_extra = 0);
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out = nullptr, int num_extra = 0, bool pdl = false);
+int launch_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
+                                  float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
+                                  cudaStream_t stream, bool pdl);
+// MERV_PDL=0 disables programmatic dependent launch inside merv_fused_forward (A/B measurements); read per call
+bool pdl_enabled();
 int launch_gemm_simt(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* Y, long long ldy,
                      int M, int N, int K, int act, int dtype, cudaStream_t s);
 
 // ---- device helpers ---------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  pdl_launch_dependents(): the next kernel in the stream, if it was launched with
+// programmatic stream serialization, may start being scheduled now (it still cannot read this grid's results before its own
+// pdl_wait()).  pdl_wait(): blocks until every prerequisite grid has completed and its writes are visible; a no-op for a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> struct VecTraits;
 template <> struct VecTraits<__nv_bfloat16> { static constexpr int kVec = 8; };  // 16 bytes
 template <> struct VecTraits<float> { static constexpr int kVec = 4; };          // 16 bytes

@@ -283,6 +283,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // PDL: everything above touched only shared memory / TMEM and may have run while the previous kernel of the stream was
+  // still finishing; from here on operands and per-video scales are read from global memory.
+  pdl_wait();
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -534,7 +537,7 @@ static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra) {
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -611,13 +614,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   cfg.gridDim = dim3(unsigned(units * ctas));
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = unsigned(ctas);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   if (act == MERV_ACT_GELU_ERF) return ctas == 2 ? launch_variant<2, false, true>(cfg, maps, p) : launch_variant<1, false, true>(cfg, maps, p);
   if (ctas == 2) return wide ? launch_variant<2, true, false>(cfg, maps, p) : launch_variant<2, false, false>(cfg, maps, p);
   return wide ? launch_variant<1, true, false>(cfg, maps, p) : launch_variant<1, false, false>(cfg, maps, p);

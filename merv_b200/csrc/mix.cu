@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(256) scores_softmax_kernel(const __grid_consta
   __shared__ float red[32];
   __shared__ float sc[MERV_MAX_ENCODERS];
   const int b = blockIdx.y, lane = threadIdx.x & 31;
+  pdl_launch_dependents();  // the GEMM behind this kernel may start its prologue now
+  pdl_wait();               // the pool kernel's score partials are complete and visible
   for (int e = 0; e < E; ++e) {
     const int n = pp.count[e];
     const float* src = pp.p[e] + (long long)b * n;
@@ -591,9 +593,10 @@ extern "C" int merv_softmax_mix(const void* const* V, const int32_t* tokens, con
 }
 
 // merv_scores_from_partials + merv_softmax_weights_ex in one launch (bf16 biases); used by merv_fused_forward
-extern "C" int merv_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
-                                           float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
-                                           void* stream) {
+namespace merv {
+int launch_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
+                                  float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
+                                  cudaStream_t stream, bool pdl) {
   MERV_REQUIRE(partial && count && bias && scores && weights && bias_mix, MERV_E_ARG, "merv_scores_softmax_weights: NULL pointer");
   MERV_REQUIRE(E >= 1 && E <= MERV_MAX_ENCODERS, MERV_E_ARG, "merv_scores_softmax_weights: E=%d", E);
   MERV_REQUIRE(B >= 0 && T > 0 && N > 0, MERV_E_SHAPE, "merv_scores_softmax_weights: B=%d T=%d N=%d", B, T, N);
@@ -608,8 +611,25 @@ extern "C" int merv_scores_softmax_weights(const float* const* partial, const in
     pp.count[e] = count[e];
     bp.bias[e] = bias[e];
   }
-  scores_softmax_kernel<__nv_bfloat16><<<dim3((N + 255) / 256, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      pp, bp, scores, weights, static_cast<__nv_bfloat16*>(weights_bf16), bias_mix, E, T, N);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N + 255) / 256, B);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, scores_softmax_kernel<__nv_bfloat16>, pp, bp, scores, weights, static_cast<__nv_bfloat16*>(weights_bf16),
+                                  bias_mix, E, T, N));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
+}
+}  // namespace merv
+
+extern "C" int merv_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
+                                           float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
+                                           void* stream) {
+  return merv::launch_scores_softmax_weights(partial, count, c, bias, scores, weights, weights_bf16, bias_mix, B, E, T, N,
+                                             static_cast<cudaStream_t>(stream), false);
 }

@@ -287,6 +287,9 @@ pool3d_tma_kernel(const __grid_constant__ PoolTmaMaps maps, const __grid_constan
   float* itab = reinterpret_cast<float*>(wtab + MERV_MAX_ENCODERS * PT_MAX_TOKENS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // PDL: a dependent kernel launched with programmatic stream serialization (the scores kernel of merv_fused_forward) may be
+  // made resident already; it blocks in griddepcontrol.wait until this grid has completed.  No-op otherwise.
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int i = 0; i < PT_STAGES; ++i) {
       pt_mbar_init(full_bar + 8 * i, 1);

@@ -358,6 +358,42 @@ def test_full_size_batch_properties(fused, B):
         assert torch.equal(oh, out[B // 2:]) and torch.equal(wh, w[B // 2:])
 
 
+def test_benchmark_batch_matches_the_oracle_directly():
+    """The exact run bench.py times (merv-full, B = 64, bf16, the single-call production path) checked DIRECTLY against the CPU
+    oracle: three videos are pulled out of the batch of 64 and recomputed by oracle.merv_fusion_forward in fp64 from the same
+    bf16-rounded inputs and weights (tolerance 2e-2, BASELINE.json) — and, where the staged reference file travelled with the
+    snapshot (oracle/_ref), by the unmodified reference modules in fp32."""
+    B = 64
+    m = _full_module(True)
+    feats = _full_features(B)
+    with torch.inference_mode():
+        out, w = m(feats)      # builds the plan
+        out, w = m(feats)      # re-runs the cached single-call plan: what the timed loop of bench.py executes
+    torch.cuda.synchronize()
+    pp = [{k: _np(v).astype(np.float64) for k, v in p.projector.state_dict().items()} for p in m.projectors]
+    fp = {k: _np(v).astype(np.float64) for k, v in m.feature_fusion.state_dict().items()}
+    picks = [0, 37, B - 1]
+    sub = [_np(f[picks]).astype(np.float64) for f in feats]
+    want, want_w, _ = O.merv_fusion_forward(sub, pp, fp, (16, 16, 16, 16), 8, "linear", 1024)
+    got, got_w = _np(out[picks]), _np(w[picks])
+    assert got.shape == want.shape == (3, 1024, 4096)
+    assert O.rel_err(got, want) < BF16_TOL, O.rel_err(got, want)
+    assert np.abs(got_w - want_w).max() < 1e-2
+    assert (want_w.max(-1) - want_w.min(-1)).mean() > 0.02, "degenerate softmax: the score path would not be exercised"
+    from oracle.ref_loader import reference_available
+
+    if reference_available():  # the real reference modules (CPU, fp32) on the same three videos
+        from oracle import reference_model
+
+        fwd, (projs, ff) = reference_model.build_reference([1024, 1024, 768, 768], 4096, [16] * 4, 8, "linear", 1024, q_scale=64.0)
+        for rp, mp in zip(projs, m.projectors):  # the module under test rounded its seeded fp32 weights to bf16: give the reference those
+            rp.projector.load_state_dict({k: v.float().cpu() for k, v in mp.projector.state_dict().items()})
+        ff.load_state_dict({k: v.float().cpu() for k, v in m.feature_fusion.state_dict().items()})
+        ref_out, ref_w = fwd([f[picks].float().cpu() for f in feats])
+        assert O.rel_err(got, ref_out.numpy()) < BF16_TOL
+        assert np.abs(got_w - ref_w.numpy()).max() < 1e-2
+
+
 def test_full_size_fused_matches_unfused():
     B = 4
     feats = _full_features(B, seed=9)

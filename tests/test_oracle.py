@@ -182,3 +182,31 @@ def test_token_concat_and_first():
     V = [rng.standard_normal((2, 3, 4)).astype(np.float32) for _ in range(3)]
     out = O.token_concat_forward(V)
     assert out.shape == (2, 9, 4) and np.array_equal(out[:, 3:6], V[1])
+
+
+def test_reference_arm_port_weights_equal_the_reference_modules():
+    """bench.py --impl reference builds its weights without merv_b200: the torch.nn containers of oracle/reference_model.port_state
+    must consume the RNG exactly like the reference's modules (merv.py:87,152-163,214-216), and both CPU arms must agree."""
+    import torch
+
+    from oracle import reference_model as RM
+    from oracle.ref_loader import reference_available
+
+    if not reference_available():
+        import pytest
+
+        pytest.skip("needs the reference's nn_utils.py")
+    dims, llm, frames, S = [64, 48], 96, [4, 4], 2
+    for mlp_type in ("linear", "gelu-mlp"):
+        fwd_ref, (projs, ff) = RM.build_reference(dims, llm, frames, S, mlp_type, 16, q_scale=8.0)
+        pps, fp = RM.port_state(dims, llm, mlp_type, q_scale=8.0)
+        for p, sd in zip(projs, pps):
+            ref_sd = p.projector.state_dict()
+            assert sorted(ref_sd) == sorted(sd) and all(torch.equal(ref_sd[k], sd[k]) for k in sd)
+        ref_sd = ff.state_dict()
+        assert sorted(ref_sd) == sorted(fp) and all(torch.equal(ref_sd[k], fp[k]) for k in fp)
+        fwd_port, _ = RM.build_port(dims, llm, frames, S, mlp_type, 16, q_scale=8.0)
+        g = torch.Generator().manual_seed(3)
+        feats = [torch.randn((2, 4, n, c), generator=g) + mu for n, c, mu in zip((16, 9), dims, (0.3, -0.4))]
+        (o1, w1), (o2, w2) = fwd_ref(feats), fwd_port(feats)
+        assert float((o1 - o2).abs().max() / o1.abs().max()) < 1e-5 and float((w1 - w2).abs().max()) < 1e-6
