@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MERV_ABI_VERSION 3
+#define MERV_ABI_VERSION 4
 
 enum { MERV_F32 = 0, MERV_BF16 = 1 };
 enum { MERV_ACT_NONE = 0, MERV_ACT_GELU_ERF = 1 };
@@ -206,6 +206,16 @@ int merv_fused_linear_mix_gather(const void* const* A, const int64_t* lda, const
                                  const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
                                  int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,
                                  void* const* peer_out, int num_peers, void* stream);
+
+/* The same all-gather through the NVSwitch MULTICAST mapping of the symmetric buffers: `mc_out` is the multicast address of this
+ * rank's block (one virtual address that the switch replicates into the buffer of EVERY rank, the caller's included), and every
+ * finished output box is written exactly once with multimem.st (16 bytes per thread, 128-byte rows) instead of once per peer.
+ * NVLink egress per GPU drops from (ranks - 1) x block to 1 x block; what remains is each GPU's ingress of the other ranks'
+ * blocks.  `out` receives nothing separately (the multicast covers the local buffer) but must be the local address of the
+ * same block: it only provides the shape checks.  Flat [M, N] output with leading dimension ldo; bf16. */
+int merv_fused_linear_mix_multicast(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                    const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                    int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* mc_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Whole fused path in ONE call (affine "linear" projectors, bf16): pool -> scores -> softmax -> fused GEMM, i.e.

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1
 MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 64
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}
 
@@ -93,6 +93,8 @@ _SIGNATURES = {
     "merv_softmax_weights_ex": (c_int, [c_void_p, c_void_p, c_void_p, _PP, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "merv_fused_linear_mix_gather": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
                                              c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, _PP, c_int, c_void_p]),
+    "merv_fused_linear_mix_multicast": (c_int, [_PP, POINTER(c_int64), _PP, POINTER(c_int64), POINTER(c_int32), c_int, c_void_p, c_void_p,
+                                                c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "merv_concat_linear": (c_int, [_PP, POINTER(c_int64), c_void_p, c_int64, POINTER(c_int32), c_int, c_void_p, c_void_p, c_int64, c_int, c_int,
                                    c_void_p]),
     "merv_fused_forward": (c_int, [POINTER(FusedDesc), c_void_p]),

@@ -168,6 +168,21 @@ extern "C" int merv_fused_linear_mix_gather(const void* const* A, const int64_t*
                              M, N, max_ctas, static_cast<cudaStream_t>(stream), peer_out, num_peers);
 }
 
+extern "C" int merv_fused_linear_mix_multicast(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
+                                               const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
+                                               int64_t ldo, int M, int N, int rows_per_video, int max_ctas, void* mc_out, void* stream) {
+  MERV_REQUIRE(A && lda && W && ldw && K && scale && out && mc_out, MERV_E_ARG, "merv_fused_linear_mix_multicast: NULL pointer");
+  MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "merv_fused_linear_mix_multicast: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
+  MERV_REQUIRE(M >= 0 && N > 0 && rows_per_video > 0 && M % rows_per_video == 0, MERV_E_SHAPE,
+               "merv_fused_linear_mix_multicast: M=%d N=%d rows_per_video=%d", M, N, rows_per_video);
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  GemmSegment seg[MERV_MAX_SEGMENTS];
+  for (int s = 0; s < nseg; ++s) seg[s] = GemmSegment{A[s], lda[s], W[s], ldw[s], K[s]};
+  return launch_gemm_tcgen05(seg, nseg, scale, bias_mix, rows_per_video, nullptr, MERV_ACT_NONE, nullptr, nullptr, out, ldo, 0, M, N, max_ctas,
+                             static_cast<cudaStream_t>(stream), nullptr, 0, false, mc_out);
+}
+
 extern "C" int merv_fused_linear_mix(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                                      const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
                                      int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas, void* stream) {

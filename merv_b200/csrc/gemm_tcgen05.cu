@@ -72,6 +72,9 @@ struct GemmParams {
   __nv_bfloat16* Y;
   long long ldy;
   int m_blocks, n_blocks;
+  // fused all-gather through the NVSwitch multicast mapping: when set, every output box is written ONCE with multimem.st to this
+  // address (replicated by the switch into every rank's buffer, the local one included) and no TMA store is issued
+  __nv_bfloat16* mc_out;
   int num_out;   // destinations of every output tile: 1 (local) + peers' buffers over NVLink (fused all-gather)
   int out_flat;  // 1: Y is one contiguous [M, N] matrix (output map = [1, M, N]); 0: [videos, rows_per_video, N] with a batch stride
 };
@@ -138,6 +141,16 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4_g(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+// one 16-byte store to a multicast (multimem) address: the NVSwitch replicates it into the mapped buffer of every rank
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
 __device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -413,6 +426,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
           }
           sts_v4(my_row + ((uint32_t(c8) ^ sw) << 4), packed);
         }
+        if (p.mc_out != nullptr) {
+          // multicast all-gather: the group's 128 threads copy the staged box to the multicast address, 16 bytes each, a quarter
+          // warp per 128-byte (64-byte) row: coalesced rows, conflict-free shared reads, ONE NVLink egress write per byte
+          named_bar_sync(1 + h, 128);
+          const int tg = (q * 32 + lane);
+          const int colbase = col0 + pass * OUT_BOX_COLS;
+#pragma unroll
+          for (int i = 0; i < CHUNKS; ++i) {
+            const int idx = i * 128 + tg;
+            const int r = idx / CHUNKS, c = idx % CHUNKS;
+            const uint32_t rsw = kWide ? (uint32_t(r) & 7u) : (uint32_t(r >> 1) & 3u);
+            const uint4 v = lds_v4_g(my_box + uint32_t(r) * uint32_t(OUT_BOX_COLS * 2) + ((uint32_t(c) ^ rsw) << 4));
+            if (m_base + r < p.M && colbase + c * 8 < p.N)
+              multimem_st_v4(p.mc_out + (long long)(m_base + r) * p.ldy + colbase + c * 8, v);
+          }
+          return;  // the next pass's first barrier orders these shared reads before the box is overwritten
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
         named_bar_sync(1 + h, 128);
         if (issuer && col0 + pass * OUT_BOX_COLS < p.N) {
@@ -537,7 +567,7 @@ static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl) {
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl, void* mc_out) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -552,12 +582,12 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
-  bool wide = num_extra >= 2;
+  bool wide = num_extra >= 2 || mc_out != nullptr;  // multicast stores: 128-byte rows per quarter warp
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
   MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
   if (act != MERV_ACT_NONE) {
     MERV_REQUIRE(nseg == 1 && seg_scale == nullptr, MERV_E_ARG, "gemm: an activation needs a single segment without per-video scales");
-    MERV_REQUIRE(num_extra == 0, MERV_E_ARG, "gemm: extra output destinations are only supported without an activation");
+    MERV_REQUIRE(num_extra == 0 && mc_out == nullptr, MERV_E_ARG, "gemm: extra / multicast output destinations are only supported without an activation");
     wide = false;
   }
   const int out_box_cols = wide ? Cfg<1, true>::OUT_BOX_COLS : Cfg<1, false>::OUT_BOX_COLS;
@@ -583,6 +613,9 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     MERV_REQUIRE(flat || (rows_per_video % BM == 0 && y_batch_stride % 8 == 0 && y_batch_stride >= (long long)rows_per_video * ldy), MERV_E_SHAPE,
                  "gemm: a batch-strided output needs rows_per_video %% %d == 0 and a 16-byte aligned batch stride >= rows_per_video * ldo", BM);
     p.out_flat = flat ? 1 : 0;
+    MERV_REQUIRE(mc_out == nullptr || (flat && num_extra == 0 && aligned16(mc_out)), MERV_E_ARG,
+                 "gemm: the multicast output needs a flat [M, N] destination, no unicast peers and a 16-byte aligned address");
+    p.mc_out = static_cast<__nv_bfloat16*>(mc_out);
     const unsigned long long dims[3] = {(unsigned long long)N, (unsigned long long)(flat ? M : rows_per_video), (unsigned long long)(flat ? 1 : (M / rows_per_video))};
     const unsigned long long strides[2] = {(unsigned long long)ldy * 2, (unsigned long long)(flat ? (long long)M * ldy : y_batch_stride) * 2};
     const unsigned box[3] = {(unsigned)out_box_cols, BM, 1};

@@ -966,7 +966,11 @@ class CrossAttentionAdapterLearnableQuery(nn.Module):
             scores = ops.scores_from_partials(partials, [vc[1] for vc in vcs], B, T)
             weights, bias_mix = ops.softmax_weights(scores, biases, K)
             gather.barrier()  # every rank has finished reading the previous contents of the buffers
-            ops.fused_linear_mix(acts, Ws, weights, bias_mix, T, out=gather.local_block(), peer_out_ptrs=gather.peer_block_ptrs())
+            mc = gather.multicast_block_ptr() if hasattr(gather, "multicast_block_ptr") else 0
+            if mc:  # one multimem.st per output byte, replicated by the NVSwitch into every rank's buffer (the local one included)
+                ops.fused_linear_mix(acts, Ws, weights, bias_mix, T, out=gather.local_block(), multicast_out_ptr=mc)
+            else:
+                ops.fused_linear_mix(acts, Ws, weights, bias_mix, T, out=gather.local_block(), peer_out_ptrs=gather.peer_block_ptrs())
             gather.barrier()  # every rank's stores have landed
             return gather.buf, weights.to(dtype)
         timer = ops._timer
@@ -1312,8 +1316,8 @@ class MervFusion(nn.Module):
         if ff.positional_embedding:
             ps.append(ff.pe)
         for p in self.projectors:
-            lin = p.projector.projector
-            ps += [lin.weight, lin.bias]
+            for lin, _ in p.layers():
+                ps += [lin.weight] + ([lin.bias] if lin.bias is not None else [])
         if any(_is_volatile(t) for t in ps):  # FSDP views: contents change behind a constant (data_ptr, version)
             return None
         return tuple((t.data_ptr(), _version(t)) for t in ps)

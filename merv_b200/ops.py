@@ -391,11 +391,15 @@ def softmax_mix(
 def fused_linear_mix(
     As: Sequence[torch.Tensor], Ws: Sequence[torch.Tensor], scale: torch.Tensor, bias_mix: Optional[torch.Tensor],
     rows_per_video: int, out: Optional[torch.Tensor] = None, max_ctas: int = 0, peer_out_ptrs: Optional[Sequence[int]] = None,
+    multicast_out_ptr: Optional[int] = None,
 ) -> torch.Tensor:
     """out[m] = sum_s scale[m // rows_per_video, s] * (A_s[m] @ W_s.T) + bias_mix[m // rows_per_video]  (bf16, tcgen05).
 
     `peer_out_ptrs`: device addresses (peer-mapped, e.g. from torch symmetric memory) of the same [M, N] block in other
     ranks' buffers; every output tile is then also stored there over NVLink (fused all-gather, see merv_b200.parallel).
+
+    `multicast_out_ptr`: NVSwitch multicast address of the same block (torch symmetric memory's ``multicast_ptr`` + block offset);
+    every output box is then written ONCE with multimem.st and the switch replicates it into every rank's buffer, `out` included.
 
     `out` may be a preallocated [M, N] matrix (row stride >= N) or a [B, rows_per_video, N] view with an arbitrary batch
     stride, e.g. `embeddings[:, bos:bos + T, :]` of the multimodal embedding buffer (merv.py:633-640): the prefix is then
@@ -422,6 +426,12 @@ def fused_linear_mix(
             assert out.shape == (M, N)
             ldo, batch_stride = out.stride(0), 0
         peers = list(peer_out_ptrs or [])
+        if multicast_out_ptr:
+            assert not peers and out.is_contiguous(), "multicast output: one contiguous block, no unicast peers"
+            _call('merv_fused_linear_mix', lib.merv_fused_linear_mix_multicast, ptr_array([a.data_ptr() for a in As]), i64_array([a.stride(0) for a in As]),
+                  ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]), i32_array([a.shape[1] for a in As]), len(As),
+                  scale.data_ptr(), _p(bias_mix), out.data_ptr(), N, M, N, rows_per_video, max_ctas, multicast_out_ptr, _stream())
+            return out
         _call('merv_fused_linear_mix', lib.merv_fused_linear_mix_gather, ptr_array([a.data_ptr() for a in As]), i64_array([a.stride(0) for a in As]),
               ptr_array([w.data_ptr() for w in Ws]), i64_array([w.stride(0) for w in Ws]), i32_array([a.shape[1] for a in As]), len(As),
               scale.data_ptr(), _p(bias_mix), out.data_ptr(), ldo, batch_stride, M, N, rows_per_video, max_ctas,

@@ -91,6 +91,20 @@ class SymmetricPrefixBuffer:
         self.buf = symm_mem.empty((self.world * batch_per_rank, tokens, width), dtype=torch.bfloat16, device=device)
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.block_bytes = batch_per_rank * tokens * width * 2
+        # NVSwitch multicast mapping of the buffers (NVLS): one store is replicated by the switch into every rank's buffer.
+        # 0 / absent where the fabric or driver has no multicast support; MERV_GATHER_TRANSPORT=unicast forces the peer-to-peer path.
+        import os
+
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        if os.environ.get("MERV_GATHER_TRANSPORT", "") == "unicast":
+            mc = 0
+        self.multicast_ptr = mc
+        self.transport = ("multimem.st to the NVSwitch multicast mapping (one egress write per byte)" if mc
+                          else f"unicast TMA stores to {self.world - 1} peer-mapped buffers")
+
+    def multicast_block_ptr(self) -> int:
+        """Multicast address of THIS rank's block (0 when multicast is unavailable)."""
+        return self.multicast_ptr + self.rank * self.block_bytes if self.multicast_ptr else 0
 
     def local_block(self) -> torch.Tensor:
         lo = self.rank * self.batch_per_rank
