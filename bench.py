@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[3] / configs[4] sub-records (N = 1)")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--gather-timeout", type=float, default=240.0, help="watchdog (s) around the multi-GPU gather sub-records")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -340,57 +341,6 @@ def main():
                       "note": "compare with the N=1 line's value (64 videos on one GPU): strong-scaling speed-up = this value / that value"}
             del ssets
 
-        # ---- all-gather of the fused prefixes (the only collective of the path) ---------------------------
-        gather = None
-        if world > 1 and not args.no_gather:
-            gather = {}
-            from merv_b200.parallel import SymmetricPrefixBuffer, all_gather_prefix
-
-            for name, Bg in (("strong_shards", GLOBAL_BATCH // world if GLOBAL_BATCH % world == 0 else 0), ("weak_shards", B)):
-                if Bg <= 0:
-                    continue
-                rec = {"batch_per_gpu": Bg, "gathered_videos": Bg * world, "recv_bytes_per_gpu": (world - 1) * Bg * BYTES_OUT}
-                try:
-                    gsets = sets if Bg == B else make_sets(Bg, 4, seed0=207)
-                    res = {}
-
-                    def g_compute(i):
-                        res["o"], _ = module(gsets[i % len(gsets)])
-
-                    def g_nccl(i):
-                        o, _ = module(gsets[i % len(gsets)])
-                        res["g"] = all_gather_prefix(o, Bg * world)
-
-                    def g_only(i):
-                        res["g"] = all_gather_prefix(res["o"], Bg * world)
-
-                    n_g = int(min(200, max(10, 100.0 / (0.03 * Bg * world))))
-                    rec["steps"] = n_g
-                    rec["compute_ms"], _ = timed(g_compute, n_g, warmup=3, clocks=False)
-                    rec["nccl_allgather_only_ms"], _ = timed(g_only, n_g, warmup=3, clocks=False)
-                    rec["compute_then_nccl_ms"], rec["clocks"] = timed(g_nccl, n_g, warmup=3)
-                    buf = SymmetricPrefixBuffer(Bg, OUT_TOKENS, LLM_DIM, device=dev)
-
-                    def g_fused(i):
-                        res["f"], _ = module(gsets[i % len(gsets)], gather=buf)
-
-                    g_nccl(0)
-                    g_fused(0)
-                    torch.cuda.synchronize()
-                    same = torch.tensor([1 if torch.equal(res["f"], res["g"]) else 0], device=dev)
-                    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-                    rec["fused_bit_identical_to_nccl_on_all_ranks"] = bool(same.item())
-                    rec["fused_gemm_allgather_ms"], _ = timed(g_fused, n_g, warmup=3, clocks=False)
-                    rec["fused_egress_GBps_per_gpu"] = rec["recv_bytes_per_gpu"] / rec["fused_gemm_allgather_ms"] / 1e6
-                    rec["fused_over_compute"] = rec["fused_gemm_allgather_ms"] / rec["compute_ms"]
-                    rec["transport"] = getattr(buf, "transport", "unicast TMA stores to peer-mapped buffers")
-                    del buf, res
-                    if Bg != B:
-                        del gsets
-                except Exception as e:  # a sub-record never takes the primary line down
-                    rec["error"] = repr(e)[:300]
-                gather[name] = rec
-
         # ---- e2e: host buffers in, host buffers out, through the public host API ------------------------------------------
         e2e = None
         if not args.no_e2e:
@@ -436,171 +386,245 @@ def main():
                             "of one root complex); frac_of_h2d_limit = that copy alone / e2e step")
             del host_in, host_out, dev_out, pipe
 
+    def emit(gather):
+        """Rank 0: derive the rooflines, run the N = 1 extras and print THE line."""
+        # ---- rooflines (SURVEY.md §8d algorithmic bytes/FLOPs per video x videos per launch / measured duration) ----
+        def avg(name):
+            d = durations.get(name, [])
+            return (sum(d) / len(d)) if d else None
+
+        kernels = {}
+        pool_calls = durations.get("merv_pool3d", [])
+        pool_ms = (sum(pool_calls) / args.steps) if pool_calls else None  # per step (module-by-module mode pools each encoder separately)
+        if pool_ms:
+            gbs = (BYTES_IN + BYTES_POOLED) * B / (pool_ms * 1e-3) / 1e9
+            kernels["merv_pool3d"] = {"bound": "hbm", "ms": pool_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                                      "algorithmic_bytes": (BYTES_IN + BYTES_POOLED) * B,
+                                      "traffic": ncu_traffic_bytes("r2_prof_pool3d_tma.txt", "r1g_prof_pool3d_tma.txt") if B == 64 else None}
+        flops = FLOPS_LINEAR if args.projector == "linear" else FLOPS_GELU
+        roofline = None
+        if args.mode == "fused":
+            gemm_name = "merv_fused_linear_mix"
+            gemm_flops = (FLOPS_LINEAR if args.projector == "linear" else 4 * 2 * OUT_TOKENS * LLM_DIM * LLM_DIM) * B
+            g_ms = avg(gemm_name)
+            if g_ms:
+                tf = gemm_flops / (g_ms * 1e-3) / 1e12
+                # a 20-step timed region runs in the burst regime (boost clocks, no power cap yet): the burst cuBLAS figure is its peak;
+                # the sustained fraction is stated next to it
+                roofline = {"kernel": "gemm_bf16_tcgen05_kernel (merv_fused_linear_mix)", "bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"],
+                            "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "frac_of_sustained_peak": tf / peaks["tf_sustained"],
+                            "peak_source": peaks["source"] + " (burst cuBLAS bf16: the kernel is timed inside a short region)",
+                            "ms_per_launch": g_ms, "timing": f"CUDA events around the launch in an instrumented pass over the same {args.steps} steps "
+                                                             f"(step {ms_instr:.4f} ms with events vs {ms_step:.4f} ms in the timed region)",
+                            "traffic": ncu_traffic_bytes("r2_prof_gemm_bf16_tcgen05.txt", "r1g_prof_gemm_bf16_tcgen05.txt") if (args.projector == "linear" and B == 64) else None,
+                            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                            "algorithmic_bytes": (BYTES_POOLED + BYTES_OUT) * B + sum(LLM_DIM * c * 2 for c in DIMS)}
+                kernels[gemm_name] = roofline
+        else:
+            d = durations.get("merv_linear_bias_act", [])
+            if d:
+                per_step = sum(d) / args.steps
+                tf = flops * B / (per_step * 1e-3) / 1e12
+                roofline = {"kernel": "gemm_bf16_tcgen05_kernel (merv_linear_bias_act, all projector GEMMs of a step)", "bound": "tensor", "achieved": tf,
+                            "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "frac_of_sustained_peak": tf / peaks["tf_sustained"],
+                            "peak_source": peaks["source"] + " (burst cuBLAS bf16)", "ms_per_step": per_step, "traffic": None}
+            mix_ms = avg("merv_softmax_mix")
+            if mix_ms:
+                gbs = (4 * BYTES_Y + BYTES_OUT) * B / (mix_ms * 1e-3) / 1e9
+                kernels["merv_softmax_mix"] = {"bound": "hbm", "ms": mix_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
+        for name, d in durations.items():
+            kernels.setdefault(name, {"ms": sum(d) / len(d)})
+            kernels[name]["calls_per_step"] = len(d) / args.steps
+
+        # ---- N = 1 extras: the other BASELINE.json configs, the torch-eager comparator, the CPU baseline ----
+        configs = None
+        if world == 1 and not args.no_configs:
+            configs = {}
+            with torch.no_grad():
+                try:  # configs[3]: single-encoder SigLIP baseline (projector + spatial pool only, E = 1 mix is the identity), B = 256
+                    B4 = 256
+                    m4 = build_module([768], [16], "linear")
+                    g = torch.Generator(device=dev).manual_seed(1)
+                    x4 = [[torch.randn((B4, 16, 196, 768), generator=g, device=dev).to(torch.bfloat16)] for _ in range(2)]  # 2 x 1.23 GB > L2
+                    r4 = {}
+
+                    def step4(i):
+                        r4["o"], r4["w"] = m4(x4[i % 2])
+
+                    ms4, clk4 = timed(step4, 30, warmup=5)
+                    fl4, by4 = 2 * OUT_TOKENS * LLM_DIM * 768 * B4, (16 * 196 * 768 * 2 + BYTES_OUT) * B4
+                    configs["siglip_single_b256"] = {"workload": "single-encoder SigLIP (16 x 196 x 768) -> pool -> Linear(768, 4096), batch 256, bf16", "ms_per_step": ms4,
+                                                     "value": B4 * 1e3 / ms4, "unit": "videos/s", "TFLOPs": fl4 / ms4 / 1e9, "frac_of_burst_tensor_peak": fl4 / ms4 / 1e9 / peaks["tf_burst"],
+                                                     "compulsory_GBps": by4 / ms4 / 1e6, "weights_all_one": bool((r4["w"].float() == 1).all()), "steps": 30, "clocks": clk4}
+                    del x4, r4, m4
+                    torch.cuda.empty_cache()
+                except Exception as e:
+                    configs["siglip_single_b256"] = {"error": repr(e)[:300]}
+                try:  # configs[4]: generate — fusion prefix feeding a random-init Llama-2-7B prefill (the LLM is a library consumer)
+                    from transformers import LlamaConfig, LlamaForCausalLM
+
+                    cfg = LlamaConfig()  # defaults = Llama-2-7B (4096 / 32 layers / 32 heads / 11008 / 32000)
+                    cfg.vocab_size = 32064  # the reference pads the vocabulary to a multiple of 64 (llama2.py:74-76)
+                    with torch.device("meta"):
+                        llm = LlamaForCausalLM(cfg)
+                    llm = llm.to_empty(device=dev).to(torch.bfloat16)
+                    for p_ in llm.parameters():
+                        p_.normal_(0, 0.02)
+                    llm.eval()
+                    g = torch.Generator(device=dev).manual_seed(2)
+                    feats1 = [torch.randn((1, t, n, c), generator=g, device=dev).to(torch.bfloat16) for t, n, c in zip(TOKENS_T, PATCHES, DIMS)]
+                    ids = torch.randint(0, 32000, (1, 33), device=dev)  # BOS + 32 text tokens (no tokenizer offline)
+
+                    def prefix_only(i):
+                        module(feats1)
+
+                    def ttft(i):
+                        emb = llm.get_input_embeddings()(ids)
+                        buf, _ = module.forward_into_embeddings(feats1, emb, bos_token_length=1)  # [BOS | 1024 prefix | text], prefix written in place
+                        llm(inputs_embeds=buf, use_cache=True).logits[:, -1].argmax(-1)
+
+                    t_prefix, clk5 = timed(prefix_only, 200, warmup=10)
+                    t_ttft, _ = timed(ttft, 5, warmup=2, clocks=False)
+                    configs["generate_b1"] = {"workload": "merv-full generate, B = 1: fusion prefix -> random-init Llama-2-7B (bf16, HF transformers sdpa) prefill of 1 + 1024 + 32 tokens",
+                                              "time_to_visual_prefix_ms": t_prefix, "ttft_ms": t_ttft, "prefill_tokens": 1 + OUT_TOKENS + 32, "clocks": clk5}
+                    del llm, feats1
+                    torch.cuda.empty_cache()
+                except Exception as e:  # the LLM is only a timing sink
+                    configs["generate_b1"] = {"error": repr(e)[:300]}
+
+        # second comparator (SURVEY.md §8d "the real bar"): the reference's op sequence in PyTorch eager on this same B200
+        torch_eager = None
+        if world == 1 and not args.no_torch_eager:
+            try:
+                from oracle import torch_port
+
+                pp = [{k: v for k, v in p.projector.state_dict().items()} for p in module.projectors]
+                fp = dict(module.feature_fusion.state_dict())
+                run = lambda i: torch_port.fusion_forward(sets[i % len(sets)], pp, fp, TOKENS_T, 8, args.projector, OUT_TOKENS)  # noqa: E731
+                for i in range(3):
+                    ref_out, _ = run(i)
+                torch.cuda.synchronize()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for i in range(5):
+                    ref_out, _ = run(i)
+                t1.record()
+                torch.cuda.synchronize()
+                ms_ref = t0.elapsed_time(t1) / 5
+                with torch.inference_mode():
+                    ours_out, _ = module(sets[4 % len(sets)])
+                diff = float((ours_out.float() - ref_out.float()).abs().max() / ref_out.float().abs().max())
+                torch_eager = {"value": B / (ms_ref * 1e-3), "unit": "videos/s", "ms_per_step": ms_ref, "speedup_of_this_repo": ms_ref / ms_step,
+                               "max_rel_diff_vs_this_repo": diff,
+                               "what": "oracle/torch_port.py (the reference's ATen op sequence: permute, adaptive_avg_pool3d, F.linear, stack, mean, MHA, bmm) in torch eager bf16 on the same GPU, same inputs"}
+                del ref_out, ours_out
+            except Exception as e:  # a comparator, never a dependency
+                torch_eager = {"error": repr(e)[:200]}
+
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            # bounded sample of the same workload: ~10-20 s of CPU work (a probe pass sizes the number of timed passes)
+            _, probe_ms, _, _, _ = cpu_reference_run(args.projector, args.cpu_sample_videos, 1, 1)
+            passes = max(3, min(40, int(12e3 / max(probe_ms, 1.0))))
+            v, ms, cores, kind, what = cpu_reference_run(args.projector, args.cpu_sample_videos, passes, 1)
+            cpu_baseline = {"value": v, "unit": "videos/s", "cores": cores, "cpu": cpu_model(), "kind": kind, "what": what, "ms_per_video": 1e3 / v,
+                            "sample": f"{args.cpu_sample_videos} merv-full videos per pass (bf16), {passes} passes (~{passes * ms / 1e3:.0f} s) after 1 warm-up"}
+
+        line = {
+            "metric": "merv-full fusion videos/sec", "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "fused_tokens_per_s": value * OUT_TOKENS,
+            "path_effective_GBps_per_gpu": (BYTES_IN + BYTES_OUT) * B / (ms_step * 1e-3) / 1e9,
+            "path_TFLOPs_per_gpu": flops * B / (ms_step * 1e-3) / 1e12,
+            "path_frac_of_burst_tensor_peak": flops * B / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
+            "roofline": roofline, "kernels": kernels, "sustained": sustained, "strong": strong, "gather": gather, "configs": configs,
+            "cpu_baseline": cpu_baseline, "torch_eager_same_gpu": torch_eager, "e2e": e2e, "gpu_launches": launches,
+            "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "output_abs_mean": checksum,
+            "call": "MervFusion.forward -> one C call per step (merv_fused_forward: pool3d_tma_kernel, scores_softmax_kernel, gemm_bf16_tcgen05_kernel chained by PDL)"
+                    if args.mode == "fused" and args.projector == "linear" else "module-by-module",
+            "peaks": peaks,
+        }
+        print(json.dumps(line), flush=True)
+
+    gather = {}
+
+    def finish(gather_rec, hard_exit: bool = False):
+        if rank == 0:
+            emit(gather_rec if gather_rec else None)
+        if hard_exit:
+            sys.stdout.flush()
+            os._exit(0)
+
+    with torch.inference_mode():
+        # ---- all-gather of the fused prefixes (the only collective of the path; SURVEY.md §8e) ---------------------------
+        # Runs LAST and under a watchdog: it is the only part of the bench in which the ranks depend on each other inside a
+        # kernel (peer / multicast stores, symmetric-memory barriers).  If it does not finish in time every rank leaves and rank 0
+        # still prints the line with everything measured so far.
+        if world > 1 and not args.no_gather:
+            gather.clear()
+            watchdog = threading.Timer(args.gather_timeout, lambda: (finish({"error": f"watchdog: the gather sub-records did not finish within {args.gather_timeout} s",
+                                                                             **gather}, hard_exit=True)))
+            watchdog.daemon = True
+            watchdog.start()
+            from merv_b200.parallel import SymmetricPrefixBuffer, all_gather_prefix
+
+            for name, Bg in (("strong_shards", GLOBAL_BATCH // world if GLOBAL_BATCH % world == 0 else 0), ("weak_shards", B)):
+                if Bg <= 0:
+                    continue
+                rec = {"batch_per_gpu": Bg, "gathered_videos": Bg * world, "recv_bytes_per_gpu": (world - 1) * Bg * BYTES_OUT}
+                try:
+                    gsets = sets if Bg == B else make_sets(Bg, 4, seed0=207)
+                    res = {}
+
+                    def g_compute(i):
+                        res["o"], _ = module(gsets[i % len(gsets)])
+
+                    def g_nccl(i):
+                        o, _ = module(gsets[i % len(gsets)])
+                        res["g"] = all_gather_prefix(o, Bg * world)
+
+                    def g_only(i):
+                        res["g"] = all_gather_prefix(res["o"], Bg * world)
+
+                    n_g = int(min(200, max(10, 100.0 / (0.03 * Bg * world))))
+                    rec["steps"] = n_g
+                    rec["compute_ms"], _ = timed(g_compute, n_g, warmup=3, clocks=False)
+                    rec["nccl_allgather_only_ms"], _ = timed(g_only, n_g, warmup=3, clocks=False)
+                    rec["compute_then_nccl_ms"], rec["clocks"] = timed(g_nccl, n_g, warmup=3)
+                    buf = SymmetricPrefixBuffer(Bg, OUT_TOKENS, LLM_DIM, device=dev)
+
+                    def g_fused(i):
+                        res["f"], _ = module(gsets[i % len(gsets)], gather=buf)
+
+                    g_nccl(0)
+                    g_fused(0)
+                    torch.cuda.synchronize()
+                    same = torch.tensor([1 if torch.equal(res["f"], res["g"]) else 0], device=dev)
+                    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                    rec["fused_bit_identical_to_nccl_on_all_ranks"] = bool(same.item())
+                    rec["fused_gemm_allgather_ms"], _ = timed(g_fused, n_g, warmup=3, clocks=False)
+                    rec["fused_ingress_GBps_per_gpu"] = rec["recv_bytes_per_gpu"] / rec["fused_gemm_allgather_ms"] / 1e6
+                    rec["fused_over_compute"] = rec["fused_gemm_allgather_ms"] / rec["compute_ms"]
+                    # B200_PROFILING.md: the target of a fused compute + collective kernel is the slower of the compute and the bytes
+                    # that must cross NVLink at the measured 770 GB/s per direction per GPU (every rank RECEIVES world - 1 blocks)
+                    nvlink_ms = rec["recv_bytes_per_gpu"] / 770e9 * 1e3
+                    rec["roofline"] = {"compute_ms": rec["compute_ms"], "nvlink_ingress_ms_at_770GBps": nvlink_ms, "floor_ms": max(rec["compute_ms"], nvlink_ms),
+                                       "frac_of_floor": max(rec["compute_ms"], nvlink_ms) / rec["fused_gemm_allgather_ms"],
+                                       "bound": "nvlink ingress" if nvlink_ms > rec["compute_ms"] else "tensor"}
+                    rec["transport"] = getattr(buf, "transport", "unicast TMA stores to peer-mapped buffers")
+                    del buf, res
+                    if Bg != B:
+                        del gsets
+                except Exception as e:  # a sub-record never takes the primary line down
+                    rec["error"] = repr(e)[:300]
+                gather[name] = rec
+            watchdog.cancel()
+
+
     if world > 1:
         barrier()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- rooflines (SURVEY.md §8d algorithmic bytes/FLOPs per video x videos per launch / measured duration) ----
-    def avg(name):
-        d = durations.get(name, [])
-        return (sum(d) / len(d)) if d else None
-
-    kernels = {}
-    pool_calls = durations.get("merv_pool3d", [])
-    pool_ms = (sum(pool_calls) / args.steps) if pool_calls else None  # per step (module-by-module mode pools each encoder separately)
-    if pool_ms:
-        gbs = (BYTES_IN + BYTES_POOLED) * B / (pool_ms * 1e-3) / 1e9
-        kernels["merv_pool3d"] = {"bound": "hbm", "ms": pool_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                                  "algorithmic_bytes": (BYTES_IN + BYTES_POOLED) * B,
-                                  "traffic": ncu_traffic_bytes("r2_prof_pool3d_tma.txt", "r1g_prof_pool3d_tma.txt") if B == 64 else None}
-    flops = FLOPS_LINEAR if args.projector == "linear" else FLOPS_GELU
-    roofline = None
-    if args.mode == "fused":
-        gemm_name = "merv_fused_linear_mix"
-        gemm_flops = (FLOPS_LINEAR if args.projector == "linear" else 4 * 2 * OUT_TOKENS * LLM_DIM * LLM_DIM) * B
-        g_ms = avg(gemm_name)
-        if g_ms:
-            tf = gemm_flops / (g_ms * 1e-3) / 1e12
-            # a 20-step timed region runs in the burst regime (boost clocks, no power cap yet): the burst cuBLAS figure is its peak;
-            # the sustained fraction is stated next to it
-            roofline = {"kernel": "gemm_bf16_tcgen05_kernel (merv_fused_linear_mix)", "bound": "tensor", "achieved": tf, "peak": peaks["tf_burst"],
-                        "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "frac_of_sustained_peak": tf / peaks["tf_sustained"],
-                        "peak_source": peaks["source"] + " (burst cuBLAS bf16: the kernel is timed inside a short region)",
-                        "ms_per_launch": g_ms, "timing": f"CUDA events around the launch in an instrumented pass over the same {args.steps} steps "
-                                                         f"(step {ms_instr:.4f} ms with events vs {ms_step:.4f} ms in the timed region)",
-                        "traffic": ncu_traffic_bytes("r2_prof_gemm_bf16_tcgen05.txt", "r1g_prof_gemm_bf16_tcgen05.txt") if (args.projector == "linear" and B == 64) else None,
-                        "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                        "algorithmic_bytes": (BYTES_POOLED + BYTES_OUT) * B + sum(LLM_DIM * c * 2 for c in DIMS)}
-            kernels[gemm_name] = roofline
-    else:
-        d = durations.get("merv_linear_bias_act", [])
-        if d:
-            per_step = sum(d) / args.steps
-            tf = flops * B / (per_step * 1e-3) / 1e12
-            roofline = {"kernel": "gemm_bf16_tcgen05_kernel (merv_linear_bias_act, all projector GEMMs of a step)", "bound": "tensor", "achieved": tf,
-                        "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "frac_of_sustained_peak": tf / peaks["tf_sustained"],
-                        "peak_source": peaks["source"] + " (burst cuBLAS bf16)", "ms_per_step": per_step, "traffic": None}
-        mix_ms = avg("merv_softmax_mix")
-        if mix_ms:
-            gbs = (4 * BYTES_Y + BYTES_OUT) * B / (mix_ms * 1e-3) / 1e9
-            kernels["merv_softmax_mix"] = {"bound": "hbm", "ms": mix_ms, "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]}
-    for name, d in durations.items():
-        kernels.setdefault(name, {"ms": sum(d) / len(d)})
-        kernels[name]["calls_per_step"] = len(d) / args.steps
-
-    # ---- N = 1 extras: the other BASELINE.json configs, the torch-eager comparator, the CPU baseline ----
-    configs = None
-    if world == 1 and not args.no_configs:
-        configs = {}
-        with torch.no_grad():
-            try:  # configs[3]: single-encoder SigLIP baseline (projector + spatial pool only, E = 1 mix is the identity), B = 256
-                B4 = 256
-                m4 = build_module([768], [16], "linear")
-                g = torch.Generator(device=dev).manual_seed(1)
-                x4 = [[torch.randn((B4, 16, 196, 768), generator=g, device=dev).to(torch.bfloat16)] for _ in range(2)]  # 2 x 1.23 GB > L2
-                r4 = {}
-
-                def step4(i):
-                    r4["o"], r4["w"] = m4(x4[i % 2])
-
-                ms4, clk4 = timed(step4, 30, warmup=5)
-                fl4, by4 = 2 * OUT_TOKENS * LLM_DIM * 768 * B4, (16 * 196 * 768 * 2 + BYTES_OUT) * B4
-                configs["siglip_single_b256"] = {"workload": "single-encoder SigLIP (16 x 196 x 768) -> pool -> Linear(768, 4096), batch 256, bf16", "ms_per_step": ms4,
-                                                 "value": B4 * 1e3 / ms4, "unit": "videos/s", "TFLOPs": fl4 / ms4 / 1e9, "frac_of_burst_tensor_peak": fl4 / ms4 / 1e9 / peaks["tf_burst"],
-                                                 "compulsory_GBps": by4 / ms4 / 1e6, "weights_all_one": bool((r4["w"].float() == 1).all()), "steps": 30, "clocks": clk4}
-                del x4, r4, m4
-                torch.cuda.empty_cache()
-            except Exception as e:
-                configs["siglip_single_b256"] = {"error": repr(e)[:300]}
-            try:  # configs[4]: generate — fusion prefix feeding a random-init Llama-2-7B prefill (the LLM is a library consumer)
-                from transformers import LlamaConfig, LlamaForCausalLM
-
-                cfg = LlamaConfig()  # defaults = Llama-2-7B (4096 / 32 layers / 32 heads / 11008 / 32000)
-                cfg.vocab_size = 32064  # the reference pads the vocabulary to a multiple of 64 (llama2.py:74-76)
-                with torch.device("meta"):
-                    llm = LlamaForCausalLM(cfg)
-                llm = llm.to_empty(device=dev).to(torch.bfloat16)
-                for p_ in llm.parameters():
-                    p_.normal_(0, 0.02)
-                llm.eval()
-                g = torch.Generator(device=dev).manual_seed(2)
-                feats1 = [torch.randn((1, t, n, c), generator=g, device=dev).to(torch.bfloat16) for t, n, c in zip(TOKENS_T, PATCHES, DIMS)]
-                ids = torch.randint(0, 32000, (1, 33), device=dev)  # BOS + 32 text tokens (no tokenizer offline)
-
-                def prefix_only(i):
-                    module(feats1)
-
-                def ttft(i):
-                    emb = llm.get_input_embeddings()(ids)
-                    buf, _ = module.forward_into_embeddings(feats1, emb, bos_token_length=1)  # [BOS | 1024 prefix | text], prefix written in place
-                    llm(inputs_embeds=buf, use_cache=True).logits[:, -1].argmax(-1)
-
-                t_prefix, clk5 = timed(prefix_only, 200, warmup=10)
-                t_ttft, _ = timed(ttft, 5, warmup=2, clocks=False)
-                configs["generate_b1"] = {"workload": "merv-full generate, B = 1: fusion prefix -> random-init Llama-2-7B (bf16, HF transformers sdpa) prefill of 1 + 1024 + 32 tokens",
-                                          "time_to_visual_prefix_ms": t_prefix, "ttft_ms": t_ttft, "prefill_tokens": 1 + OUT_TOKENS + 32, "clocks": clk5}
-                del llm, feats1
-                torch.cuda.empty_cache()
-            except Exception as e:  # the LLM is only a timing sink
-                configs["generate_b1"] = {"error": repr(e)[:300]}
-
-    # second comparator (SURVEY.md §8d "the real bar"): the reference's op sequence in PyTorch eager on this same B200
-    torch_eager = None
-    if world == 1 and not args.no_torch_eager:
-        try:
-            from oracle import torch_port
-
-            pp = [{k: v for k, v in p.projector.state_dict().items()} for p in module.projectors]
-            fp = dict(module.feature_fusion.state_dict())
-            run = lambda i: torch_port.fusion_forward(sets[i % len(sets)], pp, fp, TOKENS_T, 8, args.projector, OUT_TOKENS)  # noqa: E731
-            for i in range(3):
-                ref_out, _ = run(i)
-            torch.cuda.synchronize()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for i in range(5):
-                ref_out, _ = run(i)
-            t1.record()
-            torch.cuda.synchronize()
-            ms_ref = t0.elapsed_time(t1) / 5
-            with torch.inference_mode():
-                ours_out, _ = module(sets[4 % len(sets)])
-            diff = float((ours_out.float() - ref_out.float()).abs().max() / ref_out.float().abs().max())
-            torch_eager = {"value": B / (ms_ref * 1e-3), "unit": "videos/s", "ms_per_step": ms_ref, "speedup_of_this_repo": ms_ref / ms_step,
-                           "max_rel_diff_vs_this_repo": diff,
-                           "what": "oracle/torch_port.py (the reference's ATen op sequence: permute, adaptive_avg_pool3d, F.linear, stack, mean, MHA, bmm) in torch eager bf16 on the same GPU, same inputs"}
-            del ref_out, ours_out
-        except Exception as e:  # a comparator, never a dependency
-            torch_eager = {"error": repr(e)[:200]}
-
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        # bounded sample of the same workload: ~10-20 s of CPU work (a probe pass sizes the number of timed passes)
-        _, probe_ms, _, _, _ = cpu_reference_run(args.projector, args.cpu_sample_videos, 1, 1)
-        passes = max(3, min(40, int(12e3 / max(probe_ms, 1.0))))
-        v, ms, cores, kind, what = cpu_reference_run(args.projector, args.cpu_sample_videos, passes, 1)
-        cpu_baseline = {"value": v, "unit": "videos/s", "cores": cores, "cpu": cpu_model(), "kind": kind, "what": what, "ms_per_video": 1e3 / v,
-                        "sample": f"{args.cpu_sample_videos} merv-full videos per pass (bf16), {passes} passes (~{passes * ms / 1e3:.0f} s) after 1 warm-up"}
-
-    line = {
-        "metric": "merv-full fusion videos/sec", "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(args, world),
-        "fused_tokens_per_s": value * OUT_TOKENS,
-        "path_effective_GBps_per_gpu": (BYTES_IN + BYTES_OUT) * B / (ms_step * 1e-3) / 1e9,
-        "path_TFLOPs_per_gpu": flops * B / (ms_step * 1e-3) / 1e12,
-        "path_frac_of_burst_tensor_peak": flops * B / (ms_step * 1e-3) / 1e12 / peaks["tf_burst"],
-        "roofline": roofline, "kernels": kernels, "sustained": sustained, "strong": strong, "gather": gather, "configs": configs,
-        "cpu_baseline": cpu_baseline, "torch_eager_same_gpu": torch_eager, "e2e": e2e, "gpu_launches": launches,
-        "gpu_launches_per_step": launches / args.steps, "clocks": clocks, "output_abs_mean": checksum,
-        "call": "MervFusion.forward -> one C call per step (merv_fused_forward: pool3d_tma_kernel, scores_softmax_kernel, gemm_bf16_tcgen05_kernel chained by PDL)"
-                if args.mode == "fused" and args.projector == "linear" else "module-by-module",
-        "peaks": peaks,
-    }
-    print(json.dumps(line), flush=True)
+    finish(gather)
     if world > 1:
         dist.destroy_process_group()
 
