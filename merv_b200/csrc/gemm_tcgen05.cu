@@ -582,10 +582,9 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
-  // Multicast stores leave each GPU ONCE (block bytes / step time ~ 0.3 TB/s of egress at merv-full sizes), so the 64-byte rows
-  // of the standard boxes are enough for them and the ring keeps all its stages; what bounds the multicast gather is every
-  // GPU's INGRESS of the other ranks' blocks.
-  bool wide = num_extra >= 2;
+  // multimem.st is packetised per contiguous run like the peer stores: measured at 2 GPUs, 64 videos each, the multicast gather takes
+  // 2.15 ms with 128-byte rows and 2.75 ms with 64-byte rows (compute alone 1.71 ms) — so the multicast variant uses the wide boxes too
+  bool wide = num_extra >= 2 || mc_out != nullptr;
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
   MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
   if (act != MERV_ACT_NONE) {

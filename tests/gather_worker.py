@@ -37,11 +37,8 @@ def main():
         with torch.no_grad():
             m.feature_fusion.Q.mul_(32.0)
         m = m.to(device=dev, dtype=torch.bfloat16).eval().requires_grad_(False)
-        for transport in ("auto", "unicast"):
-            if transport == "unicast":
-                os.environ["MERV_GATHER_TRANSPORT"] = "unicast"
-            else:
-                os.environ.pop("MERV_GATHER_TRANSPORT", None)
+        for transport in ("multicast", "unicast"):  # forced either way: the automatic choice depends on the number of ranks
+            os.environ["MERV_GATHER_TRANSPORT"] = transport
             buf = SymmetricPrefixBuffer(c["B"], c["tok"], c["llm"], device=dev)
             same = True
             with torch.inference_mode():
