@@ -30,7 +30,16 @@ def run_ranks(script: str, nproc: int, *args: str, timeout: int = 900):
            "--master-port", str(_free_port()), os.path.join(REPO, "tests", script), *args]
     env = dict(os.environ, OMP_NUM_THREADS="2", PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=REPO, env=env)
-    lines = [json.loads(l.split(" ", 1)[1]) for l in r.stdout.splitlines() if l.startswith(("FSDP_WORKER ", "GATHER_WORKER "))]
+    # the ranks share one stdout and their reports can land on the same line: scan for every "<TAG> {json}" occurrence
+    lines, dec, pos = [], json.JSONDecoder(), 0
+    while True:
+        hits = [i for i in (r.stdout.find(tag, pos) for tag in ("FSDP_WORKER ", "GATHER_WORKER ")) if i >= 0]
+        if not hits:
+            break
+        start = r.stdout.index("{", min(hits))
+        obj, end = dec.raw_decode(r.stdout, start)
+        lines.append(obj)
+        pos = end
     assert r.returncode == 0, f"ranks failed (rc {r.returncode}):\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}"
     assert len(lines) == nproc, f"expected one report per rank, got {len(lines)}:\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}"
     return lines
