@@ -92,15 +92,18 @@ class SymmetricPrefixBuffer:
         self.handle = symm_mem.rendezvous(self.buf, group)
         self.block_bytes = batch_per_rank * tokens * width * 2
         # NVSwitch multicast mapping of the buffers (NVLS): one store is replicated by the switch into every rank's buffer.
-        # 0 / absent where the fabric or driver has no multicast support; MERV_GATHER_TRANSPORT=unicast forces the peer-to-peer path.
+        # 0 / absent where the fabric or driver has no multicast support.
         import os
 
         mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
-        # With ONE peer a unicast TMA store per box is already a single egress write and keeps the GEMM's 4-stage ring (measured at
-        # 2 GPUs x 64 videos: unicast 1.93 ms, multicast 2.15 ms, compute alone 1.85 ms); from two peers on the switch-replicated
-        # store sends each byte once instead of (ranks - 1) times.  MERV_GATHER_TRANSPORT=unicast|multicast overrides.
+        # Measured on B200 x 2 / x 8 (64 videos per rank, compute alone 1.75-1.85 ms): unicast 1.93 / 6.33 ms, multicast 2.15 / 6.68 ms.
+        # The all-gather is bound by every GPU's NVLink INGRESS (world - 1 blocks; NCCL's own all-gather of the same bytes takes
+        # 5.9 ms at 8 GPUs), not by its egress: unicast loads both directions of the full-duplex links equally, while a multicast
+        # store also loops the sender's own block back through the switch (world instead of world - 1 blocks of ingress) and pays
+        # the per-thread multimem.st issue.  So unicast TMA stores are the default; MERV_GATHER_TRANSPORT=multicast selects the
+        # switch-replicated path (kept tested: it is the right choice where egress, not ingress, is the scarce direction).
         choice = os.environ.get("MERV_GATHER_TRANSPORT", "")
-        if choice == "unicast" or (choice != "multicast" and self.world < 3):
+        if choice != "multicast":
             mc = 0
         self.multicast_ptr = mc
         self.transport = ("multimem.st to the NVSwitch multicast mapping (one egress write per byte)" if mc
