@@ -533,16 +533,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-// Which variant runs.  Measured on B200 (65536 x 4096, bf16): the CTA pair is 5 % faster for a plain K = 1024 GEMM
-// (1288 vs 1229 TFLOP/s: less L2->SM and shared-memory operand traffic) but 2 % slower for the fused 4-segment
-// K = 3584 GEMM (1393 vs 1421), which is power-bound, not operand-bound; for the fused K = 16384 GEMM it is 3 % faster
-// again.  So: pair for plain GEMMs (activated or not) and very deep fused ones, single CTA otherwise; MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
-static int gemm_cta_group(int nseg, int act, long long total_k) {
+// Which variant runs.  Round-2 measurements on B200 (65536 x 4096 bf16, 24 back-to-back calls from an idle GPU,
+// scripts/gpu_gemm_lab.py -> profiles/r2_gemm_lab.json): the CTA pair wins everywhere — fused 4-segment K = 3584: 1.315 ms (1464 TFLOP/s)
+// vs 1.377 (1398) for the single CTA; plain K = 1024: 0.424 (1297) vs 0.454 (1210); + GELU 0.452 vs 0.463; M = 262144, K = 768: 1.372 vs
+// 1.378.  (Round 1 had the fused GEMM 2 % slower on the pair; that was measured inside long power-capped loops.)  cuBLAS on the same
+// shapes: 1.225 / 0.402 / - / 1.265 ms.  MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
+static int gemm_cta_group(int M) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
-  if (nseg == 1) return 2;  // also with the GELU epilogue since it runs on the packed fp32 pipe (1262 vs 1228 TFLOP/s at K = 1024)
-  return total_k >= 8192 ? 2 : 1;  // fused K = 4 x 4096 (second MLP layer): pair 6.30 ms vs 6.47; fused K = 3584: single wins
+  return M > BM ? 2 : 1;  // a pair computes 256 rows: with at most 128 rows its second CTA would only multiply padding
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
@@ -578,7 +578,8 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   MERV_REQUIRE((rowdot_vec == nullptr) == (rowdot_out == nullptr), MERV_E_ARG, "gemm: rowdot_vec and rowdot_out go together");
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
-  const int ctas = gemm_cta_group(nseg, act, total_k);
+  (void)total_k;
+  const int ctas = gemm_cta_group(M);
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
