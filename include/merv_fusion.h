@@ -100,6 +100,16 @@ int merv_linear_bias_act(const void* A, int64_t lda, const void* W, int64_t ldw,
                          int64_t ldy, int M, int N, int K, int act, int dtype, const float* rowdot_vec,
                          float* rowdot_out, void* stream);
 
+/* The same GEMM with either operand given TRANSPOSED in memory (bf16, tensor cores only): a_mn != 0: A is stored as [K, M] row-major
+ * (lda = its row stride), w_mn != 0: W is stored as [K, N] row-major.  tcgen05 reads MN-major operands straight from shared memory
+ * (TMA boxes of 64 M / N elements x 64 k-rows, 128-byte swizzle), so the backward of a Linear needs no transposed copies:
+ *   dW [N_out, K_in] = dY^T X : A = dY [M, N_out] with a_mn, W-operand = X [M, K_in] with w_mn, contraction over the M tokens
+ *   dX [M, K_in]     = dY W   : A = dY (K-major),           W-operand = W [N_out, K_in] with w_mn, contraction over N_out
+ * (autograd of merv/util/nn_utils.py:31-32,46-55 inside the training step, base_strategy.py:240-241).  With both operands MN-major K
+ * may be any positive number (the k tail is zero-filled); otherwise K % 8 == 0. */
+int merv_gemm_ex(const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, int w_mn, const void* bias, void* Y, int64_t ldy,
+                 int M, int N, int K, int act, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * The learnable-query "cross attention" collapses to a dot product with an input-independent vector
  * (SURVEY.md §3.3): weights[b,:] = softmax_e(u . mean_t V[b,e,t,:]),
@@ -307,6 +317,10 @@ int merv_video_colsum(const void* x, float* out, int B, int T, int K, int64_t ld
                       void* stream);
 int merv_pair_dot_chunks(void);
 int merv_pair_dot(const void* x, const void* y, float* partial, int B, int64_t n, int dtype, void* stream);
+/* merv_pair_dot that also writes y_scaled[b, i] = scale[b * scale_stride] * y[b, i] in the same pass: w_e (.) P_e, the MN-major
+ * W-operand of dW_e = dOut^T (w_e (.) P_e) for merv_gemm_ex (no transposed copy of P_e, and P_e is read once for both). */
+int merv_pair_dot_scale(const void* x, const void* y, float* partial, const float* scale, int64_t scale_stride, void* y_scaled,
+                        int B, int64_t n, int dtype, void* stream);
 int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,
                             int64_t scale_stride, int rows_per_scale, int dtype, void* stream);
 size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* desc);

@@ -21,7 +21,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(REPO, "include")
 LIB = os.path.join(PKG, "libmerv_fusion.so")
 OBJ_DIR = os.path.join(PKG, "csrc", "build")
-SOURCES = ["api.cu", "pool3d.cu", "mix.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "backward.cu", "norm.cu", "attention.cu"]
+SOURCES = ["api.cu", "pool3d.cu", "mix.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "backward.cu", "norm.cu", "attention.cu", "attention_tcgen05.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

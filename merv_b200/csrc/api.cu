@@ -152,6 +152,17 @@ extern "C" int merv_linear_bias_act(const void* A, int64_t lda, const void* W, i
   return launch_gemm_simt(A, lda, W, ldw, bias, Y, ldy, M, N, K, act, dtype, s);
 }
 
+extern "C" int merv_gemm_ex(const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, int w_mn, const void* bias, void* Y, int64_t ldy,
+                            int M, int N, int K, int act, void* stream) {
+  MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_DTYPE, "merv_gemm_ex: unknown activation %d", act);
+  MERV_REQUIRE(A && W && Y, MERV_E_ARG, "merv_gemm_ex: NULL operand");
+  MERV_REQUIRE(M >= 0 && N > 0 && K > 0 && ldy >= N, MERV_E_SHAPE, "merv_gemm_ex: M=%d N=%d K=%d ldy=%lld", M, N, K, (long long)ldy);
+  if (int rc = require_sm100()) return rc;
+  if (M == 0) return MERV_OK;
+  GemmSegment seg = {A, lda, W, ldw, K, a_mn ? 1 : 0, w_mn ? 1 : 0};
+  return launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, M, bias, act, nullptr, nullptr, Y, ldy, 0, M, N, 0, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int merv_fused_linear_mix_gather(const void* const* A, const int64_t* lda, const void* const* W, const int64_t* ldw,
                                             const int32_t* K, int nseg, const float* scale, const float* bias_mix, void* out,
                                             int64_t ldo, int64_t out_batch_stride, int M, int N, int rows_per_video, int max_ctas,

@@ -257,6 +257,10 @@ extern "C" int merv_cross_attention(const void* q, int64_t ldq, int64_t q_batch_
   if (int rc = require_sm100()) return rc;
   if (batches == 0) return MERV_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // bf16: both contractions on the tensor cores whenever the frame fits the tcgen05 kernel's tile (MERV_ATTN_IMPL=simt forces this
+  // file's CUDA-core kernel, which stays the fp32 parity path and the fallback for other shapes)
+  if (dtype == MERV_BF16 && attention_tcgen05_supported(n_q, n_kv, heads, head_dim, ldq, q_batch_stride, ldkv, ldo))
+    return launch_attention_tcgen05(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);
   if (dtype == MERV_BF16)
     return launch_attention<__nv_bfloat16>(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);
   return launch_attention<float>(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);

@@ -357,11 +357,16 @@ __global__ void __launch_bounds__(256) video_colsum_kernel(const T* __restrict__
 
 // ---- partial[b, chunk] = sum over the chunk of x[b, i] * y[b, i]  (both [B, n] contiguous) --------------------------------
 constexpr int kPairDotChunks = 32;
+// Optionally also writes ys[b, i] = scale[b * scale_stride] * y[b, i] in the same pass (the per-video mixing weight applied to the pooled
+// tokens: the MN-major W-operand of dW_e = dOut^T (w_e (.) P_e)), so P_e is read once for both.
 template <typename T>
-__global__ void __launch_bounds__(256) pair_dot_kernel(const T* __restrict__ x, const T* __restrict__ y, float* __restrict__ partial, long long nvec) {
+__global__ void __launch_bounds__(256) pair_dot_kernel(const T* __restrict__ x, const T* __restrict__ y, float* __restrict__ partial, long long nvec,
+                                                       const float* __restrict__ scale = nullptr, long long scale_stride = 0, T* __restrict__ ys = nullptr) {
   constexpr int VEC = Vec16<T>::kN;
   __shared__ float red[32];
   const int chunk = blockIdx.x, b = blockIdx.y;
+  const float sc = scale != nullptr ? scale[(long long)b * scale_stride] : 1.0f;
+  T* ysb = ys != nullptr ? ys + (long long)b * nvec * VEC : nullptr;
   const long long per = (nvec + kPairDotChunks - 1) / kPairDotChunks;
   const long long v0 = chunk * per, v1 = v0 + per < nvec ? v0 + per : nvec;
   const T* xb = x + (long long)b * nvec * VEC;
@@ -381,10 +386,20 @@ __global__ void __launch_bounds__(256) pair_dot_kernel(const T* __restrict__ x, 
     Vec16<T>::unpack(b1, fb);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc = fmaf(fa[c], fb[c], acc);
+    if (ysb != nullptr) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) fb[c] *= sc;
+      stg_na_v4(ysb + v * VEC, Vec16<T>::pack(fb));
+    }
     Vec16<T>::unpack(a2, fa);
     Vec16<T>::unpack(b2, fb);
 #pragma unroll
     for (int c = 0; c < VEC; ++c) acc = fmaf(fa[c], fb[c], acc);
+    if (ysb != nullptr && has2) {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) fb[c] *= sc;
+      stg_na_v4(ysb + v2 * VEC, Vec16<T>::pack(fb));
+    }
   }
   acc = bwd_block_sum<256>(acc, red);
   if (threadIdx.x == 0) partial[(long long)b * kPairDotChunks + chunk] = acc;
@@ -808,22 +823,29 @@ extern "C" int merv_video_colsum(const void* x, float* out, int B, int T, int K,
 
 extern "C" int merv_pair_dot_chunks(void) { return kPairDotChunks; }
 
-extern "C" int merv_pair_dot(const void* x, const void* y, float* partial, int B, int64_t n, int dtype, void* stream) {
+extern "C" int merv_pair_dot_scale(const void* x, const void* y, float* partial, const float* scale, int64_t scale_stride, void* y_scaled, int B,
+                                   int64_t n, int dtype, void* stream) {
   MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_pair_dot: unknown dtype %d", dtype);
   MERV_REQUIRE(x && y && partial, MERV_E_ARG, "merv_pair_dot: NULL pointer");
+  MERV_REQUIRE((scale == nullptr) == (y_scaled == nullptr), MERV_E_ARG, "merv_pair_dot_scale: scale and y_scaled go together");
   const int vec = dtype == MERV_BF16 ? 8 : 4;
   MERV_REQUIRE(B >= 0 && n > 0 && n % vec == 0, MERV_E_SHAPE, "merv_pair_dot: B=%d n=%lld", B, (long long)n);
-  MERV_REQUIRE(aligned16(x) && aligned16(y), MERV_E_ALIGN, "merv_pair_dot: operands must be 16-byte aligned");
+  MERV_REQUIRE(aligned16(x) && aligned16(y) && (y_scaled == nullptr || aligned16(y_scaled)), MERV_E_ALIGN, "merv_pair_dot: operands must be 16-byte aligned");
   if (int rc = require_sm100()) return rc;
   if (B == 0) return MERV_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid(kPairDotChunks, B);
   if (dtype == MERV_BF16)
-    pair_dot_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, partial, n / vec);
+    pair_dot_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)y, partial, n / vec, scale, scale_stride,
+                                                        (__nv_bfloat16*)y_scaled);
   else
-    pair_dot_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)y, partial, n / vec);
+    pair_dot_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)y, partial, n / vec, scale, scale_stride, (float*)y_scaled);
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
+}
+
+extern "C" int merv_pair_dot(const void* x, const void* y, float* partial, int B, int64_t n, int dtype, void* stream) {
+  return merv_pair_dot_scale(x, y, partial, nullptr, 0, nullptr, B, n, dtype, stream);
 }
 
 extern "C" int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,

@@ -37,6 +37,11 @@ struct GemmSegment {
   const void* W;
   long long ldw;
   int K;
+  // Operand majorness.  0 (default): K-major — A is [M, K] and W is [N, K] row-major, the contraction dimension contiguous.
+  // 1: MN-major — the operand is given TRANSPOSED in memory, A as [K, M] / W as [K, N] row-major (ld = its row stride), i.e. the
+  // M / N dimension contiguous.  tcgen05 reads either form straight from shared memory, so a weight gradient dW = dY^T X or an
+  // input gradient dX = dY W needs no transposed copy of dY, X or W.
+  int a_mn = 0, b_mn = 0;
 };
 // pdl: launch with programmatic stream serialization — the kernel's prologue (barrier init, TMEM allocation, tensor-map
 // prefetch) may overlap the tail of the preceding kernel in the stream; it executes griddepcontrol.wait before touching global memory.
@@ -47,6 +52,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
 int launch_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
                                   float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
                                   cudaStream_t stream, bool pdl);
+// tcgen05 cross attention (attention_tcgen05.cu): bf16, at most 128 queries and 256 keys per frame, head_dim % 32 == 0 and <= 128
+bool attention_tcgen05_supported(int n_q, int n_kv, int heads, int hd, long long ldq, long long q_batch_stride, long long ldkv, long long ldo);
+int launch_attention_tcgen05(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, void* out, long long ldo,
+                             int batches, int n_q, int n_kv, int heads, int hd, float scale, cudaStream_t stream);
 // MERV_PDL=0 disables programmatic dependent launch inside merv_fused_forward (A/B measurements); read per call
 bool pdl_enabled();
 int launch_gemm_simt(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* Y, long long ldy,

@@ -24,12 +24,12 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tcgen05_util.cuh"
 #include "tmap.cuh"
 
 namespace merv {
 
 constexpr int BM = 128, BN = 256, BK = 64;  // BM = rows per CTA; a CTA pair (cta_group::2) computes 256 x 256
-constexpr int UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;
 // per-CTA stage: its 128 rows of A and, for a CTA pair, its half (128 rows) of the W tile
 constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the epilogue (erf-GELU, bias, row-dot) is issue/latency bound
@@ -60,6 +60,7 @@ struct GemmParams {
   int M, N;
   int nseg;
   int kblocks[MERV_MAX_SEGMENTS];
+  int a_mn_mask, b_mn_mask;  // bit s: segment s has an MN-major A / W operand (see GemmSegment)
   const float* seg_scale;  // [videos, nseg] or NULL (=1)
   const float* bias_rows;  // [videos, N] fp32 or NULL
   int rows_per_video;
@@ -86,154 +87,6 @@ struct TensorMaps {
   // destination, out[1..] the same rows of the peers' symmetric buffers (peer-mapped addresses)
   CUtensorMap out[MERV_MAX_ENCODERS];
 };
-
-// ---- PTX wrappers -----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Spin with a watchdog: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
-// hung GPU.  The timer is only read on the slow path.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) {
-      printf("merv gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-
-// L2 eviction-priority policies (the encodings createpolicy.fractional.L2::evict_{normal,last} produce for fraction 1.0)
-constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
-constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int x, int y, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-               ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ uint4 lds_v4_g(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
-  return r;
-}
-// one 16-byte store to a multicast (multimem) address: the NVSwitch replicates it into the mapped buffer of every rank
-__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-               ::"l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
-}
-__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-// ---- CTA-pair (cta_group::2) variants ----
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load issued by either CTA of a pair; completes its bytes on the LEADER's mbarrier (cluster address)
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int x, int y, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-               ::"r"(dst), "l"(map), "r"(leader_bar), "r"(x), "r"(y), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrives (once the pair's MMAs so far have completed) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// smem matrix descriptor: K-major, 128-byte swizzle, 8-row atoms of 1024 B (SBO), Blackwell descriptor version 1
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);  // start address [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                      // leading byte offset (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;              // stride byte offset [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                      // version [46,48)
-  d |= static_cast<uint64_t>(2) << 61;                      // layout type: SWIZZLE_128B
-  return d;
-}
-// instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- the kernel -------------------------------------------------------------------------------------------
 // kCtas == 1: one CTA per 128 x 256 tile.  kCtas == 2: a CTA pair (cluster 2x1, cta_group::2) per 256 x 256 tile — each CTA
@@ -314,27 +167,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar + 8 * stage, ph ^ 1u);  // own barrier: the pair's MMA commit is multicast to both CTAs
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
-            if constexpr (kCtas == 2) {
-              // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
-              if (rank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * STAGE_BYTES);
-              tma_load_2d_pair(&maps.a[s], leader_full + 8 * stage, sa, kb * BK, (m_blk * 2 + int(rank)) * BM, L2_EVICT_NORMAL);
-              tma_load_2d_pair(&maps.b[s], leader_full + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN + int(rank) * (BN / 2), L2_EVICT_LAST);
-              continue;
-            }
-            mbar_expect_tx(full_bar + 8 * stage, STAGE_BYTES);
+            const bool a_mn = (p.a_mn_mask >> s) & 1, b_mn = (p.b_mn_mask >> s) & 1;
+            const int m0 = (m_blk * kCtas + int(rank)) * BM, n0 = n_blk * BN + int(rank) * C::B_ROWS;
+            const uint32_t bar = (kCtas == 2 ? leader_full : full_bar) + 8 * stage;
+            // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
+            if (kCtas == 1 || rank == 0) mbar_expect_tx(full_bar + 8 * stage, kCtas * STAGE_BYTES);
+            auto load = [&](const CUtensorMap* map, uint32_t dst, int x, int y, uint64_t policy) {
+              if constexpr (kCtas == 2) tma_load_2d_pair(map, bar, dst, x, y, policy);
+              else tma_load_2d(map, bar, dst, x, y, policy);
+            };
             // activations stream through once per wave of tiles; the weights are re-read by every M block, so they
             // are kept in L2 preferentially (for the 4096 x 16384 second MLP layer they barely fit: 134 of 126 MB)
-            tma_load_2d(&maps.a[s], full_bar + 8 * stage, sa, kb * BK, m_blk * BM, L2_EVICT_NORMAL);
-            tma_load_2d(&maps.b[s], full_bar + 8 * stage, sa + A_BYTES, kb * BK, n_blk * BN, L2_EVICT_LAST);
+            if (!a_mn) {
+              load(&maps.a[s], sa, kb * BK, m0, L2_EVICT_NORMAL);
+            } else {  // A given as [K, M]: one [64 m x BK k] box per 64 rows of the tile
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) load(&maps.a[s], sa + j * MN_CHUNK_BYTES, m0 + 64 * j, kb * BK, L2_EVICT_NORMAL);
+            }
+            if (!b_mn) {
+              load(&maps.b[s], sa + A_BYTES, kb * BK, n0, L2_EVICT_LAST);
+            } else {
+#pragma unroll
+              for (int j = 0; j < C::B_ROWS / 64; ++j) load(&maps.b[s], sa + A_BYTES + j * MN_CHUNK_BYTES, n0 + 64 * j, kb * BK, L2_EVICT_LAST);
+            }
           }
         }
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
       // ===== MMA issuer (the leader CTA's single thread drives both SMs of a pair) =====
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN);
       uint32_t it = 0, acc_it = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+          const bool a_mn = (p.a_mn_mask >> s) & 1, b_mn = (p.b_mn_mask >> s) & 1;
+          const uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN, a_mn, b_mn);
+          // per UMMA (16 k): +32 bytes inside the swizzle atom for a K-major operand, +2 atoms of 8 k-rows for an MN-major one
+          const uint32_t a_step = a_mn ? (2048u >> 4) : 2u, b_step = b_mn ? (2048u >> 4) : 2u;
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           mbar_wait(tempty_bar + 8 * buf, aph ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
@@ -345,11 +212,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             mbar_wait(full_bar + 8 * stage, ph);
             tc_fence_after();
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
-            const uint64_t a_desc = umma_desc_sw128(sa), b_desc = umma_desc_sw128(sa + A_BYTES);
+            const uint64_t a_desc = a_mn ? umma_desc_mn_sw128(sa) : umma_desc_sw128(sa);
+            const uint64_t b_desc = b_mn ? umma_desc_mn_sw128(sa + A_BYTES) : umma_desc_sw128(sa + A_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 bytes along K inside the swizzle atom = +2 in the address field
-              if constexpr (kCtas == 2) umma_bf16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if constexpr (kCtas == 2) umma_bf16_pair(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
             }
             // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
             if constexpr (kCtas == 2) umma_commit_pair(empty_bar + 8 * stage);
@@ -538,11 +406,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 // vs 1.377 (1398) for the single CTA; plain K = 1024: 0.424 (1297) vs 0.454 (1210); + GELU 0.452 vs 0.463; M = 262144, K = 768: 1.372 vs
 // 1.378.  (Round 1 had the fused GEMM 2 % slower on the pair; that was measured inside long power-capped loops.)  cuBLAS on the same
 // shapes: 1.225 / 0.402 / - / 1.265 ms.  MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
-static int gemm_cta_group(int M) {
+// The pair only pays for wide outputs: at N = 1024 / 768 (the backward's Z_e = dOut W_e and dW_e GEMMs, 4 / 3 column blocks) it is 13-25 %
+// SLOWER than the single CTA (65536 x 1024 x 4096: 0.480 vs 0.417 ms; dW 4096 x 1024 x 65536: 0.528 vs 0.419 — profiles/r2_bwd_lab.json).
+static int gemm_cta_group(int M, int N) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
-  return M > BM ? 2 : 1;  // a pair computes 256 rows: with at most 128 rows its second CTA would only multiply padding
+  if (M <= BM) return 1;  // a pair computes 256 rows: with at most 128 rows its second CTA would only multiply padding
+  return N >= 2048 ? 2 : 1;
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
@@ -579,7 +450,7 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
   (void)total_k;
-  const int ctas = gemm_cta_group(M);
+  const int ctas = gemm_cta_group(M, N);
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
@@ -601,11 +472,27 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   for (int s = 0; s < nseg; ++s) {
     const GemmSegment& g = seg[s];
     MERV_REQUIRE(g.A && g.W, MERV_E_ARG, "gemm: segment %d has a NULL operand", s);
-    MERV_REQUIRE(g.K > 0 && g.K % 8 == 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && g.lda >= g.K && g.ldw >= g.K, MERV_E_ALIGN,
-                 "gemm: segment %d: K=%d lda=%lld ldw=%lld must be multiples of 8 with ld >= K", s, g.K, g.lda, g.ldw);
+    MERV_REQUIRE(g.K > 0 && g.lda % 8 == 0 && g.ldw % 8 == 0 && (g.K % 8 == 0 || (g.a_mn && g.b_mn)), MERV_E_ALIGN,
+                 "gemm: segment %d: K=%d lda=%lld ldw=%lld: leading dimensions must be multiples of 8, and so must K unless both operands are MN-major",
+                 s, g.K, g.lda, g.ldw);
     MERV_REQUIRE(aligned16(g.A) && aligned16(g.W), MERV_E_ALIGN, "gemm: segment %d: operands must be 16-byte aligned", s);
-    if (int rc = make_tmap(&maps.a[s], g.A, M, g.K, g.lda, BM)) return rc;
-    if (int rc = make_tmap(&maps.b[s], g.W, N, g.K, g.ldw, BN / ctas)) return rc;  // a CTA of a pair loads half of the W tile
+    // K-major: tensor [rows = M (N), cols = K], box [BM (BN / ctas) x BK].  MN-major: tensor [rows = K, cols = M (N)], box [BK x 64]
+    if (g.a_mn) {
+      MERV_REQUIRE(g.lda >= M, MERV_E_ALIGN, "gemm: segment %d: an MN-major A ([K, M]) needs lda >= M", s);
+      if (int rc = make_tmap(&maps.a[s], g.A, g.K, M, g.lda, BK, 64)) return rc;
+      p.a_mn_mask |= 1 << s;
+    } else {
+      MERV_REQUIRE(g.lda >= g.K, MERV_E_ALIGN, "gemm: segment %d: lda=%lld < K=%d", s, g.lda, g.K);
+      if (int rc = make_tmap(&maps.a[s], g.A, M, g.K, g.lda, BM)) return rc;
+    }
+    if (g.b_mn) {
+      MERV_REQUIRE(g.ldw >= N, MERV_E_ALIGN, "gemm: segment %d: an MN-major W ([K, N]) needs ldw >= N", s);
+      if (int rc = make_tmap(&maps.b[s], g.W, g.K, N, g.ldw, BK, 64)) return rc;
+      p.b_mn_mask |= 1 << s;
+    } else {
+      MERV_REQUIRE(g.ldw >= g.K, MERV_E_ALIGN, "gemm: segment %d: ldw=%lld < K=%d", s, g.ldw, g.K);
+      if (int rc = make_tmap(&maps.b[s], g.W, N, g.K, g.ldw, BN / ctas)) return rc;  // a CTA of a pair loads half of the W tile
+    }
     p.kblocks[s] = (g.K + BK - 1) / BK;  // the K tail is zero-filled by TMA
   }
   for (int s = nseg; s < MERV_MAX_SEGMENTS; ++s) { maps.a[s] = maps.a[0]; maps.b[s] = maps.b[0]; }

@@ -168,11 +168,18 @@ class _ProjectorFn(torch.autograd.Function):
             if zs[i] is not None:
                 g = ops.gelu(zs[i].reshape(g.shape), g)  # dZ_i
             x2 = xs[i].reshape(-1, xs[i].shape[-1])
-            dW, _ = ops.linear_bias_act(ops.transpose(g, pad=True), ops.transpose(x2, pad=True), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
+            tc = g.dtype == torch.bfloat16  # tensor cores read dZ, X and W MN-major in place; the fp32 parity path (SIMT, K-major) transposes
+            if tc:
+                dW = ops.gemm_ex(g, x2, a_t=True, w_t=True)  # dW_i = dZ_i^T X_i: contraction over the tokens
+            else:
+                dW, _ = ops.linear_bias_act(ops.transpose(g, pad=True), ops.transpose(x2, pad=True), None, ACT_NONE)  # [N, M] x [K, M]^T -> [N, K]
             grads[off + 2 * i] = dW.to(ctx.param_dtypes[off + 2 * i])
             grads[off + 2 * i + 1] = ops.colsum(g).to(ctx.param_dtypes[off + 2 * i + 1])
             if i > 0 or need_dx or has_ln:
-                g, _ = ops.linear_bias_act(g, ops.transpose(ws[i]), None, ACT_NONE)  # dX_i = dZ_i W_i: [M, N] x [K, N]^T -> [M, K]
+                if tc:
+                    g = ops.gemm_ex(g, ws[i], w_t=True)  # dX_i = dZ_i W_i
+                else:
+                    g, _ = ops.linear_bias_act(g, ops.transpose(ws[i]), None, ACT_NONE)  # [M, N] x [K, N]^T -> [M, K]
         dx = g if need_dx else None
         if has_ln:
             x_in, gamma = saved[-2], saved[-1]
@@ -297,16 +304,14 @@ class _FusedLinearFn(torch.autograd.Function):
             g = g.contiguous()
         dwo = None if dweights is None else dweights.float().contiguous()
         gsum = ops.video_colsum(g.view(B, T, K))
-        gT = ops.transpose(g, pad=True)  # [K, M'] : A operand of every dW_e GEMM
         dw_partials, pbars, dWs = [], [], []
-        for e in range(E):
+        for e in range(E):  # dOut, P_e and W_e are all read in place: the tensor cores take them MN-major (no transposed copies)
             P = pooled[e].reshape(B * T, -1)
-            Z, _ = ops.linear_bias_act(g, ops.transpose(Ws[e]), None, ACT_NONE)  # dOut W_e : [M, K] x [C_e, K]^T -> [M, C_e]
-            dw_partials.append(ops.pair_dot(Z.reshape(B, -1), P.reshape(B, -1)))
+            Z = ops.gemm_ex(g, Ws[e], w_t=True)  # dOut W_e : [M, K] x [K, C_e] -> [M, C_e]
+            dwp, Ps = ops.pair_dot(Z.reshape(B, -1), P.reshape(B, -1), scale=weights[:, e])  # <Z_e, P_e> partials and w_e (.) P_e in one pass
+            dw_partials.append(dwp)
             pbars.append(ops.video_colsum(P.reshape(B, T, -1), 1.0 / T))
-            PsT = ops.transpose(P, pad=True, row_scale=weights[:, e], rows_per_scale=T)  # (w_e (.) P_e)^T : [C_e, M']
-            dW, _ = ops.linear_bias_act(gT, PsT, None, ACT_NONE)  # [K, M'] x [C_e, M']^T -> [K, C_e]
-            dWs.append(dW)
+            dWs.append(ops.gemm_ex(g, Ps.view(B * T, -1), a_t=True, w_t=True))  # dOut^T (w_e (.) P_e) : contraction over the tokens -> [K, C_e]
         _, dbs, dQ, dWq, dWk, dbias = ops.fused_backward(weights, dwo, u, gsum, dw_partials, pbars, Ws, biases, Qc, Wqc, Wkc, bc, dWs)
         grads = [dQ.reshape(1, -1), dWq, dWk, dbias]
         for e in range(E):

@@ -53,7 +53,7 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
 # ---- launch accounting ----------------------------------------------------------------------------------------
 # kernels launched by one call of each entry point (used for bench.py's `gpu_launches` and per-kernel timing)
 KERNELS_PER_CALL = {
-    "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_fusion_query_vec": 3, "merv_affine_score_vec": 3,
+    "merv_pool3d": 1, "merv_linear_bias_act": 1, "merv_gemm_ex": 1, "merv_fusion_query_vec": 3, "merv_affine_score_vec": 3,
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
@@ -194,6 +194,29 @@ def linear_bias_act(
         _call('merv_linear_bias_act', lib.merv_linear_bias_act, a2.data_ptr(), a2.stride(0), w.data_ptr(), w.stride(0), _p(bias), y.data_ptr(), y.stride(0),
                                        M, N, K, act, code, _p(rowdot_vec), _p(rd), _stream())
     return y.reshape(*a.shape[:-1], N), rd
+
+
+def gemm_ex(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, a_t: bool = False,
+            w_t: bool = False) -> torch.Tensor:
+    """y [M, N] = act(A W^T + bias) on the tcgen05 GEMM (bf16) with either operand handed over TRANSPOSED, without a copy:
+    ``a_t``: ``a`` is A^T, a [K, M] matrix; ``w_t``: ``w`` is W^T, a [K, N] matrix (row-major, any 16-byte aligned row stride).
+
+    The backward of a Linear (autograd of nn_utils.py:31-32,46-55): ``dW = gemm_ex(dY, X, a_t=True, w_t=True)`` (contraction over the
+    tokens) and ``dX = gemm_ex(dY, W, w_t=True)`` — no transposed copies of dY, X or W."""
+    lib = _lib.load()
+    dev = _require_cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and (bias is None or bias.dtype == torch.bfloat16), "gemm_ex is bf16 only"
+    assert a.dim() == 2 and w.dim() == 2
+    a = a if a.stride(1) == 1 and a.stride(0) % 8 == 0 and a.data_ptr() % 16 == 0 else a.contiguous()
+    w = w if w.stride(1) == 1 and w.stride(0) % 8 == 0 and w.data_ptr() % 16 == 0 else w.contiguous()
+    K, M = (a.shape if a_t else a.shape[::-1])
+    Kw, N = (w.shape if w_t else w.shape[::-1])
+    assert K == Kw, f"contraction lengths differ: {K} vs {Kw}"
+    with torch.cuda.device(dev):
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        _call('merv_gemm_ex', lib.merv_gemm_ex, a.data_ptr(), a.stride(0), int(a_t), w.data_ptr(), w.stride(0), int(w_t), _p(bias), y.data_ptr(),
+              y.stride(0), M, N, K, act, _stream())
+    return y
 
 
 def fusion_query_vec(Q: torch.Tensor, Wq: torch.Tensor, Wk: torch.Tensor, in_proj_bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -624,17 +647,27 @@ def video_colsum(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     return out
 
 
-def pair_dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """Fixed-order partial sums [B, chunks] of sum_i x[b, i] * y[b, i] for x, y [B, ...] of equal shape."""
+def pair_dot(x: torch.Tensor, y: torch.Tensor, scale: Optional[torch.Tensor] = None):
+    """Fixed-order partial sums [B, chunks] of sum_i x[b, i] * y[b, i] for x, y [B, ...] of equal shape.
+
+    With ``scale`` (fp32 [B], any stride) also returns ``scale[b] * y[b]`` (shape of y) written in the same pass: the per-video mixing
+    weight applied to the pooled tokens, the W-operand of the fused backward's dW GEMM."""
     lib = _lib.load()
-    dev = _require_cuda(x, y)
+    dev = _require_cuda(x, y, scale)
     assert x.shape == y.shape and x.dtype == y.dtype
     B = x.shape[0]
+    shape = y.shape
     x, y = x.reshape(B, -1).contiguous(), y.reshape(B, -1).contiguous()
     with torch.cuda.device(dev):
         out = torch.empty((B, lib.merv_pair_dot_chunks()), dtype=torch.float32, device=dev)
-        _call('merv_pair_dot', lib.merv_pair_dot, x.data_ptr(), y.data_ptr(), out.data_ptr(), B, x.shape[1], dtype_code(x.dtype), _stream())
-    return out
+        if scale is None:
+            _call('merv_pair_dot', lib.merv_pair_dot, x.data_ptr(), y.data_ptr(), out.data_ptr(), B, x.shape[1], dtype_code(x.dtype), _stream())
+            return out
+        assert scale.dtype == torch.float32 and scale.dim() == 1 and scale.numel() == B
+        ys = torch.empty_like(y)
+        _call('merv_pair_dot', lib.merv_pair_dot_scale, x.data_ptr(), y.data_ptr(), out.data_ptr(), scale.data_ptr(), scale.stride(0), ys.data_ptr(), B,
+              x.shape[1], dtype_code(x.dtype), _stream())
+    return out, ys.view(shape)
 
 
 def fused_backward(weights: torch.Tensor, dweights_out: Optional[torch.Tensor], u: torch.Tensor, gsum: torch.Tensor,

@@ -188,10 +188,24 @@ def video_colsum(x, scale=1.0):
     return x.float().sum(1) * scale
 
 
-def pair_dot(x, y):
+def pair_dot(x, y, scale=None):
     B = x.shape[0]
     full = (x.float().reshape(B, -1) * y.float().reshape(B, -1)).sum(1, keepdim=True)
-    return torch.cat([full, torch.zeros(B, 15)], 1)  # the real kernel emits 16 partials; only their sum is contractual
+    part = torch.cat([full, torch.zeros(B, 15)], 1)  # the real kernel emits several partials; only their sum is contractual
+    if scale is None:
+        return part
+    return part, (y.float() * scale.float().reshape(B, *([1] * (y.dim() - 1)))).to(y.dtype)
+
+
+def gemm_ex(a, w, bias=None, act=0, a_t=False, w_t=False):
+    A = a.float().T if a_t else a.float()
+    W = w.float().T if w_t else w.float()
+    y = A @ W.T
+    if bias is not None:
+        y = y + bias.float()
+    if act == 1:
+        y = F.gelu(y)
+    return y.to(a.dtype)
 
 
 def fused_backward(weights, dweights_out, u, gsum, dw_partials, pbars, Ws, biases, Q, Wq, Wk, in_proj_bias, dWs):
@@ -277,7 +291,7 @@ class FusedLinearPlan:
 
 _NAMES = ["pool3d", "linear_bias_act", "fusion_query_vec", "affine_score_vec", "scores_from_tokens", "score_consts", "scores_from_partials",
           "softmax_weights", "softmax_mix", "fused_linear_mix", "concat_linear", "layernorm", "layernorm_backward", "transpose", "gelu",
-          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "fused_backward", "cross_attention", "add_rows"]
+          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "gemm_ex", "fused_backward", "cross_attention", "add_rows"]
 
 
 def emulate(monkeypatch) -> None:

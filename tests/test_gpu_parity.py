@@ -161,6 +161,36 @@ def test_tcgen05_linear_matches_oracle(M, N, K, act, cta_group, monkeypatch):
     assert np.abs(_np(rd) - want_rd).max() < 1e-3 * max(1.0, np.abs(want_rd).max())
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (128, 256, 64), (104, 136, 72), (1000, 264, 200), (4096, 1024, 2048), (768, 384, 4997)])
+@pytest.mark.parametrize("a_t,w_t", [(True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tcgen05_gemm_with_mn_major_operands_matches_oracle(M, N, K, a_t, w_t, cta_group, monkeypatch):
+    """merv_gemm_ex: either operand handed over transposed ([K, M] / [K, N]) and read MN-major by the tensor cores — the forms the
+    backward of a Linear needs (dW = dY^T X contracts over the tokens; dX = dY W).  K = 5000 with both operands MN-major: a k tail that
+    is not a multiple of 8 (any number of tokens), zero-filled by TMA."""
+    from merv_b200 import ops
+
+    if K % 8 and not (a_t and w_t):
+        pytest.skip("K % 8 != 0 needs both operands MN-major")
+    monkeypatch.setenv("MERV_GEMM_CTA_GROUP", str(cta_group))
+    rng = np.random.default_rng(M + 3 * N + 7 * K)
+    a = _bf16_round(rng.standard_normal((M, K), dtype=np.float32))
+    w = _bf16_round(rng.uniform(-1, 1, (N, K)).astype(np.float32) / np.sqrt(K))
+    b = _bf16_round(rng.uniform(-0.5, 0.5, N).astype(np.float32))
+    ta = _t(a.T if a_t else a, torch.bfloat16)
+    tw = _t(w.T if w_t else w, torch.bfloat16)
+    y = ops.gemm_ex(ta, tw, _t(b, torch.bfloat16), 0, a_t=a_t, w_t=w_t)
+    torch.cuda.synchronize()
+    want = a.astype(np.float64) @ w.astype(np.float64).T + b
+    assert y.shape == (M, N)
+    assert O.rel_err(_np(y), want) < 6e-3
+    # strided views (a column slice of a wider matrix) are read in place
+    if a_t and M >= 256:
+        wide = _t(np.concatenate([a.T, a.T], 1), torch.bfloat16)  # [K, 2M]
+        y2 = ops.gemm_ex(wide[:, M:], tw, _t(b, torch.bfloat16), 0, a_t=True, w_t=w_t)
+        assert torch.equal(y2, y)
+
+
 def test_simt_fp32_linear_matches_oracle():
     from merv_b200 import ops
 
@@ -984,11 +1014,18 @@ def test_affine_score_vec_two_stage_gemv(N, K, dtype):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("heads,hd,n_q,n_kv,batches,shared_q", [(8, 128, 64, 256, 3, True), (8, 96, 64, 196, 2, True), (4, 8, 5, 9, 2, False),
-                                                                  (2, 32, 37, 70, 1, True)])
-def test_cross_attention_kernel_matches_oracle(heads, hd, n_q, n_kv, batches, shared_q, dtype):
-    # head dims 128 / 96 / 32 / 8, ragged query and key counts (tails of the 32-query pass and of the key chunks), shared and per-entry queries
+                                                                  (2, 32, 37, 70, 1, True), (8, 128, 64, 256, 40, True), (3, 64, 128, 200, 5, False)])
+@pytest.mark.parametrize("impl", ["tcgen05", "simt"])
+def test_cross_attention_kernel_matches_oracle(heads, hd, n_q, n_kv, batches, shared_q, dtype, impl, monkeypatch):
+    # head dims 128 / 96 / 32 / 8, ragged query and key counts (tails of the 32-query pass and of the key chunks), shared and per-entry queries.
+    # bf16 with head_dim % 32 == 0 runs both contractions on the tensor cores (attention_tcgen05.cu: S = Q K^T and O = P V as tcgen05.mma,
+    # P rounded to bf16 in between, as in flash attention); impl == "simt" forces the CUDA-core kernel for the same inputs.
     from merv_b200 import ops
 
+    if impl == "simt":
+        monkeypatch.setenv("MERV_ATTN_IMPL", "simt")
+    elif dtype != torch.bfloat16 or hd % 32:
+        pytest.skip("the tcgen05 kernel covers bf16 with head_dim % 32 == 0")
     rng = np.random.default_rng(heads * 1000 + hd)
     C_ = heads * hd
     q = _t(rng.standard_normal((n_q, C_) if shared_q else (batches, n_q, C_), dtype=np.float32), dtype)
@@ -1003,7 +1040,7 @@ def test_cross_attention_kernel_matches_oracle(heads, hd, n_q, n_kv, batches, sh
     att = O._softmax_last((qh @ k.transpose(0, 1, 3, 2)) * hd ** -0.5)
     want = (att @ v).transpose(0, 2, 1, 3).reshape(batches, n_q, C_)
     assert out.shape == want.shape and out.dtype == dtype
-    assert O.rel_err(_np(out), want) < (FP32_TOL if dtype == torch.float32 else 6e-3)
+    assert O.rel_err(_np(out), want) < (FP32_TOL if dtype == torch.float32 else (1e-2 if impl == "tcgen05" else 6e-3))
     a = _t(rng.standard_normal((batches * n_q, C_), dtype=np.float32), dtype)
     b = _t(rng.standard_normal((n_q, C_), dtype=np.float32), dtype)
     got = ops.add_rows(a, b)
