@@ -339,6 +339,13 @@ int merv_fused_backward(const merv_fused_bwd_desc* desc, int dtype, void* stream
  * ------------------------------------------------------------------------------------------------------- */
 int merv_cross_attention(const void* q, int64_t ldq, int64_t q_batch_stride, const void* kv, int64_t ldkv, void* out, int64_t ldo,
                          int batches, int n_q, int n_kv, int heads, int head_dim, float scale, int dtype, void* stream);
+/* Backward of merv_cross_attention on the tensor cores (bf16; n_q <= 64, n_kv <= 256, head_dim % 32 == 0 and <= 128): S and P are
+ * recomputed, dP = dO V^T, dS = scale P (.) (dP - rowsum(P (.) dP)), dV = P^T dO, dK = dS^T Q, dQ = dS K — five tcgen05 contractions per
+ * (frame, head).  dout [batches, n_q, C] (lddo), dq [batches, n_q, C] (lddq): dQ of EVERY frame (with shared queries, q_batch_stride == 0,
+ * the caller sums the frames), dkv [batches * n_kv, 2C] (lddkv) = [dK | dV] in the layout of kv. */
+int merv_cross_attention_backward(const void* q, int64_t ldq, int64_t q_batch_stride, const void* kv, int64_t ldkv, const void* dout,
+                                  int64_t lddo, void* dq, int64_t lddq, void* dkv, int64_t lddkv, int batches, int n_q, int n_kv,
+                                  int heads, int head_dim, float scale, void* stream);
 int merv_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int C, int period, int dtype,
                   void* stream);
 

@@ -266,6 +266,20 @@ extern "C" int merv_cross_attention(const void* q, int64_t ldq, int64_t q_batch_
   return launch_attention<float>(q, ldq, q_batch_stride, kv, ldkv, out, ldo, batches, n_q, n_kv, heads, head_dim, scale, s);
 }
 
+extern "C" int merv_cross_attention_backward(const void* q, int64_t ldq, int64_t q_batch_stride, const void* kv, int64_t ldkv, const void* dout,
+                                             int64_t lddo, void* dq, int64_t lddq, void* dkv, int64_t lddkv, int batches, int n_q, int n_kv, int heads,
+                                             int head_dim, float scale, void* stream) {
+  MERV_REQUIRE(q && kv && dout && dq && dkv, MERV_E_ARG, "merv_cross_attention_backward: NULL pointer");
+  MERV_REQUIRE(batches >= 0 && n_q > 0 && n_kv > 0 && heads > 0 && head_dim > 0, MERV_E_SHAPE,
+               "merv_cross_attention_backward: batches=%d n_q=%d n_kv=%d heads=%d head_dim=%d", batches, n_q, n_kv, heads, head_dim);
+  const long long C = (long long)heads * head_dim;
+  MERV_REQUIRE(ldq >= C && ldkv >= 2 * C && lddo >= C && lddq >= C && lddkv >= 2 * C, MERV_E_SHAPE, "merv_cross_attention_backward: leading dimensions too small");
+  if (int rc = require_sm100()) return rc;
+  if (batches == 0) return MERV_OK;
+  return launch_attention_bwd_tcgen05(q, ldq, q_batch_stride, kv, ldkv, dout, lddo, dq, lddq, dkv, lddkv, batches, n_q, n_kv, heads, head_dim, scale,
+                                      static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int merv_add_rows(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t M, int C, int period, int dtype,
                              void* stream) {
   MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_add_rows: unknown dtype %d", dtype);

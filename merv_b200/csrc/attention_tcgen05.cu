@@ -243,6 +243,325 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_tcgen05_kernel(
   }
 }
 
+// ============================================================================================================
+// Backward of the cross attention (training the "attntv" resampler): all five contractions on the tensor cores.
+//   S  = Q K^T, P = softmax(scale S)                       (recomputed, not stored by the forward)
+//   dP = dO V^T;   D_i = sum_j P_ij dP_ij;   dS = scale P (.) (dP - D)
+//   dV = P^T dO;   dK = dS^T Q;   dQ = dS K                (dQ per frame; the caller sums the frames when the queries are shared)
+// One shared-memory image per operand serves BOTH of its roles, because a [rows x 128 B] swizzled tile is K-major with respect to its
+// rows and MN-major with respect to its columns: Q is the K-major A of S and the MN-major B of dK, dO the K-major A of dP and the MN-major
+// B of dV, K the K-major B of S and the MN-major B of dQ, V the K-major B of dP; P and dS (written by the softmax warps) are the
+// MN-major A of dV / dK (M = keys) and dS also the K-major A of dQ.  n_q <= 64 (the resampler's queries per frame), n_kv <= 256.
+// TMEM: S -> [0, 256), dP -> [256, 512); once both are consumed, dV_half -> [0, hd), dK_half -> [128, 128 + hd) for the two halves of the
+// keys in turn and dQ -> [256, 256 + hd).
+// ============================================================================================================
+constexpr int AB_ROWS = 64;                 // query rows held in shared memory (the UMMAs still run M = 128: rows past 64 read the next buffer)
+constexpr int AB_CH = AB_ROWS * 128;        // [64 rows x 64 elements] chunk, 8 KB
+constexpr int AB_Q_OFF = 0;                                         // 2 chunks (head dims 0-63, 64-127)
+constexpr int AB_DO_OFF = AB_Q_OFF + AT_HD_CHUNKS * AB_CH;
+constexpr int AB_K_OFF = AB_DO_OFF + AT_HD_CHUNKS * AB_CH;
+constexpr int AB_V_OFF = AB_K_OFF + AT_HD_CHUNKS * AT_KV_CHUNK;
+constexpr int AB_DS_OFF = AB_V_OFF + AT_HD_CHUNKS * AT_KV_CHUNK;    // 4 chunks (keys 0-63, ...); its M = 128 reads run over into P: finite data
+constexpr int AB_P_OFF = AB_DS_OFF + (AT_KEYS / 64) * AB_CH;
+constexpr int AB_BAR_OFF = AB_P_OFF + (AT_KEYS / 64) * AB_CH;  // P is only read MN-major (k = query rows < 64): nothing runs over its end
+constexpr int AB_SMEM = 1024 + AB_BAR_OFF + 128;
+static_assert(AB_SMEM <= 232448, "227 KB of shared memory per CTA");
+
+struct AttnBwdParams {
+  __nv_bfloat16* dkv;  // [batches * n_kv, 2 C] = [dK | dV]
+  long long lddkv;
+  __nv_bfloat16* dq;   // [batches, n_q, C]: dQ of every frame
+  long long lddq;
+  int batches, heads, n_q, n_kv, hd;
+  int q_per_batch;
+  float scale, scale_log2e;
+};
+struct AttnBwdMaps {
+  CUtensorMap q, kv, dout;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_kernel(const __grid_constant__ AttnBwdMaps maps,
+                                                                                    const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t at_smem_raw[];
+  const uint32_t raw = smem_u32(at_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* aligned = at_smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aligned + AB_BAR_OFF);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t ld_full = bar0, ld_empty = bar0 + 8, sdp_full = bar0 + 16, pds_full = bar0 + 24, dvk_full0 = bar0 + 32, dvk_full1 = bar0 + 40,
+                 dvk_empty0 = bar0 + 48, dvk_empty1 = bar0 + 56, dq_full = bar0 + 64, dq_empty = bar0 + 72;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.batches * p.heads;
+  const int hd_chunks = (p.hd + 63) / 64;
+  constexpr int ROW_WARPS = AB_ROWS / 32;  // softmax warps that own query rows
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tmap(&maps.q);
+    prefetch_tmap(&maps.kv);
+    prefetch_tmap(&maps.dout);
+    mbar_init(ld_full, 1); mbar_init(ld_empty, 1); mbar_init(sdp_full, 1); mbar_init(pds_full, ROW_WARPS);
+    mbar_init(dvk_full0, 1); mbar_init(dvk_full1, 1); mbar_init(dvk_empty0, 4); mbar_init(dvk_empty1, 4);
+    mbar_init(dq_full, 1); mbar_init(dq_empty, ROW_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "n"(AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // the run-over reads of the M = 128 UMMAs must see finite data from the first item on
+  for (int i = threadIdx.x; i < (AB_BAR_OFF - AB_DS_OFF) / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(aligned + AB_DS_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int n_keys16 = (p.n_kv + 15) & ~15;
+  const int n_q16 = (p.n_q + 15) & ~15;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===== producer: Q_h, dO_h, K_h, V_h of one (frame, head) =====
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int b = item / p.heads, h = item - b * p.heads;
+        mbar_wait(ld_empty, (it & 1u) ^ 1u);
+        mbar_expect_tx(ld_full, uint32_t(hd_chunks) * (2 * AB_CH + 2 * AT_KV_CHUNK));
+        for (int c = 0; c < hd_chunks; ++c) {
+          tma_load_4d(&maps.q, ld_full, base + AB_Q_OFF + c * AB_CH, c * 64, h, 0, p.q_per_batch ? b : 0);
+          tma_load_4d(&maps.dout, ld_full, base + AB_DO_OFF + c * AB_CH, c * 64, h, 0, b);
+          tma_load_4d(&maps.kv, ld_full, base + AB_K_OFF + c * AT_KV_CHUNK, c * 64, h, 0, b);
+          tma_load_4d(&maps.kv, ld_full, base + AB_V_OFF + c * AT_KV_CHUNK, c * 64, p.heads + h, 0, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      const uint32_t idesc_s = umma_idesc_bf16(AT_M, n_keys16, 0, 0);   // S, dP: [128 x keys], K-major operands
+      const uint32_t idesc_t = umma_idesc_bf16(AT_M, p.hd, 1, 1);       // dV, dK: [128 keys x hd], both operands MN-major
+      const uint32_t idesc_q = umma_idesc_bf16(AT_M, p.hd, 0, 1);       // dQ: [128 x hd], A = dS K-major, B = K_h MN-major
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1u;
+        mbar_wait(ld_full, ph);
+        mbar_wait(dvk_empty1, ph ^ 1u);  // the previous item's accumulators have been drained
+        mbar_wait(dq_empty, ph ^ 1u);
+        tc_fence_after();
+        for (int ks = 0; ks < p.hd / UMMA_K; ++ks) {  // S = Q K^T and dP = dO V^T
+          const uint32_t off = uint32_t(ks >> 2), k2 = 2u * uint32_t(ks & 3);
+          umma_bf16(tmem_base, umma_desc_sw128(base + AB_Q_OFF + off * AB_CH) + k2, umma_desc_sw128(base + AB_K_OFF + off * AT_KV_CHUNK) + k2, idesc_s,
+                    ks != 0 ? 1u : 0u);
+        }
+        for (int ks = 0; ks < p.hd / UMMA_K; ++ks) {
+          const uint32_t off = uint32_t(ks >> 2), k2 = 2u * uint32_t(ks & 3);
+          umma_bf16(tmem_base + AT_KEYS, umma_desc_sw128(base + AB_DO_OFF + off * AB_CH) + k2, umma_desc_sw128(base + AB_V_OFF + off * AT_KV_CHUNK) + k2,
+                    idesc_s, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, ph);
+        tc_fence_after();
+        auto dvk = [&](int half) {  // dV_half = P[:, half]^T dO -> columns [0, hd); dK_half = dS[:, half]^T Q -> columns [128, 128 + hd)
+          for (int ks = 0; ks < n_q16 / UMMA_K; ++ks) {
+            const uint64_t kstep = uint64_t(ks) * (2048u >> 4);
+            umma_bf16(tmem_base, umma_desc_mn_sw128_lbo(base + AB_P_OFF + half * 2 * AB_CH, AB_CH) + kstep,
+                      umma_desc_mn_sw128_lbo(base + AB_DO_OFF, AB_CH) + kstep, idesc_t, ks != 0 ? 1u : 0u);
+          }
+          for (int ks = 0; ks < n_q16 / UMMA_K; ++ks) {
+            const uint64_t kstep = uint64_t(ks) * (2048u >> 4);
+            umma_bf16(tmem_base + 128, umma_desc_mn_sw128_lbo(base + AB_DS_OFF + half * 2 * AB_CH, AB_CH) + kstep,
+                      umma_desc_mn_sw128_lbo(base + AB_Q_OFF, AB_CH) + kstep, idesc_t, ks != 0 ? 1u : 0u);
+          }
+        };
+        dvk(0);
+        umma_commit(dvk_full0);
+        for (int ks = 0; ks < n_keys16 / UMMA_K; ++ks) {  // dQ = dS K -> columns [256, 256 + hd)
+          const uint64_t a = umma_desc_sw128(base + AB_DS_OFF + (ks >> 2) * AB_CH) + 2 * (ks & 3);
+          const uint64_t bd = umma_desc_mn_sw128_lbo(base + AB_K_OFF, AT_KV_CHUNK) + uint64_t(ks) * (2048u >> 4);
+          umma_bf16(tmem_base + AT_KEYS, a, bd, idesc_q, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(dq_full);
+        mbar_wait(dvk_empty0, ph);
+        tc_fence_after();
+        dvk(1);
+        umma_commit(dvk_full1);
+        umma_commit(ld_empty);  // every operand of this item has been read
+      }
+    }
+  } else {
+    // ===== softmax / dS (warps 0 .. ROW_WARPS-1: thread = query row) and accumulator drains (all four warps: thread = key or query row) =====
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t sw = uint32_t(row) & 7u;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int b = item / p.heads, h = item - b * p.heads;
+      const uint32_t ph = it & 1u;
+      if (warp < ROW_WARPS) {
+        mbar_wait(sdp_full, ph);
+        tc_fence_after();
+        const int nc = (n_keys16 + 31) / 32;
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + lane_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < p.n_kv) m = fmaxf(m, __uint_as_float(v[i]));
+        }
+        const float mo = m * p.scale_log2e;
+        float sum = 0.f, dn = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+          uint32_t v[32], g[32];
+          tmem_ld32(tmem_base + lane_addr + c * 32, v);
+          tmem_ld32(tmem_base + AT_KEYS + lane_addr + c * 32, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < p.n_kv) {
+              const float e = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mo));
+              sum += e;
+              dn = fmaf(e, __uint_as_float(g[i]), dn);
+            }
+          }
+        }
+        const float inv = 1.0f / sum;
+        const float D = dn * inv;
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+          uint32_t v[32], g[32];
+          tmem_ld32(tmem_base + lane_addr + c * 32, v);
+          tmem_ld32(tmem_base + AT_KEYS + lane_addr + c * 32, g);
+          tmem_ld_wait();
+          uint32_t pp[16], ds[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = 0.f, p1 = 0.f;
+            if (c * 32 + i < p.n_kv) p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -mo)) * inv;
+            if (c * 32 + i + 1 < p.n_kv) p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -mo)) * inv;
+            pp[i >> 1] = pack_bf16x2(p0, p1);
+            ds[i >> 1] = pack_bf16x2(p.scale * p0 * (__uint_as_float(g[i]) - D), p.scale * p1 * (__uint_as_float(g[i + 1]) - D));
+          }
+          const uint32_t chunk = uint32_t(c >> 1) * AB_CH + uint32_t(row) * 128u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t c16 = ((uint32_t((c & 1) * 4 + j)) ^ sw) << 4;
+            sts_v4(base + AB_P_OFF + chunk + c16, make_uint4(pp[4 * j], pp[4 * j + 1], pp[4 * j + 2], pp[4 * j + 3]));
+            sts_v4(base + AB_DS_OFF + chunk + c16, make_uint4(ds[4 * j], ds[4 * j + 1], ds[4 * j + 2], ds[4 * j + 3]));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+      }
+      auto drain_dvk = [&](int half, uint32_t full_bar, uint32_t empty_bar) {
+        mbar_wait(full_bar, ph);
+        tc_fence_after();
+        const int key = half * 128 + row;
+        __nv_bfloat16* dst = p.dkv + ((long long)b * p.n_kv + key) * p.lddkv + (long long)h * p.hd;
+        const long long v_off = (long long)p.heads * p.hd;  // the dV half of the row
+#pragma unroll 1
+        for (int c = 0; c < p.hd / 32; ++c) {
+          uint32_t dv[32], dk[32];
+          tmem_ld32(tmem_base + lane_addr + c * 32, dv);
+          tmem_ld32(tmem_base + 128 + lane_addr + c * 32, dk);
+          tmem_ld_wait();
+          if (key < p.n_kv) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[8], bb[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                a[i] = __uint_as_float(dk[8 * j + i]);
+                bb[i] = __uint_as_float(dv[8 * j + i]);
+              }
+              *reinterpret_cast<uint4*>(dst + c * 32 + 8 * j) = Vec16<__nv_bfloat16>::pack(a);
+              *reinterpret_cast<uint4*>(dst + v_off + c * 32 + 8 * j) = Vec16<__nv_bfloat16>::pack(bb);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar);
+      };
+      drain_dvk(0, dvk_full0, dvk_empty0);
+      if (warp < ROW_WARPS) {
+        mbar_wait(dq_full, ph);
+        tc_fence_after();
+        __nv_bfloat16* dst = p.dq + ((long long)b * p.n_q + row) * p.lddq + (long long)h * p.hd;
+#pragma unroll 1
+        for (int c = 0; c < p.hd / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + AT_KEYS + lane_addr + c * 32, v);
+          tmem_ld_wait();
+          if (row < p.n_q) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[8 * j + i]);
+              *reinterpret_cast<uint4*>(dst + c * 32 + 8 * j) = Vec16<__nv_bfloat16>::pack(a);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+      }
+      drain_dvk(1, dvk_full1, dvk_empty1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AT_TMEM_COLS) : "memory");
+  }
+}
+
+static int make_attn_map(CUtensorMap* map, const void* ptr, int hd, int heads_dim, int rows, long long ld, long long batch_stride, int batches, int box_rows) {
+  const unsigned long long dims[4] = {(unsigned long long)hd, (unsigned long long)heads_dim, (unsigned long long)rows, (unsigned long long)batches};
+  const unsigned long long strides[3] = {(unsigned long long)hd * 2, (unsigned long long)ld * 2, (unsigned long long)batch_stride * 2};
+  const unsigned box[4] = {64, 1, (unsigned)box_rows, 1};
+  return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int launch_attention_bwd_tcgen05(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, const void* dout, long long lddo,
+                                 void* dq, long long lddq, void* dkv, long long lddkv, int batches, int n_q, int n_kv, int heads, int hd, float scale,
+                                 cudaStream_t stream) {
+  MERV_REQUIRE(n_q <= AB_ROWS && n_kv <= AT_KEYS && hd % 32 == 0 && hd <= AT_MAX_HD, MERV_E_SHAPE,
+               "cross attention backward: at most %d queries and %d keys per frame, head_dim a multiple of 32 up to %d (got n_q=%d n_kv=%d head_dim=%d)",
+               AB_ROWS, AT_KEYS, AT_MAX_HD, n_q, n_kv, hd);
+  MERV_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0 && q_batch_stride % 8 == 0 && aligned16(q) && aligned16(kv) &&
+                   aligned16(dout) && aligned16(dq) && aligned16(dkv),
+               MERV_E_ALIGN, "cross attention backward: rows must be 16-byte aligned");
+  AttnBwdMaps maps;
+  AttnBwdParams p = {};
+  p.dkv = static_cast<__nv_bfloat16*>(dkv); p.lddkv = lddkv; p.dq = static_cast<__nv_bfloat16*>(dq); p.lddq = lddq;
+  p.batches = batches; p.heads = heads; p.n_q = n_q; p.n_kv = n_kv; p.hd = hd;
+  p.q_per_batch = q_batch_stride != 0 ? 1 : 0;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  if (int rc = make_attn_map(&maps.q, q, hd, heads, n_q, ldq, p.q_per_batch ? q_batch_stride : (long long)n_q * ldq, p.q_per_batch ? batches : 1, AB_ROWS)) return rc;
+  if (int rc = make_attn_map(&maps.dout, dout, hd, heads, n_q, lddo, (long long)n_q * lddo, batches, AB_ROWS)) return rc;
+  if (int rc = make_attn_map(&maps.kv, kv, hd, 2 * heads, n_kv, ldkv, (long long)n_kv * ldkv, batches, AT_KEYS)) return rc;
+  static const cudaError_t attr_rc =
+      cudaFuncSetAttribute(cross_attention_bwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+  MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", AB_SMEM, cudaGetErrorString(attr_rc));
+  const long long items = (long long)batches * heads;
+  const int sms = sm_count();
+  const unsigned grid = unsigned(items < sms ? items : sms);
+  cross_attention_bwd_tcgen05_kernel<<<grid, AT_THREADS, AB_SMEM, stream>>>(maps, p);
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
 bool attention_tcgen05_supported(int n_q, int n_kv, int heads, int hd, long long ldq, long long q_batch_stride, long long ldkv, long long ldo) {
   const char* e = getenv("MERV_ATTN_IMPL");
   if (e != nullptr && strcmp(e, "simt") == 0) return false;

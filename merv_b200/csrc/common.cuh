@@ -56,6 +56,9 @@ int launch_scores_softmax_weights(const float* const* partial, const int32_t* co
 bool attention_tcgen05_supported(int n_q, int n_kv, int heads, int hd, long long ldq, long long q_batch_stride, long long ldkv, long long ldo);
 int launch_attention_tcgen05(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, void* out, long long ldo,
                              int batches, int n_q, int n_kv, int heads, int hd, float scale, cudaStream_t stream);
+int launch_attention_bwd_tcgen05(const void* q, long long ldq, long long q_batch_stride, const void* kv, long long ldkv, const void* dout, long long lddo,
+                                 void* dq, long long lddq, void* dkv, long long lddkv, int batches, int n_q, int n_kv, int heads, int hd, float scale,
+                                 cudaStream_t stream);
 // MERV_PDL=0 disables programmatic dependent launch inside merv_fused_forward (A/B measurements); read per call
 bool pdl_enabled();
 int launch_gemm_simt(const void* A, long long lda, const void* W, long long ldw, const void* bias, void* Y, long long ldy,

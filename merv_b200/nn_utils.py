@@ -214,6 +214,75 @@ class _MixFn(torch.autograd.Function):
         return (None, None, *grads, *[g.to(t) for g, t in zip(dVs, vdt)])
 
 
+class _AttentivePoolFn(torch.autograd.Function):
+    """AttentivePooler.forward up to (not including) its projector (nn_utils.py:229-237 with CrossAttentionBlock.forward :447-451 and
+    CrossAttention.forward :393-412), bf16, with a hand-written backward; the patch features get no gradient (frozen backbones).
+
+    forward : xn = LN1(x);  kv = xn Wkv^T + bkv;  qp = qt Wq^T + bq;  a = attention(qp, kv) (tcgen05);  y = a Wp^T + bp;  q1 = y + qt;
+              hn = LN2(q1);  z1 = hn W1^T + b1;  g1 = gelu(z1);  h2 = g1 W2^T + b2;  q2 = q1 + h2
+    backward: every Linear through the MN-major tcgen05 GEMM (dW = dY^T X, dX = dY W, no transposed copies), the attention through
+              merv_cross_attention_backward (five tcgen05 contractions per frame and head), LayerNorm / GELU / reductions through their
+              HBM-bound kernels.  The learned queries are shared by all frames: their gradient sums the frames."""
+
+    @staticmethod
+    def forward(ctx, x, cache, heads, scale, eps1, eps2, qt3, g1w, g1b, Wkv, bkv, Wq, bq, Wp, bp, g2w, g2b, W1, b1, W2, b2):
+        dt = torch.bfloat16
+        c = cache
+        B, F, N, C_ = x.shape
+        n = qt3.shape[1]
+        xf = x.reshape(B * F * N, C_)
+        P = [c.get(t, dt) for t in (qt3, g1w, g1b, Wkv, bkv, Wq, bq, Wp, bp, g2w, g2b, W1, b1, W2, b2)]
+        qt3c, g1wc, g1bc, Wkvc, bkvc, Wqc, bqc, Wpc, bpc, g2wc, g2bc, W1c, b1c, W2c, b2c = P
+        qt = qt3c[0]
+        xn = ops.layernorm([xf], g1wc, g1bc, eps1)
+        kv, _ = ops.linear_bias_act(xn, Wkvc, bkvc, ACT_NONE)
+        qp, _ = ops.linear_bias_act(qt, Wqc, bqc, ACT_NONE)
+        a = ops.cross_attention(qp, kv, B * F, heads, scale)
+        a2 = a.view(B * F * n, C_)
+        y, _ = ops.linear_bias_act(a2, Wpc, bpc, ACT_NONE)
+        q1 = ops.add_rows(y, qt)
+        hn = ops.layernorm([q1], g2wc, g2bc, eps2)
+        z1, _ = ops.linear_bias_act(hn, W1c, b1c, ACT_NONE)
+        g1 = ops.gelu(z1)
+        h2, _ = ops.linear_bias_act(g1, W2c, b2c, ACT_NONE)
+        q2 = ops.add_rows(q1, h2)
+        ctx.meta = (heads, scale, eps1, eps2, (B, F, N, C_, n), [t.dtype for t in (qt3, g1w, g1b, Wkv, bkv, Wq, bq, Wp, bp, g2w, g2b, W1, b1, W2, b2)])
+        ctx.save_for_backward(xf, xn, kv, qp, a2, q1, hn, z1, g1, qt, g1wc, Wkvc, Wqc, Wpc, g2wc, W1c, W2c)
+        return q2
+
+    @staticmethod
+    def backward(ctx, dq2):
+        heads, scale, eps1, eps2, (B, F, N, C_, n), pdt = ctx.meta
+        xf, xn, kv, qp, a2, q1, hn, z1, g1, qt, g1wc, Wkvc, Wqc, Wpc, g2wc, W1c, W2c = ctx.saved_tensors
+        dt = torch.bfloat16
+        g = dq2.reshape(-1, C_)
+        g = (g if g.dtype == dt else g.to(dt)).contiguous()
+        BF = B * F
+        # q2 = q1 + fc2(gelu(fc1(LN2(q1))))
+        dW2 = ops.gemm_ex(g, g1, a_t=True, w_t=True)
+        db2 = ops.colsum(g)
+        dz1 = ops.gelu(z1, ops.gemm_ex(g, W2c, w_t=True))
+        dW1 = ops.gemm_ex(dz1, hn, a_t=True, w_t=True)
+        db1 = ops.colsum(dz1)
+        dq1_ln, dg2w, dg2b = ops.layernorm_backward([q1], ops.gemm_ex(dz1, W1c, w_t=True), g2wc, eps2)
+        dq1 = ops.add_rows(g, dq1_ln)
+        # q1 = proj(attention) + query tokens (the same tokens for every frame)
+        dqt = ops.video_colsum(dq1.view(1, BF, n * C_)).view(n, C_)  # fp32
+        dWp = ops.gemm_ex(dq1, a2, a_t=True, w_t=True)
+        dbp = ops.colsum(dq1)
+        da = ops.gemm_ex(dq1, Wpc, w_t=True)
+        dq_frames, dkv = ops.cross_attention_backward(qp, kv, da.view(BF, n, C_), BF, heads, scale)
+        dqp = ops.video_colsum(dq_frames.view(1, BF, n * C_)).view(n, C_).to(dt)
+        dWq = ops.gemm_ex(dqp, qt, a_t=True, w_t=True)
+        dbq = ops.colsum(dqp)
+        dqt = dqt + ops.gemm_ex(dqp, Wqc, w_t=True).float()
+        dWkv = ops.gemm_ex(dkv, xn, a_t=True, w_t=True)
+        dbkv = ops.colsum(dkv)
+        _, dg1w, dg1b = ops.layernorm_backward([xf], ops.gemm_ex(dkv, Wkvc, w_t=True), g1wc, eps1, need_dx=False)
+        grads = [dqt.view(1, n, C_), dg1w, dg1b, dWkv, dbkv, dWq, dbq, dWp, dbp, dg2w, dg2b, dW1, db1, dW2, db2]
+        return (None, None, None, None, None, None, *[gr.to(t) for gr, t in zip(grads, pdt)])
+
+
 def _version(p: torch.Tensor) -> int:
     """In-place-update counter of a parameter; inference tensors do not track one (and cannot be updated in place
     outside inference mode), so they count as version 0."""
@@ -656,8 +725,9 @@ class AttentivePooler(TokenResampler):
 
     Same constructor signature, module tree (hence state-dict keys: ``query_tokens``, ``cross_attn.{norm1,xattn.{q,kv,proj},norm2,
     mlp.{fc1,fc2}}``, ``projector.*``) and initialisation sequence as the reference.  forward: LayerNorm (merv_layernorm), the kv / proj /
-    MLP / projector Linears on the tcgen05 GEMM (GELU in the epilogue), merv_cross_attention, merv_add_rows for the two residuals.
-    Inference only: the backward of this ablation resampler is not built (raises)."""
+    MLP / projector Linears on the tcgen05 GEMM (GELU in the epilogue), merv_cross_attention (both contractions as tcgen05.mma in bf16),
+    merv_add_rows for the two residuals.  Training (bf16 compute): _AttentivePoolFn, a hand-written backward whose attention part runs
+    five tcgen05 contractions per frame and head (merv_cross_attention_backward)."""
 
     def __init__(self, fused_vision_dim: int, llm_dim: int, num_query_tokens: int, num_heads: int = 8, output_frames: int = 8,
                  mlp_type: str = "gelu-mlp") -> None:
@@ -709,8 +779,6 @@ class AttentivePooler(TokenResampler):
         num_frames = x.shape[1]
         assert num_frames == self.output_frames  # nn_utils.py:232
         _require_device(x)
-        if _needs_grad(self, x):
-            raise NotImplementedError("the backward of the attentive pooler is not built (ablation resampler; inference only)")
         dtype = _compute_dtype(x)
         c = self._cast_cache
         blk, att = self.cross_attn, self.cross_attn.xattn
@@ -719,6 +787,22 @@ class AttentivePooler(TokenResampler):
         layers = _projector_layers(self.projector)
         if B == 0:
             return torch.empty((0, F * n, layers[-1][0].out_features), dtype=dtype, device=x.device)
+        if _needs_grad(self, x):
+            if x.requires_grad:
+                raise NotImplementedError("gradients w.r.t. the patch features are not implemented (frozen backbones, merv.py:316)")
+            if dtype != torch.bfloat16:
+                raise NotImplementedError("training the attentive pooler needs bf16 compute (torch.autocast): its attention backward runs on the "
+                                          "tensor cores only")
+            lins = (att.kv, att.q, att.proj, blk.mlp.fc1, blk.mlp.fc2)
+            if any(l.bias is None for l in lins) or any(ln.weight is None or ln.bias is None for ln in (blk.norm1, blk.norm2)):
+                raise NotImplementedError("bias-free layers / non-affine LayerNorms of the attentive pooler are not covered by the backward")
+            xb = x.detach()
+            xb = xb if xb.dtype == dtype else xb.to(dtype)
+            q2 = _AttentivePoolFn.apply(xb, c, att.num_heads, att.scale, blk.norm1.eps, blk.norm2.eps, self.query_tokens, blk.norm1.weight,
+                                        blk.norm1.bias, att.kv.weight, att.kv.bias, att.q.weight, att.q.bias, att.proj.weight, att.proj.bias,
+                                        blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.weight, blk.mlp.fc1.bias, blk.mlp.fc2.weight, blk.mlp.fc2.bias)
+            out = self.projector(q2)
+            return out.view(B, F * n, out.shape[-1])
         xf = (x if x.dtype == dtype else x.to(dtype)).reshape(B * F * N, C_)
         xn = ops.layernorm([xf], c.get(blk.norm1.weight, dtype), c.get(blk.norm1.bias, dtype), blk.norm1.eps)
         kv, _ = ops.linear_bias_act(xn, c.get(att.kv.weight, dtype), c.get(att.kv.bias, dtype), ACT_NONE)  # [B F N, 2C] = [K | V]

@@ -57,7 +57,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
-    "merv_cross_attention": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10,
+    "merv_cross_attention": 1, "merv_cross_attention_backward": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10,
     "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
@@ -615,6 +615,30 @@ def cross_attention(q: torch.Tensor, kv: torch.Tensor, batches: int, heads: int,
         _call('merv_cross_attention', lib.merv_cross_attention, q.data_ptr(), q.stride(-2), qbs, kv.data_ptr(), kv.stride(0), out.data_ptr(), C_,
               batches, n_q, n_kv, heads, hd, float(hd ** -0.5 if scale is None else scale), dtype_code(q.dtype), _stream())
     return out
+
+
+def cross_attention_backward(q: torch.Tensor, kv: torch.Tensor, dout: torch.Tensor, batches: int, heads: int,
+                             scale: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Gradients of `cross_attention` (bf16, tensor cores): returns (dq [batches, n_q, C] — one dQ per batch entry, to be summed by the
+    caller when the queries are shared — and dkv [batches * n_kv, 2C] = [dK | dV])."""
+    lib = _lib.load()
+    dev = _require_cuda(q, kv, dout)
+    C_ = q.shape[-1]
+    assert q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and dout.dtype == torch.bfloat16, "the attention backward is bf16 only"
+    assert kv.dim() == 2 and kv.shape[1] == 2 * C_ and kv.shape[0] % max(batches, 1) == 0 and C_ % heads == 0
+    n_q, n_kv, hd = q.shape[-2], kv.shape[0] // max(batches, 1), C_ // heads
+    assert dout.shape == (batches, n_q, C_)
+    q = q if q.stride(-1) == 1 else q.contiguous()
+    kv = kv if kv.stride(1) == 1 else kv.contiguous()
+    dout = dout.contiguous()
+    qbs = 0 if q.dim() == 2 else q.stride(0)
+    with torch.cuda.device(dev):
+        dq = torch.empty((batches, n_q, C_), dtype=torch.bfloat16, device=dev)
+        dkv = torch.empty((batches * n_kv, 2 * C_), dtype=torch.bfloat16, device=dev)
+        _call('merv_cross_attention_backward', lib.merv_cross_attention_backward, q.data_ptr(), q.stride(-2), qbs, kv.data_ptr(), kv.stride(0),
+              dout.data_ptr(), dout.stride(1), dq.data_ptr(), dq.stride(1), dkv.data_ptr(), dkv.stride(0), batches, n_q, n_kv, heads, hd,
+              float(hd ** -0.5 if scale is None else scale), _stream())
+    return dq, dkv
 
 
 def add_rows(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:

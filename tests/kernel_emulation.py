@@ -180,6 +180,22 @@ def cross_attention(q, kv, batches, heads, scale=None):
     return (att @ v).permute(0, 2, 1, 3).reshape(batches, -1, Cc).to(q.dtype)
 
 
+def cross_attention_backward(q, kv, dout, batches, heads, scale=None):
+    """autograd through the emulated forward (shared queries are expanded so every batch entry gets its own dQ)"""
+    C_ = q.shape[-1]
+    n_q = q.shape[-2]
+    with torch.enable_grad():
+        qq = (q.float().unsqueeze(0).expand(batches, n_q, C_) if q.dim() == 2 else q.float()).clone().requires_grad_(True)
+        kk = kv.float().clone().requires_grad_(True)
+        n_kv, hd = kv.shape[0] // batches, C_ // heads
+        k = kk.view(batches, n_kv, 2, heads, hd)
+        qh = qq.view(batches, n_q, heads, hd).permute(0, 2, 1, 3)
+        att = torch.softmax(qh @ k[:, :, 0].permute(0, 2, 3, 1) * (hd ** -0.5 if scale is None else scale), -1)
+        out = (att @ k[:, :, 1].permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(batches, n_q, C_)
+        dq, dkv = torch.autograd.grad(out, [qq, kk], dout.float())
+    return dq.to(q.dtype), dkv.to(kv.dtype)
+
+
 def add_rows(a, b):
     return (a.float().reshape(-1, b.shape[0], a.shape[1]) + b.float()).reshape(a.shape).to(a.dtype)
 
@@ -291,7 +307,7 @@ class FusedLinearPlan:
 
 _NAMES = ["pool3d", "linear_bias_act", "fusion_query_vec", "affine_score_vec", "scores_from_tokens", "score_consts", "scores_from_partials",
           "softmax_weights", "softmax_mix", "fused_linear_mix", "concat_linear", "layernorm", "layernorm_backward", "transpose", "gelu",
-          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "gemm_ex", "fused_backward", "cross_attention", "add_rows"]
+          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "gemm_ex", "fused_backward", "cross_attention", "cross_attention_backward", "add_rows"]
 
 
 def emulate(monkeypatch) -> None:

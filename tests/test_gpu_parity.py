@@ -1046,3 +1046,73 @@ def test_cross_attention_kernel_matches_oracle(heads, hd, n_q, n_kv, batches, sh
     got = ops.add_rows(a, b)
     want_add = (_np(a).reshape(batches, n_q, C_) + _np(b)).reshape(batches * n_q, C_)
     assert O.rel_err(_np(got), want_add) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("heads,hd,n_q,n_kv,batches,shared_q", [(8, 128, 64, 256, 3, True), (8, 96, 64, 196, 2, True), (2, 32, 37, 70, 1, True),
+                                                                  (3, 64, 64, 200, 5, False), (8, 128, 64, 256, 37, True)])
+def test_cross_attention_backward_kernel_matches_autograd(heads, hd, n_q, n_kv, batches, shared_q):
+    """merv_cross_attention_backward (five tcgen05 contractions per frame and head; S / P recomputed) against fp64 autograd through the
+    attention of CrossAttention.forward (nn_utils.py:393-412) on the same bf16-rounded inputs."""
+    from merv_b200 import ops
+
+    rng = np.random.default_rng(heads * 100 + hd + n_kv)
+    C_ = heads * hd
+    q = _t(rng.standard_normal((n_q, C_) if shared_q else (batches, n_q, C_), dtype=np.float32), torch.bfloat16)
+    kv = _t(rng.standard_normal((batches * n_kv, 2 * C_), dtype=np.float32), torch.bfloat16)
+    dout = _t(rng.standard_normal((batches, n_q, C_), dtype=np.float32), torch.bfloat16)
+    dq, dkv = ops.cross_attention_backward(q, kv, dout, batches, heads)
+    torch.cuda.synchronize()
+    qq = (q.double().unsqueeze(0).expand(batches, n_q, C_) if shared_q else q.double()).clone().requires_grad_(True)
+    kk = kv.double().clone().requires_grad_(True)
+    k5 = kk.view(batches, n_kv, 2, heads, hd)
+    qh = qq.view(batches, n_q, heads, hd).permute(0, 2, 1, 3)
+    att = torch.softmax(qh @ k5[:, :, 0].permute(0, 2, 3, 1) * hd ** -0.5, -1)
+    out = (att @ k5[:, :, 1].permute(0, 2, 1, 3)).permute(0, 2, 1, 3).reshape(batches, n_q, C_)
+    want_dq, want_dkv = torch.autograd.grad(out, [qq, kk], dout.double())
+    assert dq.shape == (batches, n_q, C_) and dkv.shape == (batches * n_kv, 2 * C_)
+    assert O.rel_err(_np(dq), want_dq.cpu().numpy()) < 1.5e-2
+    assert O.rel_err(_np(dkv[:, :C_]), want_dkv[:, :C_].cpu().numpy()) < 1.5e-2   # dK
+    assert O.rel_err(_np(dkv[:, C_:]), want_dkv[:, C_:].cpu().numpy()) < 1.5e-2   # dV
+    dq2, dkv2 = ops.cross_attention_backward(q, kv, dout, batches, heads)
+    assert torch.equal(dq, dq2) and torch.equal(dkv, dkv2)  # deterministic
+
+
+@pytest.mark.parametrize("C_,llm,n,heads,F,N,B,mlp_type", [(256, 128, 16, 8, 3, 49, 2, "gelu-mlp"), (1024, 512, 64, 8, 4, 256, 2, "linear"),
+                                                          (768, 256, 64, 8, 2, 196, 1, "linear")])
+def test_attentive_pooler_training_matches_reference_autograd(C_, llm, n, heads, F, N, B, mlp_type):
+    """Forward + backward of the `attntv` resampler (bf16, attention and every Linear on the tensor cores) against torch autograd through
+    the UNMODIFIED reference AttentivePooler in fp32 on the same bf16-rounded parameters (oracle/_ref travels with the snapshot)."""
+    import copy
+
+    import merv_b200 as M
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    assert reference_available(), "oracle/_ref/nn_utils.py did not travel with the snapshot: run __graft_entry__.build() in the build container"
+    ref = load_reference_nn_utils()
+    torch.manual_seed(C_ + n)
+    r = ref.AttentivePooler(C_, llm, num_query_tokens=n, num_heads=heads, output_frames=F, mlp_type=mlp_type)
+    with torch.no_grad():
+        for name, p in r.named_parameters():
+            if name.endswith("bias") or "norm" in name:
+                p.add_(0.1 * torch.randn_like(p))
+        r.query_tokens.mul_(20.0)
+    m = M.AttentivePooler.from_reference(copy.deepcopy(r)).to(device=DEV, dtype=torch.bfloat16)
+    r = r.to(torch.bfloat16).float().to(DEV)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((B, F, N, C_), generator=g).to(torch.bfloat16).to(DEV)
+    G = torch.randn((B, F * n, llm), generator=g).to(DEV)
+    out = m(x)
+    out.backward(G.to(torch.bfloat16))
+    want = r(x.float())
+    want.backward(G)
+    torch.cuda.synchronize()
+    assert O.rel_err(_np(out), _np(want)) < BF16_TOL
+    got = dict(m.named_parameters())
+    for name, p in r.named_parameters():
+        assert got[name].grad is not None, name
+        scale = float(p.grad.abs().max())
+        err = float((got[name].grad.float() - p.grad).abs().max())
+        assert err <= 4e-2 * scale + 1e-6, (name, err / max(scale, 1e-12))
+    with torch.inference_mode():  # and the inference path agrees with the training path's forward
+        out_inf = m(x)
+    assert O.rel_err(_np(out_inf), _np(out)) < 1e-2

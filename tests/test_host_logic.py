@@ -346,3 +346,44 @@ def test_fused_training_is_automatic_unless_fsdp_manages_a_parameter():
     g = torch.Generator().manual_seed(1)
     out, w = m([torch.randn(2, 2, 16, c, generator=g).to(torch.bfloat16) for c in (16, 24)])
     assert out.requires_grad and not type(out.grad_fn).__name__.startswith("_FusedLinearFn")
+
+
+def test_attentive_pooler_backward_wiring_matches_reference_autograd(monkeypatch):
+    """Training the `attntv` resampler: _AttentivePoolFn (hand-written backward; every Linear as dW = dY^T X / dX = dY W, the attention
+    through cross_attention_backward, the query tokens' gradient summed over the frames) against torch autograd through the UNMODIFIED
+    reference AttentivePooler in fp32.  CPU: the kernels are emulated, so this pins the wiring; the kernels are checked on the GPU."""
+    import copy
+
+    import merv_b200 as M
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    if not reference_available():
+        pytest.skip("needs the reference's nn_utils.py")
+    kernel_emulation.emulate(monkeypatch)
+    ref = load_reference_nn_utils()
+    torch.manual_seed(11)
+    r = ref.AttentivePooler(64, 48, num_query_tokens=8, num_heads=2, output_frames=3, mlp_type="gelu-mlp")
+    with torch.no_grad():  # non-trivial biases / norms / queries (zeros / ones / std 0.02 by default)
+        for name, p in r.named_parameters():
+            if name.endswith("bias") or "norm" in name:
+                p.add_(0.1 * torch.randn_like(p))
+        r.query_tokens.mul_(20.0)
+    m = M.AttentivePooler.from_reference(copy.deepcopy(r)).to(torch.bfloat16)
+    r = r.to(torch.bfloat16).float()  # the same bf16-rounded parameters on both sides
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, 3, 9, 64), generator=g).to(torch.bfloat16)
+    G = torch.randn((2, 3 * 8, 48), generator=g)
+    out = m(x)
+    assert out.dtype == torch.bfloat16 and out.requires_grad
+    out.backward(G.to(torch.bfloat16))
+    want = r(x.float())
+    want.backward(G)
+    assert O.rel_err(_np(out), _np(want)) < 2e-2
+    got = dict(m.named_parameters())
+    seen = 0
+    for name, p in r.named_parameters():
+        assert got[name].grad is not None, name
+        scale = float(p.grad.abs().max())
+        assert float((got[name].grad.float() - p.grad).abs().max()) <= 4e-2 * scale + 1e-6, name
+        seen += 1
+    assert seen == 19  # query tokens, 2 LayerNorms, kv / q / proj / fc1 / fc2, the 2-layer projector
