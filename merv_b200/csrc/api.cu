@@ -94,6 +94,14 @@ int encode_tmap_cached(CUtensorMap* out, int dtype, int rank, const void* base, 
   }
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return fail(MERV_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread, and a thread whose first CUDA work is this
+  // call (autograd's worker thread entering a backward that starts with a GEMM) has none yet -> CUDA_ERROR_INVALID_CONTEXT.  One
+  // runtime call binds the device's primary context to the thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   cuuint64_t d[5], st[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }

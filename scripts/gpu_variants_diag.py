@@ -100,10 +100,42 @@ try:
             pool(xa[0])
         per = {k: round(sum(v), 4) for k, v in kt.durations_ms().items()}
     att_flop = 2 * 2 * 64 * 256 * 1024 * 16 * Ba  # QK^T and PV
+    kv_bytes = Ba * 16 * 256 * 2048 * 2  # the attention's compulsory read: K and V of every frame once
     rep["attentive_pooler_languagebind_16_videos"] = {
         "ms": ms_all, "device_ms_by_entry_point": dict(sorted(per.items(), key=lambda kv: -kv[1])),
-        "attention_TFLOPs_fp32_simt": att_flop / per.get("merv_cross_attention", float("nan")) / 1e9,
+        "attention_TFLOPs_tcgen05": att_flop / per.get("merv_cross_attention", float("nan")) / 1e9,
+        "attention_kv_GBps": kv_bytes / per.get("merv_cross_attention", float("nan")) / 1e6,
     }
+    os.environ["MERV_ATTN_IMPL"] = "simt"
+    with torch.inference_mode():
+        with ops.KernelTimer(timing=True) as kt:
+            pool(xa[0])
+    os.environ.pop("MERV_ATTN_IMPL")
+    rep["attentive_pooler_languagebind_16_videos"]["attention_ms_simt_fp32_kernel"] = round(sum(kt.durations_ms()["merv_cross_attention"]), 4)
+    # training step of the resampler (forward + backward, bf16)
+    poolt = M.AttentivePooler(1024, 4096, num_query_tokens=64, num_heads=8, output_frames=16, mlp_type="linear").to(device=dev, dtype=torch.bfloat16).train()
+    Gt = torch.randn(Ba, 16 * 64, 4096, generator=g, device=dev).to(torch.bfloat16)
+
+    def train_step(xx):
+        out = poolt(xx)
+        out.backward(Gt)
+        poolt.zero_grad(set_to_none=True)
+
+    for _ in range(2):  # plain event timing: autograd's worker thread does not take part in a CUDA-graph capture
+        train_step(xa[0])
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(6):
+        train_step(xa[i % 2])
+    t1.record()
+    torch.cuda.synchronize()
+    ms_train = t0.elapsed_time(t1) / 6
+    with ops.KernelTimer(timing=True) as kt:
+        train_step(xa[0])
+    per_t = {k: round(sum(v), 4) for k, v in kt.durations_ms().items()}
+    rep["attentive_pooler_languagebind_16_videos"]["train_step_ms"] = ms_train
+    rep["attentive_pooler_languagebind_16_videos"]["train_device_ms_by_entry_point"] = dict(sorted(per_t.items(), key=lambda kv: -kv[1]))
     print("attentive_pooler", rep["attentive_pooler_languagebind_16_videos"])
     json.dump(rep, open(os.path.join(REPO, "gpurun_out", "variants_diag.json"), "w"), indent=1)
 except Exception as e:  # noqa: BLE001
