@@ -1434,7 +1434,7 @@ class MervFusion(nn.Module):
         if tag is None:
             return None
         if hit is not None and hit[0] == tag:
-            return hit[1].run(xs, out, batch_index)
+            return hit[1].run(xs, out, batch_index, xs_checked=True)  # `key` holds exactly what run() would re-check about xs
         # general path once; remember the plan it used (if it took the single-call route)
         ff.__dict__["_last_plan"] = None
         projected = [proj(x) for proj, x in zip(self.projectors, xs)]

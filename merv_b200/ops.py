@@ -542,12 +542,14 @@ class FusedLinearPlan:
             d.pool[e].score_vec = vs[e].data_ptr()
             d.W[e], d.ldw[e], d.bias[e], d.c[e] = Ws[e].data_ptr(), Ws[e].stride(0), _p(biases[e]), cs[e].data_ptr()
 
-    def run(self, xs: Sequence[torch.Tensor], out: Optional[torch.Tensor], batch_index: Optional[torch.Tensor]):
+    def run(self, xs: Sequence[torch.Tensor], out: Optional[torch.Tensor], batch_index: Optional[torch.Tensor], xs_checked: bool = False):
+        """`xs_checked`: the caller looked this plan up under the shapes, strides, dtype and device of `xs` (MervFusion's per-call
+        cache key), so they need not be compared again — at B = 1 the call is host-bound and every microsecond of Python shows."""
         d = self.desc
         # the descriptor was built for these shapes / strides and this device: anything else would read or write out of bounds
         if len(xs) != self.E:
             raise ValueError(f"plan was built for {self.E} encoders, got {len(xs)}")
-        for x, (shape, stride) in zip(xs, self.x_meta):
+        for x, (shape, stride) in (() if xs_checked else zip(xs, self.x_meta)):
             if tuple(x.shape) != shape or tuple(x.stride()) != stride or x.dtype != torch.bfloat16 or x.device != self.dev:
                 raise ValueError(f"plan was built for bf16 features {shape} with strides {stride} on {self.dev}, "
                                  f"got {x.dtype} {tuple(x.shape)} with strides {tuple(x.stride())} on {x.device}")

@@ -292,7 +292,7 @@ class FusedLinearPlan:
     def rebind(self, vs, cs, Ws, biases):
         self.a = (*self.a[:2], list(vs), list(cs), list(Ws), list(biases))
 
-    def run(self, xs, out, batch_index):
+    def run(self, xs, out, batch_index, xs_checked=False):
         assert [(tuple(x.shape), tuple(x.stride())) for x in xs] == self.x_meta, "plan re-run with different shapes / strides"
         out_frames, out_size, vs, cs, Ws, biases = self.a
         pooled, partials = pool3d(xs, out_frames, out_size, score_vecs=vs, batch_index=batch_index)
