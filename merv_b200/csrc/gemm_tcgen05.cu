@@ -52,7 +52,7 @@ constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;    // 640
 constexpr int EPI_COLS = BN / (EPI_WARPS / 4);         // 64 accumulator columns per epilogue warp
 static_assert(MERV_ROWDOT_BLOCK == EPI_COLS, "one row-dot partial per epilogue warp slice");
 constexpr int TMEM_COLS = 512;
-constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 40, EPILOGUE_REGS = 104;  // see setmaxnreg below
+constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 64, EPILOGUE_REGS = 104;  // see setmaxnreg below
 static_assert(GEMM_THREADS * KERNEL_REGS <= 65536, "register file");
 static_assert(128 * PRODUCER_REGS + EPI_WARPS * 32 * EPILOGUE_REGS <= GEMM_THREADS * KERNEL_REGS, "setmaxnreg.inc must fit in what setmaxnreg.dec released");
 
@@ -92,7 +92,9 @@ struct TensorMaps {
 // kCtas == 1: one CTA per 128 x 256 tile.  kCtas == 2: a CTA pair (cluster 2x1, cta_group::2) per 256 x 256 tile — each CTA
 // holds its 128 rows of A and HALF of the W tile, the leader's single thread issues UMMA 256x256x16 for both SMs, each
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
-template <int kCtas, bool kWide, bool kGelu>
+// kMn: the variant that honours MN-major operand flags (backward GEMMs).  It is a separate instantiation because the single producer /
+// MMA threads run on 40 registers: the per-segment majorness selects cost the forward kernels 14 % when they were runtime branches.
+template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
   using C = Cfg<kCtas, kWide>;
@@ -154,7 +156,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   pdl_wait();
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");  // 128 x 64 + 512 x 104 = 61440 = the whole launch-time allocation
     if (warp == 0 && lane == 0) {
       // ===== TMA producer =====
       uint32_t it = 0;
@@ -167,7 +169,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar + 8 * stage, ph ^ 1u);  // own barrier: the pair's MMA commit is multicast to both CTAs
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
-            const bool a_mn = (p.a_mn_mask >> s) & 1, b_mn = (p.b_mn_mask >> s) & 1;
+            const bool a_mn = kMn && ((p.a_mn_mask >> s) & 1), b_mn = kMn && ((p.b_mn_mask >> s) & 1);
             const int m0 = (m_blk * kCtas + int(rank)) * BM, n0 = n_blk * BN + int(rank) * C::B_ROWS;
             const uint32_t bar = (kCtas == 2 ? leader_full : full_bar) + 8 * stage;
             // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
@@ -198,7 +200,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       uint32_t it = 0, acc_it = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         for (int s = 0; s < p.nseg; ++s, ++acc_it) {
-          const bool a_mn = (p.a_mn_mask >> s) & 1, b_mn = (p.b_mn_mask >> s) & 1;
+          const bool a_mn = kMn && ((p.a_mn_mask >> s) & 1), b_mn = kMn && ((p.b_mn_mask >> s) & 1);
           const uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN, a_mn, b_mn);
           // per UMMA (16 k): +32 bytes inside the swizzle atom for a K-major operand, +2 atoms of 8 k-rows for an MN-major one
           const uint32_t a_step = a_mn ? (2048u >> 4) : 2u, b_step = b_mn ? (2048u >> 4) : 2u;
@@ -406,14 +408,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
 // vs 1.377 (1398) for the single CTA; plain K = 1024: 0.424 (1297) vs 0.454 (1210); + GELU 0.452 vs 0.463; M = 262144, K = 768: 1.372 vs
 // 1.378.  (Round 1 had the fused GEMM 2 % slower on the pair; that was measured inside long power-capped loops.)  cuBLAS on the same
 // shapes: 1.225 / 0.402 / - / 1.265 ms.  MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
-// The pair only pays for wide outputs: at N = 1024 / 768 (the backward's Z_e = dOut W_e and dW_e GEMMs, 4 / 3 column blocks) it is 13-25 %
-// SLOWER than the single CTA (65536 x 1024 x 4096: 0.480 vs 0.417 ms; dW 4096 x 1024 x 65536: 0.528 vs 0.419 — profiles/r2_bwd_lab.json).
-static int gemm_cta_group(int M, int N) {
+// K-major operands: the pair wins at every shape measured with more than one row block (65536 x 1024 x 4096: 0.403 vs 0.417 ms; 65536 x
+// 768 x 4096: 0.293 vs 0.338; the shapes above).  MN-major operands (the backward's dW = dY^T X, dX = dY W): the single CTA reads them as
+// fast as K-major ones (0.416 vs 0.414 ms) but the pair does not (0.533 vs 0.400) — profiles/r2_bwd_lab.json — so those run on one CTA.
+static int gemm_cta_group(int M, bool mn_major) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
   if (M <= BM) return 1;  // a pair computes 256 rows: with at most 128 rows its second CTA would only multiply padding
-  return N >= 2048 ? 2 : 1;
+  return mn_major ? 1 : 2;
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
@@ -424,14 +427,14 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int kCtas, bool kWide, bool kGelu>
+template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
 static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const GemmParams& p) {
   constexpr int smem = Cfg<kCtas, kWide>::SMEM_BYTES;
   static const cudaError_t attr_rc =  // once per variant (thread-safe static init)
-      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
   cfg.dynamicSmemBytes = smem;
-  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu>, maps, p));
+  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMn>, maps, p));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }
@@ -450,7 +453,9 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
   (void)total_k;
-  const int ctas = gemm_cta_group(M, N);
+  bool any_mn = false;
+  for (int i = 0; i < nseg; ++i) any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
+  const int ctas = gemm_cta_group(M, any_mn);
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
@@ -546,6 +551,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
+  if (p.a_mn_mask | p.b_mn_mask) {
+    MERV_REQUIRE(act == MERV_ACT_NONE && !wide, MERV_E_ARG, "gemm: MN-major operands are supported without an activation and without extra output destinations");
+    return ctas == 2 ? launch_variant<2, false, false, true>(cfg, maps, p) : launch_variant<1, false, false, true>(cfg, maps, p);
+  }
   if (act == MERV_ACT_GELU_ERF) return ctas == 2 ? launch_variant<2, false, true>(cfg, maps, p) : launch_variant<1, false, true>(cfg, maps, p);
   if (ctas == 2) return wide ? launch_variant<2, true, false>(cfg, maps, p) : launch_variant<2, false, false>(cfg, maps, p);
   return wide ? launch_variant<1, true, false>(cfg, maps, p) : launch_variant<1, false, false>(cfg, maps, p);
