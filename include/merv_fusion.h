@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MERV_ABI_VERSION 4
+#define MERV_ABI_VERSION 5
 
 enum { MERV_F32 = 0, MERV_BF16 = 1 };
 enum { MERV_ACT_NONE = 0, MERV_ACT_GELU_ERF = 1 };
@@ -77,6 +77,12 @@ typedef struct {
   int32_t F, H, W, C, T, S;
   int64_t x_batch_stride, x_frame_stride, x_token_stride;
   int64_t y_batch_stride, y_row_stride;
+  /* ABI v5: the pooling windows read x displaced by (shift_f, shift_h, shift_w) frames / patch rows / patch columns, positions that
+   * fall outside the [F, H, W] grid contributing ZERO while the divisor stays the full window size — i.e. the adaptive average pool of
+   * one tap of a zero-padded "same" convolution.  pool(conv3d(x)) = sum_taps W_tap pool(shift_tap(x)) + b, so the 27 shifted poolings
+   * written side by side ([B, T*S*S, 27*C], y_row_stride = 27*C) are the A operand of ONE GEMM that evaluates
+   * Convolutional3DProjector.convolution_pooling (merv/util/nn_utils.py:349-352,364) on the pooled grid.  All zero: plain pooling. */
+  int32_t shift_f, shift_h, shift_w, reserved_;
 } merv_pool_desc;
 
 /* parts[e] = number of score partials per video the pool kernel emits for encoder e (independent of B). */
@@ -237,6 +243,13 @@ int merv_fused_linear_mix_multicast(const void* const* A, const int64_t* lda, co
  *   W, ldw, bias, c: last-layer weights [N, C_e], biases [N] (bf16) and score constants c_e (fp32 [1]) per encoder
  *   scores, weights: workspaces fp32 [B, E]; bias_mix fp32 [B, N]; weights_bf16 (optional) bf16 [B, E] copy of weights
  *   out            : bf16 [B, rows_per_video, N] with row stride ldo and batch stride out_batch_stride (0 = contiguous)
+ * Pool assist (large batches of the shipped encoder shapes: square 16 x 16 / 14 x 14 patch grids -> 8 x 8, one input frame per output
+ * frame, sync_ws given, B > assist_head): the pool is HBM-bound with an idle tensor pipe and the GEMM tensor-bound with idle HBM, so
+ * only the first assist_head videos go through the standalone pool + scores kernels; the rest are pooled, scored and soft-maxed by two
+ * spare warps of every GEMM CTA while the tensor cores multiply the videos before them (per-video ready flags, release / acquire).
+ * Pooled tokens, scores, weights and the prefix are bit-identical to the three-launch path.  Opt-in: MERV_POOL_ASSIST=1 in the
+ * environment (read per call; measured neutral-to-slower on B200 under the power cap); MERV_ASSIST_HEAD=n
+ * overrides the head.
  * ------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t num_encoders, B, N, rows_per_video;
@@ -252,6 +265,11 @@ typedef struct {
   void* weights_bf16; /* may be NULL */
   void* out;
   int64_t ldo, out_batch_stride;
+  /* ABI v5: workspace of the in-GEMM pooling ("pool assist", see below), int32 [sync_ws_ints] on the device with
+   * sync_ws_ints >= 4 + 2 * B, or NULL (then the three-launch path always runs).  Contents need no initialisation. */
+  int32_t* sync_ws;
+  int32_t sync_ws_ints;
+  int32_t assist_head; /* videos pooled by the standalone kernel before the GEMM starts; 0 = library default */
 } merv_fused_desc;
 
 int merv_fused_forward(const merv_fused_desc* d, void* stream);

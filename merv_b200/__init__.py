@@ -15,6 +15,7 @@ _lib.load()  # fail loudly at import time if the CUDA library has not been built
 
 from .nn_utils import (  # noqa: E402
     AttentivePooler,
+    Convolutional3DProjector,
     AveragePooling3DProjector,
     AveragePoolingProjector,
     ConcatChannelFusion,
@@ -36,6 +37,6 @@ from .nn_utils import (  # noqa: E402
 )
 
 __all__ = [
-    "AttentivePooler", "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
+    "AttentivePooler", "Convolutional3DProjector", "AveragePooling3DProjector", "AveragePoolingProjector", "ScalarAdapter", "ConcatChannelFusion", "ConcatChannelLNFusion", "MLPDeepProjector", "CrossAttentionAdapterLearnableQuery", "DeferredProjection", "FusedMLPProjector",
     "LinearProjector", "MervFusion", "MLPProjector", "TokenResampler", "fsdp_wrap_policy", "get_mlp_projector", "link_fused", "patch_merv", "unlink",
 ]

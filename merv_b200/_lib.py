@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1
 MAX_ENCODERS, MAX_SEGMENTS, ROWDOT_BLOCK = 8, 4, 64
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ERROR_NAMES = {-1: "MERV_E_SHAPE", -2: "MERV_E_ALIGN", -3: "MERV_E_DTYPE", -4: "MERV_E_ARCH", -5: "MERV_E_CUDA", -6: "MERV_E_ARG"}
 
@@ -35,6 +35,7 @@ class PoolDesc(C.Structure):
         ("F", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("T", c_int32), ("S", c_int32),
         ("x_batch_stride", c_int64), ("x_frame_stride", c_int64), ("x_token_stride", c_int64),
         ("y_batch_stride", c_int64), ("y_row_stride", c_int64),
+        ("shift_f", c_int32), ("shift_h", c_int32), ("shift_w", c_int32), ("reserved_", c_int32),
     ]
 
 
@@ -47,6 +48,7 @@ class FusedDesc(C.Structure):
         ("W", c_void_p * 4), ("ldw", c_int64 * 4), ("bias", c_void_p * 4), ("c", c_void_p * 4),
         ("scores", c_void_p), ("weights", c_void_p), ("bias_mix", c_void_p), ("weights_bf16", c_void_p),
         ("out", c_void_p), ("ldo", c_int64), ("out_batch_stride", c_int64),
+        ("sync_ws", c_void_p), ("sync_ws_ints", c_int32), ("assist_head", c_int32),
     ]
 
 

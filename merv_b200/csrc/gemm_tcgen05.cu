@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "pool_assist.cuh"
 #include "tcgen05_util.cuh"
 #include "tmap.cuh"
 
@@ -36,15 +37,19 @@ constexpr int EPI_WARPS = 16;                          // 4 per scheduler: the e
 constexpr int OUT_GROUPS = EPI_WARPS / 4;              // 4 groups of 4 warps, one staging box each
 // kWide (the fused all-gather variant): output boxes of 128-byte rows instead of 64-byte rows — NVLink peer writes are
 // packetised per box row, and 64-byte payloads only reach ~380 GB/s of egress — paid for with one ring stage.
-template <int kCtas, bool kWide> struct Cfg {
-  static constexpr int STAGES = (kCtas == 1 ? 4 : 6) - (kWide ? 1 : 0);
+// kAssist (pool_assist.cuh): one ring stage becomes the quarter-slab buffers of the two pooling warps.
+template <int kCtas, bool kWide, bool kAssist = false> struct Cfg {
+  static_assert(!kAssist || (kCtas == 2 && !kWide), "the pooling warps ride on the CTA-pair forward kernel");
+  static constexpr int STAGES = (kCtas == 1 ? 4 : 6) - (kWide ? 1 : 0) - (kAssist ? 1 : 0);
   static constexpr int B_ROWS = BN / kCtas;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;  // 192 KB (144 / 160 KB when wide)
   static constexpr int OUT_BOX_COLS = kWide ? 64 : 32;      // one staged output box: 128 rows x 32 (64) bf16, 64B (128B) swizzle
   static constexpr int OUT_BOX_BYTES = BM * OUT_BOX_COLS * 2;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + 256 /*barriers*/;
+  static constexpr int ASSIST_BYTES = kAssist ? ASSIST_SMEM_BYTES : 0;
+  static_assert(!kAssist || ASSIST_SMEM_BYTES == STAGE_BYTES, "the pooling buffers take exactly the ring stage given up");
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + ASSIST_BYTES + 256 /*barriers*/;
   static_assert(RING_BYTES % 1024 == 0 && OUT_BOX_BYTES % 1024 == 0, "swizzle atoms need 1024-byte aligned boxes");
   static_assert(SMEM_BYTES <= 232448, "227 KB of shared memory per CTA");
 };
@@ -94,10 +99,9 @@ struct TensorMaps {
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
 // kMn: the variant that honours MN-major operand flags (backward GEMMs).  It is a separate instantiation because the single producer /
 // MMA threads run on 40 registers: the per-segment majorness selects cost the forward kernels 14 % when they were runtime branches.
-template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
-  using C = Cfg<kCtas, kWide>;
+template <int kCtas, bool kWide, bool kGelu, bool kMn, bool kAssist>
+__device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmParams& p, const AssistArgs* ap) {
+  using C = Cfg<kCtas, kWide, kAssist>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RING_BYTES = C::RING_BYTES;
   constexpr int OUT_BOX_COLS = C::OUT_BOX_COLS, OUT_BOX_BYTES = C::OUT_BOX_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -105,12 +109,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
   const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* tiles = smem_raw + (tiles_addr - raw_addr);
   const uint32_t stage_out_addr = tiles_addr + RING_BYTES;  // 4 x 8 KB, 1024-byte aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES);
+  const uint32_t assist_addr = stage_out_addr + OUT_GROUPS * OUT_BOX_BYTES;  // kAssist: 2 warps x 2 quarter slabs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + RING_BYTES + OUT_GROUPS * OUT_BOX_BYTES + C::ASSIST_BYTES);
   const uint32_t full_bar = smem_u32(bars);                  // [STAGES]
   const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
   const uint32_t tfull_bar = empty_bar + 8 * STAGES;         // [2]
   const uint32_t tempty_bar = tfull_bar + 16;                // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t assist_bar = full_bar + 8 * (2 * STAGES + 4) + 16;  // [ASSIST_WARPS][2], behind the TMEM pointer
+  static_assert(8 * (2 * 6 + 4) + 16 + 8 * 2 * ASSIST_WARPS <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;  // 0 = leader of the pair
@@ -134,6 +141,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       mbar_init(tfull_bar + 8 * i, 1);
       mbar_init(tempty_bar + 8 * i, EPI_WARPS * kCtas);  // in a pair, both CTAs' epilogue warps arrive on the leader's barrier
     }
+    if constexpr (kAssist)
+      for (int i = 0; i < 2 * ASSIST_WARPS; ++i) mbar_init(assist_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -161,8 +170,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
       // ===== TMA producer =====
       uint32_t it = 0;
       const uint32_t leader_full = kCtas == 2 ? mapa_rank(full_bar, 0) : full_bar;
+      int ready_video = -1;  // kAssist: last video whose ready flag this thread has acquired
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
+        if constexpr (kAssist) {
+          // the pooled rows of this CTA's half of the tile (and the video's mixing weights / bias row the epilogue will read) are
+          // produced inside this launch by the pooling warps of whatever CTAs are resident: acquire the video's flag first
+          const int video = ((m_blk * kCtas + int(rank)) * BM) / p.rows_per_video;
+          if (video != ready_video) {
+            if (video >= ap->head && !(MERV_ASSIST_PROFILE && (ap->dbg & 8))) {
+              const int* flag = ap->sync + ASSIST_SYNC_HEADER + ap->B + video;
+              if (ld_acquire_gpu(flag) == 0) {
+                const unsigned long long t0 = globaltimer_ns();
+                while (ld_acquire_gpu(flag) == 0) {
+                  __nanosleep(128);
+                  if (globaltimer_ns() - t0 > 4000000000ull) {
+                    printf("merv gemm: pool assist never published video %d (block %d)\n", video, blockIdx.x);
+                    __trap();
+                  }
+                }
+              }
+              fence_proxy_async_all();  // generic-proxy stores of the pooling warps -> this thread's async-proxy (TMA) reads
+            }
+            ready_video = video;
+          }
+        }
         for (int s = 0; s < p.nseg; ++s) {
           const int nkb = p.kblocks[s];
           for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -230,6 +262,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
           else umma_commit(tfull_bar + 8 * buf);
         }
       }
+    } else if (kAssist && warp >= 2) {
+      // ===== pooling warps (pool_assist.cuh): pool, score and soft-max the videos ahead of the tiles being multiplied =====
+      if constexpr (kAssist)
+        if (!(MERV_ASSIST_PROFILE && (ap->dbg & 16)))
+        assist_warp_loop(*ap, assist_addr + uint32_t(warp - 2) * 2u * ASSIST_QUARTER_BYTES, assist_bar + 16u * uint32_t(warp - 2), lane,
+                         int(blockIdx.x) * ASSIST_WARPS + (warp - 2));
     }
   } else {
     // Register redistribution happens INSIDE the CTA's launch-time allocation (640 threads x 96 = 61440): warps 0-3 give
@@ -271,7 +309,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
               Vec16<__nv_bfloat16>::unpack(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
             } else if (p.bias_rows != nullptr) {
               const float4* br = reinterpret_cast<const float4*>(p.bias_rows + (long long)video * p.N + n);
-              const float4 b0 = __ldg(br), b1 = __ldg(br + 1);
+              const float4 b0 = kAssist ? __ldcg(br) : __ldg(br), b1 = kAssist ? __ldcg(br + 1) : __ldg(br + 1);
               b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
             } else {
 #pragma unroll
@@ -360,8 +398,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
         for (int i = 0; i < EPI_COLS; ++i) sum[i] = 0.f;
         for (int s = 0; s < p.nseg; ++s, ++acc_it) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
-          const float scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
+          float scale = 1.0f;
+          if constexpr (!kAssist) scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
           mbar_wait(tfull_bar + 8 * buf, aph);
+          // pool assist: the video's mixing weights are written inside this launch; the full accumulator implies (mbarrier chain from
+          // the producer's acquire) that they are published — read them from L2
+          if constexpr (kAssist) scale = __ldcg(p.seg_scale + (long long)video * p.nseg + s);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
 #pragma unroll
@@ -400,6 +442,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_c
     else
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
+}
+
+template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
+  gemm_body<kCtas, kWide, kGelu, kMn, false>(maps, p, nullptr);
+}
+
+// the fused forward GEMM (CTA pair, K-major operands) whose two spare warps pool the videos ahead of the tiles (pool_assist.cuh)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pool_assist_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p,
+                                const __grid_constant__ AssistArgs assist) {
+  gemm_body<2, false, false, false, true>(maps, p, &assist);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -441,7 +496,8 @@ static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
-                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl, void* mc_out) {
+                        int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl, void* mc_out,
+                        const AssistArgs* assist) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -455,7 +511,10 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   (void)total_k;
   bool any_mn = false;
   for (int i = 0; i < nseg; ++i) any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
-  const int ctas = gemm_cta_group(M, any_mn);
+  const int ctas = assist != nullptr ? 2 : gemm_cta_group(M, any_mn);
+  MERV_REQUIRE(assist == nullptr || (!any_mn && M > BM && num_extra == 0 && mc_out == nullptr && act == MERV_ACT_NONE && seg_scale && bias_rows &&
+                                     rowdot_vec == nullptr),
+               MERV_E_ARG, "gemm: pool assist rides on the plain fused forward GEMM only");
   // wide output boxes only pay when the kernel is NVLink-bound: with one peer (2 GPUs) it still is tensor-bound and the
   // ring stage given up for the staging costs more (2.05 vs 1.95 ms); from 2 peers on the link decides (3.15 vs 4.36 ms
   // at 4 GPUs).  MERV_GEMM_WIDE_OUT=0|1 overrides, for the tests.
@@ -463,6 +522,7 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   // 2.15 ms with 128-byte rows and 2.75 ms with 64-byte rows (compute alone 1.71 ms) — so the multicast variant uses the wide boxes too
   bool wide = num_extra >= 2 || mc_out != nullptr;
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
+  if (assist != nullptr) wide = false;
   MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
   if (act != MERV_ACT_NONE) {
     MERV_REQUIRE(nseg == 1 && seg_scale == nullptr, MERV_E_ARG, "gemm: an activation needs a single segment without per-video scales");
@@ -551,6 +611,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
+  if (assist != nullptr) {
+    constexpr int smem = Cfg<2, false, true>::SMEM_BYTES;
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_pool_assist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
+    cfg.dynamicSmemBytes = smem;
+    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_pool_assist_tcgen05_kernel, maps, p, *assist));
+    MERV_CUDA_OK(cudaGetLastError());
+    return MERV_OK;
+  }
   if (p.a_mn_mask | p.b_mn_mask) {
     MERV_REQUIRE(act == MERV_ACT_NONE && !wide, MERV_E_ARG, "gemm: MN-major operands are supported without an activation and without extra output destinations");
     return ctas == 2 ? launch_variant<2, false, false, true>(cfg, maps, p) : launch_variant<1, false, false, true>(cfg, maps, p);

@@ -29,6 +29,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "pool_assist.cuh"
 #include "tmap.cuh"
 
 namespace merv {
@@ -96,6 +97,7 @@ struct PoolTmaEnc {
   int nf_max;    // frames per slab (longest temporal window)
   int item_begin, items;  // range in the global item list; items = B * T * nchunks
   int slab_bytes;
+  int sf, sh, sw;         // displacement of the windows (a convolution tap); out-of-grid positions are zero-filled by the TMA unit
   long long ybs, yrs;
 };
 struct PoolTmaParams {
@@ -149,24 +151,6 @@ __device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, 
   asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global [%0, {%1, %2, %3, %4, %5}];"
                ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-  return r;
-}
-
-// predicated 128-bit shared load: zeros when !ok, no branch
-__device__ __forceinline__ uint4 lds_v4_if(uint32_t addr, bool ok) {
-  uint4 r;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %5, 0;\n\t"
-      "mov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
-      "@p ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
-      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr), "r"(uint32_t(ok)));
-  return r;
-}
-
 __device__ __forceinline__ int pt_find_encoder(const PoolTmaParams& p, int item) {
   int e = 0;
 #pragma unroll 1
@@ -182,12 +166,6 @@ __device__ __forceinline__ int pt_find_encoder(const PoolTmaParams& p, int item)
 // every input row of its half it sums the 2-3 taps of its column window ONCE (packed fp32 adds) and adds that row sum to
 // the 1-2 output rows whose window holds the row.  ~2x fewer instructions per output, same shared-memory traffic pattern
 // (8 lanes cover one 128-byte row: conflict-free).
-template <int N_IN, int N_OUT>
-struct PoolWin {
-  __host__ __device__ static constexpr int lo(int i) { return (i * N_IN) / N_OUT; }
-  __host__ __device__ static constexpr int hi(int i) { return ((i + 1) * N_IN + N_OUT - 1) / N_OUT; }
-};
-
 template <typename T, int H, int S, int HF>
 __device__ __forceinline__ void pool_square_half(uint32_t slab, int nf, int v, int wo, T* __restrict__ yb, long long yrs, bool c_ok,
                                                  const float* sv, float inv_nf, float& dot) {
@@ -336,7 +314,7 @@ pool3d_tma_kernel(const __grid_constant__ PoolTmaMaps maps, const __grid_constan
         t = bt % e.T;
         b = bt / e.T;
         window(t, e.F, e.T, f0, f1);
-        if (MERV_POOL_L2_PREFETCH) tma_prefetch_5d(&maps.m[ei], chunk * e.cb, 0, 0, f0, b);  // the whole batch, up front
+        if (MERV_POOL_L2_PREFETCH) tma_prefetch_5d(&maps.m[ei], chunk * e.cb, e.sw, e.sh, f0 + e.sf, b);  // the whole batch, up front
       }
       __syncwarp();
       const int remaining = (p.total_items - base_item + stride - 1) / stride;
@@ -350,7 +328,7 @@ pool3d_tma_kernel(const __grid_constant__ PoolTmaMaps maps, const __grid_constan
           smeta[stage] = make_int4(ei | ((f1 - f0) << 8), chunk, b, t);  // ordered before the consumers' acquire by the arrive below
           pt_mbar_expect_tx(full_bar + 8 * stage, e.slab_bytes);
           // the box always spans nf_max frames starting at f0; frames past the window (or past F: zero-filled) are ignored
-          tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, 0, 0, f0,
+          tma_load_5d(&maps.m[ei], full_bar + 8 * stage, slab_addr + stage * PT_STAGE_BYTES, chunk * e.cb, e.sw, e.sh, f0 + e.sf,
                       e.batch_index ? __ldg(e.batch_index + b) : b);
         }
         __syncwarp();
@@ -461,6 +439,7 @@ struct PoolEnc {
   const int* batch_index;
   int F, H, W, C, T, S;
   int src_batch;              // videos in x (bound of the batch_index gather)
+  int sf, sh, sw;             // displacement of the windows (a convolution tap); out-of-grid positions contribute zero
   int rows_per_item, groups;  // output rows handled by one CTA; groups = ceil(S / rows_per_item)
   int items;                  // B * T * groups
   long long xbs, xfs, xts, ybs, yrs;
@@ -505,12 +484,18 @@ __global__ void __launch_bounds__(256) pool3d_direct_kernel(const __grid_constan
 #pragma unroll
         for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
         for (int f = f0; f < f1; ++f) {
+          const int fs = f + e.sf;
+          if (fs < 0 || fs >= e.F) continue;
           for (int h = h0; h < h1; ++h) {
-            const T* row = xb + (long long)f * e.xfs + (long long)(h * e.W) * e.xts + (long long)v * VEC;
+            const int hs = h + e.sh;
+            if (hs < 0 || hs >= e.H) continue;
+            const T* row = xb + (long long)fs * e.xfs + (long long)(hs * e.W) * e.xts + (long long)v * VEC;
 #pragma unroll 3
             for (int w = w0; w < w1; ++w) {
+              const int ws = w + e.sw;
+              if (ws < 0 || ws >= e.W) continue;
               float val[VEC];
-              Vec16<T>::unpack(ldg_v4(row + (long long)w * e.xts), val);
+              Vec16<T>::unpack(ldg_v4(row + (long long)ws * e.xts), val);
 #pragma unroll
               for (int c = 0; c < VEC; ++c) acc[c] += val[c];
             }
@@ -631,6 +616,7 @@ static int launch_tma(const merv_pool_desc* enc, int n, int B, int dtype, int ma
     e.F = d.F; e.H = d.H; e.W = d.W; e.C = d.C; e.T = d.T; e.S = d.S;
     e.nf_max = pl.nf_max; e.cb = pl.cb; e.vpr = pl.vpr; e.vshift = pl.vpr == 8 ? 3 : pl.vpr == 4 ? 2 : pl.vpr == 2 ? 1 : 0; e.nchunks = pl.nchunks; e.units = pl.units; e.slab_bytes = pl.slab_bytes;
     e.item_begin = begin; e.items = B * d.T * pl.nchunks;
+    e.sf = d.shift_f; e.sh = d.shift_h; e.sw = d.shift_w;
     begin += e.items;
     e.ybs = d.y_batch_stride; e.yrs = d.y_row_stride;
     // x as a 5-D tensor (C, W, H, F, B), channel innermost; one box = the [nf_max, H, W, cb] slab of one output frame
@@ -664,6 +650,7 @@ static int launch_direct(const merv_pool_desc* enc, int n, int B, int dtype, cud
     e.x = d.x; e.y = d.y; e.score_vec = d.score_vec; e.score_partial = d.score_partial; e.batch_index = d.batch_index;
     e.F = d.F; e.H = d.H; e.W = d.W; e.C = d.C; e.T = d.T; e.S = d.S;
     e.src_batch = d.batch_index && d.src_batch > 0 ? d.src_batch : B;
+    e.sf = d.shift_f; e.sh = d.shift_h; e.sw = d.shift_w;
     e.rows_per_item = direct_rows_per_item(d.S);
     e.groups = (d.S + e.rows_per_item - 1) / e.rows_per_item;
     e.items = B * d.T * e.groups;
@@ -681,6 +668,63 @@ static int launch_direct(const merv_pool_desc* enc, int n, int B, int dtype, cud
     pool3d_direct_kernel<float><<<grid, threads, 0, s>>>(p);
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
+}
+
+// ---- pool assist (pool_assist.cuh): argument block of the in-GEMM pooling for merv_fused_forward ----
+bool build_pool_assist(const merv_fused_desc* d, int head, AssistArgs* args, int* rc) {
+  *rc = MERV_OK;
+  const int E = d->num_encoders;
+  if (E < 1 || E > MERV_MAX_SEGMENTS || d->sync_ws == nullptr || head < 1 || head >= d->B) return false;
+  if (d->sync_ws_ints < ASSIST_SYNC_HEADER + 2 * d->B) return false;
+  if (!use_tma(d->pool, E, MERV_BF16)) return false;
+  AssistArgs a;
+  memset(&a, 0, sizeof(a));
+  int begin = 0;
+  for (int e = 0; e < E; ++e) {
+    const merv_pool_desc& p = d->pool[e];
+    const TmaPlan pl = plan_tma(p, MERV_BF16);
+    // the shipped encoders: square 16 x 16 / 14 x 14 patch grids pooled to 8 x 8, one input frame per output frame, 128-byte channel chunks
+    if (p.shift_f != 0 || p.shift_h != 0 || p.shift_w != 0) return false;
+    if (!(pl.ok && pl.vpr == 8 && pl.nf_max == 1 && p.F == p.T && p.S == ASSIST_S && p.H == p.W && (p.H == 16 || p.H == 14) && pl.nchunks <= 511 &&
+          p.T < (1 << 18)))
+      return false;
+    AssistEnc& en = a.enc[e];
+    en.y = static_cast<__nv_bfloat16*>(p.y); en.score_vec = p.score_vec; en.score_partial = p.score_partial; en.batch_index = p.batch_index;
+    en.c = d->c[e]; en.bias = static_cast<const __nv_bfloat16*>(d->bias[e]);
+    en.ybs = p.y_batch_stride; en.yrs = p.y_row_stride;
+    en.H = p.H; en.C = p.C; en.T = p.T; en.nchunks = pl.nchunks;
+    en.item_begin = begin;
+    en.parts = p.T * pl.nchunks * PT_GROUP_WARPS;
+    if (en.parts != d->parts[e]) return false;  // the caller sized the partials for another kernel plan
+    begin += p.T * pl.nchunks * 2;
+    const unsigned long long dims[5] = {(unsigned long long)p.C, (unsigned long long)p.W, (unsigned long long)p.H, (unsigned long long)p.F,
+                                        (unsigned long long)(p.batch_index && p.src_batch > 0 ? p.src_batch : d->B)};
+    const unsigned long long strides[4] = {(unsigned long long)p.x_token_stride * 2, (unsigned long long)p.x_token_stride * p.W * 2,
+                                           (unsigned long long)p.x_frame_stride * 2, (unsigned long long)p.x_batch_stride * 2};
+    const unsigned box[5] = {ASSIST_CB, (unsigned)p.W, ASSIST_ROWS, 1, 1};
+    if ((*rc = encode_tmap_cached(&a.m[e], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) != MERV_OK) return false;
+  }
+  for (int e = E; e < MERV_MAX_SEGMENTS; ++e) a.m[e] = a.m[0];
+  const long long total = (long long)begin * (d->B - head);
+  if (total > 0x7fffffffLL - 4096) return false;
+  a.n_enc = E; a.head = head; a.B = d->B; a.items_per_video = begin; a.total_items = int(total); a.N = d->N; a.rows_per_video = d->rows_per_video;
+  // items per fetch: amortises the release fence + completion atomic; must divide a video's item count (always even: two halves)
+  a.group = 2;
+  for (int g = 8; g > 2; g >>= 1)
+    if (begin % g == 0) { a.group = g; break; }
+  if (const char* e = getenv("MERV_ASSIST_GROUP")) {
+    const int g = atoi(e);
+    if (g >= 1 && begin % g == 0) a.group = g;
+  }
+  a.prof = nullptr;
+  a.dbg = 0;
+  if (const char* e = getenv("MERV_ASSIST_DBG")) a.dbg = atoi(e);
+  if (const char* e = getenv("MERV_ASSIST_PROFILE"))
+    if (e[0] == '1' && d->sync_ws_ints >= ASSIST_SYNC_HEADER + 2 * d->B + 8 * ASSIST_WARPS * sm_count()) a.prof = d->sync_ws + ASSIST_SYNC_HEADER + 2 * d->B;
+  a.sync = d->sync_ws; a.scores = d->scores; a.weights = d->weights; a.weights_bf16 = static_cast<__nv_bfloat16*>(d->weights_bf16);
+  a.bias_mix = d->bias_mix;
+  *args = a;
+  return true;
 }
 
 }  // namespace merv

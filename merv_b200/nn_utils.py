@@ -12,6 +12,7 @@ error behaviour as the reference (paths below are relative to the reference root
     AveragePoolingProjector              merv/util/nn_utils.py:136-174    (2-D "avg")
     AttentivePooler (+ CrossAttention, MLP, CrossAttentionBlock containers)   merv/util/nn_utils.py:177-246,380-452  ("attntv", inference)
     AveragePooling3DProjector            merv/util/nn_utils.py:306-338
+    Convolutional3DProjector             merv/util/nn_utils.py:341-377    ("3dconv": 27 displaced poolings + one GEMM on the pooled grid)
     CrossAttentionAdapterLearnableQuery  merv/util/nn_utils.py:455-521    (averagetoken either way, positional embedding)
     ScalarAdapter                        merv/util/nn_utils.py:524-537
     ConcatChannelFusion / ConcatChannelLNFusion                               merv/models/vidlms/merv.py:217-223,603-606
@@ -188,6 +189,40 @@ class _ProjectorFn(torch.autograd.Function):
         if dx is not None:
             dx = dx.reshape(xs[0].shape)
         return (dx, None, None, None, None, *grads)
+
+
+class _ConvTapsFn(torch.autograd.Function):
+    """pool(conv3d(x)) as ONE GEMM over the 27 pooled taps (Convolutional3DProjector.convolution_pooling, nn_utils.py:349-352,364).
+
+    forward : Y = A W2^T + b with A [M, 27 C] = ops.pool3d_conv_taps(x) and W2 [K, 27 C] the tap-major view of the Conv3d weight
+    backward: dW2 = dY^T A (tensor cores read both operands MN-major in place), db = colsum(dY); nothing flows into the patch features
+              (frozen backbones, merv.py:316,339,361)."""
+
+    @staticmethod
+    def forward(ctx, A, dtype, module, weight, bias):
+        W2, b = module._conv_operands(dtype)
+        y, _ = ops.linear_bias_act(A, W2, b, ACT_NONE)
+        ctx.save_for_backward(A)
+        ctx.wshape, ctx.wdtype, ctx.bdtype = tuple(weight.shape), weight.dtype, None if bias is None else bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (A,) = ctx.saved_tensors
+        A2 = A.reshape(-1, A.shape[-1])
+        g = dy.reshape(-1, dy.shape[-1])
+        if g.dtype != A2.dtype:
+            g = g.to(A2.dtype)
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        if g.dtype == torch.bfloat16:
+            dW2 = ops.gemm_ex(g, A2, a_t=True, w_t=True)
+        else:
+            dW2, _ = ops.linear_bias_act(ops.transpose(g, pad=True), ops.transpose(A2, pad=True), None, ACT_NONE)
+        K, C = ctx.wshape[0], ctx.wshape[1]
+        dW = dW2.reshape(K, 3, 3, 3, C).permute(0, 4, 1, 2, 3).to(ctx.wdtype)  # back to Conv3d's [K, C, kf, kh, kw]
+        db = None if ctx.bdtype is None else ops.colsum(g).to(ctx.bdtype)
+        return None, None, None, dW, db
 
 
 class _MixFn(torch.autograd.Function):
@@ -677,6 +712,88 @@ class AveragePoolingProjector(AveragePooling3DProjector):
         assert fused_img_patches.dim() == 4
         assert fused_img_patches.shape[1] == self.output_frames  # nn_utils.py:154-155
         return super().forward(fused_img_patches)
+
+
+class Convolutional3DProjector(TokenResampler):
+    """3D-convolutional projector ("3dconv" resampler, nn_utils.py:341-377; constructed at merv.py:142-150): Conv3d(C -> llm_dim, 3 x 3 x 3,
+    padding 1) -> AdaptiveAvgPool3d -> projector(llm_dim -> llm_dim).
+
+    B200 form: the pool is linear and the convolution is a sum over 27 displaced copies of the input, so
+    ``pool(conv(x)) = sum_tap W_tap pool(shift_tap(x)) + b``: the pool kernel writes the 27 displaced poolings side by side (5-D TMA loads
+    with displaced box coordinates; the TMA unit zero-fills what falls outside the grid = the convolution's zero padding) and ONE tcgen05
+    GEMM with K = 27 C evaluates the convolution on the POOLED grid — T*S*S instead of F*H*W positions per video, no channel-major
+    permute, no im2col of the un-pooled features.  Module tree, parameter names and init order are the reference's."""
+
+    def __init__(
+        self, fused_vision_dim: int, llm_dim: int, output_frames: int, output_size: int, mlp_type: str = "gelu-mlp"
+    ) -> None:
+        super().__init__()
+        self.output_frames = output_frames
+        self.output_size = output_size
+        self.convolution_pooling = nn.Sequential(
+            nn.Conv3d(fused_vision_dim, llm_dim, kernel_size=3, stride=1, padding=1),
+            nn.AdaptiveAvgPool3d((output_frames, output_size, output_size)),
+        )
+        self.projector = get_mlp_projector(llm_dim, llm_dim, mlp_type)
+        self._conv_cache = None
+
+    @classmethod
+    def from_reference(cls, ref_module: nn.Module) -> "Convolutional3DProjector":
+        """Adopt a reference ``Convolutional3DProjector``: the Conv3d and the inner projector are shared, not copied."""
+        conv = ref_module.convolution_pooling[0]
+        assert isinstance(conv, nn.Conv3d) and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1) \
+            and conv.dilation == (1, 1, 1) and conv.groups == 1 and conv.padding_mode == "zeros"
+        new = cls.__new__(cls)
+        nn.Module.__init__(new)
+        new.output_frames, new.output_size = ref_module.output_frames, ref_module.output_size
+        new.convolution_pooling = ref_module.convolution_pooling
+        new.projector = _adopt_plain_projector(ref_module.projector) if type(ref_module.projector).__name__ in _PLAIN_PROJECTORS else ref_module.projector
+        new._conv_cache = None
+        return new
+
+    def _conv_operands(self, dtype: torch.dtype):
+        """(W2 [K, 27 C] tap-major — column (kf*9 + kh*3 + kw) * C + c holds weight[k, c, kf, kh, kw] — and the bias), in the compute dtype;
+        rebuilt when the parameters change (version counter) and never cached for FSDP views."""
+        conv = _unwrap(self.convolution_pooling[0])
+        w, b = conv.weight, conv.bias
+        tag = (w.data_ptr(), _version(w), None if b is None else (b.data_ptr(), _version(b)), dtype)
+        hit = self._conv_cache
+        if hit is not None and hit[0] == tag and not (_is_volatile(w) or _is_volatile(b)):
+            return hit[1], hit[2]
+        with torch.no_grad():
+            W2 = w.detach().to(dtype).permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1).contiguous()
+            b2 = None if b is None else b.detach().to(dtype).contiguous()
+        self._conv_cache = (tag, W2, b2)
+        return W2, b2
+
+    def forward(self, fused_img_patches: torch.Tensor) -> torch.Tensor:
+        assert fused_img_patches.dim() == 4  # nn_utils.py:361
+        _require_device(fused_img_patches)
+        dtype = _compute_dtype(fused_img_patches)
+        if torch.is_grad_enabled() and fused_img_patches.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the patch features are not implemented (frozen backbones, merv.py:316)")
+        x = fused_img_patches.detach()
+        x = x if x.dtype == dtype else x.to(dtype)
+        if not _tma_readable(x):
+            x = x.contiguous()
+        conv = _unwrap(self.convolution_pooling[0])
+        if x.shape[0] == 0:
+            return self.projector(torch.empty((0, self.output_frames * self.output_size**2, conv.out_channels), dtype=dtype, device=x.device))
+        A = ops.pool3d_conv_taps(x, self.output_frames, self.output_size)
+        if _needs_grad(conv):
+            y = _ConvTapsFn.apply(A, dtype, self, conv.weight, conv.bias)
+        else:
+            W2, b = self._conv_operands(dtype)
+            y, _ = ops.linear_bias_act(A, W2, b, ACT_NONE)
+        return self.projector(y.reshape(A.shape[0], A.shape[1], -1))
+
+    @property
+    def output_token_length(self) -> int:
+        return self.output_size * self.output_size
+
+    @property
+    def output_frame_length(self) -> int:
+        return self.output_frames
 
 
 class CrossAttention(nn.Module):
@@ -1311,8 +1428,9 @@ class MervFusion(nn.Module):
         ``seed=-1`` reproduces it, ``None`` leaves the RNG alone) — same consistency asserts and the same exceptions.
 
         ``vision_dims[i]`` / ``temporal_resolutions[i]`` / ``num_patches[i]`` stand for ``video_backbones[i].embed_dim`` /
-        ``.temporal_resolution`` / ``.num_patches``.  The ``conv`` / ``3dconv`` resamplers and the ``query_mlp`` mixer are ablations
-        outside the accelerated path (DESIGN.md "Out of scope"): they raise NotImplementedError instead of falling back."""
+        ``.temporal_resolution`` / ``.num_patches``.  The ``conv`` resampler (timm RegStage blocks) and the ``query_mlp`` mixer (no forward
+        branch in the reference, merv.py:598-612) are outside the accelerated path (DESIGN.md "Out of scope"): they raise
+        NotImplementedError instead of falling back."""
         import re
         from functools import partial
 
@@ -1347,8 +1465,9 @@ class MervFusion(nn.Module):
         elif "3davg" in parts:
             factor = frame_factor()
             tokens_resampled, Projector = True, partial(AveragePooling3DProjector, output_size=size)
-        elif "3dconv" in parts:
-            raise NotImplementedError("the `3dconv` resampler (Convolutional3DProjector, nn_utils.py:341-377) is not part of the accelerated path")
+        elif "3dconv" in parts:  # merv.py:142-150
+            factor = frame_factor()
+            tokens_resampled, Projector = True, partial(Convolutional3DProjector, output_size=size)
         # merv.py:152-172
         if tokens_resampled:
             projs = [Projector(c, llm_dim, output_frames=t // factor, mlp_type=mlp_type) for c, t in zip(vision_dims, temporal_resolutions)]
@@ -1583,7 +1702,7 @@ def fsdp_wrap_policy(fused_training: Optional[bool] = None):
     from torch.distributed.fsdp.wrap import _module_wrap_policy
 
     classes = set() if fused_training else {LinearProjector, MLPProjector, FusedMLPProjector, AveragePoolingProjector, MLPDeepProjector,
-                                            AveragePooling3DProjector}
+                                            AveragePooling3DProjector, Convolutional3DProjector}
     return partial(_module_wrap_policy, module_classes=classes)
 
 
@@ -1631,9 +1750,13 @@ def patch_merv(vidlm: nn.Module, fused: bool = True, fused_training: Optional[bo
             new_projs.append(p if isinstance(p, AttentivePooler) else AttentivePooler.from_reference(p))
             fused = False
             continue
+        if name == "Convolutional3DProjector":  # "3dconv" (merv.py:142-150): pooled taps + one GEMM, then the inner projector
+            new_projs.append(p if isinstance(p, Convolutional3DProjector) else Convolutional3DProjector.from_reference(p))
+            fused = False
+            continue
         cls = proj_classes.get(name)
         if cls is None:
-            raise TypeError(f"patch_merv supports the 3davg / avg / attntv arch_specifiers and the un-resampled projectors, found {name}")
+            raise TypeError(f"patch_merv supports the 3davg / avg / attntv / 3dconv arch_specifiers and the un-resampled projectors, found {name}")
         new_projs.append(p if isinstance(p, AveragePooling3DProjector) else cls.from_reference(p))
     ff = vidlm.feature_fusion
     fusion_type = getattr(vidlm, "feature_fusion_type", None)

@@ -115,12 +115,16 @@ def _call(name, fn, *args) -> None:
 def pool3d(
     xs: Sequence[torch.Tensor], out_frames: Sequence[int], out_size: int,
     score_vecs: Optional[Sequence[torch.Tensor]] = None, max_ctas: int = 0, batch_index: Optional[torch.Tensor] = None,
+    shifts: Optional[Sequence[Tuple[int, int, int]]] = None, outs: Optional[Sequence[torch.Tensor]] = None,
 ) -> Tuple[List[torch.Tensor], Optional[List[torch.Tensor]]]:
     """Adaptive 3-D average pooling of every encoder's [B, F, N, C] features in ONE launch -> [B, T*S*S, C].
 
     Reference: AveragePooling3DProjector.forward, merv/util/nn_utils.py:320-329.  With `score_vecs` (fp32 [C_e] each)
     also returns per-encoder partial dot products [B, parts_e] of the pooled tokens with that vector.  `batch_index`
     (int32 [B']) selects/reorders the videos read from every x (the `multimodal_indices` gather of merv.py:572, fused).
+    `shifts` ((frames, rows, columns) per entry): the windows read x displaced by that much, out-of-grid positions counting as zero
+    (one tap of a zero-padded convolution, see `pool3d_conv_taps`).  `outs`: [B, T*S*S, C] destinations (any row / batch stride,
+    channels contiguous) instead of fresh tensors.
     """
     lib = _lib.load()
     dev = _require_cuda(*xs, *(score_vecs or []), batch_index)
@@ -142,8 +146,14 @@ def pool3d(
             _, F, N, Cc = x.shape
             H = int(math.sqrt(N))  # nn_utils.py:322
             assert H * H == N, f"patch count {N} is not a perfect square (einops would reject it at nn_utils.py:323-327)"
-            y = torch.empty((B, T * out_size * out_size, Cc), dtype=x.dtype, device=dev)
+            if outs is not None:
+                y = outs[i]
+                assert y.shape == (B, T * out_size * out_size, Cc) and y.dtype == x.dtype and y.stride(2) == 1 and y.device == x.device
+            else:
+                y = torch.empty((B, T * out_size * out_size, Cc), dtype=x.dtype, device=dev)
             d = descs[i]
+            if shifts is not None:
+                d.shift_f, d.shift_h, d.shift_w = (int(v) for v in shifts[i])
             d.x, d.y, d.score_vec, d.score_partial = x.data_ptr(), y.data_ptr(), None, None
             d.batch_index, d.src_batch = _p(batch_index), src_B
             d.F, d.H, d.W, d.C, d.T, d.S = F, H, H, Cc, T, out_size
@@ -162,6 +172,25 @@ def pool3d(
                 partials.append(pt)
         _call('merv_pool3d', lib.merv_pool3d, descs, n, B, code, max_ctas, _stream())
     return ys, partials
+
+
+CONV_TAPS = [(df, dh, dw) for df in (-1, 0, 1) for dh in (-1, 0, 1) for dw in (-1, 0, 1)]  # Conv3d kernel index (kf, kh, kw) = shift + 1
+
+
+def pool3d_conv_taps(x: torch.Tensor, out_frames: int, out_size: int) -> torch.Tensor:
+    """A [B, T*S*S, 27*C]: the adaptive average pooling of the 27 displaced copies of x [B, F, N, C] (zero outside the grid), tap-major
+    columns — the operand that turns `AdaptiveAvgPool3d(Conv3d(C, K, kernel_size=3, padding=1)(x))` (Convolutional3DProjector,
+    merv/util/nn_utils.py:349-352,364) into ONE GEMM on the pooled grid: pooling is linear, so it commutes with the convolution's sum
+    over taps, and pooling first cuts the contraction from F*H*W to T*S*S positions per video (4x fewer at merv-full shapes)."""
+    B, _, _, Cc = x.shape
+    n_tok = out_frames * out_size * out_size
+    A = torch.empty((B, n_tok, len(CONV_TAPS) * Cc), dtype=x.dtype, device=x.device)
+    per = _lib.MAX_ENCODERS
+    for t0 in range(0, len(CONV_TAPS), per):
+        taps = CONV_TAPS[t0:t0 + per]
+        pool3d([x] * len(taps), [out_frames] * len(taps), out_size, shifts=taps,
+               outs=[A[:, :, (t0 + i) * Cc:(t0 + i + 1) * Cc] for i in range(len(taps))])
+    return A
 
 
 def linear_bias_act(
@@ -527,6 +556,9 @@ class FusedLinearPlan:
             self.weights = torch.empty((B, E), dtype=torch.float32, device=dev)
             self.bias_mix = torch.empty((B, N), dtype=torch.float32, device=dev)
             d.scores, d.weights, d.bias_mix = self.scores.data_ptr(), self.weights.data_ptr(), self.bias_mix.data_ptr()
+            # counters / ready flags of the in-GEMM pooling (merv_fusion.h: pool assist); the library decides per call whether it runs
+            self.sync_ws = torch.zeros(4 + 2 * B + 8 * 2 * 160, dtype=torch.int32, device=dev)  # + per-warp profile slots (MERV_ASSIST_PROFILE=1)
+            d.sync_ws, d.sync_ws_ints, d.assist_head = self.sync_ws.data_ptr(), self.sync_ws.numel(), 0
         self.N, self.T_tok = N, T_tok
         self.x_meta = [(tuple(x.shape), tuple(x.stride())) for x in xs]
         self.fn = lib.merv_fused_forward

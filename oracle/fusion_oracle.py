@@ -160,6 +160,29 @@ def attentive_pooler_forward(x: np.ndarray, params: Dict[str, np.ndarray], num_h
 # --------------------------------------------------------------------------------------------
 # learnable-query cross-attention mixer
 # --------------------------------------------------------------------------------------------
+def conv3d_projector_forward(x: np.ndarray, params: Dict[str, np.ndarray], out_frames: int, out_size: int, mlp_type: str) -> np.ndarray:
+    """Convolutional3DProjector.forward (merv/util/nn_utils.py:359-369), restated in the reference's own order — convolve the UN-pooled
+    [F, H, W] grid (nn.Conv3d(C, K, kernel_size=3, stride=1, padding=1), nn_utils.py:350: zero padding, cross-correlation), THEN
+    AdaptiveAvgPool3d, then the projector — so that it checks the product's pool-first rearrangement instead of repeating it.
+    x [B, F, H*W, C] -> [B, T*S*S, K]."""
+    x = np.asarray(x, dtype=np.float64)
+    B, F, N, C = x.shape
+    H = int(math.isqrt(N))
+    assert H * H == N
+    w = np.asarray(params["convolution_pooling.0.weight"], dtype=np.float64)  # [K, C, 3, 3, 3]
+    b = np.asarray(params["convolution_pooling.0.bias"], dtype=np.float64)
+    K = w.shape[0]
+    xp = np.zeros((B, F + 2, H + 2, H + 2, C))
+    xp[:, 1:-1, 1:-1, 1:-1] = x.reshape(B, F, H, H, C)
+    y = np.zeros((B, F, H, H, K)) + b
+    for kf in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                y += xp[:, kf:kf + F, kh:kh + H, kw:kw + H] @ w[:, :, kf, kh, kw].T
+    pooled = avg_pool3d_tokens(y.reshape(B, F, N, K), out_frames, out_size)  # nn_utils.py:351,368: token index (f, h, w), w fastest
+    return projector_forward(pooled, {k[len("projector."):]: v for k, v in params.items() if k.startswith("projector.")}, mlp_type)
+
+
 def _softmax_last(x: np.ndarray) -> np.ndarray:
     z = x - x.max(axis=-1, keepdims=True)
     e = np.exp(z)

@@ -87,6 +87,8 @@ def build_variant(ref, name: str, dtype=torch.float32):
     elif v["kind"] == "attntv":  # merv.py:124-130
         mod = ref.AttentivePooler(v["C"], v["llm_dim"], num_query_tokens=v["queries"], num_heads=v["heads"], output_frames=v["F"],
                                   mlp_type=v["mlp_type"])
+    elif v["kind"] == "conv3d":  # merv.py:142-150
+        mod = ref.Convolutional3DProjector(v["C"], v["llm_dim"], output_frames=v["T"], output_size=v["S"], mlp_type=v["mlp_type"])
     elif v["kind"] == "concat_channel_ln":  # merv.py:219-223
         mod = torch.nn.Sequential(torch.nn.LayerNorm(v["E"] * v["K"]), ref.LinearProjector(v["E"] * v["K"], v["K"]))
     else:
@@ -99,7 +101,7 @@ def build_variant(ref, name: str, dtype=torch.float32):
 @torch.no_grad()
 def run_variant(mod, inputs, v, dtype=torch.float32):
     xs = [torch.from_numpy(a).to(dtype) for a in inputs]
-    if v["kind"] in ("projector", "attntv"):
+    if v["kind"] in ("projector", "attntv", "conv3d"):
         return mod(xs[0]), None
     if v["kind"] == "concat_channel_ln":
         return mod(torch.concat(xs, -1)), None  # merv.py:603-606

@@ -9,6 +9,7 @@ Each variant exercises ONE reference module directly on seeded numpy inputs (PCG
     xattn_flat          CrossAttentionAdapterLearnableQuery(averagetoken=False)    (nn_utils.py:514-518), one T==1 encoder
     xattn_pe            CrossAttentionAdapterLearnableQuery(averagetoken=True, positional_embedding=True)  (nn_utils.py:510-511)
     attntv_*            AttentivePooler (cross-attention resampler with learned queries)                    (nn_utils.py:177-246,380-452)
+    conv3d_*            Convolutional3DProjector (Conv3d 3x3x3 -> AdaptiveAvgPool3d -> projector)            (nn_utils.py:341-377)
     *_wide              the same at tcgen05 tile sizes / CTA-per-row LayerNorm widths (E*K = 4 * 1024 channels)
 
 ``oracle/make_golden.py`` runs the unmodified reference modules on them and stores the outputs in
@@ -44,6 +45,13 @@ VARIANTS: Dict[str, dict] = {
     "attntv_wide": dict(kind="attntv", C=256, llm_dim=512, queries=64, heads=8, F=2, N=196, B=1, mlp_type="linear"),
     # the SigLIP / ViViT width: head_dim 96, 64 queries, one 14 x 14 frame
     "attntv_hd96": dict(kind="attntv", C=768, llm_dim=256, queries=64, heads=8, F=1, N=196, B=1, mlp_type="linear"),
+    # Convolutional3DProjector ("3dconv" resampler, merv/util/nn_utils.py:341-377; constructed at merv.py:142-150)
+    "conv3d_tiny": dict(kind="conv3d", C=16, llm_dim=24, F=3, H=4, T=3, S=2, B=2, mlp_type="gelu-mlp"),
+    # ragged windows in every axis (5 frames -> 2, 7 x 7 patches -> 3 x 3: overlapping 3-wide windows) and one frame / row / column of padding each way
+    "conv3d_ragged": dict(kind="conv3d", C=24, llm_dim=32, F=5, H=7, T=2, S=3, B=2, mlp_type="linear"),
+    # the shipped grid: 16 x 16 patches -> 8 x 8 (the square-grid pool consumer), tcgen05-sized GEMM (M = 256, N = 256, K = 27 * 128)
+    "conv3d_wide": dict(kind="conv3d", C=128, llm_dim=256, F=2, H=16, T=2, S=8, B=2, mlp_type="linear"),
+    "conv3d_14": dict(kind="conv3d", C=64, llm_dim=128, F=2, H=14, T=2, S=8, B=1, mlp_type="linear"),
 }
 
 
@@ -86,6 +94,17 @@ def make_variant(name: str) -> Tuple[List[np.ndarray], Dict[str, np.ndarray]]:
             p.update(_linear_params(rng, "projector.projector", C, K))
         else:
             p.update({**_linear_params(rng, "projector.projector.0", C, K), **_linear_params(rng, "projector.projector.2", K, K)})
+        return [x], p
+    if v["kind"] == "conv3d":
+        C, K = v["C"], v["llm_dim"]
+        x = rng.standard_normal((v["B"], v["F"], v["H"] * v["H"], C), dtype=np.float32) * np.float32(1.2) + np.float32(0.3)
+        bound = 1.0 / math.sqrt(27 * C)  # nn.Conv3d default init: U(+-1 / sqrt(fan_in))
+        p = {"convolution_pooling.0.weight": _uniform(rng, (K, C, 3, 3, 3), bound),
+             "convolution_pooling.0.bias": _uniform(rng, (K,), bound)}
+        if v["mlp_type"] == "linear":
+            p.update(_linear_params(rng, "projector.projector", K, K))
+        else:
+            p.update({**_linear_params(rng, "projector.projector.0", K, K), **_linear_params(rng, "projector.projector.2", K, K)})
         return [x], p
     E, T, K, B = v["E"], v["T"], v["K"], v["B"]
     offsets = (0.0, 0.5, -0.5, 0.25)

@@ -21,7 +21,7 @@ def _f(t):
     return None if t is None else t.float()
 
 
-def pool3d(xs, out_frames, out_size, score_vecs=None, max_ctas=0, batch_index=None):
+def pool3d(xs, out_frames, out_size, score_vecs=None, max_ctas=0, batch_index=None, shifts=None, outs=None):
     ys, partials = [], ([] if score_vecs is not None else None)
     for i, (x, T) in enumerate(zip(xs, out_frames)):
         if batch_index is not None:
@@ -29,7 +29,13 @@ def pool3d(xs, out_frames, out_size, score_vecs=None, max_ctas=0, batch_index=No
         B, Fr, N, C = x.shape
         H = int(math.sqrt(N))
         v = x.float().reshape(B, Fr, H, H, C).permute(0, 4, 1, 2, 3)
+        if shifts is not None:  # windows read x displaced by (sf, sh, sw); zero outside the grid, divisor = the full window
+            sf, sh, sw = shifts[i]
+            v = F.pad(v, (1, 1, 1, 1, 1, 1))[:, :, 1 + sf:1 + sf + Fr, 1 + sh:1 + sh + H, 1 + sw:1 + sw + H]
         y = F.adaptive_avg_pool3d(v, (T, out_size, out_size)).permute(0, 2, 3, 4, 1).reshape(B, T * out_size**2, C).to(x.dtype)
+        if outs is not None:
+            outs[i].copy_(y)
+            y = outs[i]
         ys.append(y)
         if score_vecs is not None:  # one partial per video (the real kernel emits several; only their sum is contractual)
             partials.append((y.float() @ score_vecs[i].float()).sum(1, keepdim=True))

@@ -184,6 +184,8 @@ _CONFIGS = [
     ("3davg+frame2+linear", "concat_channel_ln", {"visual_feature_length": 32}),
     ("avg+linear", "scalar", {}),
     ("attntv+gelu-mlp", "concat", {}),
+    ("3dconv+linear", "cross_attention_avg_lq", {}),
+    ("3dconv+frame2+gelu-mlp", "concat_channel", {"visual_feature_length": 32}),
     ("linear", "first", {"pre_proj_layernorm": True, "visual_feature_length": 4}),
     ("gelu-mlp", "concat_channel", {"visual_feature_length": 4}),
 ]
@@ -216,6 +218,8 @@ def test_from_config_builds_what_merv_init_builds(arch, fusion, kw):
         P = functools.partial(ref.AttentivePooler, num_query_tokens=ptl, num_heads=8)
     elif "3davg" in parts:
         P = functools.partial(ref.AveragePooling3DProjector, output_size=4)
+    elif "3dconv" in parts:
+        P = functools.partial(ref.Convolutional3DProjector, output_size=4)
     else:
         P = None
     if P is not None:
@@ -255,6 +259,6 @@ def test_from_config_rejects_what_merv_rejects():
                                  projector_token_length=4, visual_feature_length=8)
     with pytest.raises(NotImplementedError):  # merv.py:610-612
         M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier="3davg+linear", feature_fusion="bogus", projector_token_length=4, visual_feature_length=8)
-    for arch in ("conv+linear", "3dconv+linear"):  # ablation resamplers outside the accelerated path: loud, never a fallback
-        with pytest.raises(NotImplementedError, match="not part of the accelerated path"):
-            M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier=arch, feature_fusion="first")
+    # the one resampler outside the accelerated path (timm RegStage blocks): loud, never a fallback
+    with pytest.raises(NotImplementedError, match="not part of the accelerated path"):
+        M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier="conv+linear", feature_fusion="first")

@@ -1116,3 +1116,97 @@ def test_attentive_pooler_training_matches_reference_autograd(C_, llm, n, heads,
     with torch.inference_mode():  # and the inference path agrees with the training path's forward
         out_inf = m(x)
     assert O.rel_err(_np(out_inf), _np(out)) < 1e-2
+
+
+@pytest.mark.parametrize("B,head", [(48, None), (24, 1), (24, 23)])  # None: the library's default head (40 videos)
+def test_pool_assist_is_bit_identical_to_the_three_launch_path(B, head, monkeypatch):
+    """Pool assist (merv_b200/csrc/pool_assist.cuh, opt-in with MERV_POOL_ASSIST=1): the GEMM's spare warps pool, score and soft-max the
+    videos behind the head inside the GEMM launch, handing them to the tensor cores through per-video release / acquire flags.  Same
+    arithmetic and summation order as the standalone kernels -> prefix and weights must be BIT-identical, on the plain call, on re-runs
+    of the cached plan (the flags are reset by the scores kernel), with the gather by multimodal_indices and with the prefix written
+    into a strided slot of the embedding buffer."""
+    m = _full_module(True)
+    feats = _full_features(B)
+    idx = torch.tensor([3, 0, 7, 23, 11, 5, 19, 2, 14, 9, 21, 1, 16, 8, 22, 4, 13, 6], dtype=torch.int32, device=DEV)
+    emb = torch.zeros((B, 1 + 1024 + 7, 4096), dtype=torch.bfloat16, device=DEV)
+    with torch.inference_mode():
+        monkeypatch.setenv("MERV_POOL_ASSIST", "0")
+        want, want_w = m(feats)
+        want_g, want_gw = m(feats, batch_index=idx)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("MERV_POOL_ASSIST", "1")
+        if head is not None:
+            monkeypatch.setenv("MERV_ASSIST_HEAD", str(head))
+        for _ in range(3):
+            out, w = m(feats)
+            assert torch.equal(out, want) and torch.equal(w, want_w)
+        out_g, w_g = m(feats, batch_index=idx)
+        assert torch.equal(out_g, want_g) and torch.equal(w_g, want_gw)
+        m(feats, out=emb[:, 1:1025])
+        torch.cuda.synchronize()
+        assert torch.equal(emb[:, 1:1025], want) and not emb[:, 0].any() and not emb[:, 1025:].any()
+
+
+@pytest.mark.parametrize("F,H,T,S,Cc", [(5, 7, 2, 3, 24), (2, 16, 2, 8, 128), (3, 14, 3, 8, 64), (4, 6, 2, 2, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("impl", ["tma", "direct"])
+def test_pool3d_displaced_windows_match_oracle(F, H, T, S, Cc, dtype, impl, monkeypatch):
+    """merv_pool_desc.shift_*: the 27 displaced poolings of a zero-padded 3 x 3 x 3 convolution (ops.pool3d_conv_taps), TMA kernel (box
+    coordinates displaced, out-of-grid zero fill by the TMA unit) and the plain-load kernel, against the oracle's pooling of an explicitly
+    zero-padded, displaced copy."""
+    from merv_b200 import ops
+
+    if impl == "direct":
+        monkeypatch.setenv("MERV_POOL_IMPL", "direct")
+    if dtype == torch.bfloat16 and Cc % 8:
+        pytest.skip("channel count not a multiple of the 16-byte vector for this dtype")
+    rng = np.random.default_rng(F * 100 + H)
+    x = _t(rng.standard_normal((2, F, H * H, Cc)).astype(np.float32) + 0.3, dtype)
+    A = ops.pool3d_conv_taps(x, T, S)
+    torch.cuda.synchronize()
+    assert A.shape == (2, T * S * S, 27 * Cc) and A.dtype == dtype
+    xn = _np(x).reshape(2, F, H, H, Cc)
+    xp = np.zeros((2, F + 2, H + 2, H + 2, Cc), dtype=xn.dtype)
+    xp[:, 1:-1, 1:-1, 1:-1] = xn
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    for tap, (sf, sh, sw) in enumerate(ops.CONV_TAPS):
+        shifted = xp[:, 1 + sf:1 + sf + F, 1 + sh:1 + sh + H, 1 + sw:1 + sw + H].reshape(2, F, H * H, Cc)
+        want = O.avg_pool3d_tokens(shifted, T, S)
+        got = _np(A[:, :, tap * Cc:(tap + 1) * Cc])
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), (tap, (sf, sh, sw))
+
+
+@pytest.mark.parametrize("C_,llm,F,H,T,S,B,mlp_type", [(128, 256, 2, 16, 2, 8, 2, "linear"), (64, 128, 4, 14, 2, 8, 1, "gelu-mlp"), (24, 32, 5, 7, 2, 3, 2, "linear")])
+def test_conv3d_projector_training_matches_reference_autograd(C_, llm, F, H, T, S, B, mlp_type):
+    """Forward + backward of the `3dconv` resampler in bf16 (27 displaced poolings + ONE tcgen05 GEMM with K = 27 C; dW = dY^T A read
+    MN-major in place) against torch autograd through the UNMODIFIED reference Convolutional3DProjector in fp32 on the same bf16-rounded
+    parameters — the reference convolves the un-pooled grid and pools afterwards."""
+    import copy
+
+    import merv_b200 as M
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    assert reference_available(), "oracle/_ref/nn_utils.py did not travel with the snapshot: run __graft_entry__.build() in the build container"
+    ref = load_reference_nn_utils()
+    torch.manual_seed(C_ + H)
+    r = ref.Convolutional3DProjector(C_, llm, output_frames=T, output_size=S, mlp_type=mlp_type)
+    m = M.Convolutional3DProjector.from_reference(copy.deepcopy(r)).to(device=DEV, dtype=torch.bfloat16)
+    r = r.to(torch.bfloat16).float().to(DEV)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn((B, F, H * H, C_), generator=g) + 0.3).to(torch.bfloat16).to(DEV)
+    G = torch.randn((B, T * S * S, llm), generator=g).to(DEV)
+    out = m(x)
+    out.backward(G.to(torch.bfloat16))
+    want = r(x.float())
+    want.backward(G)
+    torch.cuda.synchronize()
+    assert O.rel_err(_np(out), _np(want)) < BF16_TOL
+    got = dict(m.named_parameters())
+    for name, p in r.named_parameters():
+        assert got[name].grad is not None and got[name].grad.shape == p.grad.shape, name
+        scale = float(p.grad.abs().max())
+        err = float((got[name].grad.float() - p.grad).abs().max())
+        assert err <= 4e-2 * scale + 1e-6, (name, err / max(scale, 1e-12))
+    with torch.inference_mode():
+        out_inf = m(x)
+    assert O.rel_err(_np(out_inf), _np(out)) < 1e-2

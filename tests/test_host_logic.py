@@ -387,3 +387,44 @@ def test_attentive_pooler_backward_wiring_matches_reference_autograd(monkeypatch
         assert float((got[name].grad.float() - p.grad).abs().max()) <= 4e-2 * scale + 1e-6, name
         seen += 1
     assert seen == 19  # query tokens, 2 LayerNorms, kv / q / proj / fc1 / fc2, the 2-layer projector
+
+
+def test_conv3d_projector_backward_wiring_and_adoption_match_the_reference(monkeypatch):
+    """The `3dconv` resampler (Convolutional3DProjector, nn_utils.py:341-377): pooled-taps GEMM forward and its hand-written backward
+    (_ConvTapsFn: dW = dY^T A folded back into Conv3d's [K, C, 3, 3, 3], db = colsum) against torch autograd through the UNMODIFIED
+    reference module, adopted with from_reference (shared parameters).  CPU: kernels emulated, so this pins the wiring."""
+    import copy
+
+    import merv_b200 as M
+    from oracle.ref_loader import load_reference_nn_utils, reference_available
+
+    if not reference_available():
+        pytest.skip("needs the reference's nn_utils.py")
+    kernel_emulation.emulate(monkeypatch)
+    ref = load_reference_nn_utils()
+    torch.manual_seed(3)
+    r = ref.Convolutional3DProjector(16, 24, output_frames=2, output_size=3, mlp_type="gelu-mlp")
+    m = M.Convolutional3DProjector.from_reference(copy.deepcopy(r))
+    assert list(m.state_dict()) == list(r.state_dict())
+    assert m.output_token_length == r.output_token_length == 9 and m.output_frame_length == r.output_frame_length == 2
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((2, 5, 49, 16), generator=g)
+    G = torch.randn((2, 2 * 9, 24), generator=g)
+    out = m(x)
+    out.backward(G)
+    want = r(x)
+    want.backward(G)
+    assert O.rel_err(_np(out), _np(want)) < 1e-5
+    got = dict(m.named_parameters())
+    for name, p in r.named_parameters():
+        assert got[name].grad is not None and got[name].grad.shape == p.grad.shape, name
+        assert float((got[name].grad - p.grad).abs().max()) <= 1e-4 * float(p.grad.abs().max()) + 1e-7, name
+    # the tap-major weight view is rebuilt when the parameter changes (version counter), not served stale
+    with torch.no_grad():
+        y0 = m(x)
+        m.convolution_pooling[0].weight.mul_(0.5)
+        m.convolution_pooling[0].bias.zero_()
+        y1 = m(x)
+        r.convolution_pooling[0].weight.mul_(0.5)
+        r.convolution_pooling[0].bias.zero_()
+        assert O.rel_err(_np(y1), _np(r(x))) < 1e-5 and not torch.equal(y0, y1)

@@ -140,6 +140,8 @@ def oracle_variant(v, inputs, params):
         return O.projector_forward(inputs[0], params, v["mlp_type"]), None
     if v["kind"] == "attntv":
         return O.attentive_pooler_forward(inputs[0], params, v["heads"], v["mlp_type"]), None
+    if v["kind"] == "conv3d":
+        return O.conv3d_projector_forward(inputs[0], params, v["T"], v["S"], v["mlp_type"]), None
     if v["kind"] == "concat_channel_ln":
         return O.concat_channel_ln_forward(inputs, params), None
     return O.cross_attention_fusion_forward(inputs, params, v["T"], averagetoken=v["averagetoken"])

@@ -15,6 +15,8 @@ def build_variant_module(name, dtype=torch.float32, device="cpu"):
     elif v["kind"] == "attntv":  # merv.py:124-130
         mod = M.AttentivePooler(v["C"], v["llm_dim"], num_query_tokens=v["queries"], num_heads=v["heads"], output_frames=v["F"],
                                 mlp_type=v["mlp_type"])
+    elif v["kind"] == "conv3d":  # merv.py:142-150
+        mod = M.Convolutional3DProjector(v["C"], v["llm_dim"], output_frames=v["T"], output_size=v["S"], mlp_type=v["mlp_type"])
     elif v["kind"] == "concat_channel_ln":  # merv.py:219-223
         mod = M.ConcatChannelLNFusion(v["E"], v["K"])
     else:
@@ -28,7 +30,7 @@ def build_variant_module(name, dtype=torch.float32, device="cpu"):
 def run_variant(mod, v, inputs, dtype=torch.float32, device="cpu", as_list=True):
     """Call the module the way MERV.forward does; returns (out, weights | None)."""
     xs = [torch.from_numpy(a).to(device).to(dtype) for a in inputs]
-    if v["kind"] in ("projector", "attntv"):
+    if v["kind"] in ("projector", "attntv", "conv3d"):
         return mod(xs[0]), None
     if v["kind"] == "concat_channel_ln":
         return mod(xs if as_list else torch.concat(xs, -1)), None  # merv.py:603-606 passes the concatenation
