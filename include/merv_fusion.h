@@ -341,6 +341,17 @@ int merv_pair_dot_scale(const void* x, const void* y, float* partial, const floa
                         int B, int64_t n, int dtype, void* stream);
 int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int64_t ldx, int64_t ldy, const float* scale,
                             int64_t scale_stride, int rows_per_scale, int dtype, void* stream);
+/* The weight gradient AND the mixing-weight gradient of one encoder from ONE pass over dOut and the pooled tokens (bf16, tcgen05):
+ *     dW [N_out, C]  = sum_b scale[b * scale_stride] * dY[b]^T X[b]        (dW_e = dOut^T (w_e (.) P_e) without materialising w_e (.) P_e)
+ *     dot_partial[b] = merv_pair_dot_chunks() partial sums of <W, dY[b]^T X[b]>   (= <dOut[b] W_e, P_e[b]>: the Z_e = dOut W_e GEMM and the
+ *                      pair-dot pass of the formulation above are not needed at all — half of the backward's tensor work)
+ * dY [videos * tokens_per_video, N_out] (lddy), X [videos * tokens_per_video, C] (ldx), W / dW [N_out, C] (ldw / lddw), all read in place
+ * (MN-major operands); the contraction runs over the tokens, the accumulator is drained once per video: scaled into the running sum in
+ * fp32 registers and dotted with the W tile.  tokens_per_video % 64 == 0.  workspace: videos * merv_wgrad_video_parts(N_out, C) floats. */
+int merv_wgrad_video_parts(int N_out, int C);
+int merv_wgrad_video(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* scale, int64_t scale_stride, const void* W,
+                     int64_t ldw, void* dW, int64_t lddw, float* dot_partial, float* workspace, int videos, int tokens_per_video, int N_out,
+                     int C, void* stream);
 size_t merv_fused_backward_workspace(const merv_fused_bwd_desc* desc);
 int merv_fused_backward(const merv_fused_bwd_desc* desc, int dtype, void* stream);
 

@@ -880,6 +880,42 @@ extern "C" int merv_video_colsum(const void* x, float* out, int B, int T, int K,
 
 extern "C" int merv_pair_dot_chunks(void) { return kPairDotChunks; }
 
+// out[b, c] = sum_{i = c, c + chunks, ...} in[b, i] (ascending i: fixed order): folds the per-(tile, warp) dots of merv_wgrad_video into the
+// [B, merv_pair_dot_chunks()] layout merv_fused_backward reads
+__global__ void __launch_bounds__(32) fold_partials_kernel(const float* __restrict__ in, float* __restrict__ out, int parts) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  float acc = 0.f;
+  for (int i = c; i < parts; i += kPairDotChunks) acc += in[(long long)b * parts + i];
+  if (c < kPairDotChunks) out[(long long)b * kPairDotChunks + c] = acc;
+}
+
+extern "C" int merv_wgrad_video_parts(int N_out, int C) { return wgrad_video_parts(N_out, C); }
+
+extern "C" int merv_wgrad_video(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* scale, int64_t scale_stride, const void* W,
+                                int64_t ldw, void* dW, int64_t lddw, float* dot_partial, float* workspace, int videos, int tokens_per_video,
+                                int N_out, int C, void* stream) {
+  MERV_REQUIRE(dY && X && W && dW && dot_partial && workspace, MERV_E_ARG, "merv_wgrad_video: NULL pointer");
+  MERV_REQUIRE(videos >= 0 && tokens_per_video > 0 && N_out > 0 && C > 0, MERV_E_SHAPE, "merv_wgrad_video: videos=%d tokens=%d N_out=%d C=%d", videos,
+               tokens_per_video, N_out, C);
+  MERV_REQUIRE(tokens_per_video % 64 == 0, MERV_E_SHAPE, "merv_wgrad_video: tokens_per_video=%d must be a multiple of 64 (one k-block never spans two videos)",
+               tokens_per_video);
+  MERV_REQUIRE((long long)videos * tokens_per_video <= 0x7fffffffLL, MERV_E_SHAPE, "merv_wgrad_video: videos * tokens overflows");
+  MERV_REQUIRE(lddy >= N_out && ldx >= C && ldw >= C && lddw >= C, MERV_E_SHAPE, "merv_wgrad_video: leading dimensions too small");
+  static_assert(kPairDotChunks == 32, "fold_partials_kernel: one lane per chunk");
+  if (int rc = require_sm100()) return rc;
+  if (videos == 0) return MERV_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // dW [N_out, C] = dY^T X: A-operand = dY [tokens, N_out] read as [K, M], W-operand = X [tokens, C] read as [K, N] (both MN-major, in place)
+  GemmSegment seg = {dY, lddy, X, ldx, videos * tokens_per_video, 1, 1};
+  WgradVideoArgs vid = {videos, tokens_per_video / 64, scale, scale_stride, W, ldw, workspace};
+  if (int rc = launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, N_out, nullptr, MERV_ACT_NONE, nullptr, nullptr, dW, lddw, 0, N_out, C, 0, s, nullptr, 0,
+                                   false, nullptr, nullptr, &vid))
+    return rc;
+  fold_partials_kernel<<<videos, 32, 0, s>>>(workspace, dot_partial, wgrad_video_parts(N_out, C));
+  MERV_CUDA_OK(cudaGetLastError());
+  return MERV_OK;
+}
+
 extern "C" int merv_pair_dot_scale(const void* x, const void* y, float* partial, const float* scale, int64_t scale_stride, void* y_scaled, int B,
                                    int64_t n, int dtype, void* stream) {
   MERV_REQUIRE(dtype == MERV_F32 || dtype == MERV_BF16, MERV_E_DTYPE, "merv_pair_dot: unknown dtype %d", dtype);

@@ -31,6 +31,17 @@ int require_sm100();   // MERV_OK or MERV_E_ARCH for the current device (cached 
 int sm_count();        // SM count of the current device
 
 struct AssistArgs;  // pool_assist.cuh
+// Weight gradient over per-video segments (gemm_tcgen05.cu, kVid): the single (A, W) segment handed to launch_gemm_tcgen05 covers all
+// `videos` x kblocks_per_video k-blocks; the kernel drains the accumulator once per video.
+struct WgradVideoArgs {
+  int videos, kblocks_per_video;
+  const float* scale;      // scale[b * scale_stride] multiplies video b's contribution to the sum (NULL: 1)
+  long long scale_stride;
+  const void* W;           // [M, N] bf16, row stride ldw: <W, per-video product> is emitted per (video, tile, epilogue warp)
+  long long ldw;
+  float* dot_out;          // [videos, wgrad_video_parts(M, N)]
+};
+int wgrad_video_parts(int M, int N);
 // one (A_s, W_s, K_s) product of the tcgen05 GEMM (see gemm_tcgen05.cu)
 struct GemmSegment {
   const void* A;
@@ -49,7 +60,7 @@ struct GemmSegment {
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
                         int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out = nullptr, int num_extra = 0, bool pdl = false,
-                        void* mc_out = nullptr, const struct AssistArgs* assist = nullptr);
+                        void* mc_out = nullptr, const struct AssistArgs* assist = nullptr, const WgradVideoArgs* vid = nullptr);
 int launch_scores_softmax_weights(const float* const* partial, const int32_t* count, const float* const* c, const void* const* bias,
                                   float* scores, float* weights, void* weights_bf16, float* bias_mix, int B, int E, int T, int N,
                                   cudaStream_t stream, bool pdl, int* sync_ws = nullptr, int sync_ints = 0);

@@ -81,6 +81,14 @@ struct GemmParams {
   // fused all-gather through the NVSwitch multicast mapping: when set, every output box is written ONCE with multimem.st to this
   // address (replicated by the switch into every rank's buffer, the local one included) and no TMA store is issued
   __nv_bfloat16* mc_out;
+  // kVid (weight gradient over per-video segments, launch_gemm_tcgen05's `vid` argument): p.nseg videos share maps a[0] / b[0]; segment s
+  // covers k-blocks [s * vid_kblocks, (s + 1) * vid_kblocks), is scaled by seg_scale[s * seg_scale_stride] when it is added to the
+  // running sum, and its accumulator is ALSO dotted with dot_w [M, N]: dot_out[(s * tiles + tile) * EPI_WARPS + epilogue warp]
+  int vid_kblocks;
+  long long seg_scale_stride;
+  const __nv_bfloat16* dot_w;
+  long long dot_ldw;
+  float* dot_out;
   int num_out;   // destinations of every output tile: 1 (local) + peers' buffers over NVLink (fused all-gather)
   int out_flat;  // 1: Y is one contiguous [M, N] matrix (output map = [1, M, N]); 0: [videos, rows_per_video, N] with a batch stride
 };
@@ -99,7 +107,7 @@ struct TensorMaps {
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
 // kMn: the variant that honours MN-major operand flags (backward GEMMs).  It is a separate instantiation because the single producer /
 // MMA threads run on 40 registers: the per-segment majorness selects cost the forward kernels 14 % when they were runtime branches.
-template <int kCtas, bool kWide, bool kGelu, bool kMn, bool kAssist>
+template <int kCtas, bool kWide, bool kGelu, bool kMn, bool kAssist, bool kVid = false>
 __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmParams& p, const AssistArgs* ap) {
   using C = Cfg<kCtas, kWide, kAssist>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RING_BYTES = C::RING_BYTES;
@@ -195,9 +203,11 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             ready_video = video;
           }
         }
-        for (int s = 0; s < p.nseg; ++s) {
-          const int nkb = p.kblocks[s];
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int s0 = 0; s0 < p.nseg; ++s0) {
+          const int s = kVid ? 0 : s0;                       // kVid: every video reads the same pair of tensors ...
+          const int nkb = kVid ? p.vid_kblocks : p.kblocks[s];
+          const int kb_end = kVid ? (s0 + 1) * nkb : nkb;    // ... at its own k-blocks
+          for (int kb = kVid ? s0 * nkb : 0; kb < kb_end; ++kb, ++it) {
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar + 8 * stage, ph ^ 1u);  // own barrier: the pair's MMA commit is multicast to both CTAs
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
@@ -231,7 +241,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
       // ===== MMA issuer (the leader CTA's single thread drives both SMs of a pair) =====
       uint32_t it = 0, acc_it = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
-        for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+        for (int s0 = 0; s0 < p.nseg; ++s0, ++acc_it) {
+          const int s = kVid ? 0 : s0;
           const bool a_mn = kMn && ((p.a_mn_mask >> s) & 1), b_mn = kMn && ((p.b_mn_mask >> s) & 1);
           const uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN, a_mn, b_mn);
           // per UMMA (16 k): +32 bytes inside the swizzle atom for a K-major operand, +2 atoms of 8 k-rows for an MN-major one
@@ -240,7 +251,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
           mbar_wait(tempty_bar + 8 * buf, aph ^ 1u);  // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
-          const int nkb = p.kblocks[s];
+          const int nkb = kVid ? p.vid_kblocks : p.kblocks[s];
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
             mbar_wait(full_bar + 8 * stage, ph);
@@ -399,13 +410,42 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
         for (int s = 0; s < p.nseg; ++s, ++acc_it) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           float scale = 1.0f;
-          if constexpr (!kAssist) scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
+          if constexpr (kVid) scale = p.seg_scale ? __ldg(p.seg_scale + (long long)s * p.seg_scale_stride) : 1.0f;
+          else if constexpr (!kAssist) scale = p.seg_scale ? __ldg(p.seg_scale + (long long)video * p.nseg + s) : 1.0f;
           mbar_wait(tfull_bar + 8 * buf, aph);
           // pool assist: the video's mixing weights are written inside this launch; the full accumulator implies (mbarrier chain from
           // the producer's acquire) that they are published — read them from L2
           if constexpr (kAssist) scale = __ldcg(p.seg_scale + (long long)video * p.nseg + s);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + h * EPI_COLS;
+          if constexpr (kVid) {
+            // per-video segment of a weight gradient: G = dY[video]^T X[video] sits in the accumulator.  It joins the running sum scaled by
+            // the video's weight, and <W, G> — the gradient w.r.t. that weight — is taken from the same registers, 16 columns at a time
+            const __nv_bfloat16* wrow = p.dot_w + (long long)(row_ok ? row : 0) * p.dot_ldw + col0;
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < EPI_COLS / 16; ++c) {
+              uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+              if (row_ok && col0 + c * 16 < p.N) w0 = __ldg(reinterpret_cast<const uint4*>(wrow + c * 16));
+              if (row_ok && col0 + c * 16 + 8 < p.N) w1 = __ldg(reinterpret_cast<const uint4*>(wrow + c * 16 + 8));
+              uint32_t v[16];
+              tmem_ld16(taddr + c * 16, v);
+              tmem_ld_wait();
+              float wf[16];
+              Vec16<__nv_bfloat16>::unpack(w0, *reinterpret_cast<float(*)[8]>(wf));
+              Vec16<__nv_bfloat16>::unpack(w1, *reinterpret_cast<float(*)[8]>(wf + 8));
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float a = __uint_as_float(v[i]);
+                dot = fmaf(a, wf[i], dot);
+                sum[c * 16 + i] = fmaf(scale, a, sum[c * 16 + i]);
+              }
+            }
+            release_accumulator(buf);
+            dot = warp_sum(dot);
+            if (lane == 0) p.dot_out[((long long)s * total_tiles + tile) * EPI_WARPS + (warp - 4)] = dot;
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < EPI_COLS / 32; ++c) {
             uint32_t v[32];
@@ -448,6 +488,12 @@ template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
   gemm_body<kCtas, kWide, kGelu, kMn, false>(maps, p, nullptr);
+}
+
+// weight gradient over per-video segments (single CTA, MN-major operands): dW = sum_b scale[b] dY[b]^T X[b] and <W, dY[b]^T X[b]> per video
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_wgrad_video_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
+  gemm_body<1, false, false, true, false, true>(maps, p, nullptr);
 }
 
 // the fused forward GEMM (CTA pair, K-major operands) whose two spare warps pool the videos ahead of the tiles (pool_assist.cuh)
@@ -494,10 +540,12 @@ static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const
   return MERV_OK;
 }
 
+int wgrad_video_parts(int M, int N) { return ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * EPI_WARPS; }
+
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
                         int M, int N, int max_ctas, cudaStream_t stream, void* const* extra_out, int num_extra, bool pdl, void* mc_out,
-                        const AssistArgs* assist) {
+                        const AssistArgs* assist, const WgradVideoArgs* vid) {
   MERV_REQUIRE(nseg >= 1 && nseg <= MERV_MAX_SEGMENTS, MERV_E_ARG, "gemm: nseg=%d not in [1,%d]", nseg, MERV_MAX_SEGMENTS);
   MERV_REQUIRE(M > 0 && N > 0, MERV_E_SHAPE, "gemm: M=%d N=%d", M, N);
   MERV_REQUIRE(N % 8 == 0 && ldy % 8 == 0 && ldy >= N, MERV_E_ALIGN, "gemm: N=%d and ldy=%lld must be multiples of 8 (16-byte rows)", N, ldy);
@@ -511,7 +559,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   (void)total_k;
   bool any_mn = false;
   for (int i = 0; i < nseg; ++i) any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
-  const int ctas = assist != nullptr ? 2 : gemm_cta_group(M, any_mn);
+  const int ctas = assist != nullptr ? 2 : vid != nullptr ? 1 : gemm_cta_group(M, any_mn);
+  if (vid != nullptr) {
+    MERV_REQUIRE(nseg == 1 && seg[0].a_mn && seg[0].b_mn && act == MERV_ACT_NONE && num_extra == 0 && mc_out == nullptr && assist == nullptr &&
+                     bias == nullptr && bias_rows == nullptr && rowdot_vec == nullptr && seg_scale == nullptr,
+                 MERV_E_ARG, "gemm: the per-video weight gradient takes one MN-major segment and no epilogue options");
+    MERV_REQUIRE(vid->videos >= 1 && vid->kblocks_per_video >= 1 && (long long)vid->videos * vid->kblocks_per_video * BK == seg[0].K, MERV_E_SHAPE,
+                 "gemm: %d videos x %d k-blocks of %d do not cover K=%d", vid->videos, vid->kblocks_per_video, BK, seg[0].K);
+    MERV_REQUIRE(vid->W && vid->dot_out && vid->ldw >= N && vid->ldw % 8 == 0 && aligned16(vid->W), MERV_E_ARG, "gemm: per-video weight gradient: W / dot_out");
+  }
   MERV_REQUIRE(assist == nullptr || (!any_mn && M > BM && num_extra == 0 && mc_out == nullptr && act == MERV_ACT_NONE && seg_scale && bias_rows &&
                                      rowdot_vec == nullptr),
                MERV_E_ARG, "gemm: pool assist rides on the plain fused forward GEMM only");
@@ -592,6 +648,11 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   p.rowdot_vec = rowdot_vec; p.rowdot_out = rowdot_out; p.rowdot_nblk = (N + MERV_ROWDOT_BLOCK - 1) / MERV_ROWDOT_BLOCK;
   p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy;
   p.m_blocks = (M + BM * ctas - 1) / (BM * ctas); p.n_blocks = (N + BN - 1) / BN;
+  if (vid != nullptr) {
+    p.nseg = vid->videos; p.vid_kblocks = vid->kblocks_per_video;
+    p.seg_scale = vid->scale; p.seg_scale_stride = vid->scale_stride;
+    p.dot_w = static_cast<const __nv_bfloat16*>(vid->W); p.dot_ldw = vid->ldw; p.dot_out = vid->dot_out;
+  }
   const long long total = (long long)p.m_blocks * p.n_blocks;
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
@@ -611,6 +672,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
+  if (vid != nullptr) {
+    constexpr int smem = Cfg<1, false>::SMEM_BYTES;
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_wgrad_video_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
+    cfg.dynamicSmemBytes = smem;
+    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_wgrad_video_tcgen05_kernel, maps, p));
+    MERV_CUDA_OK(cudaGetLastError());
+    return MERV_OK;
+  }
   if (assist != nullptr) {
     constexpr int smem = Cfg<2, false, true>::SMEM_BYTES;
     static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_pool_assist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

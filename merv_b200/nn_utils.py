@@ -364,8 +364,10 @@ class _FusedLinearFn(torch.autograd.Function):
     through the FUSED forward, with a backward that never materialises the per-encoder projections Y_e or their gradients.
 
     forward : merv_pool3d (+ score partials) -> scores -> softmax -> merv_fused_linear_mix; keeps the pooled tokens P_e and the weights
-    backward: Z_e = dOut W_e (tcgen05, [M, C_e]);  dw_e = <Z_e, P_e> + b_e . colsum_t(dOut);  ds = softmax'(dw + dweights);
-              dW_e = dOut^T (w_e (.) P_e) (tcgen05) + u (x) g_e;  db_e, du -> dQ, dWq, dWk, db_q  (include/merv_fusion.h: merv_fused_backward)
+    backward: G_e[b] = dOut[b]^T P_e[b] on tcgen05, drained once per video:  dW_e = sum_b w_e[b] G_e[b] + u (x) g_e  and
+              dw_e[b] = <W_e, G_e[b]> + b_e . colsum_t(dOut[b])  (= <dOut[b] W_e, P_e[b]> without the Z_e = dOut W_e GEMM: merv_wgrad_video);
+              ds = softmax'(dw + dweights);  db_e, du -> dQ, dWq, dWk, db_q  (include/merv_fusion.h: merv_fused_backward).
+              Token counts that are not a multiple of 64 take the two-GEMM form (Z_e = dOut W_e, dW_e = dOut^T (w_e (.) P_e)).
     Per video this moves ~100 MB less through HBM in the forward and ~130 MB less in the backward than the module-by-module
     path and keeps 7 MB instead of 41 MB of activations.  No gradient flows into the patch features (frozen backbones).
     """
@@ -411,6 +413,14 @@ class _FusedLinearFn(torch.autograd.Function):
         dw_partials, pbars, dWs = [], [], []
         for e in range(E):  # dOut, P_e and W_e are all read in place: the tensor cores take them MN-major (no transposed copies)
             P = pooled[e].reshape(B * T, -1)
+            if T % 64 == 0:
+                # ONE pass per encoder: with G_b = dOut[b]^T P_e[b] (the accumulator, drained once per video), dW_e = sum_b w_e[b] G_b and
+                # <Z_e[b], P_e[b]> = <W_e, G_b> — the Z_e = dOut W_e GEMM and the pair-dot pass below are not needed (half the tensor work)
+                dW, dwp = ops.wgrad_video(g, P, weights[:, e], Ws[e], B)
+                dw_partials.append(dwp)
+                pbars.append(ops.video_colsum(P.reshape(B, T, -1), 1.0 / T))
+                dWs.append(dW)
+                continue
             Z = ops.gemm_ex(g, Ws[e], w_t=True)  # dOut W_e : [M, K] x [K, C_e] -> [M, C_e]
             dwp, Ps = ops.pair_dot(Z.reshape(B, -1), P.reshape(B, -1), scale=weights[:, e])  # <Z_e, P_e> partials and w_e (.) P_e in one pass
             dw_partials.append(dwp)
@@ -1428,9 +1438,9 @@ class MervFusion(nn.Module):
         ``seed=-1`` reproduces it, ``None`` leaves the RNG alone) — same consistency asserts and the same exceptions.
 
         ``vision_dims[i]`` / ``temporal_resolutions[i]`` / ``num_patches[i]`` stand for ``video_backbones[i].embed_dim`` /
-        ``.temporal_resolution`` / ``.num_patches``.  The ``conv`` resampler (timm RegStage blocks) and the ``query_mlp`` mixer (no forward
-        branch in the reference, merv.py:598-612) are outside the accelerated path (DESIGN.md "Out of scope"): they raise
-        NotImplementedError instead of falling back."""
+        ``.temporal_resolution`` / ``.num_patches``.  The ``conv`` resampler (timm RegStage blocks) is outside the accelerated path
+        (DESIGN.md "Out of scope") and raises NotImplementedError instead of falling back; the ``query_mlp`` mixer is constructed as the
+        reference constructs it (merv.py:211-212) and, as in the reference (no forward branch, merv.py:598-612), raises when called."""
         import re
         from functools import partial
 
@@ -1495,7 +1505,9 @@ class MervFusion(nn.Module):
         # merv.py:211-227
         E = len(vision_dims)
         if feature_fusion == "query_mlp":
-            raise NotImplementedError("the `query_mlp` mixer (merv.py:211-212) has no forward branch in the reference either (merv.py:598-612)")
+            # merv.py:211-212 constructs it (so checkpoints carry its parameters) but MERV.forward has no branch for it (merv.py:598-612):
+            # same module tree / init here, and forward raises what the reference raises
+            ff = MLPProjector(3072, E)
         elif feature_fusion == "cross_attention_avg_lq":
             ff = CrossAttentionAdapterLearnableQuery(embed_dim=3072, llm_dim=llm_dim, token_length=visual_feature_length, averagetoken=True)
         elif feature_fusion == "concat_channel":
@@ -1590,6 +1602,9 @@ class MervFusion(nn.Module):
                     t0 += y.shape[1]
                 return out_cat, None
             return self._forward_token_concat(patch_features), None
+        if getattr(self, "feature_fusion_type", None) == "query_mlp":  # merv.py:610-612: constructed, but no forward branch in the reference
+            print(f'feature_fusion "{self.feature_fusion_type}" doesn\'t exist')
+            raise NotImplementedError
         if isinstance(self.feature_fusion, (ConcatChannelFusion, ConcatChannelLNFusion)):  # merv.py:603-606: no mixing weights
             assert out is None and batch_index is None and gather is None, "concat_channel supports the plain call only"
             return self.feature_fusion([proj(x) for proj, x in zip(self.projectors, patch_features)]), None

@@ -57,7 +57,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
-    "merv_cross_attention": 1, "merv_cross_attention_backward": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10,
+    "merv_cross_attention": 1, "merv_cross_attention_backward": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10, "merv_wgrad_video": 2,
     "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
@@ -726,6 +726,26 @@ def pair_dot(x: torch.Tensor, y: torch.Tensor, scale: Optional[torch.Tensor] = N
         _call('merv_pair_dot', lib.merv_pair_dot_scale, x.data_ptr(), y.data_ptr(), out.data_ptr(), scale.data_ptr(), scale.stride(0), ys.data_ptr(), B,
               x.shape[1], dtype_code(x.dtype), _stream())
     return out, ys.view(shape)
+
+
+def wgrad_video(dy: torch.Tensor, x: torch.Tensor, scale: torch.Tensor, w: torch.Tensor, videos: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(dW [N_out, C] = sum_b scale[b] dy[b]^T x[b],  partials [videos, pair_dot_chunks] of <w, dy[b]^T x[b]>) in ONE tcgen05 pass over
+    dy [videos * T, N_out] and x [videos * T, C], both read in place (include/merv_fusion.h: merv_wgrad_video).  `scale` fp32 [videos] (any
+    stride), w [N_out, C] bf16.  T % 64 == 0."""
+    lib = _lib.load()
+    dev = _require_cuda(dy, x, scale, w)
+    assert dy.dtype == x.dtype == w.dtype == torch.bfloat16 and scale.dtype == torch.float32 and scale.dim() == 1 and scale.numel() == videos
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0] and dy.shape[0] % videos == 0
+    assert dy.stride(1) == 1 and x.stride(1) == 1 and w.stride(1) == 1 and w.shape == (dy.shape[1], x.shape[1])
+    T = dy.shape[0] // videos
+    N_out, Cc = w.shape
+    with torch.cuda.device(dev):
+        dW = torch.empty((N_out, Cc), dtype=torch.bfloat16, device=dev)
+        partial = torch.empty((videos, lib.merv_pair_dot_chunks()), dtype=torch.float32, device=dev)
+        ws = torch.empty(videos * lib.merv_wgrad_video_parts(N_out, Cc), dtype=torch.float32, device=dev)
+        _call('merv_wgrad_video', lib.merv_wgrad_video, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), scale.data_ptr(), scale.stride(0),
+              w.data_ptr(), w.stride(0), dW.data_ptr(), dW.stride(0), partial.data_ptr(), ws.data_ptr(), videos, T, N_out, Cc, _stream())
+    return dW, partial
 
 
 def fused_backward(weights: torch.Tensor, dweights_out: Optional[torch.Tensor], u: torch.Tensor, gsum: torch.Tensor,

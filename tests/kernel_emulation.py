@@ -230,6 +230,15 @@ def gemm_ex(a, w, bias=None, act=0, a_t=False, w_t=False):
     return y.to(a.dtype)
 
 
+def wgrad_video(dy, x, scale, w, videos):
+    T = dy.shape[0] // videos
+    G = torch.einsum("btn,btc->bnc", dy.float().reshape(videos, T, -1), x.float().reshape(videos, T, -1))
+    dW = (scale.float().reshape(-1, 1, 1) * G).sum(0).to(dy.dtype)
+    partial = torch.zeros((videos, 32))
+    partial[:, 0] = (G * w.float()).sum((1, 2))
+    return dW, partial
+
+
 def fused_backward(weights, dweights_out, u, gsum, dw_partials, pbars, Ws, biases, Q, Wq, Wk, in_proj_bias, dWs):
     """The contract of merv_fused_backward (include/merv_fusion.h), restated with torch ops."""
     B, E = weights.shape
@@ -313,7 +322,7 @@ class FusedLinearPlan:
 
 _NAMES = ["pool3d", "linear_bias_act", "fusion_query_vec", "affine_score_vec", "scores_from_tokens", "score_consts", "scores_from_partials",
           "softmax_weights", "softmax_mix", "fused_linear_mix", "concat_linear", "layernorm", "layernorm_backward", "transpose", "gelu",
-          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "gemm_ex", "fused_backward", "cross_attention", "cross_attention_backward", "add_rows"]
+          "colsum", "mix_backward", "FusedLinearPlan", "video_colsum", "pair_dot", "gemm_ex", "fused_backward", "cross_attention", "cross_attention_backward", "add_rows", "wgrad_video"]
 
 
 def emulate(monkeypatch) -> None:

@@ -185,6 +185,7 @@ _CONFIGS = [
     ("avg+linear", "scalar", {}),
     ("attntv+gelu-mlp", "concat", {}),
     ("3dconv+linear", "cross_attention_avg_lq", {}),
+    ("3davg+linear", "query_mlp", {}),  # constructed (merv.py:211-212) although MERV.forward has no branch for it
     ("3dconv+frame2+gelu-mlp", "concat_channel", {"visual_feature_length": 32}),
     ("linear", "first", {"pre_proj_layernorm": True, "visual_feature_length": 4}),
     ("gelu-mlp", "concat_channel", {"visual_feature_length": 4}),
@@ -227,7 +228,9 @@ def test_from_config_builds_what_merv_init_builds(arch, fusion, kw):
     else:
         cls = {"linear": ref.LinearProjector, "gelu-mlp": ref.MLPProjector, "fused-gelu-mlp": ref.FusedMLPProjector}[mlp_type]
         projs = [cls(c, llm, pre_proj_layernorm=kw.get("pre_proj_layernorm", False)) for c in dims]
-    if fusion == "cross_attention_avg_lq":
+    if fusion == "query_mlp":
+        ff = ref.MLPProjector(3072, len(dims))
+    elif fusion == "cross_attention_avg_lq":
         ff = ref.CrossAttentionAdapterLearnableQuery(embed_dim=3072, llm_dim=llm, token_length=vfl, averagetoken=True)
     elif fusion == "concat_channel":
         ff = ref.LinearProjector(len(dims) * llm, llm)
@@ -245,6 +248,9 @@ def test_from_config_builds_what_merv_init_builds(arch, fusion, kw):
     for k in want:
         assert torch.equal(got[k], want[k]), k
     assert m.arch_specifier == arch and m.feature_fusion_type == fusion
+    if fusion == "query_mlp":  # merv.py:610-612
+        with pytest.raises(NotImplementedError):
+            m([torch.zeros(1, t, 16, c) for c, t in zip(dims, temporal)])
 
 
 def test_from_config_rejects_what_merv_rejects():

@@ -1210,3 +1210,28 @@ def test_conv3d_projector_training_matches_reference_autograd(C_, llm, F, H, T, 
     with torch.inference_mode():
         out_inf = m(x)
     assert O.rel_err(_np(out_inf), _np(out)) < 1e-2
+
+
+@pytest.mark.parametrize("videos,T,N_out,Cc", [(3, 64, 256, 128), (2, 128, 136, 200), (5, 192, 384, 776), (4, 1024, 4096, 768)])
+def test_wgrad_video_matches_fp32_reference(videos, T, N_out, Cc):
+    """merv_wgrad_video: dW = sum_b scale[b] dY[b]^T X[b] and the per-video <W, dY[b]^T X[b]> from one tcgen05 pass (accumulator drained
+    once per video), against fp32 torch on the same bf16 inputs; M / N tails, several k-blocks per video, the merv-full shape."""
+    from merv_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(videos * 1000 + T)
+    dy = torch.randn((videos * T, N_out), generator=g, device=DEV).to(torch.bfloat16)
+    x = (torch.randn((videos * T, Cc), generator=g, device=DEV) + 0.2).to(torch.bfloat16)
+    w = (torch.randn((N_out, Cc), generator=g, device=DEV) * 0.05).to(torch.bfloat16)
+    scale_full = torch.rand((videos, 4), generator=g, device=DEV) + 0.1
+    scale = scale_full[:, 2]  # strided, as the mixing weights [B, E] of one encoder are
+    dW, partial = ops.wgrad_video(dy, x, scale, w, videos)
+    dW2, partial2 = ops.wgrad_video(dy, x, scale, w, videos)
+    torch.cuda.synchronize()
+    assert torch.equal(dW, dW2) and torch.equal(partial, partial2)  # deterministic
+    G = torch.einsum("btn,btc->bnc", dy.float().view(videos, T, N_out), x.float().view(videos, T, Cc))
+    want_dW = (scale.view(-1, 1, 1) * G).sum(0)
+    want_dot = (G * w.float()).sum((1, 2))
+    assert dW.shape == (N_out, Cc) and dW.dtype == torch.bfloat16
+    assert float((dW.float() - want_dW).abs().max()) <= 6e-3 * float(want_dW.abs().max())  # bf16 rounding of the result
+    got_dot = partial.double().sum(1)
+    assert float((got_dot - want_dot.double()).abs().max()) <= 2e-4 * max(1.0, float(want_dot.abs().max()))
