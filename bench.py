@@ -514,6 +514,33 @@ def main():
                 except Exception as e:  # the LLM is only a timing sink
                     configs["generate_b1"] = {"error": repr(e)[:300]}
 
+            try:  # the FSDP training step's share of the path: forward + hand-written backward + parameter-version bump
+                tr = {}
+                for Bt in (16, 64):  # 16 = the reference's per-device batch (conf/models.py:125)
+                    gt = torch.Generator(device=dev).manual_seed(5)
+                    ft = [torch.randn((Bt, t, n, c), generator=gt, device=dev).to(torch.bfloat16) for t, n, c in zip(TOKENS_T, PATCHES, DIMS)]
+                    Gt = torch.randn((Bt, OUT_TOKENS, LLM_DIM), generator=gt, device=dev).to(torch.bfloat16)
+                    mt = build_module(DIMS, TOKENS_T, "linear").train().requires_grad_(True)
+                    mt.feature_fusion.fused_training = True
+                    pt = list(mt.parameters())
+
+                    def train_step(i):
+                        o, _ = mt(ft)
+                        o.backward(Gt)
+                        mt.zero_grad(set_to_none=True)
+                        with torch.no_grad():  # what an optimizer step does to the caches: every parameter gets a new version
+                            torch._foreach_add_(pt, 0.0)
+
+                    ms_t, clk_t = timed(train_step, 10, warmup=3)
+                    tr[f"B{Bt}"] = {"ms_per_step": ms_t, "videos_per_s": Bt * 1e3 / ms_t, "steps": 10, "clocks": clk_t}
+                    del mt, ft, Gt, pt
+                    torch.cuda.empty_cache()
+                tr["workload"] = ("merv-full fusion training step, bf16: fused forward + backward (weight gradients over per-video segments, "
+                                  "merv_wgrad_video; no gradient into the frozen backbones' features) + parameter-version bump; same input every step")
+                configs["train_step"] = tr
+            except Exception as e:
+                configs["train_step"] = {"error": repr(e)[:300]}
+
         # second comparator (SURVEY.md §8d "the real bar"): the reference's op sequence in PyTorch eager on this same B200
         torch_eager = None
         if world == 1 and not args.no_torch_eager:
