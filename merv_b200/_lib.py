@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libmerv_fusion.so")
+# MERV_FUSION_LIB: another build of the SAME library (A/B labs, merv_b200/build.py MERV_BUILD_TAG); never a different implementation
+LIB_PATH = os.environ.get("MERV_FUSION_LIB") or os.path.join(PKG, "libmerv_fusion.so")
 
 MERV_F32, MERV_BF16 = 0, 1
 ACT_NONE, ACT_GELU_ERF = 0, 1

@@ -19,8 +19,11 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(REPO, "include")
-LIB = os.path.join(PKG, "libmerv_fusion.so")
-OBJ_DIR = os.path.join(PKG, "csrc", "build")
+# A/B builds for the labs: MERV_BUILD_DEFINES="-DX=1 ..." adds compile definitions, MERV_BUILD_TAG=name writes libmerv_fusion_<name>.so
+# (load it with MERV_FUSION_LIB=<path>, merv_b200/_lib.py); the production library is the untagged one.
+_TAG = os.environ.get("MERV_BUILD_TAG", "")
+LIB = os.path.join(PKG, f"libmerv_fusion_{_TAG}.so" if _TAG else "libmerv_fusion.so")
+OBJ_DIR = os.path.join(PKG, "csrc", f"build_{_TAG}" if _TAG else "build")
 SOURCES = ["api.cu", "pool3d.cu", "mix.cu", "gemm_simt.cu", "gemm_tcgen05.cu", "backward.cu", "norm.cu", "attention.cu", "attention_tcgen05.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -28,6 +31,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-I", INCLUDE, "-I", CSRC,
+    *os.environ.get("MERV_BUILD_DEFINES", "").split(),
 ]
 
 

@@ -132,7 +132,7 @@ __device__ __forceinline__ void pt_mbar_wait(uint32_t bar, uint32_t parity) {
   if (pt_mbar_try_wait(bar, parity)) return;
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (!pt_mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_parked(bar, parity, MERV_WAIT_HINT_NS)) {  // parked in hardware until the phase completes (tcgen05_util.cuh)
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     if (t1 - t0 > 4000000000ull) {  // a protocol bug must trap, never hang the GPU

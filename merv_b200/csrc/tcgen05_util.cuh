@@ -37,12 +37,33 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Spin with a watchdog: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
-// hung GPU.  The timer is only read on the slow path.
+// try_wait with a suspend-time hint (ns): the thread stays parked in hardware (NANOSLEEP.SYNCS) until the phase completes or the hint
+// expires.  Without it a failed try_wait returns after ~100 ns; ncu's source view showed the 16 epilogue warps re-issuing the wait loop ~35
+// times per tile — a quarter of all instructions the plain GEMM executes, against cuBLAS's 4x fewer on the same shape.  Measured A/B on
+// one box (profiles/r2b_wait_hint_ab.json): throughput IDENTICAL to 0.3 % on every GEMM shape and on the whole step, so the spin is not
+// what costs the power; the hint stays a build-time option (MERV_BUILD_DEFINES=-DMERV_WAIT_HINT_NS=2000000) and the default is the
+// plain loop.  What does separate the two kernels (profiles/r2b_gemm_vs_cublas.txt): cuBLAS runs a 256 x 256 tile per CTA (512 x 256
+// per pair, the whole TMEM as ONE accumulator) and moves 25 % fewer bytes from L2 per FLOP — same 70 % tensor-pipe activity, but
+// 1.64 GHz against 1.50 GHz under the same power cap.
+#ifndef MERV_WAIT_HINT_NS
+#define MERV_WAIT_HINT_NS 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_parked(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  if (MERV_WAIT_HINT_NS == 0) return mbar_try_wait(bar, parity);
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
+// hung GPU.  The timer is only read on the slow path, once per parked interval.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_parked(bar, parity, MERV_WAIT_HINT_NS)) {
     if (globaltimer_ns() - t0 > 4000000000ull) {
       printf("merv gemm: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
