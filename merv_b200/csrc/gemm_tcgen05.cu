@@ -107,7 +107,12 @@ struct TensorMaps {
 // CTA's TMEM receives its own 128 accumulator rows: per-SM shared-memory and L2->SM operand traffic drop by a third.
 // kMn: the variant that honours MN-major operand flags (backward GEMMs).  It is a separate instantiation because the single producer /
 // MMA threads run on 40 registers: the per-segment majorness selects cost the forward kernels 14 % when they were runtime branches.
-template <int kCtas, bool kWide, bool kGelu, bool kMn, bool kAssist, bool kVid = false>
+// kMaj: operand majorness as a COMPILE-TIME value — bit 0: A is MN-major, bit 1: W is MN-major, the same for every segment.  As runtime
+// flags the selects and the predicated second set of TMA issues made the producer's per-k-block instruction stream ~170 instructions
+// long; a lone thread sustains roughly one instruction per 4 cycles, a k-block lasts ~560, and the CTA PAIR (whose two producers feed
+// one MMA stream) ran 35 % SLOWER than the single CTA on MN-major operands — on K-major ones too when sent through that code
+// (scripts/gpu_mn_pair_lab.py).
+template <int kCtas, bool kWide, bool kGelu, int kMaj, bool kAssist, bool kVid = false>
 __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmParams& p, const AssistArgs* ap) {
   using C = Cfg<kCtas, kWide, kAssist>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, RING_BYTES = C::RING_BYTES;
@@ -211,7 +216,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             const uint32_t stage = it % STAGES, ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar + 8 * stage, ph ^ 1u);  // own barrier: the pair's MMA commit is multicast to both CTAs
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
-            const bool a_mn = kMn && ((p.a_mn_mask >> s) & 1), b_mn = kMn && ((p.b_mn_mask >> s) & 1);
+            constexpr bool a_mn = (kMaj & 1) != 0, b_mn = (kMaj & 2) != 0;
             const int m0 = (m_blk * kCtas + int(rank)) * BM, n0 = n_blk * BN + int(rank) * C::B_ROWS;
             const uint32_t bar = (kCtas == 2 ? leader_full : full_bar) + 8 * stage;
             // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
@@ -243,7 +248,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         for (int s0 = 0; s0 < p.nseg; ++s0, ++acc_it) {
           const int s = kVid ? 0 : s0;
-          const bool a_mn = kMn && ((p.a_mn_mask >> s) & 1), b_mn = kMn && ((p.b_mn_mask >> s) & 1);
+          constexpr bool a_mn = (kMaj & 1) != 0, b_mn = (kMaj & 2) != 0;
           const uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN, a_mn, b_mn);
           // per UMMA (16 k): +32 bytes inside the swizzle atom for a K-major operand, +2 atoms of 8 k-rows for an MN-major one
           const uint32_t a_step = a_mn ? (2048u >> 4) : 2u, b_step = b_mn ? (2048u >> 4) : 2u;
@@ -443,7 +448,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             }
             release_accumulator(buf);
             dot = warp_sum(dot);
-            if (lane == 0) p.dot_out[((long long)s * total_tiles + tile) * EPI_WARPS + (warp - 4)] = dot;
+            if (lane == 0) p.dot_out[(((long long)s * total_tiles + tile) * kCtas + int(rank)) * EPI_WARPS + (warp - 4)] = dot;
             continue;
           }
 #pragma unroll
@@ -484,23 +489,24 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
   }
 }
 
-template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
+template <int kCtas, bool kWide, bool kGelu, int kMaj = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
-  gemm_body<kCtas, kWide, kGelu, kMn, false>(maps, p, nullptr);
+  gemm_body<kCtas, kWide, kGelu, kMaj, false>(maps, p, nullptr);
 }
 
 // weight gradient over per-video segments (single CTA, MN-major operands): dW = sum_b scale[b] dY[b]^T X[b] and <W, dY[b]^T X[b]> per video
+template <int kCtas>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_wgrad_video_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p) {
-  gemm_body<1, false, false, true, false, true>(maps, p, nullptr);
+  gemm_body<kCtas, false, false, 3, false, true>(maps, p, nullptr);
 }
 
 // the fused forward GEMM (CTA pair, K-major operands) whose two spare warps pool the videos ahead of the tiles (pool_assist.cuh)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_pool_assist_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmParams p,
                                 const __grid_constant__ AssistArgs assist) {
-  gemm_body<2, false, false, false, true>(maps, p, &assist);
+  gemm_body<2, false, false, 0, true>(maps, p, &assist);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -509,15 +515,17 @@ gemm_pool_assist_tcgen05_kernel(const __grid_constant__ TensorMaps maps, const _
 // vs 1.377 (1398) for the single CTA; plain K = 1024: 0.424 (1297) vs 0.454 (1210); + GELU 0.452 vs 0.463; M = 262144, K = 768: 1.372 vs
 // 1.378.  (Round 1 had the fused GEMM 2 % slower on the pair; that was measured inside long power-capped loops.)  cuBLAS on the same
 // shapes: 1.225 / 0.402 / - / 1.265 ms.  MERV_GEMM_CTA_GROUP=1|2 overrides (read per call so the tests can run both).
-// K-major operands: the pair wins at every shape measured with more than one row block (65536 x 1024 x 4096: 0.403 vs 0.417 ms; 65536 x
-// 768 x 4096: 0.293 vs 0.338; the shapes above).  MN-major operands (the backward's dW = dY^T X, dX = dY W): the single CTA reads them as
-// fast as K-major ones (0.416 vs 0.414 ms) but the pair does not (0.533 vs 0.400) — profiles/r2_bwd_lab.json — so those run on one CTA.
-static int gemm_cta_group(int M, bool mn_major) {
+// K-major operands: the pair wins at every shape measured with more than one row block (65536 x 1024 x 4096: 0.372 vs 0.410 ms; 65536 x
+// 768 x 4096: 0.293 vs 0.338; the shapes above).  MN-major operands (the backward's dX = dY W and dW = dY^T X), with the majorness compiled
+// in (kMaj; scripts/gpu_mn_pair_lab.py, profiles/r2b_mn_pair_lab.json): an MN-major W only (dX) — pair 0.384 vs single 0.410 ms; an
+// MN-major A (dW, contraction over 65536 tokens) — single 0.398 vs pair 0.418; the per-video weight gradient — single 0.458 vs pair 0.461.
+// (With RUNTIME majorness flags the pair took 0.50-0.54 ms on all of them: the producer's instruction stream was too long for one thread.)
+static int gemm_cta_group(int M, bool a_mn_major) {
   const char* e = getenv("MERV_GEMM_CTA_GROUP");
   if (e != nullptr && e[0] == '1') return 1;
   if (e != nullptr && e[0] == '2') return 2;
   if (M <= BM) return 1;  // a pair computes 256 rows: with at most 128 rows its second CTA would only multiply padding
-  return mn_major ? 1 : 2;
+  return a_mn_major ? 1 : 2;
 }
 
 // 2-D bf16 row-major [rows, cols] (leading dimension ld elements) -> box [box_rows, box_cols] with 128-byte swizzle
@@ -528,19 +536,24 @@ static int make_tmap(CUtensorMap* map, const void* base, long long rows, long lo
   return encode_tmap_cached(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int kCtas, bool kWide, bool kGelu, bool kMn = false>
+template <int kCtas, bool kWide, bool kGelu, int kMaj = 0>
 static int launch_variant(cudaLaunchConfig_t& cfg, const TensorMaps& maps, const GemmParams& p) {
   constexpr int smem = Cfg<kCtas, kWide>::SMEM_BYTES;
   static const cudaError_t attr_rc =  // once per variant (thread-safe static init)
-      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMn>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMaj>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
   cfg.dynamicSmemBytes = smem;
-  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMn>, maps, p));
+  MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<kCtas, kWide, kGelu, kMaj>, maps, p));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;
 }
 
-int wgrad_video_parts(int M, int N) { return ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * EPI_WARPS; }
+static int wgrad_video_ctas(int M) { return gemm_cta_group(M, true); }
+// partial dots per video: one per (tile, CTA of the tile's unit, epilogue warp)
+int wgrad_video_parts(int M, int N) {
+  const int ctas = wgrad_video_ctas(M);
+  return ((M + BM * ctas - 1) / (BM * ctas)) * ctas * ((N + BN - 1) / BN) * EPI_WARPS;
+}
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
                         const void* bias, int act, const float* rowdot_vec, float* rowdot_out, void* Y, long long ldy, long long y_batch_stride,
@@ -557,9 +570,15 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
   (void)total_k;
-  bool any_mn = false;
-  for (int i = 0; i < nseg; ++i) any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
-  const int ctas = assist != nullptr ? 2 : vid != nullptr ? 1 : gemm_cta_group(M, any_mn);
+  bool any_mn = false, a_mn_any = false;
+  for (int i = 0; i < nseg; ++i) {
+    any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
+    a_mn_any = a_mn_any || seg[i].a_mn;
+  }
+  const int ctas = assist != nullptr ? 2 : vid != nullptr ? wgrad_video_ctas(M) : gemm_cta_group(M, a_mn_any);
+  // majorness is compiled into the kernel (kMaj): one choice per launch
+  for (int i = 1; i < nseg; ++i)
+    MERV_REQUIRE(seg[i].a_mn == seg[0].a_mn && seg[i].b_mn == seg[0].b_mn, MERV_E_ARG, "gemm: all segments of a launch share the operand majorness");
   if (vid != nullptr) {
     MERV_REQUIRE(nseg == 1 && seg[0].a_mn && seg[0].b_mn && act == MERV_ACT_NONE && num_extra == 0 && mc_out == nullptr && assist == nullptr &&
                      bias == nullptr && bias_rows == nullptr && rowdot_vec == nullptr && seg_scale == nullptr,
@@ -673,11 +692,19 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 2 : 1;
   if (vid != nullptr) {
-    constexpr int smem = Cfg<1, false>::SMEM_BYTES;
-    static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_wgrad_video_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
-    cfg.dynamicSmemBytes = smem;
-    MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_wgrad_video_tcgen05_kernel, maps, p));
+    if (ctas == 2) {
+      constexpr int smem = Cfg<2, false>::SMEM_BYTES;
+      static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_wgrad_video_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
+      cfg.dynamicSmemBytes = smem;
+      MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_wgrad_video_tcgen05_kernel<2>, maps, p));
+    } else {
+      constexpr int smem = Cfg<1, false>::SMEM_BYTES;
+      static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_wgrad_video_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      MERV_REQUIRE(attr_rc == cudaSuccess, MERV_E_CUDA, "cudaFuncSetAttribute(max dynamic smem=%d) failed: %s", smem, cudaGetErrorString(attr_rc));
+      cfg.dynamicSmemBytes = smem;
+      MERV_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_wgrad_video_tcgen05_kernel<1>, maps, p));
+    }
     MERV_CUDA_OK(cudaGetLastError());
     return MERV_OK;
   }
@@ -692,7 +719,12 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   }
   if (p.a_mn_mask | p.b_mn_mask) {
     MERV_REQUIRE(act == MERV_ACT_NONE && !wide, MERV_E_ARG, "gemm: MN-major operands are supported without an activation and without extra output destinations");
-    return ctas == 2 ? launch_variant<2, false, false, true>(cfg, maps, p) : launch_variant<1, false, false, true>(cfg, maps, p);
+    const int maj = (p.a_mn_mask ? 1 : 0) | (p.b_mn_mask ? 2 : 0);
+    if (ctas == 2)
+      return maj == 3 ? launch_variant<2, false, false, 3>(cfg, maps, p) : maj == 2 ? launch_variant<2, false, false, 2>(cfg, maps, p)
+                                                                                     : launch_variant<2, false, false, 1>(cfg, maps, p);
+    return maj == 3 ? launch_variant<1, false, false, 3>(cfg, maps, p) : maj == 2 ? launch_variant<1, false, false, 2>(cfg, maps, p)
+                                                                                   : launch_variant<1, false, false, 1>(cfg, maps, p);
   }
   if (act == MERV_ACT_GELU_ERF) return ctas == 2 ? launch_variant<2, false, true>(cfg, maps, p) : launch_variant<1, false, true>(cfg, maps, p);
   if (ctas == 2) return wide ? launch_variant<2, true, false>(cfg, maps, p) : launch_variant<2, false, false>(cfg, maps, p);
