@@ -61,6 +61,23 @@ constexpr int KERNEL_REGS = 96, PRODUCER_REGS = 64, EPILOGUE_REGS = 104;  // see
 static_assert(GEMM_THREADS * KERNEL_REGS <= 65536, "register file");
 static_assert(128 * PRODUCER_REGS + EPI_WARPS * 32 * EPILOGUE_REGS <= GEMM_THREADS * KERNEL_REGS, "setmaxnreg.inc must fit in what setmaxnreg.dec released");
 
+// MERV_GEMM_WARP_UNIFORM (build-time, A/B): the TMA producer and the MMA issuer run their loops as WHOLE warps and issue under elect.sync.
+// With `lane == 0` guards the compiler cannot prove the operands of UTMALDG / UTCHMMA warp-uniform and wraps every issue in an
+// ELECT / R2UR "waterfall" loop: ~80 (producer) and ~115 (MMA issuer) instructions per k-block for threads that get an issue slot every
+// ~4 cycles, against ~512 cycles of tensor work per k-block.
+#ifndef MERV_GEMM_WARP_UNIFORM
+#define MERV_GEMM_WARP_UNIFORM 1
+#endif
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 struct GemmParams {
   int M, N;
   int nseg;
@@ -179,8 +196,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");  // 128 x 64 + 512 x 104 = 61440 = the whole launch-time allocation
-    if (warp == 0 && lane == 0) {
-      // ===== TMA producer =====
+    if (warp == 0 && (MERV_GEMM_WARP_UNIFORM || lane == 0)) {
+      // ===== TMA producer (one elected lane issues; the loop itself is warp-uniform) =====
       uint32_t it = 0;
       const uint32_t leader_full = kCtas == 2 ? mapa_rank(full_bar, 0) : full_bar;
       int ready_video = -1;  // kAssist: last video whose ready flag this thread has acquired
@@ -191,7 +208,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
           // produced inside this launch by the pooling warps of whatever CTAs are resident: acquire the video's flag first
           const int video = ((m_blk * kCtas + int(rank)) * BM) / p.rows_per_video;
           if (video != ready_video) {
-            if (video >= ap->head && !(MERV_ASSIST_PROFILE && (ap->dbg & 8))) {
+            if (video >= ap->head && !(MERV_ASSIST_PROFILE && (ap->dbg & 8)) && lane == 0) {
               const int* flag = ap->sync + ASSIST_SYNC_HEADER + ap->B + video;
               if (ld_acquire_gpu(flag) == 0) {
                 const unsigned long long t0 = globaltimer_ns();
@@ -205,6 +222,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
               }
               fence_proxy_async_all();  // generic-proxy stores of the pooling warps -> this thread's async-proxy (TMA) reads
             }
+            __syncwarp();
             ready_video = video;
           }
         }
@@ -219,6 +237,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             constexpr bool a_mn = (kMaj & 1) != 0, b_mn = (kMaj & 2) != 0;
             const int m0 = (m_blk * kCtas + int(rank)) * BM, n0 = n_blk * BN + int(rank) * C::B_ROWS;
             const uint32_t bar = (kCtas == 2 ? leader_full : full_bar) + 8 * stage;
+            if (MERV_GEMM_WARP_UNIFORM && !elect_one()) continue;  // (the next wait re-converges the warp: elect.sync takes the full mask)
             // the leader's barrier counts the bytes of BOTH CTAs' loads; only the leader arrives on it
             if (kCtas == 1 || rank == 0) mbar_expect_tx(full_bar + 8 * stage, kCtas * STAGE_BYTES);
             auto load = [&](const CUtensorMap* map, uint32_t dst, int x, int y, uint64_t policy) {
@@ -242,8 +261,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
           }
         }
       }
-    } else if (warp == 1 && lane == 0 && rank == 0) {
-      // ===== MMA issuer (the leader CTA's single thread drives both SMs of a pair) =====
+    } else if (warp == 1 && (MERV_GEMM_WARP_UNIFORM || lane == 0) && rank == 0) {
+      // ===== MMA issuer (the leader CTA's elected lane drives both SMs of a pair; the loop is warp-uniform) =====
       uint32_t it = 0, acc_it = 0;
       for (int tile = unit; tile < total_tiles; tile += num_units) {
         for (int s0 = 0; s0 < p.nseg; ++s0, ++acc_it) {
@@ -264,18 +283,23 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             const uint32_t sa = tiles_addr + stage * STAGE_BYTES;
             const uint64_t a_desc = a_mn ? umma_desc_mn_sw128(sa) : umma_desc_sw128(sa);
             const uint64_t b_desc = b_mn ? umma_desc_mn_sw128(sa + A_BYTES) : umma_desc_sw128(sa + A_BYTES);
+            if (!MERV_GEMM_WARP_UNIFORM || elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              if constexpr (kCtas == 2) umma_bf16_pair(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if constexpr (kCtas == 2) umma_bf16_pair(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+              // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+              if constexpr (kCtas == 2) umma_commit_pair(empty_bar + 8 * stage);
+              else umma_commit(empty_bar + 8 * stage);
+              // accumulator complete -> epilogue (of both CTAs): committed by the same lane, right behind the segment's last MMAs
+              if (kb == nkb - 1) {
+                if constexpr (kCtas == 2) umma_commit_pair(tfull_bar + 8 * buf);
+                else umma_commit(tfull_bar + 8 * buf);
+              }
             }
-            // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-            if constexpr (kCtas == 2) umma_commit_pair(empty_bar + 8 * stage);
-            else umma_commit(empty_bar + 8 * stage);
+            if (MERV_GEMM_WARP_UNIFORM) __syncwarp();
           }
-          // accumulator complete -> epilogue (of both CTAs)
-          if constexpr (kCtas == 2) umma_commit_pair(tfull_bar + 8 * buf);
-          else umma_commit(tfull_bar + 8 * buf);
         }
       }
     } else if (kAssist && warp >= 2) {
