@@ -593,7 +593,6 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   MERV_REQUIRE((rowdot_vec == nullptr) == (rowdot_out == nullptr), MERV_E_ARG, "gemm: rowdot_vec and rowdot_out go together");
   long long total_k = 0;
   for (int i = 0; i < nseg; ++i) total_k += seg[i].K;
-  (void)total_k;
   bool any_mn = false, a_mn_any = false;
   for (int i = 0; i < nseg; ++i) {
     any_mn = any_mn || seg[i].a_mn || seg[i].b_mn;
@@ -620,6 +619,11 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
   // multimem.st is packetised per contiguous run like the peer stores: measured at 2 GPUs, 64 videos each, the multicast gather takes
   // 2.15 ms with 128-byte rows and 2.75 ms with 64-byte rows (compute alone 1.71 ms) — so the multicast variant uses the wide boxes too
   bool wide = num_extra >= 2 || mc_out != nullptr;
+  // ... and when the epilogue is the bottleneck: with a short contraction a tile's MMAs take less time than two staged passes through
+  // the single staging box (the second pass waits for the first pass's TMA store to have read it).  One 128-byte-row pass per tile
+  // instead: M = 262144, K = 768 (SigLIP single) on the pair 1199 -> 1283 TFLOP/s; at K = 1024 the ring stage given up costs more
+  // (1374 -> 1350), at K = 3584 too (profiles/r2b_gemm_lab_wide.json)
+  if (ctas == 2 && total_k <= 832 && !any_mn && vid == nullptr && assist == nullptr) wide = true;
   if (const char* e = getenv("MERV_GEMM_WIDE_OUT")) wide = e[0] == '1';
   if (assist != nullptr) wide = false;
   MERV_REQUIRE(act == MERV_ACT_NONE || act == MERV_ACT_GELU_ERF, MERV_E_ARG, "gemm: unknown activation %d", act);
