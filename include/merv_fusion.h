@@ -347,8 +347,11 @@ int merv_transpose_rowscale(const void* x, void* y, int R, int R_pad, int C, int
  *                      pair-dot pass of the formulation above are not needed at all — half of the backward's tensor work)
  * dY [videos * tokens_per_video, N_out] (lddy), X [videos * tokens_per_video, C] (ldx), W / dW [N_out, C] (ldw / lddw), all read in place
  * (MN-major operands); the contraction runs over the tokens, the accumulator is drained once per video: scaled into the running sum in
- * fp32 registers and dotted with the W tile.  tokens_per_video % 64 == 0.  workspace: videos * merv_wgrad_video_parts(N_out, C) floats. */
+ * fp32 registers and dotted with the W tile.  tokens_per_video % 64 == 0.  When the tile count leaves SMs idle (96 - 128 tiles on 148 SMs
+ * at the merv-full shapes) the videos are split into contiguous ranges handled as separate work items whose fp32 partial tiles are folded
+ * in fixed order afterwards (deterministic).  workspace: merv_wgrad_video_workspace(videos, N_out, C) floats, 16-byte aligned. */
 int merv_wgrad_video_parts(int N_out, int C);
+size_t merv_wgrad_video_workspace(int videos, int N_out, int C);
 int merv_wgrad_video(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* scale, int64_t scale_stride, const void* W,
                      int64_t ldw, void* dW, int64_t lddw, float* dot_partial, float* workspace, int videos, int tokens_per_video, int N_out,
                      int C, void* stream);

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "merv_video_colsum": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int64, c_float, c_int, c_void_p]),
     "merv_pair_dot_chunks": (c_int, []),
     "merv_wgrad_video_parts": (c_int, [c_int, c_int]),
+    "merv_wgrad_video_workspace": (c_size_t, [c_int, c_int, c_int]),
     "merv_wgrad_video": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                  c_int, c_int, c_int, c_int, c_void_p]),
     "merv_pair_dot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),

@@ -889,7 +889,31 @@ __global__ void __launch_bounds__(32) fold_partials_kernel(const float* __restri
   if (c < kPairDotChunks) out[(long long)b * kPairDotChunks + c] = acc;
 }
 
+// dW[m, n] = bf16(sum_q partial[q, m, n]) (ascending q: fixed order) — the fold of a weight gradient that was split over the videos
+__global__ void __launch_bounds__(256) fold_wgrad_parts_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ dW, long long lddw, int M, int N,
+                                                               int parts) {
+  const long long v = (long long)blockIdx.x * 256 + threadIdx.x;  // one 4-column vector per thread
+  const int nv = N / 4;
+  if (v >= (long long)M * nv) return;
+  const long long m = v / nv, n = (v % nv) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < parts; ++q) {
+    const float4 x = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)q * M + m) * N + n));
+    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+  }
+  uint2 o = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  *reinterpret_cast<uint2*>(dW + m * lddw + n) = o;
+}
+
 extern "C" int merv_wgrad_video_parts(int N_out, int C) { return wgrad_video_parts(N_out, C); }
+/* floats of workspace merv_wgrad_video needs: the per-(video, tile, warp) dots + the fp32 partial tiles of a split over the videos */
+extern "C" size_t merv_wgrad_video_workspace(int videos, int N_out, int C) {
+  if (videos <= 0 || N_out <= 0 || C <= 0) return 0;
+  const int split = wgrad_video_split(N_out, C, videos);
+  size_t dots = (size_t)videos * wgrad_video_parts(N_out, C);
+  dots = (dots + 3) / 4 * 4;  // keeps the partial tiles 16-byte aligned
+  return dots + (split > 1 ? (size_t)split * N_out * C : 0);
+}
 
 extern "C" int merv_wgrad_video(const void* dY, int64_t lddy, const void* X, int64_t ldx, const float* scale, int64_t scale_stride, const void* W,
                                 int64_t ldw, void* dW, int64_t lddw, float* dot_partial, float* workspace, int videos, int tokens_per_video,
@@ -907,10 +931,20 @@ extern "C" int merv_wgrad_video(const void* dY, int64_t lddy, const void* X, int
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // dW [N_out, C] = dY^T X: A-operand = dY [tokens, N_out] read as [K, M], W-operand = X [tokens, C] read as [K, N] (both MN-major, in place)
   GemmSegment seg = {dY, lddy, X, ldx, videos * tokens_per_video, 1, 1};
-  WgradVideoArgs vid = {videos, tokens_per_video / 64, scale, scale_stride, W, ldw, workspace};
+  const int split = (C % 4 == 0 && lddw % 4 == 0) ? wgrad_video_split(N_out, C, videos) : 1;
+  size_t dots = (size_t)videos * wgrad_video_parts(N_out, C);
+  dots = (dots + 3) / 4 * 4;
+  float* partial = split > 1 ? workspace + dots : nullptr;
+  MERV_REQUIRE(aligned16(workspace), MERV_E_ALIGN, "merv_wgrad_video: workspace must be 16-byte aligned");
+  WgradVideoArgs vid = {videos, tokens_per_video / 64, scale, scale_stride, W, ldw, workspace, split, partial};
   if (int rc = launch_gemm_tcgen05(&seg, 1, nullptr, nullptr, N_out, nullptr, MERV_ACT_NONE, nullptr, nullptr, dW, lddw, 0, N_out, C, 0, s, nullptr, 0,
                                    false, nullptr, nullptr, &vid))
     return rc;
+  if (split > 1) {
+    const long long vecs = (long long)N_out * (C / 4);
+    fold_wgrad_parts_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, s>>>(partial, static_cast<__nv_bfloat16*>(dW), lddw, N_out, C, split);
+    MERV_CUDA_OK(cudaGetLastError());
+  }
   fold_partials_kernel<<<videos, 32, 0, s>>>(workspace, dot_partial, wgrad_video_parts(N_out, C));
   MERV_CUDA_OK(cudaGetLastError());
   return MERV_OK;

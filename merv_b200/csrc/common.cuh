@@ -40,8 +40,11 @@ struct WgradVideoArgs {
   const void* W;           // [M, N] bf16, row stride ldw: <W, per-video product> is emitted per (video, tile, epilogue warp)
   long long ldw;
   float* dot_out;          // [videos, wgrad_video_parts(M, N)]
+  int split;               // work items per tile: the videos in `split` contiguous ranges (1: no split, the result goes straight to Y)
+  float* partial;          // [split, M, N] fp32 when split > 1
 };
 int wgrad_video_parts(int M, int N);
+int wgrad_video_split(int M, int N, int videos);  // the split that fills the SMs best (1 if nothing is gained)
 // one (A_s, W_s, K_s) product of the tcgen05 GEMM (see gemm_tcgen05.cu)
 struct GemmSegment {
   const void* A;

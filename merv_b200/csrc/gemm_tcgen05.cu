@@ -106,6 +106,11 @@ struct GemmParams {
   const __nv_bfloat16* dot_w;
   long long dot_ldw;
   float* dot_out;
+  // kVid split over the videos: a tile's videos are divided into vid_parts contiguous ranges, each range a separate work item whose
+  // running sum goes to vid_partial [vid_parts, M, N] (fp32) instead of Y; folded afterwards in fixed order (fold_wgrad_parts_kernel).
+  // 96 - 128 tiles leave 14 - 35 % of the 148 SMs idle for the whole launch; 288 - 1024 items of a third / an eighth of the work do not.
+  int vid_parts;
+  float* vid_partial;
   int num_out;   // destinations of every output tile: 1 (local) + peers' buffers over NVLink (fused all-gather)
   int out_flat;  // 1: Y is one contiguous [M, N] matrix (output map = [1, M, N]); 0: [videos, rows_per_video, N] with a batch stride
 };
@@ -154,6 +159,9 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
   const int unit = kCtas == 2 ? int(blockIdx.x >> 1) : int(blockIdx.x);  // tile-processing unit: a CTA or a CTA pair
   const int num_units = int(gridDim.x) / kCtas;
   const int total_tiles = p.m_blocks * p.n_blocks;  // m_blocks counts (128 * kCtas)-row blocks
+  const int total_items = kVid ? total_tiles * p.vid_parts : total_tiles;  // kVid: (tile, range of videos) work items
+  // first segment of part q: all segments when the launch is not split; otherwise the videos in vid_parts near-equal contiguous ranges
+  auto seg_first = [&](int q) { return kVid ? int(((long long)q * p.nseg) / p.vid_parts) : (q == 0 ? 0 : p.nseg); };
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -201,7 +209,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
       uint32_t it = 0;
       const uint32_t leader_full = kCtas == 2 ? mapa_rank(full_bar, 0) : full_bar;
       int ready_video = -1;  // kAssist: last video whose ready flag this thread has acquired
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
+      for (int item = unit; item < total_items; item += num_units) {
+        const int tile = kVid ? item % total_tiles : item, part = kVid ? item / total_tiles : 0;
         const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
         if constexpr (kAssist) {
           // the pooled rows of this CTA's half of the tile (and the video's mixing weights / bias row the epilogue will read) are
@@ -226,7 +235,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             ready_video = video;
           }
         }
-        for (int s0 = 0; s0 < p.nseg; ++s0) {
+        for (int s0 = seg_first(part); s0 < seg_first(part + 1); ++s0) {
           const int s = kVid ? 0 : s0;                       // kVid: every video reads the same pair of tensors ...
           const int nkb = kVid ? p.vid_kblocks : p.kblocks[s];
           const int kb_end = kVid ? (s0 + 1) * nkb : nkb;    // ... at its own k-blocks
@@ -264,8 +273,9 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
     } else if (warp == 1 && (MERV_GEMM_WARP_UNIFORM || lane == 0) && rank == 0) {
       // ===== MMA issuer (the leader CTA's elected lane drives both SMs of a pair; the loop is warp-uniform) =====
       uint32_t it = 0, acc_it = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
-        for (int s0 = 0; s0 < p.nseg; ++s0, ++acc_it) {
+      for (int item = unit; item < total_items; item += num_units) {
+        const int part = kVid ? item / total_tiles : 0;
+        for (int s0 = seg_first(part); s0 < seg_first(part + 1); ++s0, ++acc_it) {
           const int s = kVid ? 0 : s0;
           constexpr bool a_mn = (kMaj & 1) != 0, b_mn = (kMaj & 2) != 0;
           const uint32_t idesc = umma_idesc_bf16(BM * kCtas, BN, a_mn, b_mn);
@@ -319,7 +329,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
     const int h = (warp - 4) >> 2;   // column group of the tile: columns 64 h .. 64 h + 63
     uint32_t acc_it = 0;
     const uint32_t leader_tempty = kCtas == 2 ? mapa_rank(tempty_bar, 0) : tempty_bar;
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int item = unit; item < total_items; item += num_units) {
+      const int tile = kVid ? item % total_tiles : item, part = kVid ? item / total_tiles : 0;
       const int m_blk = tile / p.n_blocks, n_blk = tile % p.n_blocks;
       const int m_base = (m_blk * kCtas + int(rank)) * BM;  // first output row of THIS CTA's half of the tile
       const int row = m_base + q * 32 + lane;
@@ -436,7 +447,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
         float sum[EPI_COLS];
 #pragma unroll
         for (int i = 0; i < EPI_COLS; ++i) sum[i] = 0.f;
-        for (int s = 0; s < p.nseg; ++s, ++acc_it) {
+        for (int s = seg_first(part); s < seg_first(part + 1); ++s, ++acc_it) {
           const uint32_t buf = acc_it & 1u, aph = (acc_it >> 1) & 1u;
           float scale = 1.0f;
           if constexpr (kVid) scale = p.seg_scale ? __ldg(p.seg_scale + (long long)s * p.seg_scale_stride) : 1.0f;
@@ -489,6 +500,16 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             }
           }
           release_accumulator(buf);
+        }
+        if (kVid && p.vid_parts > 1) {
+          // this item covered only `part` of the videos: fp32 partial tile, 64 contiguous columns per thread
+          if (row_ok) {
+            float* dst = p.vid_partial + ((long long)part * p.M + row) * p.N + col0;
+#pragma unroll
+            for (int c = 0; c < EPI_COLS; c += 4)
+              if (col0 + c < p.N) *reinterpret_cast<float4*>(dst + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+          }
+          continue;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) rd[i] = 0.f;
@@ -577,6 +598,31 @@ static int wgrad_video_ctas(int M) { return gemm_cta_group(M, true); }
 int wgrad_video_parts(int M, int N) {
   const int ctas = wgrad_video_ctas(M);
   return ((M + BM * ctas - 1) / (BM * ctas)) * ctas * ((N + BN - 1) / BN) * EPI_WARPS;
+}
+
+// Split of a per-video weight gradient over the videos: with `tiles` tiles on `units` persistent CTAs (pairs), s work items per tile take
+// ceil(tiles s / units) / s tile-times.  Measured (scripts/gpu_mn_pair_lab.py, profiles/r2b_mn_pair_lab.json): the fp32 round trip of the
+// partial tiles and the extra pipeline ramps eat most of it — C = 768 (96 tiles, 64 videos) 0.465 -> 0.415 ms with 3 ranges (predicted
+// 0.667x), C = 1024 (128 tiles) 0.443 -> 0.580 with 8 (predicted 0.875x), everything slower at 16 videos.  So: split only when the
+// prediction is at least 30 % and there are at least 32 videos; the smallest s within 2 % of the best of {1..8} wins.
+int wgrad_video_split(int M, int N, int videos) {
+  if (const char* e = getenv("MERV_WGRAD_SPLIT")) {
+    const int s = atoi(e);
+    if (s >= 1) return s < videos ? s : (videos > 0 ? videos : 1);
+  }
+  const int ctas = wgrad_video_ctas(M);
+  const long long tiles = (long long)((M + BM * ctas - 1) / (BM * ctas)) * ((N + BN - 1) / BN);
+  const long long units = sm_count() / ctas;
+  double best = 1e30;
+  double cost[9];
+  for (int s = 1; s <= 8; ++s) {
+    cost[s] = s <= videos ? double((tiles * s + units - 1) / units) / s : 1e30;
+    if (cost[s] < best) best = cost[s];
+  }
+  if (best > 0.70 * cost[1] || videos < 32) return 1;
+  for (int s = 1; s <= 8; ++s)
+    if (cost[s] <= 1.02 * best) return s;
+  return 1;
 }
 
 int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale, const float* bias_rows, int rows_per_video,
@@ -699,8 +745,11 @@ int launch_gemm_tcgen05(const GemmSegment* seg, int nseg, const float* seg_scale
     p.nseg = vid->videos; p.vid_kblocks = vid->kblocks_per_video;
     p.seg_scale = vid->scale; p.seg_scale_stride = vid->scale_stride;
     p.dot_w = static_cast<const __nv_bfloat16*>(vid->W); p.dot_ldw = vid->ldw; p.dot_out = vid->dot_out;
+    MERV_REQUIRE(vid->split >= 1 && vid->split <= vid->videos && (vid->split == 1 || (vid->partial != nullptr && aligned16(vid->partial) && N % 4 == 0)), MERV_E_ARG,
+                 "gemm: per-video weight gradient: split=%d of %d videos needs a 16-byte aligned partial buffer", vid->split, vid->videos);
+    p.vid_parts = vid->split; p.vid_partial = vid->partial;
   }
-  const long long total = (long long)p.m_blocks * p.n_blocks;
+  const long long total = (long long)p.m_blocks * p.n_blocks * (vid != nullptr ? vid->split : 1);
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   long long units = sms / ctas;  // persistent: one CTA (or CTA pair) per SM (pair)

@@ -57,7 +57,7 @@ KERNELS_PER_CALL = {
     "merv_scores_from_tokens": 2, "merv_scores_from_partials": 1, "merv_softmax_weights": 1,
     "merv_softmax_mix": 1, "merv_fused_linear_mix": 1, "merv_fused_forward": 3, "merv_softmax_weights_ex": 1,
     "merv_transpose": 1, "merv_colsum": 2, "merv_mix_backward": 10, "merv_gelu": 1,
-    "merv_cross_attention": 1, "merv_cross_attention_backward": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10, "merv_wgrad_video": 2,
+    "merv_cross_attention": 1, "merv_cross_attention_backward": 1, "merv_add_rows": 1, "merv_video_colsum": 1, "merv_pair_dot": 1, "merv_transpose_rowscale": 1, "merv_fused_backward": 10, "merv_wgrad_video": 3,
     "merv_scores_from_tokens_ex": 2, "merv_score_consts": 1, "merv_layernorm": 1, "merv_layernorm_backward": 1, "merv_concat_linear": 1,
 }
 
@@ -742,7 +742,7 @@ def wgrad_video(dy: torch.Tensor, x: torch.Tensor, scale: torch.Tensor, w: torch
     with torch.cuda.device(dev):
         dW = torch.empty((N_out, Cc), dtype=torch.bfloat16, device=dev)
         partial = torch.empty((videos, lib.merv_pair_dot_chunks()), dtype=torch.float32, device=dev)
-        ws = torch.empty(videos * lib.merv_wgrad_video_parts(N_out, Cc), dtype=torch.float32, device=dev)
+        ws = torch.empty(max(int(lib.merv_wgrad_video_workspace(videos, N_out, Cc)), 4), dtype=torch.float32, device=dev)
         _call('merv_wgrad_video', lib.merv_wgrad_video, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), scale.data_ptr(), scale.stride(0),
               w.data_ptr(), w.stride(0), dW.data_ptr(), dW.stride(0), partial.data_ptr(), ws.data_ptr(), videos, T, N_out, Cc, _stream())
     return dW, partial

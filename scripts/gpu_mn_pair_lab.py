@@ -50,4 +50,19 @@ for videos in (64, 16):
         print(f"   single vs pair: dW rel diff {ddw:.2e}, dot rel diff {ddot:.2e}", flush=True)
         rep[f"wgrad_video_B{videos}_C{C}_single_vs_pair"] = (ddw, ddot)
 os.environ.pop("MERV_GEMM_CTA_GROUP", None)
+# split over the videos (work items of a range of videos, fp32 partial tiles folded afterwards): SM utilisation of 96 - 128 tiles on 148 SMs
+for videos in (64, 16):
+    gv, sc = g[:videos * 1024], torch.rand(videos, generator=g0, device=dev) + 0.1
+    for C in (1024, 768):
+        Wc, Pc = W[:, :C].contiguous(), P[:videos * 1024, :C].contiguous()
+        flv = 2 * videos * 1024 * 4096 * C
+        for split in ("1", "2", "3", "4", "6", "8", None):
+            if split is None:
+                os.environ.pop("MERV_WGRAD_SPLIT", None)
+            else:
+                os.environ["MERV_WGRAD_SPLIT"] = split
+            t = timeit(lambda: ops.wgrad_video(gv, Pc, sc, Wc, videos))
+            rep[f"wgrad_video_B{videos}_C{C}_split{split}"] = (round(t, 4), round(flv / t / 1e9))
+            print(f"wgrad_video videos={videos} C={C} split={split}: {t:.3f} ms / {flv / t / 1e9:.0f} TF", flush=True)
+os.environ.pop("MERV_WGRAD_SPLIT", None)
 json.dump(rep, open(os.path.join(REPO, "gpurun_out", "mn_pair_lab.json"), "w"), indent=1)

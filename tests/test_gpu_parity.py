@@ -1214,12 +1214,15 @@ def test_conv3d_projector_training_matches_reference_autograd(C_, llm, F, H, T, 
 
 @pytest.mark.parametrize("videos,T,N_out,Cc", [(3, 64, 256, 128), (2, 128, 136, 200), (5, 192, 384, 776), (4, 1024, 4096, 768)])
 @pytest.mark.parametrize("cta_group", [1, 2])
-def test_wgrad_video_matches_fp32_reference(videos, T, N_out, Cc, cta_group, monkeypatch):
+@pytest.mark.parametrize("split", [None, 1, 2, 3])  # None: the library's choice; k: the videos in k ranges, fp32 partial tiles folded afterwards
+def test_wgrad_video_matches_fp32_reference(videos, T, N_out, Cc, cta_group, split, monkeypatch):
     """merv_wgrad_video: dW = sum_b scale[b] dY[b]^T X[b] and the per-video <W, dY[b]^T X[b]> from one tcgen05 pass (accumulator drained
     once per video), against fp32 torch on the same bf16 inputs; M / N tails, several k-blocks per video, the merv-full shape."""
     from merv_b200 import ops
 
     monkeypatch.setenv("MERV_GEMM_CTA_GROUP", str(cta_group))  # single CTA (the default for this kernel) / CTA pair
+    if split is not None:
+        monkeypatch.setenv("MERV_WGRAD_SPLIT", str(split))
     g = torch.Generator(device=DEV).manual_seed(videos * 1000 + T)
     dy = torch.randn((videos * T, N_out), generator=g, device=DEV).to(torch.bfloat16)
     x = (torch.randn((videos * T, Cc), generator=g, device=DEV) + 0.2).to(torch.bfloat16)
