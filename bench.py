@@ -343,6 +343,28 @@ def main():
         if not args.no_sustained and args.sustained_steps > 0:
             ms_sus, clk_sus = timed(step, args.sustained_steps)
             sustained = {"steps": args.sustained_steps, "ms_per_step": ms_sus, "value": world * B * 1e3 / ms_sus, "unit": "videos/s", "clocks": clk_sus}
+            # the opt-in pooling INSIDE the GEMM launch (MERV_POOL_ASSIST=1), A/B in the regime the sustained run has just
+            # established: alternating blocks of 100 steps, bit-identical outputs.  Off in the primary line and everywhere else.
+            if world == 1 and args.mode == "fused" and args.projector == "linear":
+                try:
+                    ab = {"base_ms": [], "assist_ms": []}
+                    for _ in range(3):
+                        os.environ["MERV_POOL_ASSIST"] = "0"
+                        ab["base_ms"].append(timed(step, 100, clocks=False)[0])
+                        os.environ["MERV_POOL_ASSIST"] = "1"
+                        ab["assist_ms"].append(timed(step, 100, clocks=False)[0])
+                    ref_o, ref_w = keep["out"].clone(), keep["w"].clone()
+                    os.environ["MERV_POOL_ASSIST"] = "0"
+                    step(99)  # the same input set as the last assisted step (index 99 of its block)
+                    ab["bit_identical"] = bool(torch.equal(ref_o, keep["out"]) and torch.equal(ref_w, keep["w"]))
+                    ab["assist_over_base"] = sum(ab["assist_ms"]) / sum(ab["base_ms"])
+                    ab["what"] = ("merv_fused_forward with the last 24 of 64 videos pooled, scored and soft-maxed by two spare warps of every GEMM CTA "
+                                  "(release / acquire flags per video) vs the three-launch path; sustained regime, 3 x 100 steps each, alternating")
+                    sustained["pool_assist_ab"] = ab
+                except Exception as e:
+                    sustained["pool_assist_ab"] = {"error": repr(e)[:300]}
+                finally:
+                    os.environ.pop("MERV_POOL_ASSIST", None)
 
         # ---- e2e: host buffers in, host buffers out, through the public host API ------------------------------------------
         e2e = None

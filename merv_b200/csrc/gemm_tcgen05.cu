@@ -217,7 +217,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
           // produced inside this launch by the pooling warps of whatever CTAs are resident: acquire the video's flag first
           const int video = ((m_blk * kCtas + int(rank)) * BM) / p.rows_per_video;
           if (video != ready_video) {
-            if (video >= ap->head && !(MERV_ASSIST_PROFILE && (ap->dbg & 8)) && lane == 0) {
+            // (every lane of the warp-uniform producer acquires and fences: whichever lane elect.sync picks has done both itself)
+            if (video >= ap->head && !(MERV_ASSIST_PROFILE && (ap->dbg & 8))) {
               const int* flag = ap->sync + ASSIST_SYNC_HEADER + ap->B + video;
               if (ld_acquire_gpu(flag) == 0) {
                 const unsigned long long t0 = globaltimer_ns();
