@@ -485,8 +485,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             release_accumulator(buf);
             dot = warp_sum(dot);
             if (lane == 0) p.dot_out[(((long long)s * total_tiles + tile) * kCtas + int(rank)) * EPI_WARPS + (warp - 4)] = dot;
-            continue;
-          }
+          } else {
 #pragma unroll
           for (int c = 0; c < EPI_COLS / 32; ++c) {
             uint32_t v[32];
@@ -501,6 +500,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmPara
             }
           }
           release_accumulator(buf);
+          }
         }
         if (kVid && p.vid_parts > 1) {
           // this item covered only `part` of the videos: fp32 partial tile, 64 contiguous columns per thread

@@ -169,7 +169,6 @@ __device__ __forceinline__ int pt_find_encoder(const PoolTmaParams& p, int item)
 template <typename T, int H, int S, int HF>
 __device__ __forceinline__ void pool_square_half(uint32_t slab, int nf, int v, int wo, T* __restrict__ yb, long long yrs, bool c_ok,
                                                  const float* sv, float inv_nf, float& dot) {
-  constexpr int VEC = Vec16<T>::kN;
   constexpr int P = Pairs<T>::kP;
   constexpr int HALF = S / 2;
   constexpr int O0 = HF * HALF;
