@@ -268,3 +268,24 @@ def test_from_config_rejects_what_merv_rejects():
     # the one resampler outside the accelerated path (timm RegStage blocks): loud, never a fallback
     with pytest.raises(NotImplementedError, match="not part of the accelerated path"):
         M.MervFusion.from_config([8, 8], 8, [2, 2], arch_specifier="conv+linear", feature_fusion="first")
+
+
+def test_wgrad_video_workspace_encodes_the_split_policy():
+    """merv_wgrad_video_workspace (no GPU needed: a B200's 148 SMs are assumed without a device): per-(video, tile, warp) dots, plus fp32
+    partial tiles only where splitting a tile's videos into ranges was measured to pay — the 96-tile encoders (C = 768) from 32 videos on
+    (3 ranges); never the 128-tile ones (C = 1024), never at 16 videos (profiles/r2b_mn_pair_lab.json)."""
+    from merv_b200 import _lib
+
+    lib = _lib.load()
+    os.environ.pop("MERV_WGRAD_SPLIT", None)
+    os.environ.pop("MERV_GEMM_CTA_GROUP", None)
+
+    def dots(videos, n_out, c):
+        d = videos * lib.merv_wgrad_video_parts(n_out, c)
+        return (d + 3) // 4 * 4
+
+    assert lib.merv_wgrad_video_parts(4096, 1024) == 32 * 4 * 16 and lib.merv_wgrad_video_parts(4096, 768) == 32 * 3 * 16
+    assert lib.merv_wgrad_video_workspace(64, 4096, 1024) == dots(64, 4096, 1024)
+    assert lib.merv_wgrad_video_workspace(64, 4096, 768) == dots(64, 4096, 768) + 3 * 4096 * 768
+    assert lib.merv_wgrad_video_workspace(16, 4096, 768) == dots(16, 4096, 768)
+    assert lib.merv_wgrad_video_workspace(0, 4096, 768) == 0
