@@ -1,24 +1,29 @@
 // bf16 projector GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands by TMA).
 //
-// One persistent, warp-specialised kernel serves two entry points:
+// One persistent, warp-specialised kernel body (gemm_body) serves every dense contraction of the path:
 //
 //   merv_linear_bias_act   Y = act(A W^T + bias)                  (nn.Linear [+ nn.GELU], merv/util/nn_utils.py:31-32,46-55)
 //   merv_fused_linear_mix  out = sum_s w[video,s] * (A_s W_s^T) + bias_mix[video]
 //                          (E LinearProjectors + the stack/bmm of CrossAttentionAdapterLearnableQuery.forward,
 //                           nn_utils.py:31-32,503,521, without ever writing the per-encoder projections to HBM)
+//   merv_gemm_ex           the same with either operand stored transposed (MN-major: the backward's dX = dY W, dW = dY^T X)
+//   merv_wgrad_video       dW = sum_b w[b] dY[b]^T X[b] and <W, dY[b]^T X[b]> per video: the accumulator is drained once per video
+//   (opt-in) the fused forward with the pooling of the following videos done by its two spare warps (pool_assist.cuh)
 //
-// Tile 128 x 256 x 64 per CTA (cta_group::1, UMMA 128x256x16), 4-stage TMA->smem ring (128B swizzle, K-major
-// A and W), two 256-column TMEM accumulators.  A "segment" is one (A_s, W_s, K_s) product; the MMA warp
-// alternates accumulators per segment, the 16 epilogue warps drain each finished accumulator into fp32
-// registers scaled by the segment's mixing weight while the next segment (or next tile) is being multiplied,
-// and after the last segment apply bias / erf-GELU / optional row-dot, stage the bf16 rows in shared memory and
-// write them with TMA stores — each output element is written exactly once.
+// Tile 128 x 256 x 64 per CTA, as a CTA pair (cluster 2 x 1, cta_group::2, UMMA 256x256x16: each CTA loads its 128 rows of A and HALF of
+// the W tile, 6-stage ring of 32 KB) or as a single CTA (UMMA 128x256x16, 4 stages of 48 KB); TMA -> shared memory with 128-byte swizzle;
+// two 256-column TMEM accumulators.  A "segment" is one (A_s, W_s, K_s) product; the MMA warp alternates accumulators per segment, the 16
+// epilogue warps drain each finished accumulator into fp32 registers scaled by the segment's mixing weight while the next segment (or
+// next tile) is being multiplied, and after the last segment apply bias / erf-GELU / optional row-dot, stage the bf16 rows in shared
+// memory and write them with TMA stores — each output element is written exactly once.
 //
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      tcgen05.mma issuer (one elected lane)
-//   warp 2      TMEM allocator
-//   warp 3      idle
+//   warp 0      TMA producer   \  warp-uniform loops; one lane issues under elect.sync (lane-0 guards made the compiler wrap every
+//   warp 1      tcgen05.mma issuer /  UTMALDG / UTCHMMA in an ELECT / R2UR waterfall loop: tensor pipe 84 % -> 95 % of elapsed without them)
+//   warp 2      TMEM allocator (+ pooling warp of the opt-in pool assist)
+//   warp 3      idle           (+ pooling warp of the opt-in pool assist)
 //   warps 4-19  epilogue: warp w owns TMEM lanes 32*(w%4)..+31 and columns 64*((w-4)/4)..+63 of the tile
+// Template parameters: kCtas (1 | 2), kWide (128-byte-row output boxes: NVLink peer stores, short contractions), kGelu, kMaj (operand
+// majorness, compile-time), kAssist, kVid.  Measured: fused forward 1614 TFLOP/s in the bench = 0.98 of the burst cuBLAS peak.
 #include <cuda.h>
 
 #include <cstdlib>
