@@ -209,6 +209,9 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record (N > 1)")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs[3] / configs[4] sub-records (N = 1)")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--assist-ab", action="store_true",
+                    help="N = 1: also A/B the opt-in pooling inside the GEMM launch (MERV_POOL_ASSIST=1) in the sustained regime; off by default so "
+                         "that the default run only ever executes the production path")
     ap.add_argument("--gather-timeout", type=float, default=240.0, help="watchdog (s) around the multi-GPU gather sub-records")
     args = ap.parse_args()
 
@@ -344,8 +347,8 @@ def main():
             ms_sus, clk_sus = timed(step, args.sustained_steps)
             sustained = {"steps": args.sustained_steps, "ms_per_step": ms_sus, "value": world * B * 1e3 / ms_sus, "unit": "videos/s", "clocks": clk_sus}
             # the opt-in pooling INSIDE the GEMM launch (MERV_POOL_ASSIST=1), A/B in the regime the sustained run has just
-            # established: alternating blocks of 100 steps, bit-identical outputs.  Off in the primary line and everywhere else.
-            if world == 1 and args.mode == "fused" and args.projector == "linear":
+            # established: alternating blocks of 100 steps, bit-identical outputs.  Only with --assist-ab (profiles/r2_bench_n1.json was taken with it).
+            if args.assist_ab and world == 1 and args.mode == "fused" and args.projector == "linear":
                 try:
                     ab = {"base_ms": [], "assist_ms": []}
                     for _ in range(3):
