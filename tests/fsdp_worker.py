@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--mode", default="per_unit", choices=["per_unit", "root_unit"])
     ap.add_argument("--mlp-type", default="linear")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--resampler", default="3davg", choices=["3davg", "3dconv"])  # merv.py:135-150
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     gpu = args.backend == "nccl"
@@ -74,8 +75,8 @@ def main():
         def __init__(self):
             super().__init__()
             torch.manual_seed(dims[0])  # merv.py:87
-            self.projectors = nn.ModuleList([ref.AveragePooling3DProjector(c, llm, output_frames=frames, output_size=S, mlp_type=args.mlp_type)
-                                             for c in dims])
+            Resampler = ref.AveragePooling3DProjector if args.resampler == "3davg" else ref.Convolutional3DProjector
+            self.projectors = nn.ModuleList([Resampler(c, llm, output_frames=frames, output_size=S, mlp_type=args.mlp_type) for c in dims])
             self.feature_fusion = ref.CrossAttentionAdapterLearnableQuery(embed_dim=embed, llm_dim=llm, token_length=T, averagetoken=True)
             self.llm_head = nn.Linear(llm, 32)  # stands for the LLM consuming the prefix (its own FSDP unit via the LLM's policy)
             with torch.no_grad():
@@ -84,7 +85,7 @@ def main():
         def get_fsdp_wrapping_policy(self):  # merv.py:465-497 with the LLM policy reduced to the stand-in head
             videolm = functools.partial(_module_wrap_policy, module_classes={
                 ref.LinearProjector, ref.MLPProjector, ref.FusedMLPProjector, ref.AveragePoolingProjector, ref.MLPDeepProjector,
-                ref.AveragePooling3DProjector})
+                ref.AveragePooling3DProjector, ref.Convolutional3DProjector})
             llm_policy = functools.partial(_module_wrap_policy, module_classes={nn.Linear}) if False else \
                 functools.partial(lambda module, recurse, nonwrapped_numel, head: True if recurse else module is head, head=self.llm_head)
             return functools.partial(_or_policy, policies=[llm_policy, videolm])
@@ -97,7 +98,8 @@ def main():
     base = FakeMerv()
     ours = copy.deepcopy(base)
     M.patch_merv(ours, fused_training=True if args.mode == "root_unit" else None)
-    assert isinstance(ours.projectors[0], M.AveragePooling3DProjector) and isinstance(ours.feature_fusion, M.CrossAttentionAdapterLearnableQuery)
+    want_cls = M.AveragePooling3DProjector if args.resampler == "3davg" else M.Convolutional3DProjector
+    assert isinstance(ours.projectors[0], want_cls) and isinstance(ours.feature_fusion, M.CrossAttentionAdapterLearnableQuery)
 
     mp = MixedPrecision(param_dtype=torch.bfloat16, reduce_dtype=torch.bfloat16, buffer_dtype=torch.bfloat16)  # fsdp.py:217-224
 
@@ -123,7 +125,7 @@ def main():
     opt_true = torch.optim.SGD(f_true.parameters(), lr=0.05)
     g = torch.Generator().manual_seed(1234 + rank)  # every rank trains on its own micro-batch (base_strategy.py:153-161)
     B = 2
-    info = {"rank": rank, "mode": args.mode, "mlp_type": args.mlp_type, "units_ours": u_ours, "losses": [], "fused_fn": None}
+    info = {"rank": rank, "mode": args.mode, "mlp_type": args.mlp_type, "resampler": args.resampler, "units_ours": u_ours, "losses": [], "fused_fn": None}
 
     def rel(a, b):
         return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-12))
@@ -195,7 +197,7 @@ def main():
     info.update(loss_err=max(abs(a - b) / max(abs(a), 1e-6) for a, b, _ in info["losses"]), bad=bad, eval_err=rel(e_ours, e_ref),
                 eval_w_err=rel(w_ours, w_ref), n_grads=len(grad_err), n_deltas=len(delta_err))
     ok = info["loss_err"] < 3e-2 and not bad and info["eval_err"] < 3e-2 and info["eval_w_err"] < 3e-2 and len(grad_err) >= 2 * len(dims) + 4
-    want_fn = "_FusedLinearFn" if (args.mode == "root_unit" and args.mlp_type == "linear") else "_MixFn"
+    want_fn = "_FusedLinearFn" if (args.mode == "root_unit" and args.mlp_type == "linear" and args.resampler == "3davg") else "_MixFn"
     ok = ok and info["fused_fn"] is not None and info["fused_fn"].startswith(want_fn)
     info["ok"] = bool(ok)
     if gpu:

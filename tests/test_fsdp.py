@@ -51,11 +51,12 @@ def _reference_staged() -> bool:
     return reference_available()
 
 
-@pytest.mark.parametrize("mode,mlp_type", [("per_unit", "linear"), ("root_unit", "linear"), ("per_unit", "gelu-mlp")])
-def test_fsdp_two_ranks_host_logic_on_cpu(mode, mlp_type):
+@pytest.mark.parametrize("mode,mlp_type,resampler", [("per_unit", "linear", "3davg"), ("root_unit", "linear", "3davg"), ("per_unit", "gelu-mlp", "3davg"),
+                                                     ("per_unit", "linear", "3dconv")])
+def test_fsdp_two_ranks_host_logic_on_cpu(mode, mlp_type, resampler):
     if not _reference_staged():
         pytest.skip("needs the reference's nn_utils.py (/root/reference or oracle/_ref staged by __graft_entry__.build())")
-    reports = run_ranks("fsdp_worker.py", 2, "--backend", "gloo", "--mode", mode, "--mlp-type", mlp_type)
+    reports = run_ranks("fsdp_worker.py", 2, "--backend", "gloo", "--mode", mode, "--mlp-type", mlp_type, "--resampler", resampler)
     for rep in reports:
         assert rep["ok"], rep
         if mode == "per_unit":  # the reference's own unit list: each resampler and its inner projector are FSDP units
@@ -67,12 +68,13 @@ def test_fsdp_two_ranks_host_logic_on_cpu(mode, mlp_type):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,mlp_type", [("per_unit", "linear"), ("root_unit", "linear"), ("per_unit", "gelu-mlp")])
-def test_fsdp_two_gpus(mode, mlp_type):
+@pytest.mark.parametrize("mode,mlp_type,resampler", [("per_unit", "linear", "3davg"), ("root_unit", "linear", "3davg"), ("per_unit", "gelu-mlp", "3davg"),
+                                                     ("per_unit", "linear", "3dconv")])
+def test_fsdp_two_gpus(mode, mlp_type, resampler):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     assert _reference_staged(), "oracle/_ref/nn_utils.py did not travel with the snapshot: run __graft_entry__.build() in the build container"
-    reports = run_ranks("fsdp_worker.py", 2, "--backend", "nccl", "--mode", mode, "--mlp-type", mlp_type)
+    reports = run_ranks("fsdp_worker.py", 2, "--backend", "nccl", "--mode", mode, "--mlp-type", mlp_type, "--resampler", resampler)
     for rep in reports:
         assert rep["ok"], rep
         assert rep["native_lib"].endswith("libmerv_fusion.so")
