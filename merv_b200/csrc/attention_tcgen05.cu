@@ -103,26 +103,32 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_tcgen05_kernel(
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + AT_KEYS;
 
   if (warp == 4) {
-    if (lane == 0) {
-      // ===== producer =====
+    {
+      // ===== producer (warp-uniform loop, one lane issues under elect.sync: tcgen05_util.cuh) =====
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int b = item / p.heads, h = item - b * p.heads;
         const uint32_t ph = it & 1u;
         mbar_wait(k_empty, ph ^ 1u);
-        mbar_expect_tx(k_full, uint32_t(hd_chunks) * (AT_Q_CHUNK + AT_KV_CHUNK));
-        for (int c = 0; c < hd_chunks; ++c) {
-          tma_load_4d(&maps.q, k_full, base + AT_Q_OFF + c * AT_Q_CHUNK, c * 64, h, 0, p.q_per_batch ? b : 0);
-          tma_load_4d(&maps.kv, k_full, base + AT_K_OFF + c * AT_KV_CHUNK, c * 64, h, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(k_full, uint32_t(hd_chunks) * (AT_Q_CHUNK + AT_KV_CHUNK));
+          for (int c = 0; c < hd_chunks; ++c) {
+            tma_load_4d(&maps.q, k_full, base + AT_Q_OFF + c * AT_Q_CHUNK, c * 64, h, 0, p.q_per_batch ? b : 0);
+            tma_load_4d(&maps.kv, k_full, base + AT_K_OFF + c * AT_KV_CHUNK, c * 64, h, 0, b);
+          }
         }
+        __syncwarp();
         mbar_wait(v_empty, ph ^ 1u);
-        mbar_expect_tx(v_full, uint32_t(hd_chunks) * AT_KV_CHUNK);
-        for (int c = 0; c < hd_chunks; ++c) tma_load_4d(&maps.kv, v_full, base + AT_V_OFF + c * AT_KV_CHUNK, c * 64, p.heads + h, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(v_full, uint32_t(hd_chunks) * AT_KV_CHUNK);
+          for (int c = 0; c < hd_chunks; ++c) tma_load_4d(&maps.kv, v_full, base + AT_V_OFF + c * AT_KV_CHUNK, c * 64, p.heads + h, 0, b);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (warp-uniform loop, one lane issues under elect.sync) =====
       const int n_keys16 = (p.n_kv + 15) & ~15;  // UMMA N of S and the k extent of P V
       const uint32_t idesc_s = umma_idesc_bf16(AT_M, n_keys16, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(AT_M, p.hd, 0, 1);  // B = V_h MN-major
@@ -132,24 +138,30 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_tcgen05_kernel(
         mbar_wait(k_full, ph);
         mbar_wait(s_empty, ph ^ 1u);
         tc_fence_after();
-        for (int ks = 0; ks < p.hd / UMMA_K; ++ks) {
-          const uint64_t a = umma_desc_sw128(base + AT_Q_OFF + (ks >> 2) * AT_Q_CHUNK) + 2 * (ks & 3);
-          const uint64_t bd = umma_desc_sw128(base + AT_K_OFF + (ks >> 2) * AT_KV_CHUNK) + 2 * (ks & 3);
-          umma_bf16(tmem_S, a, bd, idesc_s, ks != 0 ? 1u : 0u);
+        if (elect_one()) {
+          for (int ks = 0; ks < p.hd / UMMA_K; ++ks) {
+            const uint64_t a = umma_desc_sw128(base + AT_Q_OFF + (ks >> 2) * AT_Q_CHUNK) + 2 * (ks & 3);
+            const uint64_t bd = umma_desc_sw128(base + AT_K_OFF + (ks >> 2) * AT_KV_CHUNK) + 2 * (ks & 3);
+            umma_bf16(tmem_S, a, bd, idesc_s, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full);
+          umma_commit(k_empty);  // Q_h / K_h may be overwritten by the next item's loads
         }
-        umma_commit(s_full);
-        umma_commit(k_empty);  // Q_h / K_h may be overwritten by the next item's loads
+        __syncwarp();
         mbar_wait(p_full, ph);
         mbar_wait(v_full, ph);
         mbar_wait(o_empty, ph ^ 1u);
         tc_fence_after();
-        for (int ks = 0; ks < n_keys16 / UMMA_K; ++ks) {
-          const uint64_t a = umma_desc_sw128(base + AT_P_OFF + (ks >> 2) * AT_P_CHUNK) + 2 * (ks & 3);
-          const uint64_t bd = umma_desc_mn_sw128_lbo(base + AT_V_OFF, AT_KV_CHUNK) + uint64_t(ks) * (2048u >> 4);
-          umma_bf16(tmem_O, a, bd, idesc_o, ks != 0 ? 1u : 0u);
+        if (elect_one()) {
+          for (int ks = 0; ks < n_keys16 / UMMA_K; ++ks) {
+            const uint64_t a = umma_desc_sw128(base + AT_P_OFF + (ks >> 2) * AT_P_CHUNK) + 2 * (ks & 3);
+            const uint64_t bd = umma_desc_mn_sw128_lbo(base + AT_V_OFF, AT_KV_CHUNK) + uint64_t(ks) * (2048u >> 4);
+            umma_bf16(tmem_O, a, bd, idesc_o, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(o_full);
+          umma_commit(v_empty);
         }
-        umma_commit(o_full);
-        umma_commit(v_empty);
+        __syncwarp();
       }
     }
   } else {
@@ -322,24 +334,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_ker
   const int n_q16 = (p.n_q + 15) & ~15;
 
   if (warp == 4) {
-    if (lane == 0) {
-      // ===== producer: Q_h, dO_h, K_h, V_h of one (frame, head) =====
+    {
+      // ===== producer: Q_h, dO_h, K_h, V_h of one (frame, head); warp-uniform loop, one lane issues under elect.sync =====
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int b = item / p.heads, h = item - b * p.heads;
         mbar_wait(ld_empty, (it & 1u) ^ 1u);
-        mbar_expect_tx(ld_full, uint32_t(hd_chunks) * (2 * AB_CH + 2 * AT_KV_CHUNK));
-        for (int c = 0; c < hd_chunks; ++c) {
-          tma_load_4d(&maps.q, ld_full, base + AB_Q_OFF + c * AB_CH, c * 64, h, 0, p.q_per_batch ? b : 0);
-          tma_load_4d(&maps.dout, ld_full, base + AB_DO_OFF + c * AB_CH, c * 64, h, 0, b);
-          tma_load_4d(&maps.kv, ld_full, base + AB_K_OFF + c * AT_KV_CHUNK, c * 64, h, 0, b);
-          tma_load_4d(&maps.kv, ld_full, base + AB_V_OFF + c * AT_KV_CHUNK, c * 64, p.heads + h, 0, b);
+        if (elect_one()) {
+          mbar_expect_tx(ld_full, uint32_t(hd_chunks) * (2 * AB_CH + 2 * AT_KV_CHUNK));
+          for (int c = 0; c < hd_chunks; ++c) {
+            tma_load_4d(&maps.q, ld_full, base + AB_Q_OFF + c * AB_CH, c * 64, h, 0, p.q_per_batch ? b : 0);
+            tma_load_4d(&maps.dout, ld_full, base + AB_DO_OFF + c * AB_CH, c * 64, h, 0, b);
+            tma_load_4d(&maps.kv, ld_full, base + AB_K_OFF + c * AT_KV_CHUNK, c * 64, h, 0, b);
+            tma_load_4d(&maps.kv, ld_full, base + AB_V_OFF + c * AT_KV_CHUNK, c * 64, p.heads + h, 0, b);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    {
+      // ===== MMA issuer (warp-uniform loop, one lane issues under elect.sync) =====
       const uint32_t idesc_s = umma_idesc_bf16(AT_M, n_keys16, 0, 0);   // S, dP: [128 x keys], K-major operands
       const uint32_t idesc_t = umma_idesc_bf16(AT_M, p.hd, 1, 1);       // dV, dK: [128 keys x hd], both operands MN-major
       const uint32_t idesc_q = umma_idesc_bf16(AT_M, p.hd, 0, 1);       // dQ: [128 x hd], A = dS K-major, B = K_h MN-major
@@ -350,6 +365,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_ker
         mbar_wait(dvk_empty1, ph ^ 1u);  // the previous item's accumulators have been drained
         mbar_wait(dq_empty, ph ^ 1u);
         tc_fence_after();
+        if (elect_one()) {
         for (int ks = 0; ks < p.hd / UMMA_K; ++ks) {  // S = Q K^T and dP = dO V^T
           const uint32_t off = uint32_t(ks >> 2), k2 = 2u * uint32_t(ks & 3);
           umma_bf16(tmem_base, umma_desc_sw128(base + AB_Q_OFF + off * AB_CH) + k2, umma_desc_sw128(base + AB_K_OFF + off * AT_KV_CHUNK) + k2, idesc_s,
@@ -361,6 +377,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_ker
                     idesc_s, ks != 0 ? 1u : 0u);
         }
         umma_commit(sdp_full);
+        }
+        __syncwarp();
         mbar_wait(pds_full, ph);
         tc_fence_after();
         auto dvk = [&](int half) {  // dV_half = P[:, half]^T dO -> columns [0, hd); dK_half = dS[:, half]^T Q -> columns [128, 128 + hd)
@@ -375,6 +393,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_ker
                       umma_desc_mn_sw128_lbo(base + AB_Q_OFF, AB_CH) + kstep, idesc_t, ks != 0 ? 1u : 0u);
           }
         };
+        if (elect_one()) {
         dvk(0);
         umma_commit(dvk_full0);
         for (int ks = 0; ks < n_keys16 / UMMA_K; ++ks) {  // dQ = dS K -> columns [256, 256 + hd)
@@ -383,11 +402,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) cross_attention_bwd_tcgen05_ker
           umma_bf16(tmem_base + AT_KEYS, a, bd, idesc_q, ks != 0 ? 1u : 0u);
         }
         umma_commit(dq_full);
+        }
+        __syncwarp();
         mbar_wait(dvk_empty0, ph);
         tc_fence_after();
-        dvk(1);
-        umma_commit(dvk_full1);
-        umma_commit(ld_empty);  // every operand of this item has been read
+        if (elect_one()) {
+          dvk(1);
+          umma_commit(dvk_full1);
+          umma_commit(ld_empty);  // every operand of this item has been read
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -73,16 +73,6 @@ static_assert(128 * PRODUCER_REGS + EPI_WARPS * 32 * EPILOGUE_REGS <= GEMM_THREA
 #ifndef MERV_GEMM_WARP_UNIFORM
 #define MERV_GEMM_WARP_UNIFORM 1
 #endif
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 struct GemmParams {
   int M, N;
   int nseg;
